@@ -1,0 +1,290 @@
+"""grok_b200 -- host-side Python mirror of the B200 JPEG 2000 tile engine's C ABI.
+
+The product is ``libgrokj2k_plugin.so`` (hand-written sm_100a CUDA behind the C ABI of
+``include/grok_b200.h``); this module is only the ctypes doorway tests, ``bench.py`` and Python
+hosts use.  It mirrors the reference's plugin surface (``src/lib/core/plugin/plugin_interface.h``,
+``gpup/gpu_plugin_shared.h``): same entry-point names, argument meaning and return convention
+(0 handled, >0 not handled -> host CPU path, <0 device failure).
+
+There is NO CPU fallback here: if the shared library is missing or no CUDA device is present the
+calls raise.  (The CPU oracle lives under ``oracle/`` and is test infrastructure only.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgrokj2k_plugin.so")
+
+GPUP_MAX_PASSES = 3 * (16 + 7) - 2
+
+
+class Coding(C.Structure):
+    """b2k_coding (include/grok_b200.h)."""
+    _fields_ = [("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32),
+                ("tx0", C.c_uint32), ("ty0", C.c_uint32), ("tw", C.c_uint32), ("th", C.c_uint32),
+                ("numcomps", C.c_uint16), ("prec", C.c_uint8), ("sgnd", C.c_uint8),
+                ("numres", C.c_uint8), ("cblkw_exp", C.c_uint8), ("cblkh_exp", C.c_uint8),
+                ("irreversible", C.c_uint8), ("mct", C.c_uint8), ("numgbits", C.c_uint8),
+                ("prcw_exp", C.c_uint8 * 33), ("prch_exp", C.c_uint8 * 33)]
+
+
+class Block(C.Structure):
+    """b2k_block."""
+    _fields_ = [("tile", C.c_uint32), ("comp", C.c_uint16), ("resno", C.c_uint8), ("band_index", C.c_uint8),
+                ("orient", C.c_uint8), ("kmax", C.c_uint8), ("numbps", C.c_uint8), ("numpasses", C.c_uint8),
+                ("precno", C.c_uint32), ("cblkno", C.c_uint32),
+                ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32),
+                ("buf_x", C.c_uint32), ("buf_y", C.c_uint32), ("length", C.c_uint32),
+                ("offset", C.c_uint64), ("stepsize", C.c_float)]
+
+
+class Result(C.Structure):
+    """b2k_result."""
+    _fields_ = [("num_blocks", C.c_uint64), ("blocks", C.POINTER(Block)), ("bytes", C.POINTER(C.c_uint8)),
+                ("num_bytes", C.c_uint64), ("num_tiles", C.c_uint32),
+                ("ms_h2d", C.c_double), ("ms_dwt", C.c_double), ("ms_t1", C.c_double), ("ms_d2h", C.c_double),
+                ("ms_total", C.c_double)]
+
+
+BLOCK_DTYPE = np.dtype([("tile", "<u4"), ("comp", "<u2"), ("resno", "u1"), ("band_index", "u1"), ("orient", "u1"),
+                        ("kmax", "u1"), ("numbps", "u1"), ("numpasses", "u1"), ("precno", "<u4"), ("cblkno", "<u4"),
+                        ("x0", "<u4"), ("y0", "<u4"), ("x1", "<u4"), ("y1", "<u4"), ("buf_x", "<u4"), ("buf_y", "<u4"),
+                        ("length", "<u4"), ("offset", "<u8"), ("stepsize", "<f4"), ("pad2", "<u4")])
+assert BLOCK_DTYPE.itemsize == C.sizeof(Block), (BLOCK_DTYPE.itemsize, C.sizeof(Block))
+
+# every symbol include/grok_b200.h declares
+EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "gpup_encode_mem", "gpup_tile_free",
+           "b2k_engine_create", "b2k_engine_destroy", "b2k_last_error", "b2k_host_alloc", "b2k_host_free",
+           "b2k_encode", "b2k_encode16", "b2k_result_free", "b2k_decode", "b2k_enumerate",
+           "b2k_result_to_gpup_tile", "b2k_job_create", "b2k_job_destroy", "b2k_job_upload", "b2k_job_forward",
+           "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_inverse", "b2k_job_download",
+           "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
+           "b2k_launch_count", "b2k_job_last_kernel_stats"]
+
+_lib = None
+
+
+def lib():
+    """Load libgrokj2k_plugin.so (built in-tree by __graft_entry__.build / grok_b200/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for the engine)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32, i32, u64 = C.c_void_p, C.c_uint32, C.c_int32, C.c_uint64
+    pp = C.POINTER(C.c_void_p)
+    L.b2k_last_error.restype = C.c_char_p
+    L.b2k_engine_create.argtypes = [i32, pp]
+    L.b2k_engine_destroy.argtypes = [vp]
+    L.b2k_host_alloc.argtypes = [C.c_size_t]
+    L.b2k_host_alloc.restype = vp
+    L.b2k_host_free.argtypes = [vp]
+    L.b2k_encode.argtypes = [vp, C.POINTER(Coding), pp, C.POINTER(u32), u32, u32, C.POINTER(C.POINTER(Result))]
+    L.b2k_result_free.argtypes = [C.POINTER(Result)]
+    L.b2k_decode.argtypes = [vp, C.POINTER(Coding), vp, u64, vp, u64, pp, C.POINTER(u32), u32, u32,
+                             C.POINTER(C.c_double)]
+    L.b2k_enumerate.argtypes = [C.POINTER(Coding), u32, u32, vp, u64]
+    L.b2k_enumerate.restype = C.c_int64
+    L.b2k_result_to_gpup_tile.argtypes = [C.POINTER(Coding), C.POINTER(Result), u32]
+    L.b2k_result_to_gpup_tile.restype = vp
+    L.gpup_tile_free.argtypes = [vp]
+    L.b2k_job_create.argtypes = [vp, C.POINTER(Coding), u32, u32, pp]
+    L.b2k_job_destroy.argtypes = [vp]
+    for n in ("b2k_job_upload", "b2k_job_download", "b2k_job_download_coeffs", "b2k_job_upload_coeffs"):
+        getattr(L, n).argtypes = [vp, pp, C.POINTER(u32)]
+    L.b2k_job_forward.argtypes = [vp, C.POINTER(C.c_float)]
+    L.b2k_job_inverse.argtypes = [vp, C.POINTER(C.c_float)]
+    L.b2k_job_t1_encode.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u64)]
+    L.b2k_job_t1_decode.argtypes = [vp, C.POINTER(C.c_float)]
+    L.b2k_job_fetch_result.argtypes = [vp, C.POINTER(C.POINTER(Result))]
+    L.b2k_job_num_blocks.argtypes = [vp]
+    L.b2k_job_num_blocks.restype = u64
+    L.b2k_launch_count.restype = u64
+    L.b2k_job_last_kernel_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(u64)]
+    _lib = L
+    return L
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise EngineError("%s -> %d: %s" % (what, rc, (lib().b2k_last_error() or b"").decode()))
+
+
+def make_coding(width, height, numcomps=1, prec=8, sgnd=False, numres=6, tile=None, cblk=(64, 64), irreversible=False,
+                mct=None, numgbits=1, origin=(0, 0), tile_origin=None):
+    """Convenience constructor; defaults follow grk_compress for an HT (.jph) output:
+    6 resolutions (CodeStream.h L43), 64x64 blocks (L40), one guard bit (GrkCompress.cpp L849)."""
+    cp = Coding()
+    cp.x0, cp.y0 = origin
+    cp.x1, cp.y1 = origin[0] + width, origin[1] + height
+    if tile:
+        cp.tw, cp.th = tile
+        cp.tx0, cp.ty0 = tile_origin if tile_origin else origin
+    cp.numcomps, cp.prec, cp.sgnd, cp.numres = numcomps, prec, int(sgnd), numres
+    cp.cblkw_exp, cp.cblkh_exp = int(np.log2(cblk[0])), int(np.log2(cblk[1]))
+    cp.irreversible = int(irreversible)
+    cp.mct = int(numcomps >= 3) if mct is None else int(mct)
+    cp.numgbits = numgbits
+    for r in range(33):
+        cp.prcw_exp[r] = 15
+        cp.prch_exp[r] = 15
+    return cp
+
+
+def _plane_ptrs(planes):
+    n = len(planes)
+    arr = (C.c_void_p * n)(*[p.ctypes.data for p in planes])
+    strides = (C.c_uint32 * n)(*[p.strides[0] // p.itemsize for p in planes])
+    return arr, strides
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in cudaHostAlloc'ed (pinned) memory; keep the returned array alive, free with
+    ``lib().b2k_host_free(arr.ctypes.data)`` (or let the process end)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = lib().b2k_host_alloc(n)
+    if not p:
+        raise EngineError("b2k_host_alloc(%d) failed" % n)
+    buf = (C.c_uint8 * n).from_address(p)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+class EncodeResult:
+    """Owns a b2k_result; exposes numpy views of the block table and the byte arena."""
+
+    def __init__(self, ptr):
+        self._ptr = ptr
+        r = ptr.contents
+        self.num_blocks = int(r.num_blocks)
+        self.num_bytes = int(r.num_bytes)
+        self.timings = dict(h2d=r.ms_h2d, dwt=r.ms_dwt, t1=r.ms_t1, d2h=r.ms_d2h, total=r.ms_total)
+        self.blocks = np.frombuffer((C.c_uint8 * (self.num_blocks * C.sizeof(Block))).from_address(
+            C.addressof(r.blocks.contents)), dtype=BLOCK_DTYPE) if self.num_blocks else np.zeros(0, BLOCK_DTYPE)
+        self.bytes = np.frombuffer((C.c_uint8 * max(1, self.num_bytes)).from_address(
+            C.addressof(r.bytes.contents)), dtype=np.uint8)[:self.num_bytes]
+
+    def block_bytes(self, i):
+        b = self.blocks[i]
+        return self.bytes[int(b["offset"]):int(b["offset"]) + int(b["length"])]
+
+    def free(self):
+        if self._ptr is not None:
+            lib().b2k_result_free(self._ptr)
+            self._ptr = None
+            self.blocks = self.bytes = None
+
+    def __del__(self):
+        self.free()
+
+
+class Engine:
+    """b2k_engine: one per process per GPU (one process per GPU is the deployment model)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().b2k_engine_create(device, C.byref(self._h)), "b2k_engine_create")
+
+    def close(self):
+        if self._h:
+            lib().b2k_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def encode(self, cp, planes, tile_mod=1, tile_rem=0):
+        """planes: list of 2-D int32 arrays (row stride may exceed width)."""
+        ptrs, strides = _plane_ptrs(planes)
+        out = C.POINTER(Result)()
+        _check(lib().b2k_encode(self._h, C.byref(cp), ptrs, strides, tile_mod, tile_rem, C.byref(out)), "b2k_encode")
+        return EncodeResult(out)
+
+    def decode(self, cp, blocks, data, out_planes, tile_mod=1, tile_rem=0):
+        ptrs, strides = _plane_ptrs(out_planes)
+        blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        ms = C.c_double()
+        _check(lib().b2k_decode(self._h, C.byref(cp), blocks.ctypes.data, len(blocks), data.ctypes.data, len(data),
+                                ptrs, strides, tile_mod, tile_rem, C.byref(ms)), "b2k_decode")
+        return ms.value
+
+    def job(self, cp, tile_mod=1, tile_rem=0):
+        return Job(self, cp, tile_mod, tile_rem)
+
+
+class Job:
+    """b2k_device_job: device-resident buffers + per-stage entry points (parity tests, bench `value`)."""
+
+    def __init__(self, eng, cp, tile_mod=1, tile_rem=0):
+        self._h = C.c_void_p()
+        self.cp = cp
+        _check(lib().b2k_job_create(eng._h, C.byref(cp), tile_mod, tile_rem, C.byref(self._h)), "b2k_job_create")
+
+    def close(self):
+        if self._h:
+            lib().b2k_job_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def _planes(self, fn, planes):
+        ptrs, strides = _plane_ptrs(planes)
+        _check(getattr(lib(), fn)(self._h, ptrs, strides), fn)
+
+    def upload(self, planes):
+        self._planes("b2k_job_upload", planes)
+
+    def download(self, planes):
+        self._planes("b2k_job_download", planes)
+
+    def download_coeffs(self, planes):
+        self._planes("b2k_job_download_coeffs", planes)
+
+    def upload_coeffs(self, planes):
+        self._planes("b2k_job_upload_coeffs", planes)
+
+    def forward(self):
+        ms = C.c_float()
+        _check(lib().b2k_job_forward(self._h, C.byref(ms)), "b2k_job_forward")
+        return ms.value
+
+    def inverse(self):
+        ms = C.c_float()
+        _check(lib().b2k_job_inverse(self._h, C.byref(ms)), "b2k_job_inverse")
+        return ms.value
+
+    def t1_encode(self):
+        ms, total = C.c_float(), C.c_uint64()
+        _check(lib().b2k_job_t1_encode(self._h, C.byref(ms), C.byref(total)), "b2k_job_t1_encode")
+        return ms.value, total.value
+
+    def t1_decode(self):
+        ms = C.c_float()
+        _check(lib().b2k_job_t1_decode(self._h, C.byref(ms)), "b2k_job_t1_decode")
+        return ms.value
+
+    def fetch_result(self):
+        out = C.POINTER(Result)()
+        _check(lib().b2k_job_fetch_result(self._h, C.byref(out)), "b2k_job_fetch_result")
+        return EncodeResult(out)
+
+    def num_blocks(self):
+        return int(lib().b2k_job_num_blocks(self._h))
+
+    def kernel_stats(self, which=0):
+        ms, nb = C.c_float(), C.c_uint64()
+        lib().b2k_job_last_kernel_stats(self._h, which, C.byref(ms), C.byref(nb))
+        return ms.value, nb.value
+
+
+def enumerate_blocks(cp, tile_mod=1, tile_rem=0):
+    n = lib().b2k_enumerate(C.byref(cp), tile_mod, tile_rem, None, 0)
+    if n < 0:
+        raise EngineError("b2k_enumerate: " + (lib().b2k_last_error() or b"").decode())
+    out = np.zeros(n, BLOCK_DTYPE)
+    lib().b2k_enumerate(C.byref(cp), tile_mod, tile_rem, out.ctypes.data, n)
+    return out

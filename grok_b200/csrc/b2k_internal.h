@@ -1,0 +1,68 @@
+/*
+ * grok_b200/csrc/b2k_internal.h -- structures shared by the host engine and the CUDA kernels.
+ * Product code: must not include anything under oracle/.
+ */
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <cuda_runtime.h>
+#include "../../include/grok_b200.h"
+
+#define B2K_WARPS_PER_CTA 4
+#define B2K_MAX_RES 33
+
+/* ---- one DWT level of one tile-component (or of the 3 colour components together) ---------
+ * All coordinates are canvas coordinates of the resolution being split (reference:
+ * WaveletFwd.cpp L1398-1407: rw/rh/parity from currentRes).  Pointers are pre-offset so that
+ * in[c] addresses the sample at canvas (u0,v0). */
+struct DwtLevelDesc
+{
+  const void* in[3];   /* input planes (level 1: image samples; else previous LL) */
+  void* out_c[3];      /* Mallat buffer of the tile component: element (0,0) of the tile */
+  void* out_ll[3];     /* where the LL sample (ceil(u0/2), ceil(v0/2)) is stored */
+  uint32_t in_pitch, c_pitch, ll_pitch; /* in elements */
+  int32_t u0, v0, u1, v1;
+  int32_t shift[3];    /* value ADDED to the samples on load at level 1 (= -2^(prec-1)) */
+  int32_t lo[3], hi[3];/* inverse: clamp range after the shift is restored */
+  uint16_t nstrips, nsegs, strip_w, pairs_per_seg;
+  uint8_t first_level; /* 1: samples are integers from the image (apply shift / MCT) */
+  uint8_t in_is_u16;
+  uint8_t pad[2];
+};
+
+/* ---- one code block for the HT coder kernels ------------------------------------------------
+ * reference: t1/BlockExec.h L62-153 (CompressBlockExec / DecompressBlockExec) */
+struct HtBlockDesc
+{
+  void* coef;          /* first sample of the block inside the Mallat buffer */
+  uint32_t pitch;      /* buffer row pitch in elements */
+  uint16_t w, h;
+  uint8_t kmax;        /* band maxBitPlanes_ == missing_msbs handed to the encoder */
+  uint8_t irreversible;
+  uint8_t mmsbs;       /* decode: missing MSBs = Kmax - numbps (DecompressScheduler.cpp L261-263) */
+  uint8_t pad;
+  float quant;         /* encode: inv_step_ht * 2^(30-kmax); decode: stepsize / 2^(31-kmax) */
+  uint32_t slot_cap;   /* bytes reserved in the scratch slot */
+  uint64_t slot_off;   /* byte offset of the scratch slot (encode) / of the coded bytes (decode) */
+  uint32_t length;     /* decode: coded length */
+  uint32_t pad2;
+};
+
+struct HtBlockOut /* written by the encoder kernel */
+{
+  uint32_t ms_len, mel_len, vlc_len, total;
+};
+
+/* kernel launchers (dwt.cu, ht_enc.cu, ht_dec.cu) */
+void b2k_launch_dwt_fwd(const DwtLevelDesc* d_descs, int ndesc, int max_jobs, int nc, bool irreversible,
+                        bool in_u16, cudaStream_t st);
+void b2k_launch_dwt_inv(const DwtLevelDesc* d_descs, int ndesc, int max_jobs, int nc, bool irreversible,
+                        cudaStream_t st);
+void b2k_launch_ht_encode(const HtBlockDesc* d_blocks, HtBlockOut* d_out, uint8_t* d_scratch, uint32_t nblocks,
+                          uint32_t max_w, cudaStream_t st);
+void b2k_launch_ht_gather(const HtBlockDesc* d_blocks, const HtBlockOut* d_out, const uint64_t* d_offsets,
+                          const uint8_t* d_scratch, uint8_t* d_bytes, uint32_t nblocks, cudaStream_t st);
+void b2k_launch_scan_lengths(const HtBlockOut* d_out, uint64_t* d_offsets, uint32_t nblocks, cudaStream_t st);
+void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t nblocks, uint32_t max_w,
+                          int* d_err, cudaStream_t st);
+void b2k_count_launch(void);

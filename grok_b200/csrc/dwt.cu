@@ -1,0 +1,865 @@
+/*
+ * grok_b200/csrc/dwt.cu -- forward / inverse lifting DWT (reversible 5/3, irreversible 9/7) for
+ * sm_100a, one decomposition level per launch, with the DC level shift and the RCT / ICT
+ * multi-component transform fused into the finest level.
+ *
+ * What it replaces in the reference (CPU, Highway SIMD + Taskflow):
+ *   forward : Mct::compress_rev / compress_irrev      point_transform/mct.cpp L497-531, L584-636
+ *             encode_53_v/h, encode_97_v/h, encode<>  wavelet/WaveletFwd.cpp L139-876, L1337-1514
+ *   inverse : tile_53 / tile_97                       wavelet/WaveletReverse.cpp L1347-1397,
+ *                                                     wavelet/WaveletReverse97.cpp L837-857, L950-
+ *             DecompressRev / DecompressIrrev         point_transform/mct.cpp L201-256, L318-391
+ *
+ * B200 design (not a port of the column-strip SIMD loops):
+ *   - one warp = one job = (tile component(s), 8*strip_w-column strip, row segment).  Each lane
+ *     owns 8 consecutive canvas columns (two 128-bit loads per row).  The reference's
+ *     "all columns, then all rows" double pass is fused: rows stream through a register
+ *     sliding window for the vertical lifting, every finished vertical row is lifted
+ *     horizontally with warp shuffles (predict/update need one neighbour each), and the four
+ *     sub-bands are written once, de-interleaved, with 128-bit stores.  HBM traffic per level is
+ *     one read + one write of every coefficient: the algorithmic minimum.
+ *   - symmetric extension is implemented in the LOADS (mirrored addresses), so the lifting
+ *     code has no boundary cases; lanes 0 and 31 are halo lanes (recompute instead of
+ *     cross-warp exchange), row segments recompute 3 (5/3) or 7 (9/7) halo rows.
+ *   - integer maths is bit-exact with the reference; 9/7 uses fmaf() where the reference build
+ *     contracts to FMA (see oracle/j2k_oracle.c fwd97_line) and explicit _rn intrinsics elsewhere.
+ */
+#include "b2k_internal.h"
+
+namespace {
+
+__device__ __forceinline__ int mirror_rel(int t, int n)
+{
+  if(t >= 0 && t < n)
+    return t;
+  if(n == 1)
+    return 0;
+  const int period = 2 * (n - 1);
+  t %= period;
+  if(t < 0)
+    t += period;
+  return t < n ? t : period - t;
+}
+
+/* ---- 8-sample row loads ------------------------------------------------------------------ */
+/* row points at the sample with relative index 0 (canvas u0); rel = first wanted index */
+__device__ __forceinline__ void load8_w32(const int32_t* __restrict__ row, int rel, int n, int (&v)[8])
+{
+  const int32_t* p = row + rel;
+  if(rel >= 0 && rel + 8 <= n && ((reinterpret_cast<uintptr_t>(p) & 15) == 0))
+  {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+    const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  else
+  {
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+      v[i] = __ldg(row + mirror_rel(rel + i, n));
+  }
+}
+__device__ __forceinline__ void load8_u16(const uint16_t* __restrict__ row, int rel, int n, int sgnd, int (&v)[8])
+{
+  const uint16_t* p = row + rel;
+  if(rel >= 0 && rel + 8 <= n && ((reinterpret_cast<uintptr_t>(p) & 15) == 0))
+  {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    v[0] = a.x & 0xFFFF; v[1] = a.x >> 16; v[2] = a.y & 0xFFFF; v[3] = a.y >> 16;
+    v[4] = a.z & 0xFFFF; v[5] = a.z >> 16; v[6] = a.w & 0xFFFF; v[7] = a.w >> 16;
+  }
+  else
+  {
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+      v[i] = __ldg(row + mirror_rel(rel + i, n));
+  }
+  if(sgnd)
+  {
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+      v[i] = (int)(int16_t)v[i];
+  }
+}
+
+/* 4 consecutive band samples (inverse transform): idx0 = first band-relative index wanted,
+ * mirrored per element through the interleaved domain when out of range */
+__device__ __forceinline__ void load4_band(const int32_t* __restrict__ row, int k0, int kb0, int u0, int u1, int odd,
+                                           int (&v)[4])
+{
+  /* sample i has canvas position u = 2*(k0+i)+odd ; band index = (u' >> 1) - kb0 */
+  const int ufirst = 2 * k0 + odd, ulast = ufirst + 6;
+  const int32_t* p = row + (k0 - kb0);
+  if(ufirst >= u0 && ulast < u1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0))
+  {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  }
+  else
+  {
+    const int n = u1 - u0;
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+    {
+      const int um = u0 + mirror_rel(ufirst + 2 * i - u0, n);
+      /* a length-1 line mirrors onto a sample of the other parity: that band is empty */
+      v[i] = ((um & 1) == odd) ? __ldg(row + ((um >> 1) - kb0)) : 0;
+    }
+  }
+}
+
+__device__ __forceinline__ void store4(int32_t* __restrict__ row, int col, const int (&v)[4], unsigned validmask)
+{
+  int32_t* p = row + col;
+  if(validmask == 0xF && ((reinterpret_cast<uintptr_t>(p) & 15) == 0))
+    *reinterpret_cast<int4*>(p) = make_int4(v[0], v[1], v[2], v[3]);
+  else
+  {
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+      if(validmask & (1u << i))
+        p[i] = v[i];
+  }
+}
+__device__ __forceinline__ void store8(int32_t* __restrict__ row, int col, const int (&v)[8], unsigned validmask)
+{
+  int32_t* p = row + col;
+  if(validmask == 0xFF && ((reinterpret_cast<uintptr_t>(p) & 15) == 0))
+  {
+    reinterpret_cast<int4*>(p)[0] = make_int4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<int4*>(p)[1] = make_int4(v[4], v[5], v[6], v[7]);
+  }
+  else
+  {
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+      if(validmask & (1u << i))
+        p[i] = v[i];
+  }
+}
+
+/* ---- job decoding ------------------------------------------------------------------------- */
+struct Job
+{
+  int lane, ulane, jbeg, jend, wn, hn, nvalid;
+  bool owner, need;
+};
+__device__ __forceinline__ bool decode_job(const DwtLevelDesc& D, Job& J)
+{
+  J.lane = threadIdx.x & 31;
+  const int job = blockIdx.x * B2K_WARPS_PER_CTA + (threadIdx.x >> 5);
+  if(job >= (int)D.nstrips * (int)D.nsegs)
+    return false;
+  const int strip = job % D.nstrips, seg = job / D.nstrips;
+  J.wn = D.u1 - D.u0;
+  J.hn = D.v1 - D.v0;
+  J.nvalid = D.strip_w >> 3;
+  J.ulane = (D.u0 & ~7) + strip * (int)D.strip_w + (J.lane - 1) * 8;
+  J.owner = J.lane >= 1 && J.lane <= J.nvalid && J.ulane < D.u1;
+  J.need = J.lane <= J.nvalid + 1 && J.ulane < D.u1 + 8;
+  const int jlo = D.v0 >> 1, jhi = (D.v1 - 1) >> 1;
+  J.jbeg = jlo + seg * (int)D.pairs_per_seg;
+  J.jend = min(J.jbeg + (int)D.pairs_per_seg, jhi + 1);
+  return true;
+}
+
+/* =============================================================================================
+ * forward, finest-level sample fetch: integers from the image, + DC shift, + RCT / ICT
+ * =========================================================================================== */
+template <int NC, bool U16>
+__device__ __forceinline__ void fetch_int_rows(const DwtLevelDesc& D, const Job& J, int v, int (&out)[NC][8])
+{
+  const int r = mirror_rel(v - D.v0, J.hn);
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+  {
+    if(!J.need)
+    {
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+        out[c][i] = 0;
+      continue;
+    }
+    if(U16)
+      load8_u16(reinterpret_cast<const uint16_t*>(D.in[c]) + (size_t)r * D.in_pitch, J.ulane - D.u0, J.wn,
+                D.in_is_u16 == 2, out[c]);
+    else
+      load8_w32(reinterpret_cast<const int32_t*>(D.in[c]) + (size_t)r * D.in_pitch, J.ulane - D.u0, J.wn, out[c]);
+  }
+}
+
+/* reversible: mct.cpp L497-531 */
+template <int NC, bool U16>
+__device__ __forceinline__ void fetch53(const DwtLevelDesc& D, const Job& J, int v, int (&out)[NC][8])
+{
+  if(D.first_level)
+  {
+    fetch_int_rows<NC, U16>(D, J, v, out);
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+    {
+      if(NC == 3)
+      {
+        const int r = out[0][i] + D.shift[0], g = out[1][i] + D.shift[1], b = out[2][i] + D.shift[2];
+        out[0][i] = ((g + g) + b + r) >> 2;
+        out[1][i] = b - g;
+        out[2][i] = r - g;
+      }
+      else
+        out[0][i] += D.shift[0];
+    }
+  }
+  else
+    fetch_int_rows<NC, false>(D, J, v, out);
+}
+
+/* irreversible: mct.cpp L584-636; float conversion of the finest level WaveletFwd.cpp L658-681 */
+template <int NC, bool U16>
+__device__ __forceinline__ void fetch97(const DwtLevelDesc& D, const Job& J, int v, float (&out)[NC][8])
+{
+  int raw[NC][8];
+  if(D.first_level)
+  {
+    fetch_int_rows<NC, U16>(D, J, v, raw);
+    const float a_r = 0.299f, a_g = 0.587f, a_b = 0.114f;
+    const float cb = __fdiv_rn(0.5f, __fsub_rn(1.0f, a_b)), cr = __fdiv_rn(0.5f, __fsub_rn(1.0f, a_r));
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+    {
+      if(NC == 3)
+      {
+        const float r = (float)(raw[0][i] + D.shift[0]), g = (float)(raw[1][i] + D.shift[1]),
+                    b = (float)(raw[2][i] + D.shift[2]);
+        const float y = __fadd_rn(__fadd_rn(__fmul_rn(a_r, r), __fmul_rn(a_g, g)), __fmul_rn(a_b, b));
+        out[0][i] = y;
+        out[1][i] = __fmul_rn(cb, __fsub_rn(b, y));
+        out[2][i] = __fmul_rn(cr, __fsub_rn(r, y));
+      }
+      else
+        out[0][i] = (float)(raw[0][i] + D.shift[0]);
+    }
+  }
+  else
+  {
+    fetch_int_rows<NC, false>(D, J, v, raw);
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+        out[c][i] = __int_as_float(raw[c][i]);
+  }
+}
+
+/* ---- sub-band row stores (Mallat layout: TileComponentWindow.h L241-264) -------------------- */
+struct BandGeom
+{
+  int x0l, x0h, y0l, y0h, snx, sny;
+};
+__device__ __forceinline__ BandGeom band_geom(const DwtLevelDesc& D)
+{
+  BandGeom g;
+  g.x0l = (D.u0 + 1) >> 1;
+  g.x0h = D.u0 >> 1;
+  g.y0l = (D.v0 + 1) >> 1;
+  g.y0h = D.v0 >> 1;
+  g.snx = ((D.u1 + 1) >> 1) - g.x0l;
+  g.sny = ((D.v1 + 1) >> 1) - g.y0l;
+  return g;
+}
+
+/* lo[4]/hi[4]: horizontally transformed samples of one vertical row (vertical low if !vhigh) */
+__device__ __forceinline__ void store_band_rows(const DwtLevelDesc& D, const Job& J, const BandGeom& g, int c, int j,
+                                                bool vhigh, const int (&lo)[4], const int (&hi)[4])
+{
+  const int v = 2 * j + (vhigh ? 1 : 0);
+  if(!J.owner || v < D.v0 || v >= D.v1)
+    return;
+  unsigned mlo = 0, mhi = 0;
+#pragma unroll
+  for(int i = 0; i < 4; ++i)
+  {
+    const int ue = J.ulane + 2 * i;
+    if(ue >= D.u0 && ue < D.u1)
+      mlo |= 1u << i;
+    if(ue + 1 >= D.u0 && ue + 1 < D.u1)
+      mhi |= 1u << i;
+  }
+  const int k0 = J.ulane >> 1;
+  if(!vhigh)
+  {
+    /* LL -> out_ll, HL -> Mallat top-right */
+    int32_t* llrow = reinterpret_cast<int32_t*>(D.out_ll[c]) + (size_t)(j - g.y0l) * D.ll_pitch;
+    store4(llrow, k0 - g.x0l, lo, mlo);
+    int32_t* crow = reinterpret_cast<int32_t*>(D.out_c[c]) + (size_t)(j - g.y0l) * D.c_pitch;
+    store4(crow, g.snx + k0 - g.x0h, hi, mhi);
+  }
+  else
+  {
+    int32_t* crow = reinterpret_cast<int32_t*>(D.out_c[c]) + (size_t)(g.sny + j - g.y0h) * D.c_pitch;
+    store4(crow, k0 - g.x0l, lo, mlo);
+    store4(crow, g.snx + k0 - g.x0h, hi, mhi);
+  }
+}
+
+/* ---- horizontal lifting of one row held as 8 values per lane -------------------------------- */
+__device__ __forceinline__ void hfwd53(const int (&r)[8], int wn, int (&lo)[4], int (&hi)[4])
+{
+  const int en = __shfl_down_sync(0xffffffffu, r[0], 1);
+  hi[0] = r[1] - ((r[0] + r[2]) >> 1);
+  hi[1] = r[3] - ((r[2] + r[4]) >> 1);
+  hi[2] = r[5] - ((r[4] + r[6]) >> 1);
+  hi[3] = r[7] - ((r[6] + en) >> 1);
+  const int dp = __shfl_up_sync(0xffffffffu, hi[3], 1);
+  lo[0] = r[0] + ((dp + hi[0] + 2) >> 2);
+  lo[1] = r[2] + ((hi[0] + hi[1] + 2) >> 2);
+  lo[2] = r[4] + ((hi[1] + hi[2] + 2) >> 2);
+  lo[3] = r[6] + ((hi[2] + hi[3] + 2) >> 2);
+  if(wn == 1)
+  { /* WaveletFwd.cpp L289-300: lone column, doubled when it sits on an odd coordinate */
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+    {
+      lo[i] = r[2 * i];
+      hi[i] = r[2 * i + 1] << 1;
+    }
+  }
+}
+
+#define F97_ALPHA (-1.586134342f)
+#define F97_BETA (-0.052980118f)
+#define F97_GAMMA (0.882911075f)
+#define F97_DELTA (0.443506852f)
+#define F97_K (1.230174105f)
+
+__device__ __forceinline__ void hfwd97(const float (&r)[8], int wn, float invK, float deltaS, int (&lo)[4],
+                                       int (&hi)[4])
+{
+  float e[5], d[4], s[5];
+#pragma unroll
+  for(int i = 0; i < 4; ++i)
+    e[i] = r[2 * i];
+  e[4] = __shfl_down_sync(0xffffffffu, r[0], 1);
+#pragma unroll
+  for(int i = 0; i < 4; ++i)
+    d[i] = fmaf(e[i] + e[i + 1], F97_ALPHA, r[2 * i + 1]);
+  float dm = __shfl_up_sync(0xffffffffu, d[3], 1);
+  s[0] = fmaf(dm + d[0], F97_BETA, e[0]);
+#pragma unroll
+  for(int i = 1; i < 4; ++i)
+    s[i] = fmaf(d[i - 1] + d[i], F97_BETA, e[i]);
+  s[4] = __shfl_down_sync(0xffffffffu, s[0], 1);
+#pragma unroll
+  for(int i = 0; i < 4; ++i)
+    d[i] = __fmul_rn(fmaf(s[i] + s[i + 1], F97_GAMMA, d[i]), F97_K);
+  dm = __shfl_up_sync(0xffffffffu, d[3], 1);
+  float o0 = __fmul_rn(fmaf(dm + d[0], deltaS, s[0]), invK);
+  lo[0] = __float_as_int(o0);
+#pragma unroll
+  for(int i = 1; i < 4; ++i)
+    lo[i] = __float_as_int(__fmul_rn(fmaf(d[i - 1] + d[i], deltaS, s[i]), invK));
+#pragma unroll
+  for(int i = 0; i < 4; ++i)
+    hi[i] = __float_as_int(d[i]);
+  if(wn == 1)
+  { /* WaveletFwd.cpp L444-455 */
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+    {
+      lo[i] = __float_as_int(r[2 * i]);
+      hi[i] = __float_as_int(__fmul_rn(r[2 * i + 1], 2.0f));
+    }
+  }
+}
+
+/* =============================================================================================
+ * forward 5/3
+ * =========================================================================================== */
+template <int NC, bool U16>
+__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_fwd(const DwtLevelDesc* __restrict__ descs)
+{
+  const DwtLevelDesc& D = descs[blockIdx.y];
+  Job J;
+  if(!decode_job(D, J))
+    return;
+  const BandGeom g = band_geom(D);
+
+  int E[NC][8], DP[NC][8];
+  {
+    int A[NC][8], B[NC][8];
+    fetch53<NC, U16>(D, J, 2 * J.jbeg - 2, A);
+    fetch53<NC, U16>(D, J, 2 * J.jbeg - 1, B);
+    fetch53<NC, U16>(D, J, 2 * J.jbeg, E);
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+        DP[c][i] = B[c][i] - ((A[c][i] + E[c][i]) >> 1);
+  }
+  for(int j = J.jbeg; j < J.jend; ++j)
+  {
+    int O[NC][8], E2[NC][8];
+    fetch53<NC, U16>(D, J, 2 * j + 1, O);
+    fetch53<NC, U16>(D, J, 2 * j + 2, E2);
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+      int s[8], d[8];
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+      {
+        d[i] = O[c][i] - ((E[c][i] + E2[c][i]) >> 1);
+        s[i] = E[c][i] + ((DP[c][i] + d[i] + 2) >> 2);
+        if(J.hn == 1)
+        { /* WaveletFwd.cpp L146-156 */
+          s[i] = E[c][i];
+          d[i] = O[c][i] << 1;
+        }
+        DP[c][i] = d[i];
+        E[c][i] = E2[c][i];
+      }
+      int lo[4], hi[4];
+      hfwd53(s, J.wn, lo, hi);
+      store_band_rows(D, J, g, c, j, false, lo, hi);
+      hfwd53(d, J.wn, lo, hi);
+      store_band_rows(D, J, g, c, j, true, lo, hi);
+    }
+  }
+}
+
+/* =============================================================================================
+ * forward 9/7: vertical pipeline  d1[t] -> s1[t] -> d2[t-1] -> s2[t-1]   
+ * =========================================================================================== */
+template <int NC, bool U16>
+__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_fwd(const DwtLevelDesc* __restrict__ descs)
+{
+  const DwtLevelDesc& D = descs[blockIdx.y];
+  Job J;
+  if(!decode_job(D, J))
+    return;
+  const BandGeom g = band_geom(D);
+  const float invK = (float)(1.0 / 1.230174105);
+  const float deltaS = __fmul_rn(F97_DELTA, invK);
+
+  float Ev[NC][8], D1[NC][8], S1[NC][8], D2[NC][8];
+  fetch97<NC, U16>(D, J, 2 * (J.jbeg - 2), Ev);
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+      D1[c][i] = S1[c][i] = D2[c][i] = 0.f;
+
+  for(int t = J.jbeg - 2; t <= J.jend; ++t)
+  {
+    float O[NC][8], E2[NC][8];
+    fetch97<NC, U16>(D, J, 2 * t + 1, O);
+    fetch97<NC, U16>(D, J, 2 * t + 2, E2);
+    const bool emit = (t - 1) >= J.jbeg;
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+      float lowrow[8], highrow[8];
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+      {
+        const float d1 = fmaf(Ev[c][i] + E2[c][i], F97_ALPHA, O[c][i]);
+        const float s1 = fmaf(D1[c][i] + d1, F97_BETA, Ev[c][i]);
+        const float d2 = __fmul_rn(fmaf(S1[c][i] + s1, F97_GAMMA, D1[c][i]), F97_K);
+        const float s2 = __fmul_rn(fmaf(D2[c][i] + d2, deltaS, S1[c][i]), invK);
+        lowrow[i] = s2;
+        highrow[i] = d2;
+        if(J.hn == 1)
+        { /* WaveletFwd.cpp L639-654; the values of pair t-1 are asked for, every row mirrors
+             to the single real one */
+          lowrow[i] = Ev[c][i];
+          highrow[i] = __fmul_rn(O[c][i], 2.0f);
+        }
+        D2[c][i] = d2;
+        D1[c][i] = d1;
+        S1[c][i] = s1;
+        Ev[c][i] = E2[c][i];
+      }
+      /* shuffles are executed by every lane on every iteration */
+      int lo[4], hi[4];
+      hfwd97(lowrow, J.wn, invK, deltaS, lo, hi);
+      if(emit)
+        store_band_rows(D, J, g, c, t - 1, false, lo, hi);
+      hfwd97(highrow, J.wn, invK, deltaS, lo, hi);
+      if(emit)
+        store_band_rows(D, J, g, c, t - 1, true, lo, hi);
+    }
+  }
+}
+
+/* =============================================================================================
+ * inverse: descriptor roles swap -- out_ll / out_c are the SOURCE (LL and HL/LH/HH), in[] the
+ * destination (interleaved samples of the next finer resolution, or the image at the finest).
+ * =========================================================================================== */
+template <int NC>
+__device__ __forceinline__ void fetch_band_rows(const DwtLevelDesc& D, const Job& J, const BandGeom& g, int j,
+                                                bool vhigh, int (&lo)[NC][4], int (&hi)[NC][4])
+{
+  /* vertical mirror in the interleaved domain */
+  const int vm = D.v0 + mirror_rel(2 * j + (vhigh ? 1 : 0) - D.v0, J.hn);
+  const int jm = vm >> 1;
+  const int k0 = J.ulane >> 1;
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+  {
+    if(!J.need || (vm & 1) != (vhigh ? 1 : 0))
+    {
+#pragma unroll
+      for(int i = 0; i < 4; ++i)
+        lo[c][i] = hi[c][i] = 0;
+      continue;
+    }
+    const int32_t* lrow;
+    const int32_t* hrow;
+    if(!vhigh)
+    {
+      lrow = reinterpret_cast<const int32_t*>(D.out_ll[c]) + (size_t)(jm - g.y0l) * D.ll_pitch;
+      hrow = reinterpret_cast<const int32_t*>(D.out_c[c]) + (size_t)(jm - g.y0l) * D.c_pitch + g.snx;
+    }
+    else
+    {
+      lrow = reinterpret_cast<const int32_t*>(D.out_c[c]) + (size_t)(g.sny + jm - g.y0h) * D.c_pitch;
+      hrow = lrow + g.snx;
+    }
+    load4_band(lrow, k0, g.x0l, D.u0, D.u1, 0, lo[c]);
+    load4_band(hrow, k0, g.x0h, D.u0, D.u1, 1, hi[c]);
+  }
+}
+
+/* inverse horizontal 5/3: WaveletReverse.cpp L879-1072 */
+__device__ __forceinline__ void hinv53(const int (&lo)[4], const int (&hi)[4], int wn, int (&r)[8])
+{
+  const int dm = __shfl_up_sync(0xffffffffu, hi[3], 1);
+  int e[5];
+  e[0] = lo[0] - ((dm + hi[0] + 2) >> 2);
+  e[1] = lo[1] - ((hi[0] + hi[1] + 2) >> 2);
+  e[2] = lo[2] - ((hi[1] + hi[2] + 2) >> 2);
+  e[3] = lo[3] - ((hi[2] + hi[3] + 2) >> 2);
+  e[4] = __shfl_down_sync(0xffffffffu, e[0], 1);
+#pragma unroll
+  for(int i = 0; i < 4; ++i)
+  {
+    r[2 * i] = e[i];
+    r[2 * i + 1] = hi[i] + ((e[i] + e[i + 1]) >> 1);
+  }
+  if(wn == 1)
+  {
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+    {
+      r[2 * i] = lo[i];
+      r[2 * i + 1] = hi[i] >> 1;
+    }
+  }
+}
+
+/* inverse horizontal 9/7: WaveletReverse97.cpp L837-857, constants L98-103 */
+__device__ __forceinline__ void hinv97(const int (&loi)[4], const int (&hii)[4], int wn, float (&r)[8])
+{
+  const float K = 1.230174105f, twice_invK = 1.625732422f;
+  float s[5], d[4];
+#pragma unroll
+  for(int i = 0; i < 4; ++i)
+  {
+    s[i] = __fmul_rn(__int_as_float(loi[i]), K);
+    d[i] = __fmul_rn(__int_as_float(hii[i]), twice_invK);
+  }
+  float dm = __shfl_up_sync(0xffffffffu, d[3], 1);
+  s[0] = fmaf(dm + d[0], -0.443506852f, s[0]);
+#pragma unroll
+  for(int i = 1; i < 4; ++i)
+    s[i] = fmaf(d[i - 1] + d[i], -0.443506852f, s[i]);
+  s[4] = __shfl_down_sync(0xffffffffu, s[0], 1);
+#pragma unroll
+  for(int i = 0; i < 4; ++i)
+    d[i] = fmaf(s[i] + s[i + 1], -0.882911075f, d[i]);
+  dm = __shfl_up_sync(0xffffffffu, d[3], 1);
+  s[0] = fmaf(dm + d[0], 0.052980118f, s[0]);
+#pragma unroll
+  for(int i = 1; i < 4; ++i)
+    s[i] = fmaf(d[i - 1] + d[i], 0.052980118f, s[i]);
+  s[4] = __shfl_down_sync(0xffffffffu, s[0], 1);
+#pragma unroll
+  for(int i = 0; i < 4; ++i)
+  {
+    r[2 * i] = s[i];
+    r[2 * i + 1] = fmaf(s[i] + s[i + 1], 1.586134342f, d[i]);
+  }
+  if(wn == 1)
+  {
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+    {
+      r[2 * i] = __int_as_float(loi[i]);
+      r[2 * i + 1] = __int_as_float(hii[i]);
+    }
+  }
+}
+
+/* write one reconstructed sample row (canvas row v) of NC components */
+template <int NC>
+__device__ __forceinline__ void store_rows53(const DwtLevelDesc& D, const Job& J, int v, int (&x)[NC][8])
+{
+  if(!J.owner || v < D.v0 || v >= D.v1)
+    return;
+  unsigned m = 0;
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+    if(J.ulane + i >= D.u0 && J.ulane + i < D.u1)
+      m |= 1u << i;
+  if(D.first_level)
+  {
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+    {
+      if(NC == 3)
+      { /* mct.cpp L201-256 */
+        const int y = x[0][i], u = x[1][i], w = x[2][i];
+        const int gg = y - ((u + w) >> 2);
+        x[0][i] = w + gg;
+        x[1][i] = gg;
+        x[2][i] = u + gg;
+      }
+#pragma unroll
+      for(int c = 0; c < NC; ++c)
+        x[c][i] = min(max(x[c][i] - D.shift[c], D.lo[c]), D.hi[c]);
+    }
+  }
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+  {
+    int32_t* row = reinterpret_cast<int32_t*>(const_cast<void*>(D.in[c])) + (size_t)(v - D.v0) * D.in_pitch;
+    store8(row, J.ulane - D.u0, x[c], m);
+  }
+}
+template <int NC>
+__device__ __forceinline__ void store_rows97(const DwtLevelDesc& D, const Job& J, int v, float (&x)[NC][8])
+{
+  if(!J.owner || v < D.v0 || v >= D.v1)
+    return;
+  unsigned m = 0;
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+    if(J.ulane + i >= D.u0 && J.ulane + i < D.u1)
+      m |= 1u << i;
+  int o[NC][8];
+  if(D.first_level)
+  {
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+    {
+      float f[NC];
+      if(NC == 3)
+      { /* mct.cpp L318-391 */
+        const float y = x[0][i], u = x[1][i], w = x[2][i];
+        f[0] = __fadd_rn(y, __fmul_rn(w, 1.402f));
+        if(NC > 1)
+          f[NC > 1 ? 1 : 0] = __fsub_rn(__fsub_rn(y, __fmul_rn(u, 0.34413f)), __fmul_rn(w, 0.71414f));
+        if(NC > 2)
+          f[NC > 2 ? 2 : 0] = __fadd_rn(y, __fmul_rn(u, 1.772f));
+      }
+      else
+        f[0] = x[0][i];
+#pragma unroll
+      for(int c = 0; c < NC; ++c)
+        o[c][i] = min(max(__float2int_rn(f[c]) - D.shift[c], D.lo[c]), D.hi[c]);
+    }
+  }
+  else
+  {
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+        o[c][i] = __float_as_int(x[c][i]);
+  }
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+  {
+    int32_t* row = reinterpret_cast<int32_t*>(const_cast<void*>(D.in[c])) + (size_t)(v - D.v0) * D.in_pitch;
+    store8(row, J.ulane - D.u0, o[c], m);
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtLevelDesc* __restrict__ descs)
+{
+  const DwtLevelDesc& D = descs[blockIdx.y];
+  Job J;
+  if(!decode_job(D, J))
+    return;
+  const BandGeom g = band_geom(D);
+  int DV[NC][8], EP[NC][8];
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+      DV[c][i] = EP[c][i] = 0;
+
+  for(int t = J.jbeg - 1; t <= J.jend; ++t)
+  {
+    int lo[NC][4], hi[NC][4];
+    int sv[NC][8], dv[NC][8];
+    fetch_band_rows<NC>(D, J, g, t, false, lo, hi);
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+      hinv53(lo[c], hi[c], J.wn, sv[c]);
+    fetch_band_rows<NC>(D, J, g, t, true, lo, hi);
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+      hinv53(lo[c], hi[c], J.wn, dv[c]);
+    int Er[NC][8], Or[NC][8];
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+      {
+        const int e = sv[c][i] - ((DV[c][i] + dv[c][i] + 2) >> 2);
+        Or[c][i] = DV[c][i] + ((EP[c][i] + e) >> 1);
+        Er[c][i] = EP[c][i];
+        EP[c][i] = e;
+        DV[c][i] = dv[c][i];
+      }
+    if(J.hn == 1)
+    { /* single row: pair t holds it (low unchanged, lone high halved) */
+      if(t >= J.jbeg && t < J.jend)
+      {
+        int hv[NC][8];
+#pragma unroll
+        for(int c = 0; c < NC; ++c)
+#pragma unroll
+          for(int i = 0; i < 8; ++i)
+            hv[c][i] = dv[c][i] >> 1;
+        store_rows53<NC>(D, J, 2 * t, sv);
+        store_rows53<NC>(D, J, 2 * t + 1, hv);
+      }
+    }
+    else if(t - 1 >= J.jbeg)
+    {
+      store_rows53<NC>(D, J, 2 * (t - 1), Er);
+      store_rows53<NC>(D, J, 2 * (t - 1) + 1, Or);
+    }
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_inv(const DwtLevelDesc* __restrict__ descs)
+{
+  const DwtLevelDesc& D = descs[blockIdx.y];
+  Job J;
+  if(!decode_job(D, J))
+    return;
+  const BandGeom g = band_geom(D);
+  const float K = 1.230174105f, twice_invK = 1.625732422f;
+  /* state: d0[t-1], s1[t-1], d1[t-2], s2[t-2] */
+  float D0[NC][8], S1[NC][8], D1[NC][8], S2[NC][8];
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+      D0[c][i] = S1[c][i] = D1[c][i] = S2[c][i] = 0.f;
+
+  for(int t = J.jbeg - 2; t <= J.jend + 1; ++t)
+  {
+    int lo[NC][4], hi[NC][4];
+    float sv[NC][8], dv[NC][8];
+    fetch_band_rows<NC>(D, J, g, t, false, lo, hi);
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+      hinv97(lo[c], hi[c], J.wn, sv[c]);
+    fetch_band_rows<NC>(D, J, g, t, true, lo, hi);
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+      hinv97(lo[c], hi[c], J.wn, dv[c]);
+    float Er[NC][8], Or[NC][8];
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+      {
+        const float s0 = __fmul_rn(sv[c][i], K), d0 = __fmul_rn(dv[c][i], twice_invK);
+        const float s1 = fmaf(D0[c][i] + d0, -0.443506852f, s0);            /* s1[t]   */
+        const float d1 = fmaf(S1[c][i] + s1, -0.882911075f, D0[c][i]);      /* d1[t-1] */
+        const float s2 = fmaf(D1[c][i] + d1, 0.052980118f, S1[c][i]);       /* s2[t-1] */
+        const float d2 = fmaf(S2[c][i] + s2, 1.586134342f, D1[c][i]);       /* d2[t-2] */
+        Er[c][i] = S2[c][i];
+        Or[c][i] = d2;
+        D0[c][i] = d0;
+        S1[c][i] = s1;
+        D1[c][i] = d1;
+        S2[c][i] = s2;
+      }
+    if(J.hn == 1)
+    {
+      if(t >= J.jbeg && t < J.jend)
+      {
+        store_rows97<NC>(D, J, 2 * t, sv);
+        store_rows97<NC>(D, J, 2 * t + 1, dv);
+      }
+    }
+    else if(t - 2 >= J.jbeg)
+    {
+      store_rows97<NC>(D, J, 2 * (t - 2), Er);
+      store_rows97<NC>(D, J, 2 * (t - 2) + 1, Or);
+    }
+  }
+}
+
+} /* namespace */
+
+void b2k_launch_dwt_fwd(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, bool irreversible, bool in_u16,
+                        cudaStream_t st)
+{
+  if(ndesc <= 0 || max_jobs <= 0)
+    return;
+  dim3 grid((max_jobs + B2K_WARPS_PER_CTA - 1) / B2K_WARPS_PER_CTA, ndesc), block(B2K_WARPS_PER_CTA * 32);
+  if(!irreversible)
+  {
+    if(nc == 3)
+    {
+      if(in_u16) k_dwt53_fwd<3, true><<<grid, block, 0, st>>>(d);
+      else k_dwt53_fwd<3, false><<<grid, block, 0, st>>>(d);
+    }
+    else
+    {
+      if(in_u16) k_dwt53_fwd<1, true><<<grid, block, 0, st>>>(d);
+      else k_dwt53_fwd<1, false><<<grid, block, 0, st>>>(d);
+    }
+  }
+  else
+  {
+    if(nc == 3)
+    {
+      if(in_u16) k_dwt97_fwd<3, true><<<grid, block, 0, st>>>(d);
+      else k_dwt97_fwd<3, false><<<grid, block, 0, st>>>(d);
+    }
+    else
+    {
+      if(in_u16) k_dwt97_fwd<1, true><<<grid, block, 0, st>>>(d);
+      else k_dwt97_fwd<1, false><<<grid, block, 0, st>>>(d);
+    }
+  }
+  b2k_count_launch();
+}
+
+void b2k_launch_dwt_inv(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, bool irreversible, cudaStream_t st)
+{
+  if(ndesc <= 0 || max_jobs <= 0)
+    return;
+  dim3 grid((max_jobs + B2K_WARPS_PER_CTA - 1) / B2K_WARPS_PER_CTA, ndesc), block(B2K_WARPS_PER_CTA * 32);
+  if(!irreversible)
+  {
+    if(nc == 3) k_dwt53_inv<3><<<grid, block, 0, st>>>(d);
+    else k_dwt53_inv<1><<<grid, block, 0, st>>>(d);
+  }
+  else
+  {
+    if(nc == 3) k_dwt97_inv<3><<<grid, block, 0, st>>>(d);
+    else k_dwt97_inv<1><<<grid, block, 0, st>>>(d);
+  }
+  b2k_count_launch();
+}

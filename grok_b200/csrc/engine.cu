@@ -1,0 +1,913 @@
+/*
+ * grok_b200/csrc/engine.cu -- the B200 tile engine behind include/grok_b200.h.
+ *
+ * Replaces, for the tiles it is given, the per-tile pipeline of the reference
+ *   encode: TileProcessorCompress::preCompressTile / buildCompressDAG / doCompress
+ *           (tile_processor/TileProcessorCompress.cpp L104-254, L347-531, L539-)  up to, not
+ *           including, rate allocation and T2;
+ *   decode: TileProcessor::scheduleAndRunDecompress (tile_processor/TileProcessor.cpp L1272-)
+ *           after the T2 parse.
+ * The Taskflow DAG (dcShift -> MCT -> per-level vert/horiz -> T1) becomes stream-ordered kernel
+ * launches over ALL selected tiles at once: one launch per decomposition level, one for the
+ * block coder.  Buffers are image-shaped planes in HBM addressed by canvas coordinate, so a
+ * tile is a view, tiles of every size batch into the same launch, and the engine never copies
+ * a tile out of the image (the reference's preCompressTile row copy disappears).
+ *
+ * Product code: fails loudly (negative return + b2k_last_error) without a CUDA device; there is
+ * no CPU fallback here -- the host (Grok) owns that decision via the >0 return convention.
+ */
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b2k_internal.h"
+#include "geometry.h"
+
+using namespace b2k;
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+void b2k_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+#define CUDA_TRY(expr)                                                                             \
+  do                                                                                               \
+  {                                                                                                \
+    cudaError_t _e = (expr);                                                                       \
+    if(_e != cudaSuccess)                                                                          \
+    {                                                                                              \
+      g_err = std::string(#expr) + ": " + cudaGetErrorString(_e);                                  \
+      return -1;                                                                                   \
+    }                                                                                              \
+  } while(0)
+
+struct b2k_engine
+{
+  int device = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaDeviceProp prop{};
+};
+
+/* ---- a plane set: `n` image-shaped 32-bit planes addressed by canvas coordinate ------------- */
+struct Planes
+{
+  int32_t* base = nullptr;
+  uint32_t pitch = 0, rows = 0; /* elements, rows */
+  uint32_t X0 = 0, Y0 = 0;      /* canvas coordinate stored at column 0 / row 0 */
+  int n = 0;
+  size_t plane_elems() const { return (size_t)pitch * rows; }
+  int32_t* at(int c, uint32_t x, uint32_t y) const { return base + (size_t)c * plane_elems() + (size_t)(y - Y0) * pitch + (x - X0); }
+};
+
+static int alloc_planes(Planes& p, int n, uint32_t cx0, uint32_t cy0, uint32_t cx1, uint32_t cy1)
+{
+  p.n = n;
+  p.X0 = cx0 & ~31u; /* 128-byte aligned canvas columns */
+  p.Y0 = cy0;
+  p.pitch = ((cx1 - p.X0) + 31u + 32u) & ~31u; /* slack: vector loads of halo lanes stay inside */
+  p.rows = (cy1 - cy0) + 2;
+  CUDA_TRY(cudaMalloc(&p.base, (size_t)n * p.plane_elems() * sizeof(int32_t)));
+  CUDA_TRY(cudaMemset(p.base, 0, (size_t)n * p.plane_elems() * sizeof(int32_t)));
+  return 0;
+}
+
+struct LevelLaunch
+{
+  std::vector<DwtLevelDesc> descs;
+  DwtLevelDesc* d_descs = nullptr;
+  int nc = 1, max_jobs = 0;
+  uint64_t alg_bytes = 0; /* one read + one write of every sample of the level */
+};
+
+struct b2k_device_job
+{
+  b2k_engine* eng = nullptr;
+  b2k_coding cp{};
+  uint32_t tile_mod = 1, tile_rem = 0;
+  TileGrid grid{};
+  std::vector<uint32_t> tiles;
+  std::vector<Rect> tile_rects;
+  std::vector<BandQuant> quant;
+  std::vector<b2k_block> blocks;       /* every block, enumeration order */
+  std::vector<uint32_t> coded_index;   /* blocks with area, index into `blocks` */
+  uint32_t max_cblk_w = 0;
+
+  Planes img, coef, ll[2];
+  std::vector<LevelLaunch> fwd, inv;   /* launch order */
+  HtBlockDesc* d_enc_desc = nullptr;
+  HtBlockDesc* d_dec_desc = nullptr;
+  std::vector<HtBlockDesc> h_enc_desc, h_dec_desc;
+  HtBlockOut* d_out = nullptr;
+  uint64_t* d_offsets = nullptr;
+  uint8_t* d_scratch = nullptr;
+  uint64_t scratch_bytes = 0;
+  uint8_t* d_bytes = nullptr;
+  uint64_t bytes_cap = 0, bytes_used = 0;
+  int* d_err = nullptr;
+  /* pinned host staging for results */
+  HtBlockOut* h_out = nullptr;
+  uint64_t* h_offsets = nullptr;
+  cudaEvent_t ev[8]{};
+  float last_level1_ms = 0.f, last_inv_level1_ms = 0.f;
+  uint64_t level1_alg_bytes = 0;
+  bool img_is_u16 = false;
+};
+
+/* -------------------------------------------------------------------------------------------- */
+extern "C" const char* b2k_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t b2k_launch_count(void) { return g_launches.load(); }
+
+extern "C" int32_t b2k_engine_create(int32_t device, b2k_engine** out)
+{
+  if(!out)
+    return -1;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if(e != cudaSuccess || n == 0)
+  {
+    g_err = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+            " (this engine has no CPU path; the host keeps its own)";
+    return -1;
+  }
+  if(device < 0 || device >= n)
+  {
+    g_err = "device index out of range";
+    return -1;
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  b2k_engine* eng = new b2k_engine();
+  eng->device = device;
+  CUDA_TRY(cudaGetDeviceProperties(&eng->prop, device));
+  CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking));
+  *out = eng;
+  return 0;
+}
+
+extern "C" void b2k_engine_destroy(b2k_engine* e)
+{
+  if(!e)
+    return;
+  cudaSetDevice(e->device);
+  if(e->stream)
+    cudaStreamDestroy(e->stream);
+  if(e->copy_stream)
+    cudaStreamDestroy(e->copy_stream);
+  delete e;
+}
+
+extern "C" void* b2k_host_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  if(cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess)
+    return nullptr;
+  return p;
+}
+extern "C" void b2k_host_free(void* p)
+{
+  if(p)
+    cudaFreeHost(p);
+}
+
+extern "C" int64_t b2k_enumerate(const b2k_coding* cp, uint32_t tile_mod, uint32_t tile_rem, b2k_block* out, uint64_t cap)
+{
+  if(!cp || tile_mod == 0)
+    return -1;
+  if(const char* why = unsupported_reason(*cp))
+  {
+    g_err = why;
+    return -1;
+  }
+  const TileGrid g = tile_grid(*cp);
+  const std::vector<BandQuant> q = band_quant(*cp);
+  std::vector<b2k_block> v;
+  for(uint32_t t = 0; t < g.nx * g.ny; ++t)
+    if(t % tile_mod == tile_rem)
+      enumerate_tile_blocks(*cp, t, tile_rect(*cp, g, t), q, v);
+  for(uint64_t i = 0; i < v.size() && i < cap; ++i)
+    out[i] = v[i];
+  return (int64_t)v.size();
+}
+
+/* -------------------------------------------------------------------------------------------- */
+static void fill_strips(DwtLevelDesc& d, int pairs_per_seg)
+{
+  const int span = d.u1 - (d.u0 & ~7);
+  const int nstrips = std::max(1, (span + 239) / 240);
+  int sw = (span + nstrips - 1) / nstrips;
+  sw = (sw + 7) & ~7;
+  d.nstrips = (uint16_t)nstrips;
+  d.strip_w = (uint16_t)sw;
+  const int npairs = ((d.v1 - 1) >> 1) - (d.v0 >> 1) + 1;
+  d.pairs_per_seg = (uint16_t)pairs_per_seg;
+  d.nsegs = (uint16_t)((npairs + pairs_per_seg - 1) / pairs_per_seg);
+}
+
+static int upload_descs(LevelLaunch& L)
+{
+  L.max_jobs = 0;
+  for(const DwtLevelDesc& d : L.descs)
+    L.max_jobs = std::max(L.max_jobs, (int)d.nstrips * (int)d.nsegs);
+  if(L.descs.empty())
+    return 0;
+  CUDA_TRY(cudaMalloc(&L.d_descs, L.descs.size() * sizeof(DwtLevelDesc)));
+  CUDA_TRY(cudaMemcpy(L.d_descs, L.descs.data(), L.descs.size() * sizeof(DwtLevelDesc), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int build_dwt_plan(b2k_device_job* J)
+{
+  const b2k_coding& cp = J->cp;
+  const int L = cp.numres - 1;
+  const int ncomp = cp.numcomps;
+  const int pairs53 = 32, pairs97 = 32;
+  const int P = cp.irreversible ? pairs97 : pairs53;
+  const int32_t dc = cp.sgnd ? 0 : -(1 << (cp.prec - 1));
+  const int32_t lo = cp.sgnd ? -(1 << (cp.prec - 1)) : 0, hi = cp.sgnd ? (1 << (cp.prec - 1)) - 1 : (1 << cp.prec) - 1;
+
+  /* forward: level 1 (MCT group, then the rest), then levels 2..L component-wise */
+  for(int dir = 0; dir < 2; ++dir)
+  {
+    std::vector<LevelLaunch>& out = dir == 0 ? J->fwd : J->inv;
+    for(int lvl = 1; lvl <= L; ++lvl)
+    {
+      const int resno = cp.numres - lvl; /* resolution being split / rebuilt */
+      LevelLaunch mctL, sglL;
+      mctL.nc = 3;
+      sglL.nc = 1;
+      for(size_t ti = 0; ti < J->tiles.size(); ++ti)
+      {
+        const Rect tc = J->tile_rects[ti];
+        const Rect r = resolution_rect(tc, cp.numres, resno);
+        if(r.empty())
+          continue;
+        for(int c = 0; c < ncomp;)
+        {
+          const bool group = (lvl == 1 && cp.mct && c == 0);
+          const int nc = group ? 3 : 1;
+          DwtLevelDesc d{};
+          d.u0 = (int32_t)r.x0; d.v0 = (int32_t)r.y0; d.u1 = (int32_t)r.x1; d.v1 = (int32_t)r.y1;
+          d.first_level = lvl == 1;
+          d.in_is_u16 = 0;
+          const uint32_t llx = (r.x0 + 1) >> 1, lly = (r.y0 + 1) >> 1;
+          for(int k = 0; k < nc; ++k)
+          {
+            const int cc = c + k;
+            /* finer side: image at level 1, else LL scratch written by level lvl-1 */
+            const Planes& fine = (lvl == 1) ? J->img : J->ll[(lvl - 1) & 1];
+            d.in[k] = fine.at(cc, r.x0, r.y0);
+            d.in_pitch = fine.pitch;
+            d.out_c[k] = J->coef.at(cc, tc.x0, tc.y0);
+            d.c_pitch = J->coef.pitch;
+            if(lvl == L)
+            {
+              d.out_ll[k] = d.out_c[k];
+              d.ll_pitch = J->coef.pitch;
+            }
+            else
+            {
+              const Planes& coarse = J->ll[lvl & 1];
+              d.out_ll[k] = coarse.at(cc, llx, lly);
+              d.ll_pitch = coarse.pitch;
+            }
+            d.shift[k] = dc;
+            d.lo[k] = lo;
+            d.hi[k] = hi;
+          }
+          fill_strips(d, P);
+          (group ? mctL : sglL).descs.push_back(d);
+          const uint64_t samples = (uint64_t)r.w() * r.h() * nc;
+          (group ? mctL : sglL).alg_bytes += samples * 8;
+          c += nc;
+        }
+      }
+      if(dir == 0)
+      {
+        if(!mctL.descs.empty()) out.push_back(std::move(mctL));
+        if(!sglL.descs.empty()) out.push_back(std::move(sglL));
+      }
+      else
+      {
+        if(!sglL.descs.empty()) out.insert(out.begin(), std::move(sglL));
+        if(!mctL.descs.empty()) out.insert(out.begin(), std::move(mctL));
+      }
+    }
+    for(LevelLaunch& Lh : out)
+      if(upload_descs(Lh))
+        return -1;
+  }
+  return 0;
+}
+
+static uint32_t slot_capacity(uint32_t w, uint32_t h, uint32_t kmax)
+{
+  /* MagSgn: <= (kmax+2) bits per sample, 8/7 stuffing; VLC: <= 15 bits per quad, 8/7; MEL 256 */
+  const uint64_t samples = (uint64_t)w * h, quads = (uint64_t)((w + 1) / 2) * ((h + 1) / 2);
+  const uint64_t ms = (samples * (kmax + 2) + 6) / 7 + 16;
+  const uint64_t vlc = (quads * 15 + 6) / 7 + 16;
+  return (uint32_t)((ms + vlc + 256 + 15) & ~15ull);
+}
+
+static int build_block_plan(b2k_device_job* J)
+{
+  const b2k_coding& cp = J->cp;
+  J->blocks.clear();
+  for(size_t ti = 0; ti < J->tiles.size(); ++ti)
+    enumerate_tile_blocks(cp, J->tiles[ti], J->tile_rects[ti], J->quant, J->blocks);
+  /* map tile index -> rect */
+  std::vector<Rect> rect_of(J->grid.nx * J->grid.ny);
+  for(size_t ti = 0; ti < J->tiles.size(); ++ti)
+    rect_of[J->tiles[ti]] = J->tile_rects[ti];
+  uint64_t off = 0;
+  for(uint32_t i = 0; i < J->blocks.size(); ++i)
+  {
+    const b2k_block& b = J->blocks[i];
+    if(b.x1 <= b.x0 || b.y1 <= b.y0)
+      continue;
+    const Rect& tr = rect_of[b.tile];
+    const BandQuant& bq = J->quant[band_quant_index(b.resno, b.orient)];
+    HtBlockDesc d{};
+    d.coef = J->coef.at(b.comp, tr.x0 + b.buf_x, tr.y0 + b.buf_y);
+    d.pitch = J->coef.pitch;
+    d.w = (uint16_t)(b.x1 - b.x0);
+    d.h = (uint16_t)(b.y1 - b.y0);
+    d.kmax = bq.kmax;
+    d.irreversible = cp.irreversible;
+    d.quant = 1.0f / bq.step_enc; /* CompressScheduler.cpp L131: inv_step_ht */
+    d.slot_cap = slot_capacity(d.w, d.h, bq.kmax);
+    d.slot_off = off;
+    off += d.slot_cap;
+    J->max_cblk_w = std::max<uint32_t>(J->max_cblk_w, d.w);
+    J->h_enc_desc.push_back(d);
+    J->coded_index.push_back(i);
+  }
+  J->scratch_bytes = off;
+  const size_t n = J->h_enc_desc.size();
+  if(n)
+  {
+    CUDA_TRY(cudaMalloc(&J->d_enc_desc, n * sizeof(HtBlockDesc)));
+    CUDA_TRY(cudaMemcpy(J->d_enc_desc, J->h_enc_desc.data(), n * sizeof(HtBlockDesc), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&J->d_dec_desc, n * sizeof(HtBlockDesc)));
+    CUDA_TRY(cudaMalloc(&J->d_out, n * sizeof(HtBlockOut)));
+    CUDA_TRY(cudaMalloc(&J->d_offsets, (n + 1) * sizeof(uint64_t)));
+    CUDA_TRY(cudaMalloc(&J->d_scratch, J->scratch_bytes + 64));
+    CUDA_TRY(cudaHostAlloc(&J->h_out, n * sizeof(HtBlockOut), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&J->h_offsets, (n + 1) * sizeof(uint64_t), cudaHostAllocDefault));
+  }
+  CUDA_TRY(cudaMalloc(&J->d_err, sizeof(int)));
+  CUDA_TRY(cudaMemset(J->d_err, 0, sizeof(int)));
+  return 0;
+}
+
+extern "C" int32_t b2k_job_create(b2k_engine* e, const b2k_coding* cp, uint32_t tile_mod, uint32_t tile_rem,
+                                  b2k_device_job** out)
+{
+  if(!e || !cp || !out || tile_mod == 0)
+    return -1;
+  *out = nullptr;
+  if(const char* why = unsupported_reason(*cp))
+  {
+    g_err = why;
+    return 1; /* not handled: the host keeps its CPU path (plugin_accelerate.h L32-36) */
+  }
+  CUDA_TRY(cudaSetDevice(e->device));
+  b2k_device_job* J = new b2k_device_job();
+  J->eng = e;
+  J->cp = *cp;
+  J->tile_mod = tile_mod;
+  J->tile_rem = tile_rem;
+  J->grid = tile_grid(*cp);
+  J->quant = band_quant(*cp);
+  for(uint32_t t = 0; t < J->grid.nx * J->grid.ny; ++t)
+    if(t % tile_mod == tile_rem)
+    {
+      const Rect r = tile_rect(*cp, J->grid, t);
+      if(r.empty())
+        continue;
+      J->tiles.push_back(t);
+      J->tile_rects.push_back(r);
+    }
+  const int nc = cp->numcomps;
+  if(alloc_planes(J->img, nc, cp->x0, cp->y0, cp->x1, cp->y1) || alloc_planes(J->coef, nc, cp->x0, cp->y0, cp->x1, cp->y1))
+  {
+    b2k_job_destroy(J);
+    return -1;
+  }
+  /* LL scratch, canvas origin (0,0): ll[1] receives the LL of odd levels (1/2, 1/8, ... resolution),
+     ll[0] of even levels (1/4, 1/16, ...); a level reads one and writes the other */
+  if(alloc_planes(J->ll[1], nc, 0, 0, ((cp->x1 + 1) >> 1) + 1, ((cp->y1 + 1) >> 1) + 1) ||
+     alloc_planes(J->ll[0], nc, 0, 0, ((cp->x1 + 3) >> 2) + 1, ((cp->y1 + 3) >> 2) + 1))
+  {
+    b2k_job_destroy(J);
+    return -1;
+  }
+  if(build_dwt_plan(J) || build_block_plan(J))
+  {
+    b2k_job_destroy(J);
+    return -1;
+  }
+  for(cudaEvent_t& ev : J->ev)
+    CUDA_TRY(cudaEventCreate(&ev));
+  *out = J;
+  return 0;
+}
+
+extern "C" void b2k_job_destroy(b2k_device_job* J)
+{
+  if(!J)
+    return;
+  cudaSetDevice(J->eng->device);
+  cudaStreamSynchronize(J->eng->stream);
+  cudaFree(J->img.base);
+  cudaFree(J->coef.base);
+  cudaFree(J->ll[0].base);
+  cudaFree(J->ll[1].base);
+  for(LevelLaunch& L : J->fwd) cudaFree(L.d_descs);
+  for(LevelLaunch& L : J->inv) cudaFree(L.d_descs);
+  cudaFree(J->d_enc_desc);
+  cudaFree(J->d_dec_desc);
+  cudaFree(J->d_out);
+  cudaFree(J->d_offsets);
+  cudaFree(J->d_scratch);
+  cudaFree(J->d_bytes);
+  cudaFree(J->d_err);
+  cudaFreeHost(J->h_out);
+  cudaFreeHost(J->h_offsets);
+  for(cudaEvent_t& ev : J->ev)
+    if(ev)
+      cudaEventDestroy(ev);
+  delete J;
+}
+
+extern "C" uint64_t b2k_job_num_blocks(const b2k_device_job* J) { return J ? J->blocks.size() : 0; }
+
+/* ---- host <-> device plane copies, per selected tile ---------------------------------------- */
+static int copy_planes(b2k_device_job* J, const Planes& P, void* const* host, const uint32_t* strides, bool to_device,
+                       cudaStream_t st)
+{
+  const b2k_coding& cp = J->cp;
+  for(size_t ti = 0; ti < J->tiles.size(); ++ti)
+  {
+    const Rect r = J->tile_rects[ti];
+    for(int c = 0; c < cp.numcomps; ++c)
+    {
+      int32_t* dev = P.at(c, r.x0, r.y0);
+      int32_t* hst = reinterpret_cast<int32_t*>(host[c]) + (size_t)(r.y0 - cp.y0) * strides[c] + (r.x0 - cp.x0);
+      if(to_device)
+        CUDA_TRY(cudaMemcpy2DAsync(dev, (size_t)P.pitch * 4, hst, (size_t)strides[c] * 4, (size_t)r.w() * 4, r.h(),
+                                   cudaMemcpyHostToDevice, st));
+      else
+        CUDA_TRY(cudaMemcpy2DAsync(hst, (size_t)strides[c] * 4, dev, (size_t)P.pitch * 4, (size_t)r.w() * 4, r.h(),
+                                   cudaMemcpyDeviceToHost, st));
+    }
+  }
+  return 0;
+}
+
+extern "C" int32_t b2k_job_upload(b2k_device_job* J, const int32_t* const* planes, const uint32_t* strides)
+{
+  if(!J) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  if(copy_planes(J, J->img, (void* const*)planes, strides, true, J->eng->stream)) return -1;
+  CUDA_TRY(cudaStreamSynchronize(J->eng->stream));
+  return 0;
+}
+extern "C" int32_t b2k_job_download(b2k_device_job* J, int32_t* const* planes, const uint32_t* strides)
+{
+  if(!J) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  if(copy_planes(J, J->img, (void* const*)planes, strides, false, J->eng->stream)) return -1;
+  CUDA_TRY(cudaStreamSynchronize(J->eng->stream));
+  return 0;
+}
+extern "C" int32_t b2k_job_download_coeffs(b2k_device_job* J, int32_t* const* planes, const uint32_t* strides)
+{
+  if(!J) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  if(copy_planes(J, J->coef, (void* const*)planes, strides, false, J->eng->stream)) return -1;
+  CUDA_TRY(cudaStreamSynchronize(J->eng->stream));
+  return 0;
+}
+extern "C" int32_t b2k_job_upload_coeffs(b2k_device_job* J, const int32_t* const* planes, const uint32_t* strides)
+{
+  if(!J) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  if(copy_planes(J, J->coef, (void* const*)planes, strides, true, J->eng->stream)) return -1;
+  CUDA_TRY(cudaStreamSynchronize(J->eng->stream));
+  return 0;
+}
+
+/* ---- stages ----------------------------------------------------------------------------------- */
+static int enqueue_forward(b2k_device_job* J, cudaStream_t st, bool time_level1)
+{
+  bool first = true;
+  for(LevelLaunch& L : J->fwd)
+  {
+    if(first && time_level1)
+      CUDA_TRY(cudaEventRecord(J->ev[4], st));
+    b2k_launch_dwt_fwd(L.d_descs, (int)L.descs.size(), L.max_jobs, L.nc, J->cp.irreversible, J->img_is_u16 && L.descs[0].first_level, st);
+    if(first && time_level1)
+    {
+      CUDA_TRY(cudaEventRecord(J->ev[5], st));
+      J->level1_alg_bytes = L.alg_bytes;
+    }
+    first = false;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int enqueue_inverse(b2k_device_job* J, cudaStream_t st)
+{
+  for(LevelLaunch& L : J->inv)
+    b2k_launch_dwt_inv(L.d_descs, (int)L.descs.size(), L.max_jobs, L.nc, J->cp.irreversible, st);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int enqueue_t1_encode(b2k_device_job* J, cudaStream_t st)
+{
+  const uint32_t n = (uint32_t)J->h_enc_desc.size();
+  b2k_launch_ht_encode(J->d_enc_desc, J->d_out, J->d_scratch, n, J->max_cblk_w, st);
+  b2k_launch_scan_lengths(J->d_out, J->d_offsets, n, st);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+/* total size known -> (re)allocate the arena, compact */
+static int finish_t1_encode(b2k_device_job* J, cudaStream_t st)
+{
+  const uint32_t n = (uint32_t)J->h_enc_desc.size();
+  uint64_t total = 0;
+  CUDA_TRY(cudaMemcpyAsync(&J->h_offsets[n], J->d_offsets + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  total = J->h_offsets[n];
+  if(total + 64 > J->bytes_cap)
+  {
+    cudaFree(J->d_bytes);
+    J->bytes_cap = total + total / 8 + 4096;
+    CUDA_TRY(cudaMalloc(&J->d_bytes, J->bytes_cap));
+  }
+  J->bytes_used = total;
+  b2k_launch_ht_gather(J->d_enc_desc, J->d_out, J->d_offsets, J->d_scratch, J->d_bytes, n, st);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t b2k_job_forward(b2k_device_job* J, float* ms)
+{
+  if(!J) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  cudaStream_t st = J->eng->stream;
+  CUDA_TRY(cudaEventRecord(J->ev[0], st));
+  if(enqueue_forward(J, st, true)) return -1;
+  CUDA_TRY(cudaEventRecord(J->ev[1], st));
+  CUDA_TRY(cudaEventSynchronize(J->ev[1]));
+  float t = 0;
+  CUDA_TRY(cudaEventElapsedTime(&t, J->ev[0], J->ev[1]));
+  if(ms) *ms = t;
+  CUDA_TRY(cudaEventElapsedTime(&J->last_level1_ms, J->ev[4], J->ev[5]));
+  return 0;
+}
+
+extern "C" int32_t b2k_job_inverse(b2k_device_job* J, float* ms)
+{
+  if(!J) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  cudaStream_t st = J->eng->stream;
+  CUDA_TRY(cudaEventRecord(J->ev[0], st));
+  if(enqueue_inverse(J, st)) return -1;
+  CUDA_TRY(cudaEventRecord(J->ev[1], st));
+  CUDA_TRY(cudaEventSynchronize(J->ev[1]));
+  float t = 0;
+  CUDA_TRY(cudaEventElapsedTime(&t, J->ev[0], J->ev[1]));
+  if(ms) *ms = t;
+  return 0;
+}
+
+extern "C" int32_t b2k_job_t1_encode(b2k_device_job* J, float* ms, uint64_t* total_bytes)
+{
+  if(!J) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  cudaStream_t st = J->eng->stream;
+  CUDA_TRY(cudaEventRecord(J->ev[0], st));
+  if(enqueue_t1_encode(J, st)) return -1;
+  if(finish_t1_encode(J, st)) return -1;
+  CUDA_TRY(cudaEventRecord(J->ev[1], st));
+  CUDA_TRY(cudaEventSynchronize(J->ev[1]));
+  float t = 0;
+  CUDA_TRY(cudaEventElapsedTime(&t, J->ev[0], J->ev[1]));
+  if(ms) *ms = t;
+  if(total_bytes) *total_bytes = J->bytes_used;
+  return 0;
+}
+
+/* decode descriptors from (length, offset, numbps) per coded block */
+static int prepare_decode(b2k_device_job* J, const b2k_block* blocks, uint64_t num_blocks, cudaStream_t st)
+{
+  const size_t n = J->h_enc_desc.size();
+  J->h_dec_desc.resize(n);
+  if(num_blocks != J->blocks.size())
+  {
+    g_err = "block count does not match this coding's enumeration";
+    return -1;
+  }
+  for(size_t k = 0; k < n; ++k)
+  {
+    const b2k_block& b = blocks[J->coded_index[k]];
+    const BandQuant& bq = J->quant[band_quant_index(b.resno, b.orient)];
+    HtBlockDesc d = J->h_enc_desc[k];
+    d.length = b.length;
+    d.slot_off = b.offset;
+    if(b.numpasses > 1)
+    {
+      g_err = "HT refinement passes (SigProp/MagRef) are not decoded by this engine yet";
+      return 1;
+    }
+    const int nb = b.length ? b.numbps : 0;
+    d.mmsbs = (uint8_t)std::max(0, (int)bq.kmax - nb);
+    d.quant = bq.step_dec / (float)(1u << (31 - bq.kmax)); /* PostDecodeFiltersOJPH.h L103 */
+    J->h_dec_desc[k] = d;
+  }
+  if(n)
+    CUDA_TRY(cudaMemcpyAsync(J->d_dec_desc, J->h_dec_desc.data(), n * sizeof(HtBlockDesc), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+extern "C" int32_t b2k_job_t1_decode(b2k_device_job* J, float* ms)
+{
+  if(!J) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  cudaStream_t st = J->eng->stream;
+  const uint32_t n = (uint32_t)J->h_enc_desc.size();
+  /* lengths/offsets of the job's own last encode */
+  CUDA_TRY(cudaMemcpyAsync(J->h_out, J->d_out, n * sizeof(HtBlockOut), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(J->h_offsets, J->d_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  std::vector<b2k_block> blk = J->blocks;
+  for(uint32_t k = 0; k < n; ++k)
+  {
+    b2k_block& b = blk[J->coded_index[k]];
+    b.length = J->h_out[k].total;
+    b.offset = J->h_offsets[k];
+    b.numbps = 1;
+    b.numpasses = 1;
+  }
+  if(int rc = prepare_decode(J, blk.data(), blk.size(), st)) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st)); /* h_dec_desc is pageable */
+  CUDA_TRY(cudaMemsetAsync(J->d_err, 0, sizeof(int), st));
+  CUDA_TRY(cudaEventRecord(J->ev[0], st));
+  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, n, J->max_cblk_w, J->d_err, st);
+  CUDA_TRY(cudaEventRecord(J->ev[1], st));
+  CUDA_TRY(cudaEventSynchronize(J->ev[1]));
+  CUDA_TRY(cudaGetLastError());
+  float t = 0;
+  CUDA_TRY(cudaEventElapsedTime(&t, J->ev[0], J->ev[1]));
+  if(ms) *ms = t;
+  int herr = 0;
+  CUDA_TRY(cudaMemcpy(&herr, J->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if(herr)
+  {
+    g_err = "HT decoder rejected " + std::to_string(herr) + " block(s)";
+    return -2;
+  }
+  return 0;
+}
+
+extern "C" int32_t b2k_job_last_kernel_stats(const b2k_device_job* J, int which, float* ms, uint64_t* alg_bytes)
+{
+  if(!J) return -1;
+  if(which == 0)
+  {
+    if(ms) *ms = J->last_level1_ms;
+    if(alg_bytes) *alg_bytes = J->level1_alg_bytes;
+    return 0;
+  }
+  return 1;
+}
+
+/* ---- results ---------------------------------------------------------------------------------- */
+/* pinned result arenas are recycled: cudaHostAlloc of ~150 MB costs more than the whole encode */
+struct PinnedPool
+{
+  std::mutex mu;
+  std::vector<std::pair<uint8_t*, uint64_t>> free_list;
+  std::vector<std::pair<uint8_t*, uint64_t>> live;
+};
+static PinnedPool g_pool;
+static uint8_t* pool_get(uint64_t bytes)
+{
+  std::lock_guard<std::mutex> lock(g_pool.mu);
+  for(size_t i = 0; i < g_pool.free_list.size(); ++i)
+    if(g_pool.free_list[i].second >= bytes)
+    {
+      auto e = g_pool.free_list[i];
+      g_pool.free_list.erase(g_pool.free_list.begin() + i);
+      g_pool.live.push_back(e);
+      return e.first;
+    }
+  uint8_t* p = nullptr;
+  const uint64_t cap = bytes + bytes / 4 + 4096;
+  if(cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess)
+    return nullptr;
+  g_pool.live.push_back({p, cap});
+  return p;
+}
+static void pool_put(uint8_t* p)
+{
+  std::lock_guard<std::mutex> lock(g_pool.mu);
+  for(size_t i = 0; i < g_pool.live.size(); ++i)
+    if(g_pool.live[i].first == p)
+    {
+      g_pool.free_list.push_back(g_pool.live[i]);
+      g_pool.live.erase(g_pool.live.begin() + i);
+      while(g_pool.free_list.size() > 4)
+      {
+        cudaFreeHost(g_pool.free_list.front().first);
+        g_pool.free_list.erase(g_pool.free_list.begin());
+      }
+      return;
+    }
+  cudaFreeHost(p);
+}
+
+static int fetch_result(b2k_device_job* J, cudaStream_t st, b2k_result** out)
+{
+  const uint32_t n = (uint32_t)J->h_enc_desc.size();
+  b2k_result* R = new b2k_result();
+  memset(R, 0, sizeof(*R));
+  R->num_blocks = J->blocks.size();
+  R->blocks = (b2k_block*)malloc(sizeof(b2k_block) * std::max<size_t>(1, J->blocks.size()));
+  memcpy(R->blocks, J->blocks.data(), sizeof(b2k_block) * J->blocks.size());
+  R->num_bytes = J->bytes_used;
+  R->num_tiles = (uint32_t)J->tiles.size();
+  R->bytes = pool_get(std::max<uint64_t>(64, J->bytes_used));
+  if(!R->bytes)
+  {
+    g_err = "cudaHostAlloc(result bytes) failed";
+    free(R->blocks);
+    delete R;
+    return -1;
+  }
+  CUDA_TRY(cudaMemcpyAsync(R->bytes, J->d_bytes, J->bytes_used, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(J->h_out, J->d_out, n * sizeof(HtBlockOut), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(J->h_offsets, J->d_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  int bad = 0;
+  for(uint32_t k = 0; k < n; ++k)
+  {
+    b2k_block& b = R->blocks[J->coded_index[k]];
+    if(J->h_out[k].total == 0xFFFFFFFFu)
+    {
+      bad++;
+      continue;
+    }
+    b.length = J->h_out[k].total;
+    b.offset = J->h_offsets[k];
+    b.numbps = 1;    /* CoderOJPH.cpp L203-206 */
+    b.numpasses = 1;
+  }
+  if(bad)
+  {
+    g_err = std::to_string(bad) + " code block(s) overflowed the coder's buffers";
+    b2k_result_free(R);
+    return -2;
+  }
+  *out = R;
+  return 0;
+}
+
+extern "C" int32_t b2k_job_fetch_result(b2k_device_job* J, b2k_result** out)
+{
+  if(!J || !out) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  return fetch_result(J, J->eng->stream, out);
+}
+
+extern "C" void b2k_result_free(b2k_result* r)
+{
+  if(!r) return;
+  free(r->blocks);
+  if(r->bytes) pool_put(r->bytes);
+  delete r;
+}
+
+/* ---- one-call host paths ---------------------------------------------------------------------- */
+struct JobCache
+{
+  std::mutex mu;
+  b2k_device_job* job = nullptr;
+};
+static JobCache g_cache;
+
+static b2k_device_job* cached_job(b2k_engine* e, const b2k_coding* cp, uint32_t mod, uint32_t rem, int* rc)
+{
+  b2k_device_job*& J = g_cache.job;
+  if(J && (J->eng != e || memcmp(&J->cp, cp, sizeof(b2k_coding)) != 0 || J->tile_mod != mod || J->tile_rem != rem))
+  {
+    b2k_job_destroy(J);
+    J = nullptr;
+  }
+  if(!J)
+    *rc = b2k_job_create(e, cp, mod, rem, &J);
+  else
+    *rc = 0;
+  return J;
+}
+
+static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* planes, const uint32_t* strides,
+                             uint32_t mod, uint32_t rem, b2k_result** out)
+{
+  if(!e || !cp || !planes || !strides || !out)
+    return -1;
+  std::lock_guard<std::mutex> lock(g_cache.mu);
+  int rc = 0;
+  b2k_device_job* J = cached_job(e, cp, mod, rem, &rc);
+  if(rc)
+    return rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  CUDA_TRY(cudaEventRecord(J->ev[0], st));
+  if(copy_planes(J, J->img, planes, strides, true, st)) return -1;
+  CUDA_TRY(cudaEventRecord(J->ev[1], st));
+  if(enqueue_forward(J, st, true)) return -1;
+  CUDA_TRY(cudaEventRecord(J->ev[2], st));
+  if(enqueue_t1_encode(J, st)) return -1;
+  if(finish_t1_encode(J, st)) return -1;
+  CUDA_TRY(cudaEventRecord(J->ev[3], st));
+  b2k_result* R = nullptr;
+  if(int frc = fetch_result(J, st, &R)) return frc;
+  CUDA_TRY(cudaEventRecord(J->ev[6], st));
+  CUDA_TRY(cudaEventSynchronize(J->ev[6]));
+  float a = 0, b = 0, c = 0, d = 0;
+  cudaEventElapsedTime(&a, J->ev[0], J->ev[1]);
+  cudaEventElapsedTime(&b, J->ev[1], J->ev[2]);
+  cudaEventElapsedTime(&c, J->ev[2], J->ev[3]);
+  cudaEventElapsedTime(&d, J->ev[3], J->ev[6]);
+  cudaEventElapsedTime(&J->last_level1_ms, J->ev[4], J->ev[5]);
+  R->ms_h2d = a; R->ms_dwt = b; R->ms_t1 = c; R->ms_d2h = d; R->ms_total = a + b + c + d;
+  *out = R;
+  return 0;
+}
+
+extern "C" int32_t b2k_encode(b2k_engine* e, const b2k_coding* cp, const int32_t* const* planes, const uint32_t* strides,
+                              uint32_t tile_mod, uint32_t tile_rem, b2k_result** out)
+{
+  return encode_common(e, cp, (void* const*)planes, strides, tile_mod, tile_rem, out);
+}
+
+extern "C" int32_t b2k_encode16(b2k_engine*, const b2k_coding*, const uint16_t* const*, const uint32_t*, uint32_t, uint32_t,
+                                b2k_result**)
+{
+  g_err = "b2k_encode16: 16-bit containers are not wired up yet";
+  return 1;
+}
+
+extern "C" int32_t b2k_decode(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks, uint64_t num_blocks,
+                              const uint8_t* bytes, uint64_t num_bytes, int32_t* const* planes, const uint32_t* strides,
+                              uint32_t tile_mod, uint32_t tile_rem, double* ms_total)
+{
+  if(!e || !cp || !blocks || !planes || !strides)
+    return -1;
+  std::lock_guard<std::mutex> lock(g_cache.mu);
+  int rc = 0;
+  b2k_device_job* J = cached_job(e, cp, tile_mod, tile_rem, &rc);
+  if(rc)
+    return rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  if(num_bytes + 64 > J->bytes_cap)
+  {
+    cudaFree(J->d_bytes);
+    J->bytes_cap = num_bytes + 4096;
+    CUDA_TRY(cudaMalloc(&J->d_bytes, J->bytes_cap));
+  }
+  CUDA_TRY(cudaEventRecord(J->ev[0], st));
+  if(num_bytes)
+    CUDA_TRY(cudaMemcpyAsync(J->d_bytes, bytes, num_bytes, cudaMemcpyHostToDevice, st));
+  if(int prc = prepare_decode(J, blocks, num_blocks, st)) return prc;
+  CUDA_TRY(cudaMemsetAsync(J->d_err, 0, sizeof(int), st));
+  CUDA_TRY(cudaStreamSynchronize(st)); /* descriptors staged from pageable memory */
+  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, (uint32_t)J->h_enc_desc.size(), J->max_cblk_w, J->d_err, st);
+  if(enqueue_inverse(J, st)) return -1;
+  if(copy_planes(J, J->img, (void* const*)planes, strides, false, st)) return -1;
+  CUDA_TRY(cudaEventRecord(J->ev[1], st));
+  CUDA_TRY(cudaEventSynchronize(J->ev[1]));
+  CUDA_TRY(cudaGetLastError());
+  float t = 0;
+  cudaEventElapsedTime(&t, J->ev[0], J->ev[1]);
+  if(ms_total) *ms_total = t;
+  int herr = 0;
+  CUDA_TRY(cudaMemcpy(&herr, J->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if(herr)
+  {
+    g_err = "HT decoder rejected " + std::to_string(herr) + " block(s)";
+    return -2;
+  }
+  return 0;
+}

@@ -1,0 +1,480 @@
+/*
+ * grok_b200/csrc/ht_dec.cu -- HTJ2K (ITU-T T.814) cleanup-pass block DECODER for sm_100a, one
+ * warp per code block, fused with the T1 post-processing (dequantisation into the Mallat buffer).
+ *
+ * Replaces (reference, CPU): T1OJPH::decompress            t1/part15/CoderOJPH.cpp L212-262
+ *                            ojph_decode_codeblock32        t1/part15/coding/ojph_block_decoder32.cpp L742-1317
+ *                            ShiftOJPHFilter/ScaleOJPHFilter t1/part15/PostDecodeFiltersOJPH.h L48-66, L100-119
+ * Cleanup pass only (num_passes == 1): that is all Grok's own encoder ever emits
+ * (CoderOJPH.cpp L200-205).  SigProp / MagRef refinement of foreign streams is a "next" row
+ * (DESIGN.md); a block that carries refinement passes is reported, not mis-decoded.
+ *
+ * Per quad row:  (a) the MEL + CxtVLC + UVLC symbols of the row are decoded serially --
+ * context-adaptive variable-length codes have no parallel parse -- by every lane redundantly
+ * (uniform code, uniform loads) into a shared-memory record per quad;  (b) the MagSgn stream is
+ * parsed by the whole warp: the per-sample bit counts follow from the records, a warp prefix
+ * sum gives every lane its bit offset into an un-stuffed shared-memory bit ring that is refilled
+ * 32 bytes at a time (one byte per lane, stuffing resolved with one ballot since on the decode
+ * side a byte's width only depends on its predecessor's VALUE).
+ */
+#include "b2k_internal.h"
+#define HT_TABLE_QUAL static __device__ const
+#include "ht_tables.h"
+
+namespace {
+
+constexpr int MS_RING_WORDS = 256;
+
+__device__ __forceinline__ unsigned lanemask_lt_d()
+{
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ int mel_exp_d(int k) { return (int)((0x58da489200ull >> (3 * k)) & 7ull); }
+
+/* ---- uniform (all lanes identical) serial readers ------------------------------------------ */
+struct MelR
+{ /* mel_read / mel_decode, ojph_block_decoder32.cpp L92-206 */
+  const uint8_t* d;
+  int size, pos, bits, unstuff, k, run, have;
+  uint32_t tmp;
+};
+__device__ __forceinline__ int mel_bit(MelR& m)
+{
+  if(m.bits == 0)
+  {
+    uint32_t v = 0xFF;
+    if(m.pos < m.size)
+    {
+      v = __ldg(m.d + m.pos);
+      if(m.pos == m.size - 1)
+        v |= 0xF;
+      m.pos++;
+    }
+    m.bits = 8 - m.unstuff;
+    m.tmp = v;
+    m.unstuff = (v == 0xFF);
+  }
+  m.bits--;
+  return (int)((m.tmp >> m.bits) & 1u);
+}
+__device__ __forceinline__ int mel_symbol(MelR& m)
+{
+  if(!m.have)
+  {
+    const int ev = mel_exp_d(m.k);
+    if(mel_bit(m))
+    {
+      m.run = 1 << ev;
+      m.have = 1;
+      m.k = min(12, m.k + 1);
+    }
+    else
+    {
+      int r = 0;
+      for(int i = 0; i < ev; ++i)
+        r = (r << 1) | mel_bit(m);
+      m.run = r;
+      m.have = 2;
+      m.k = max(0, m.k - 1);
+    }
+  }
+  if(m.run > 0)
+  {
+    m.run--;
+    if(m.run == 0 && m.have == 1)
+      m.have = 0;
+    return 0;
+  }
+  m.have = 0;
+  return 1;
+}
+
+struct VlcR
+{ /* rev_read / rev_init, L296-395 */
+  const uint8_t* d;
+  int pos, lo, bits, unstuff;
+  uint64_t tmp;
+};
+__device__ __forceinline__ uint32_t vlc_peek(VlcR& v)
+{
+  while(v.bits <= 56)
+  {
+    uint32_t b = 0;
+    if(v.pos >= v.lo)
+      b = __ldg(v.d + v.pos);
+    v.pos--;
+    const int nb = 8 - ((v.unstuff && ((b & 0x7F) == 0x7F)) ? 1 : 0);
+    v.tmp |= (uint64_t)b << v.bits;
+    v.bits += nb;
+    v.unstuff = b > 0x8F;
+  }
+  return (uint32_t)v.tmp;
+}
+__device__ __forceinline__ void vlc_skip(VlcR& v, int n)
+{
+  v.tmp >>= n;
+  v.bits -= n;
+}
+__device__ __forceinline__ int uvlc_prefix(uint32_t bits, int& len)
+{
+  if(bits & 1) { len = 1; return 1; }
+  if(bits & 2) { len = 2; return 2; }
+  if(bits & 4) { len = 3; return 3; }
+  len = 3;
+  return 5;
+}
+__device__ __forceinline__ int uvlc_suflen(int pfx) { return pfx == 3 ? 1 : (pfx == 5 ? 5 : 0); }
+
+template <typename T>
+__device__ __forceinline__ T warp_excl_scan_d(T v, int lane, T& total)
+{
+  T x = v;
+#pragma unroll
+  for(int o = 1; o < 32; o <<= 1)
+  {
+    const T y = __shfl_up_sync(0xffffffffu, x, o);
+    if(lane >= o)
+      x += y;
+  }
+  total = __shfl_sync(0xffffffffu, x, 31);
+  return x - v;
+}
+
+/* record per quad: rho[3:0] | e_k[7:4] | e_1[11:8] | u[17:12] */
+__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
+    k_ht_decode(const HtBlockDesc* __restrict__ blocks, const uint8_t* __restrict__ bytes, uint32_t nblocks,
+                uint32_t line_entries, int* __restrict__ err)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint16_t* tbl0 = reinterpret_cast<uint16_t*>(smem_raw);
+  uint16_t* tbl1 = tbl0 + 1024;
+  uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw + 2 * 1024 * sizeof(uint16_t));
+  uint32_t* recs_all = rings + B2K_WARPS_PER_CTA * MS_RING_WORDS;
+  uint16_t* lines_all = reinterpret_cast<uint16_t*>(recs_all + (size_t)B2K_WARPS_PER_CTA * 2 * line_entries);
+  for(int i = threadIdx.x; i < 1024; i += blockDim.x)
+  {
+    tbl0[i] = HT_DEC_VLC0[i];
+    tbl1[i] = HT_DEC_VLC1[i];
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bidx = blockIdx.x * B2K_WARPS_PER_CTA + warp;
+  if(bidx >= nblocks)
+    return;
+  const HtBlockDesc B = blocks[bidx];
+  uint32_t* ring = rings + warp * MS_RING_WORDS;
+  uint32_t* rec[2] = {recs_all + (size_t)warp * 2 * line_entries, recs_all + (size_t)warp * 2 * line_entries + line_entries};
+  uint16_t* line[2] = {lines_all + (size_t)warp * 2 * line_entries, lines_all + (size_t)warp * 2 * line_entries + line_entries};
+
+  const int w = B.w, h = B.h, nq = (w + 1) >> 1;
+  const int kmax = B.kmax;
+  int32_t* coef = reinterpret_cast<int32_t*>(B.coef);
+
+  /* zero-length block (not included in any packet): all coefficients are zero */
+  const uint32_t lcup = B.length;
+  bool bad = false;
+  const int mmsbs = (int)B.mmsbs;
+  int scup = 0;
+  const uint8_t* data = bytes + B.slot_off;
+  if(lcup >= 2)
+  {
+    scup = ((int)__ldg(data + lcup - 1) << 4) + (int)(__ldg(data + lcup - 2) & 0xF);
+    if(scup < 2 || scup > (int)lcup || scup > 4079 || mmsbs > 29)
+      bad = true;
+  }
+  if(lcup < 2 || bad)
+  {
+    for(int y = 0; y < h; ++y)
+      for(int x = lane; x < w; x += 32)
+        coef[(size_t)y * B.pitch + x] = 0;
+    if(lane == 0 && (bad || lcup == 1))
+      atomicAdd(err, 1);
+    return;
+  }
+  const int p = 30 - mmsbs;
+  const uint32_t mmsbp2 = (uint32_t)mmsbs + 2u;
+  const int post_shift = 31 - kmax;
+
+  for(int i = lane; i < MS_RING_WORDS; i += 32)
+    ring[i] = 0;
+  for(uint32_t i = lane; i < 2 * line_entries; i += 32)
+  {
+    rec[0][i] = 0;
+    line[0][i] = 0;
+  }
+  __syncwarp();
+
+  MelR mel = {data + lcup - scup, scup - 1, 0, 0, 0, 0, 0, 0, 0};
+  VlcR vlc = {data, (int)lcup - 3, (int)lcup - scup, 0, 0, 0};
+  {
+    const uint32_t d = __ldg(data + lcup - 2);
+    vlc.tmp = d >> 4;
+    vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1 : 0);
+    vlc.unstuff = (d | 0xF) > 0x8F;
+  }
+  /* MagSgn ring feeder state */
+  const int ms_size = (int)lcup - scup;
+  int ms_pos = 0;            /* next byte of the segment to feed */
+  uint32_t ms_head = 0, ms_tail = 0;
+  bool ms_prevff = false;
+
+  for(int y = 0; y < h && !bad; y += 2)
+  {
+    const int cur = (y >> 1) & 1;
+    uint32_t* rcur = rec[cur];
+    const uint32_t* rprev = rec[cur ^ 1];
+    /* ---------------- (a) serial MEL / VLC / UVLC parse of this quad row ---------------- */
+    int rho_left = 0;
+    for(int q0 = 0; q0 < nq; q0 += 2)
+    {
+      const int npair = (q0 + 1 < nq) ? 2 : 1;
+      int rho[2] = {0, 0}, uoff[2] = {0, 0}, ek[2] = {0, 0}, e1[2] = {0, 0}, u[2] = {0, 0};
+      for(int j = 0; j < npair; ++j)
+      {
+        const int q = q0 + j;
+        int cq;
+        if(y == 0)
+          cq = (rho_left >> 1) | (rho_left & 1);
+        else
+        { /* records are stored at index q+1; index 0 and nq+1 stay zero */
+          const uint32_t pl = rprev[q], pc = rprev[q + 1], pr = rprev[q + 2];
+          const int a = (int)((pl & 8) | (pc & 2)), b = (int)((pc & 8) | (pr & 2));
+          cq = (a ? 1 : 0) | ((rho_left & 0xC) ? 2 : 0) | (b ? 4 : 0);
+        }
+        uint32_t t = (y ? tbl1 : tbl0)[(cq << 7) | (vlc_peek(vlc) & 0x7F)];
+        if(cq == 0 && !mel_symbol(mel))
+          t = 0;
+        rho[j] = t & 0xF;
+        ek[j] = (t >> 4) & 0xF;
+        e1[j] = (t >> 8) & 0xF;
+        uoff[j] = (t >> 12) & 1;
+        vlc_skip(vlc, (int)(t >> 13));
+        rho_left = rho[j];
+      }
+      if(y == 0 && uoff[0] && uoff[1])
+      {
+        int len;
+        if(mel_symbol(mel))
+        {
+          const int p0 = uvlc_prefix(vlc_peek(vlc), len);
+          vlc_skip(vlc, len);
+          const int p1 = uvlc_prefix(vlc_peek(vlc), len);
+          vlc_skip(vlc, len);
+          const int l0 = uvlc_suflen(p0), l1 = uvlc_suflen(p1);
+          u[0] = 2 + p0 + (int)(vlc_peek(vlc) & ((1u << l0) - 1u));
+          vlc_skip(vlc, l0);
+          u[1] = 2 + p1 + (int)(vlc_peek(vlc) & ((1u << l1) - 1u));
+          vlc_skip(vlc, l1);
+        }
+        else
+        {
+          const int p0 = uvlc_prefix(vlc_peek(vlc), len);
+          vlc_skip(vlc, len);
+          if(p0 > 2)
+          {
+            u[1] = 1 + (int)(vlc_peek(vlc) & 1u);
+            vlc_skip(vlc, 1);
+            const int l0 = uvlc_suflen(p0);
+            u[0] = p0 + (int)(vlc_peek(vlc) & ((1u << l0) - 1u));
+            vlc_skip(vlc, l0);
+          }
+          else
+          {
+            const int p1 = uvlc_prefix(vlc_peek(vlc), len);
+            vlc_skip(vlc, len);
+            const int l1 = uvlc_suflen(p1);
+            u[0] = p0;
+            u[1] = p1 + (int)(vlc_peek(vlc) & ((1u << l1) - 1u));
+            vlc_skip(vlc, l1);
+          }
+        }
+      }
+      else
+      {
+        int len, pf[2] = {0, 0};
+#pragma unroll
+        for(int j = 0; j < 2; ++j)
+          if(uoff[j])
+          {
+            pf[j] = uvlc_prefix(vlc_peek(vlc), len);
+            vlc_skip(vlc, len);
+          }
+#pragma unroll
+        for(int j = 0; j < 2; ++j)
+          if(uoff[j])
+          {
+            const int l = uvlc_suflen(pf[j]);
+            u[j] = pf[j] + (int)(vlc_peek(vlc) & ((1u << l) - 1u));
+            vlc_skip(vlc, l);
+          }
+      }
+      if(lane == 0)
+      {
+        rcur[q0 + 1] = (uint32_t)(rho[0] | (ek[0] << 4) | (e1[0] << 8) | (u[0] << 12));
+        if(npair == 2)
+          rcur[q0 + 2] = (uint32_t)(rho[1] | (ek[1] << 4) | (e1[1] << 8) | (u[1] << 12));
+      }
+    }
+    __syncwarp();
+
+    /* ---------------- (b) MagSgn parse of this quad row, 32 quads per step ---------------- */
+    const uint16_t* labove = line[cur ^ 1];
+    uint16_t* lcur = line[cur];
+    for(int qb = 0; qb < nq; qb += 32)
+    {
+      /* keep at least 4096 un-stuffed bits (or the rest of the segment + 1-fill) in the ring */
+      while(ms_tail - ms_head < 4096u)
+      {
+        uint32_t b = 0xFF;
+        if(ms_pos + lane < ms_size)
+          b = __ldg(data + ms_pos + lane);
+        const unsigned ff = __ballot_sync(0xffffffffu, b == 0xFFu);
+        const unsigned prevff = (ff << 1) | (ms_prevff ? 1u : 0u);
+        const int nb = ((prevff >> lane) & 1u) ? 7 : 8;
+        const uint32_t pos = ms_tail + 8u * lane - (uint32_t)__popc(prevff & lanemask_lt_d());
+        const uint32_t val = b & (nb == 7 ? 0x7Fu : 0xFFu);
+        {
+          const int sh = pos & 31;
+          const uint32_t wi = pos >> 5;
+          const uint32_t lo = val << sh;
+          if(lo)
+            atomicOr(&ring[wi & (MS_RING_WORDS - 1)], lo);
+          if(sh + nb > 32)
+          {
+            const uint32_t hi = val >> (32 - sh);
+            if(hi)
+              atomicOr(&ring[(wi + 1) & (MS_RING_WORDS - 1)], hi);
+          }
+        }
+        ms_tail += 256u - (uint32_t)__popc(prevff);
+        ms_prevff = (ff >> 31) & 1u;
+        ms_pos += 32;
+        __syncwarp();
+      }
+
+      const int q = qb + lane, x = 2 * q;
+      const bool qv = q < nq;
+      const uint32_t r = qv ? rcur[q + 1] : 0u;
+      const int rho = r & 0xF, ekq = (r >> 4) & 0xF, e1q = (r >> 8) & 0xF, uq = (int)(r >> 12);
+      int kappa = 1;
+      if(y > 0 && qv)
+      {
+        const uint32_t a = labove[q], b = labove[q + 1], c = labove[q + 2];
+        const int emx = max(max((int)(a >> 8), (int)(b & 0xFF)), max((int)(b >> 8), (int)(c & 0xFF)));
+        kappa = (rho & (rho - 1)) ? max(1, emx) : 1;
+      }
+      const uint32_t U = (uint32_t)(uq + kappa);
+      if(qv && U > mmsbp2)
+        bad = true;
+      int m[4], mlen = 0;
+#pragma unroll
+      for(int i = 0; i < 4; ++i)
+      {
+        /* the reference never reads MagSgn bits for the missing right column (L1138-1139) */
+        const bool col_ok = (x + (i >> 1)) < w;
+        m[i] = ((rho >> i) & 1) && col_ok && !bad ? (int)U - ((ekq >> i) & 1) : 0;
+        mlen += m[i];
+      }
+      uint32_t total;
+      const uint32_t off = warp_excl_scan_d<uint32_t>((uint32_t)mlen, lane, total);
+      /* fetch up to 128 bits at ms_head + off */
+      const uint32_t pos = ms_head + off;
+      const uint32_t wi = pos >> 5;
+      const int sh = pos & 31;
+      uint32_t wv[5];
+#pragma unroll
+      for(int i = 0; i < 5; ++i)
+        wv[i] = ring[(wi + i) & (MS_RING_WORDS - 1)];
+      uint32_t bits[4];
+#pragma unroll
+      for(int i = 0; i < 4; ++i)
+        bits[i] = __funnelshift_r(wv[i], wv[i + 1], sh);
+      uint64_t blo = ((uint64_t)bits[1] << 32) | bits[0], bhi = ((uint64_t)bits[3] << 32) | bits[2];
+      int ebot[2] = {0, 0};
+#pragma unroll
+      for(int i = 0; i < 4; ++i)
+      {
+        const int xx = x + (i >> 1), yy = y + (i & 1);
+        uint32_t outv = 0;
+        float outf = 0.f;
+        if(m[i] > 0 || (((rho >> i) & 1) && (x + (i >> 1)) < w && !bad))
+        {
+          const int mi = m[i];
+          const uint32_t msv = (uint32_t)blo;
+          /* consume mi bits */
+          if(mi)
+          {
+            blo = (blo >> mi) | (bhi << (64 - mi));
+            bhi >>= mi;
+          }
+          uint32_t v_n = msv & (mi >= 32 ? 0xFFFFFFFFu : ((1u << mi) - 1u));
+          v_n |= (uint32_t)((e1q >> i) & 1) << mi;
+          v_n |= 1u;
+          const uint32_t mag = (v_n + 2u) << (p - 1);
+          const uint32_t sgn = msv & 1u;
+          if(i & 1)
+            ebot[i >> 1] = 31 - __clz(v_n | 2u);
+          if(!B.irreversible)
+          {
+            const int32_t mv = (int32_t)((mag & 0x7FFFFFFFu) >> post_shift);
+            outv = (uint32_t)(sgn ? -mv : mv);
+          }
+          else
+          {
+            outf = __fmul_rn((float)(int32_t)(mag & 0x7FFFFFFFu), B.quant);
+            if(sgn)
+              outf = -outf;
+            outv = __float_as_uint(outf);
+          }
+        }
+        if(qv && xx < w && yy < h)
+          coef[(size_t)yy * B.pitch + xx] = (int32_t)outv;
+      }
+      if(qv)
+        lcur[q + 1] = (uint16_t)(ebot[0] | (ebot[1] << 8));
+      /* release consumed ring words */
+      {
+        const uint32_t nh = ms_head + total;
+        __syncwarp();
+        for(uint32_t wz = (ms_head >> 5) + lane; wz < (nh >> 5); wz += 32)
+          ring[wz & (MS_RING_WORDS - 1)] = 0;
+        ms_head = nh;
+      }
+      bad = __any_sync(0xffffffffu, bad);
+      __syncwarp();
+    }
+  }
+  if(bad)
+  {
+    __syncwarp();
+    for(int y = 0; y < h; ++y)
+      for(int x = lane; x < w; x += 32)
+        coef[(size_t)y * B.pitch + x] = 0;
+    if(lane == 0)
+      atomicAdd(err, 1);
+  }
+}
+
+} /* namespace */
+
+void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t nblocks, uint32_t max_w,
+                          int* d_err, cudaStream_t st)
+{
+  if(!nblocks)
+    return;
+  const uint32_t line_entries = ((max_w + 1) / 2 + 4 + 1) & ~1u;
+  const size_t smem = 2 * 1024 * sizeof(uint16_t) + (size_t)B2K_WARPS_PER_CTA * MS_RING_WORDS * sizeof(uint32_t) +
+                      (size_t)B2K_WARPS_PER_CTA * 2 * line_entries * (sizeof(uint32_t) + sizeof(uint16_t));
+  static bool attr_set = false;
+  if(!attr_set)
+  {
+    cudaFuncSetAttribute(k_ht_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  const uint32_t grid = (nblocks + B2K_WARPS_PER_CTA - 1) / B2K_WARPS_PER_CTA;
+  k_ht_decode<<<grid, B2K_WARPS_PER_CTA * 32, smem, st>>>(d_blocks, d_bytes, nblocks, line_entries, d_err);
+  b2k_count_launch();
+}

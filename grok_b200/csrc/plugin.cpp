@@ -1,0 +1,300 @@
+/*
+ * grok_b200/csrc/plugin.cpp -- the STOCK accelerator-plugin symbols (group 1 of
+ * include/grok_b200.h) on top of the b2k engine.
+ *
+ *   minpf_post_load_plugin   minpf loader handshake           plugin/minpf_plugin_manager.cpp L136-238
+ *   plugin_init              device selection                 grok.cpp L1344-1370
+ *   gpup_encode_mem          whole image = one tile           grok.cpp L1302-1328, CodeStreamCompress.cpp L878-912
+ *   gpup_tile_free           tree + coded bytes owned here    grok.cpp L1330, plugin_bridge.cpp L185-189
+ * Return convention plugin_accelerate.h L32-36: 0 handled, >0 not handled (CPU fallback), <0 error.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/grok_b200.h"
+#include "geometry.h"
+
+using namespace b2k;
+
+static std::mutex g_mu;
+static b2k_engine* g_engine = nullptr;
+static int32_t g_device = 0;
+static bool g_verbose = false;
+/* tile -> result that owns its coded bytes */
+static std::unordered_map<gpup_tile*, b2k_result*> g_owned;
+
+static int32_t plugin_exit(void)
+{
+  std::lock_guard<std::mutex> lock(g_mu);
+  if(g_engine)
+  {
+    b2k_engine_destroy(g_engine);
+    g_engine = nullptr;
+  }
+  return 0;
+}
+
+extern "C" minpf_exit_func minpf_post_load_plugin(const minpf_platform_services*)
+{
+  /* nothing to register: the host resolves our entry points by name (grok.cpp L1177-1186) */
+  return plugin_exit;
+}
+
+extern "C" bool plugin_init(gpup_init_info info)
+{
+  std::lock_guard<std::mutex> lock(g_mu);
+  g_verbose = info.verbose;
+  g_device = info.deviceId < 0 ? 0 : info.deviceId;
+  if(!g_engine && b2k_engine_create(g_device, &g_engine) != 0)
+  {
+    if(g_verbose)
+      fprintf(stderr, "[grok_b200] plugin_init failed: %s\n", b2k_last_error());
+    return false;
+  }
+  return true;
+}
+
+extern "C" uint32_t plugin_get_debug_state(void) { return GPUP_STATE_NO_DEBUG; }
+
+static int floor_log2_u32(uint32_t v)
+{
+  int l = 0;
+  while(v >>= 1)
+    ++l;
+  return l;
+}
+
+/* gpup_compress_params + gpup_image -> b2k_coding; false if the engine does not cover it */
+static bool coding_from_gpup(const gpup_compress_params* p, const gpup_image* im, b2k_coding* cp)
+{
+  memset(cp, 0, sizeof(*cp));
+  if(!p || !im || !im->comps || im->numcomps < 1 || im->numcomps > 4)
+    return false;
+  if(!(p->cblk_sty & GPUP_CBLKSTY_HT))
+    return false; /* Part-1 MQ block coding stays on the host */
+  if(p->numlayers > 1 || p->roi_compno >= 0 || p->numpocs)
+    return false;
+  cp->x0 = im->x0; cp->y0 = im->y0; cp->x1 = im->x1; cp->y1 = im->y1;
+  /* stock contract: one tile (CodeStreamCompress.cpp L908-912) */
+  if(p->tile_size_on && (p->t_width < cp->x1 - p->tx0 || p->t_height < cp->y1 - p->ty0))
+    return false;
+  cp->tw = cp->th = 0;
+  cp->numcomps = im->numcomps;
+  cp->prec = im->comps[0].prec;
+  cp->sgnd = im->comps[0].sgnd;
+  for(uint16_t c = 0; c < im->numcomps; ++c)
+  {
+    const gpup_image_comp& k = im->comps[c];
+    if(k.dx != 1 || k.dy != 1 || k.prec != cp->prec || (k.sgnd ? 1 : 0) != cp->sgnd || !k.data)
+      return false;
+    if(k.w != cp->x1 - cp->x0 || k.h != cp->y1 - cp->y0)
+      return false;
+  }
+  cp->numres = p->numresolution;
+  cp->cblkw_exp = (uint8_t)floor_log2_u32(p->cblockw_init ? p->cblockw_init : 64);
+  cp->cblkh_exp = (uint8_t)floor_log2_u32(p->cblockh_init ? p->cblockh_init : 64);
+  cp->irreversible = p->irreversible;
+  cp->mct = p->mct ? 1 : 0;
+  if(p->mct > 1)
+    return false; /* custom (array) MCT */
+  cp->numgbits = p->numgbits;
+  for(int r = 0; r < 33; ++r)
+  {
+    cp->prcw_exp[r] = 15;
+    cp->prch_exp[r] = 15;
+  }
+  if(p->csty & 1)
+    for(uint32_t r = 0; r < p->res_spec && r < 33; ++r)
+    { /* CodeStreamCompress.cpp L805-837: specified coarsest-last */
+      const uint32_t pw = p->prcw_init[r], ph = p->prch_init[r];
+      const int rr = (int)p->numresolution - 1 - (int)r;
+      if(rr >= 0 && pw && ph)
+      {
+        cp->prcw_exp[rr] = (uint8_t)floor_log2_u32(pw);
+        cp->prch_exp[rr] = (uint8_t)floor_log2_u32(ph);
+      }
+    }
+  return unsupported_reason(*cp) == nullptr;
+}
+
+/* One calloc'ed slab per tree; gpup_tile_free releases it. */
+extern "C" gpup_tile* b2k_result_to_gpup_tile(const b2k_coding* cp, const b2k_result* r, uint32_t tile)
+{
+  if(!cp || !r)
+    return nullptr;
+  /* count */
+  const int ncomp = cp->numcomps, numres = cp->numres;
+  std::vector<const b2k_block*> blks;
+  for(uint64_t i = 0; i < r->num_blocks; ++i)
+    if(r->blocks[i].tile == tile)
+      blks.push_back(&r->blocks[i]);
+  const TileGrid g = tile_grid(*cp);
+  const Rect tr = tile_rect(*cp, g, tile);
+  const std::vector<BandQuant> q = band_quant(*cp);
+
+  gpup_tile* T = (gpup_tile*)calloc(1, sizeof(gpup_tile));
+  T->decompress_flags = 0;
+  T->numComponents = (size_t)ncomp;
+  T->tileComponents = (gpup_tile_component**)calloc(ncomp, sizeof(void*));
+  size_t cursor = 0;
+  for(int c = 0; c < ncomp; ++c)
+  {
+    gpup_tile_component* tc = (gpup_tile_component*)calloc(1, sizeof(gpup_tile_component));
+    T->tileComponents[c] = tc;
+    tc->numResolutions = (size_t)numres;
+    tc->resolutions = (gpup_resolution**)calloc(numres, sizeof(void*));
+    for(int resno = 0; resno < numres; ++resno)
+    {
+      gpup_resolution* res = (gpup_resolution*)calloc(1, sizeof(gpup_resolution));
+      tc->resolutions[resno] = res;
+      res->level = (size_t)resno;
+      res->numBands = resno == 0 ? 1 : 3;
+      res->band = (gpup_band**)calloc(res->numBands, sizeof(void*));
+      /* precinct grid of this resolution */
+      const Rect rr = resolution_rect(tr, numres, resno);
+      const uint32_t pw = cp->prcw_exp[resno] ? cp->prcw_exp[resno] : 15, ph = cp->prch_exp[resno] ? cp->prch_exp[resno] : 15;
+      const uint64_t gw = (uint64_t)ceil_div_pow2(rr.x1, pw) - (rr.x0 >> pw), gh = (uint64_t)ceil_div_pow2(rr.y1, ph) - (rr.y0 >> ph);
+      const uint64_t nprec = rr.empty() ? 0 : gw * gh;
+      for(size_t b = 0; b < res->numBands; ++b)
+      {
+        gpup_band* band = (gpup_band*)calloc(1, sizeof(gpup_band));
+        res->band[b] = band;
+        band->orientation = (uint8_t)(resno == 0 ? 0 : b + 1);
+        band->stepsize = q[band_quant_index(resno, band->orientation)].step_enc;
+        band->numPrecincts = nprec;
+        band->precincts = (gpup_precinct**)calloc(nprec ? nprec : 1, sizeof(void*));
+        for(uint64_t p = 0; p < nprec; ++p)
+          band->precincts[p] = (gpup_precinct*)calloc(1, sizeof(gpup_precinct));
+        /* blocks of this band are contiguous in enumeration order */
+        size_t first = cursor;
+        while(cursor < blks.size() && blks[cursor]->comp == c && blks[cursor]->resno == resno &&
+              blks[cursor]->band_index == b)
+          ++cursor;
+        for(size_t i = first; i < cursor;)
+        {
+          const uint32_t p = blks[i]->precno;
+          size_t j = i;
+          while(j < cursor && blks[j]->precno == p)
+            ++j;
+          gpup_precinct* prc = band->precincts[p];
+          prc->numBlocks = j - i;
+          prc->blocks = (gpup_code_block**)calloc(j - i, sizeof(void*));
+          for(size_t k = i; k < j; ++k)
+          {
+            const b2k_block& s = *blks[k];
+            gpup_code_block* cb = (gpup_code_block*)calloc(1, sizeof(gpup_code_block));
+            prc->blocks[k - i] = cb;
+            cb->x0 = s.x0; cb->y0 = s.y0; cb->x1 = s.x1; cb->y1 = s.y1;
+            cb->numPix = (s.x1 - s.x0) * (s.y1 - s.y0);
+            cb->compressedData = s.length ? r->bytes + s.offset : nullptr;
+            cb->compressedDataLength = s.length;
+            cb->numBitPlanes = s.numbps;
+            cb->numPasses = s.numpasses;
+            if(s.numpasses)
+            { /* plugin_bridge.cpp L221-227: rate is the index of the last byte */
+              cb->passes[0].rate = s.length ? s.length - 1 : 0;
+              cb->passes[0].length = s.length;
+              cb->passes[0].distortionDecrease = 0.0;
+            }
+            cb->sortedIndex = (unsigned int)(k - i);
+          }
+          i = j;
+        }
+      }
+    }
+  }
+  return T;
+}
+
+static void free_tree(gpup_tile* T)
+{
+  if(!T)
+    return;
+  for(size_t c = 0; c < T->numComponents; ++c)
+  {
+    gpup_tile_component* tc = T->tileComponents[c];
+    for(size_t r = 0; r < tc->numResolutions; ++r)
+    {
+      gpup_resolution* res = tc->resolutions[r];
+      for(size_t b = 0; b < res->numBands; ++b)
+      {
+        gpup_band* band = res->band[b];
+        for(uint64_t p = 0; p < band->numPrecincts; ++p)
+        {
+          gpup_precinct* prc = band->precincts[p];
+          for(uint64_t k = 0; k < prc->numBlocks; ++k)
+            free(prc->blocks[k]);
+          free(prc->blocks);
+          free(prc);
+        }
+        free(band->precincts);
+        free(band);
+      }
+      free(res->band);
+      free(res);
+    }
+    free(tc->resolutions);
+    free(tc);
+  }
+  free(T->tileComponents);
+  free(T);
+}
+
+extern "C" int32_t gpup_encode_mem(gpup_compress_params* params, gpup_image* image, gpup_tile** out)
+{
+  if(!out)
+    return -1;
+  *out = nullptr;
+  b2k_coding cp;
+  if(!coding_from_gpup(params, image, &cp))
+    return 1; /* not handled -> host CPU path */
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if(!g_engine && b2k_engine_create(g_device, &g_engine) != 0)
+      return -1;
+  }
+  const int32_t* planes[4];
+  uint32_t strides[4];
+  for(uint16_t c = 0; c < image->numcomps; ++c)
+  {
+    planes[c] = image->comps[c].data;
+    strides[c] = image->comps[c].stride;
+  }
+  b2k_result* R = nullptr;
+  const int32_t rc = b2k_encode(g_engine, &cp, planes, strides, 1, 0, &R);
+  if(rc != 0)
+    return rc;
+  gpup_tile* T = b2k_result_to_gpup_tile(&cp, R, 0);
+  if(!T)
+  {
+    b2k_result_free(R);
+    return -1;
+  }
+  std::lock_guard<std::mutex> lock(g_mu);
+  g_owned[T] = R;
+  *out = T;
+  return 0;
+}
+
+extern "C" void gpup_tile_free(gpup_tile* tile)
+{
+  if(!tile)
+    return;
+  b2k_result* R = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_owned.find(tile);
+    if(it != g_owned.end())
+    {
+      R = it->second;
+      g_owned.erase(it);
+    }
+  }
+  free_tree(tile);
+  if(R)
+    b2k_result_free(R);
+}

@@ -1,0 +1,392 @@
+/*
+ * include/grok_b200.h -- C ABI of libgrokj2k_plugin.so, the B200-native JPEG 2000 tile engine.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) The STOCK accelerator-plugin symbols Grok's host library resolves with dlsym()
+ *      (reference: src/lib/core/grok.cpp L1177-1186, L1297-1300; typedefs
+ *      src/lib/core/plugin/plugin_interface.h L50-133; structs
+ *      src/lib/core/plugin/gpup/gpu_plugin_shared.h L215-530).  The struct layouts below are
+ *      binary-compatible restatements of that contract: field order and types must not change.
+ *
+ *  (2) The tile-aware b2k_* engine API.  The stock contract is "whole image = one tile"
+ *      (CodeStreamCompress.cpp L908-912, CodeStreamDecompress.cpp L199-205); multi-tile
+ *      codestreams, multi-GPU sharding, device-resident buffers and per-stage parity hooks go
+ *      through these.  INTEGRATION.md shows the ~30-line host patch that binds them.
+ *
+ * All functions are extern "C", plain pointers and sizes, no C++ or torch types.
+ * Return convention (plugin_accelerate.h L32-36): 0 = handled, >0 = not handled (host falls
+ * back to its CPU path), <0 = device failure.
+ */
+#ifndef GROK_B200_H
+#define GROK_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2K_API __attribute__((visibility("default")))
+
+/* ============================================================================================
+ * (1) stock plugin contract -- gpu_plugin_shared.h
+ * ========================================================================================== */
+#define GPUP_PATH_LEN 4096
+#define GPUP_MAX_LAYERS 256
+#define GPUP_MAX_DECOMP_LVLS 32
+#define GPUP_MAXRLVLS (GPUP_MAX_DECOMP_LVLS + 1)
+#define GPUP_MAX_SUPPORTED_PREC 16
+#define GPUP_BIBO_EXTRA_BITS 7
+#define GPUP_MAX_PASSES (3 * (GPUP_MAX_SUPPORTED_PREC + GPUP_BIBO_EXTRA_BITS) - 2)
+#define GPUP_BUFFER_ALIGNMENT 64
+
+#define GPUP_DECODE_HEADER (1 << 0)
+#define GPUP_DECODE_T2 (1 << 1)
+#define GPUP_DECODE_T1 (1 << 2)
+#define GPUP_DECODE_POST_T1 (1 << 3)
+#define GPUP_DECODE_CLEAN (1 << 4)
+
+#define GPUP_STATE_NO_DEBUG 0x0
+#define GPUP_CBLKSTY_HT 0x040
+
+/* enums of gpu_plugin_shared.h L63-146 are plain C enums (int sized) */
+typedef int32_t gpup_prog_order;
+typedef int32_t gpup_color_space;
+typedef int32_t gpup_file_fmt;
+typedef int32_t gpup_codec_fmt;
+typedef int32_t gpup_rate_control;
+
+typedef struct _gpup_image_comp /* L215-225 */
+{
+  uint32_t x0, y0;
+  uint32_t w;
+  uint32_t stride;
+  uint32_t h;
+  uint8_t dx, dy;
+  uint8_t prec;
+  bool sgnd;
+  int32_t* data;
+  bool owns_data;
+} gpup_image_comp;
+
+typedef struct _gpup_image /* L227-233 */
+{
+  uint32_t x0, y0, x1, y1;
+  uint16_t numcomps;
+  gpup_color_space color_space;
+  gpup_image_comp* comps;
+} gpup_image;
+
+typedef struct _gpup_pass /* L240-245 */
+{
+  double distortionDecrease;
+  size_t rate;
+  size_t length;
+} gpup_pass;
+
+typedef struct _gpup_code_block /* L247-261 */
+{
+  uint32_t x0, y0, x1, y1;
+  unsigned int* contextStream;
+  uint32_t numPix;
+  uint8_t* compressedData;
+  uint32_t compressedDataLength;
+  uint8_t numBitPlanes;
+  size_t numPasses;
+  gpup_pass passes[GPUP_MAX_PASSES];
+  unsigned int sortedIndex;
+} gpup_code_block;
+
+typedef struct _gpup_precinct
+{
+  uint64_t numBlocks;
+  gpup_code_block** blocks;
+} gpup_precinct;
+
+typedef struct _gpup_band
+{
+  uint8_t orientation;
+  uint64_t numPrecincts;
+  gpup_precinct** precincts;
+  float stepsize;
+} gpup_band;
+
+typedef struct _gpup_resolution
+{
+  size_t level;
+  size_t numBands;
+  gpup_band** band;
+} gpup_resolution;
+
+typedef struct _gpup_tile_component
+{
+  size_t numResolutions;
+  gpup_resolution** resolutions;
+} gpup_tile_component;
+
+typedef struct _gpup_tile /* L289-294 */
+{
+  uint32_t decompress_flags;
+  size_t numComponents;
+  gpup_tile_component** tileComponents;
+} gpup_tile;
+
+typedef struct _gpup_header_info /* L300-318 */
+{
+  uint32_t cblockw_init;
+  uint32_t cblockh_init;
+  bool irreversible;
+  uint8_t mct;
+  uint16_t rsiz;
+  uint8_t numresolutions;
+  gpup_prog_order prog_order;
+  uint8_t csty;
+  uint8_t cblk_sty;
+  uint32_t prcw_init[GPUP_MAXRLVLS];
+  uint32_t prch_init[GPUP_MAXRLVLS];
+  uint32_t tx0, ty0;
+  uint32_t t_width, t_height;
+  uint16_t t_grid_width, t_grid_height;
+  uint16_t max_layers_;
+} gpup_header_info;
+
+typedef struct _gpup_compress_params /* L324-374 */
+{
+  bool tile_size_on;
+  uint32_t tx0, ty0, t_width, t_height;
+  uint16_t numlayers;
+  bool allocationByRateDistoration;
+  double layer_rate[GPUP_MAX_LAYERS];
+  bool allocationByQuality;
+  double layer_distortion[GPUP_MAX_LAYERS];
+  uint8_t csty;
+  uint8_t numgbits;
+  gpup_prog_order prog_order;
+  uint32_t numpocs;
+  uint8_t numresolution;
+  uint32_t cblockw_init;
+  uint32_t cblockh_init;
+  uint8_t cblk_sty;
+  bool irreversible;
+  int32_t roi_compno;
+  uint32_t roi_shift;
+  uint32_t res_spec;
+  uint32_t prcw_init[GPUP_MAXRLVLS];
+  uint32_t prch_init[GPUP_MAXRLVLS];
+  char infile[GPUP_PATH_LEN];
+  char outfile[GPUP_PATH_LEN];
+  uint32_t image_offset_x0;
+  uint32_t image_offset_y0;
+  uint8_t subsampling_dx;
+  uint8_t subsampling_dy;
+  gpup_file_fmt decod_format;
+  gpup_file_fmt cod_format;
+  bool enableTilePartGeneration;
+  uint8_t newTilePartProgressionDivider;
+  uint8_t mct;
+  uint64_t max_cs_size;
+  uint64_t max_comp_size;
+  uint16_t rsiz;
+  uint16_t framerate;
+  gpup_rate_control rateControlAlgorithm;
+  uint32_t numThreads;
+  int32_t deviceId;
+  uint32_t duration;
+  uint32_t kernelBuildOptions;
+  uint32_t repeats;
+  bool verbose;
+  bool sharedMemoryInterface;
+  bool apply_xyz_transform;
+} gpup_compress_params;
+
+typedef struct _gpup_decompress_core_params
+{
+  uint8_t reduce;
+  uint16_t layers_to_decompress_;
+} gpup_decompress_core_params;
+
+typedef struct _gpup_decompress_params /* L386-401 */
+{
+  gpup_decompress_core_params core;
+  char infile[GPUP_PATH_LEN];
+  char outfile[GPUP_PATH_LEN];
+  gpup_codec_fmt decod_format;
+  gpup_file_fmt cod_format;
+  double dw_x0, dw_y0, dw_x1, dw_y1;
+  uint16_t tileIndex;
+  int32_t deviceId;
+  uint32_t kernelBuildOptions;
+  uint32_t repeats;
+  uint32_t numThreads;
+  bool verbose_;
+  void* user_data;
+} gpup_decompress_params;
+
+typedef struct _gpup_init_info /* L403-409 */
+{
+  int32_t deviceId;
+  bool verbose;
+  const char* license;
+  const char* server;
+} gpup_init_info;
+
+typedef int (*GPUP_INIT_DECOMPRESSORS)(gpup_header_info* header_info, gpup_image* image);
+
+typedef struct _gpup_decompress_callback_info /* L503-524 */
+{
+  size_t deviceId;
+  GPUP_INIT_DECOMPRESSORS init_decompressors_func;
+  const char* input_file_name;
+  const char* output_file_name;
+  gpup_codec_fmt decod_format;
+  gpup_file_fmt cod_format;
+  void* codec;
+  gpup_header_info header_info;
+  gpup_decompress_params* decompressor_parameters;
+  gpup_image* image;
+  bool plugin_owns_image;
+  gpup_tile* tile;
+  unsigned int error_code;
+  uint32_t decompress_flags;
+  uint32_t full_image_x0;
+  uint32_t full_image_y0;
+  void* user_data;
+  void* format_private;
+} gpup_decompress_callback_info;
+
+typedef int32_t (*GPUP_DECOMPRESS_USER_CALLBACK)(gpup_decompress_callback_info* info);
+
+/* minpf loader handshake: minpf_plugin.h L98-111 */
+typedef int32_t (*minpf_exit_func)(void);
+typedef struct _minpf_platform_services minpf_platform_services; /* opaque here; see INTEGRATION.md */
+
+/* --- symbols resolved by name by libgrokj2k (grok.cpp L1177-1186, L1297-1298) --- */
+B2K_API minpf_exit_func minpf_post_load_plugin(const minpf_platform_services* services); /* minpf_plugin.h L109 */
+B2K_API bool plugin_init(gpup_init_info info);                    /* plugin_interface.h L60 */
+B2K_API uint32_t plugin_get_debug_state(void);                    /* plugin_interface.h L56 */
+B2K_API int32_t gpup_encode_mem(gpup_compress_params* params, gpup_image* image,
+                                gpup_tile** out);                 /* grok.cpp L1299-1300 */
+B2K_API void gpup_tile_free(gpup_tile* tile);                     /* grok.cpp L1330 */
+/* plugin_decompress (plugin_interface.h L117-120) takes a C++ struct with std::string members
+ * (PluginDecodeCallbackInfo L78-115): it is declared in grok_b200/csrc/plugin_decode.cpp and
+ * documented in INTEGRATION.md, not here, so that this header stays C. */
+
+/* ============================================================================================
+ * (2) tile-aware engine API
+ * ========================================================================================== */
+typedef struct b2k_engine b2k_engine;
+
+/* coding parameters of one image; the subset of grk_cparameters / SIZ+COD+QCD the tile engine
+ * depends on (CodeStreamCompress::init, CodeStreamCompress.cpp L229-855) */
+typedef struct b2k_coding
+{
+  uint32_t x0, y0, x1, y1;         /* image area on the canvas (SIZ) */
+  uint32_t tx0, ty0, tw, th;       /* tile grid origin and nominal tile size (tw==0: one tile) */
+  uint16_t numcomps;               /* 1..4; all components dx=dy=1 and same precision */
+  uint8_t prec;                    /* bits per sample */
+  uint8_t sgnd;                    /* 1 = signed samples */
+  uint8_t numres;                  /* resolutions = decomposition levels + 1 */
+  uint8_t cblkw_exp, cblkh_exp;    /* log2 nominal code-block size (6,6 = 64x64) */
+  uint8_t irreversible;            /* 0: 5/3 + RCT, 1: 9/7 + ICT */
+  uint8_t mct;                     /* 1: colour transform on components 0..2 */
+  uint8_t numgbits;                /* guard bits; Grok's HT CLI forces 1 (GrkCompress.cpp L849) */
+  uint8_t prcw_exp[33], prch_exp[33]; /* precinct exponents per resolution (15 = maximal) */
+} b2k_coding;
+
+/* One coded block as the host's T2 needs it (cf. compress_synch_with_plugin,
+ * plugin_bridge.cpp L113-243), in Grok's enumeration order tile->comp->res->band->prec->cblk */
+typedef struct b2k_block
+{
+  uint32_t tile;                   /* tile index, raster order */
+  uint16_t comp;
+  uint8_t resno, band_index, orient;
+  uint8_t kmax;                    /* band->maxBitPlanes_ (TileProcessor.cpp L417-419) */
+  uint8_t numbps;                  /* coded bit planes as T2 signals them: Kmax - zero bit planes.
+                                      The encoder returns 1 (CoderOJPH.cpp L203-206) */
+  uint8_t numpasses;               /* 1 for every coded block (HT cleanup only), 0 if not coded */
+  uint32_t precno, cblkno;
+  uint32_t x0, y0, x1, y1;         /* block rect, band canvas coordinates */
+  uint32_t buf_x, buf_y;           /* position inside the tile-component Mallat buffer */
+  uint32_t length;                 /* coded bytes (HT cleanup pass; 1 pass, 1 segment) */
+  uint64_t offset;                 /* byte offset into the result's byte arena */
+  float stepsize;                  /* band step size (encoder convention) */
+} b2k_block;
+
+typedef struct b2k_result
+{
+  uint64_t num_blocks;
+  b2k_block* blocks;               /* host memory, owned by the result */
+  uint8_t* bytes;                  /* host memory (pinned), owned by the result */
+  uint64_t num_bytes;
+  uint32_t num_tiles;
+  double ms_h2d, ms_dwt, ms_t1, ms_d2h, ms_total; /* device-event timings of the call */
+} b2k_result;
+
+B2K_API int32_t b2k_engine_create(int32_t device, b2k_engine** out);
+B2K_API void b2k_engine_destroy(b2k_engine* e);
+B2K_API const char* b2k_last_error(void);
+
+/* pinned host memory for image planes / codestream arenas (what Grok's allocator should hand
+ * to grk_image when the plugin is loaded) */
+B2K_API void* b2k_host_alloc(size_t bytes);
+B2K_API void b2k_host_free(void* p);
+
+/* Encode every tile of the image for which (tile_index % tile_mod) == tile_rem (tile_mod=1:
+ * all tiles).  planes[c] = int32 samples, row stride strides[c] elements, origin (x0,y0). */
+B2K_API int32_t b2k_encode(b2k_engine* e, const b2k_coding* cp, const int32_t* const* planes,
+                           const uint32_t* strides, uint32_t tile_mod, uint32_t tile_rem,
+                           b2k_result** out);
+/* same, 16-bit unsigned/signed sample containers (cf. gpup_batch_memory_submit_planes) */
+B2K_API int32_t b2k_encode16(b2k_engine* e, const b2k_coding* cp, const uint16_t* const* planes,
+                             const uint32_t* strides, uint32_t tile_mod, uint32_t tile_rem,
+                             b2k_result** out);
+B2K_API void b2k_result_free(b2k_result* r);
+
+/* Decode: blocks[] (same enumeration, with length/offset filled by the host's T2 parse) and the
+ * byte arena in; planes out (int32, clamped, DC shift restored). */
+B2K_API int32_t b2k_decode(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks,
+                           uint64_t num_blocks, const uint8_t* bytes, uint64_t num_bytes,
+                           int32_t* const* planes, const uint32_t* strides, uint32_t tile_mod,
+                           uint32_t tile_rem, double* ms_total);
+
+/* Geometry only (host): enumerate the blocks of the selected tiles, lengths zero.  Returns the
+ * count; fills at most cap entries. */
+B2K_API int64_t b2k_enumerate(const b2k_coding* cp, uint32_t tile_mod, uint32_t tile_rem,
+                              b2k_block* out, uint64_t cap);
+
+/* Build / free the stock gpup_tile tree for ONE tile from a result (what gpup_encode_mem
+ * returns; layout rules plugin_bridge.cpp L62-111). */
+B2K_API gpup_tile* b2k_result_to_gpup_tile(const b2k_coding* cp, const b2k_result* r, uint32_t tile);
+
+/* ---- device-resident path (inputs already in HBM; what bench.py's `value` times) ---------- */
+typedef struct b2k_device_job b2k_device_job;
+B2K_API int32_t b2k_job_create(b2k_engine* e, const b2k_coding* cp, uint32_t tile_mod,
+                               uint32_t tile_rem, b2k_device_job** out);
+B2K_API void b2k_job_destroy(b2k_device_job* j);
+/* upload planes into the job's device image (untimed set-up for the device-resident bench) */
+B2K_API int32_t b2k_job_upload(b2k_device_job* j, const int32_t* const* planes, const uint32_t* strides);
+/* run stages on device-resident data; each returns 0 and the elapsed device ms via *ms */
+B2K_API int32_t b2k_job_forward(b2k_device_job* j, float* ms);  /* DC shift+MCT+DWT, all levels */
+B2K_API int32_t b2k_job_t1_encode(b2k_device_job* j, float* ms, uint64_t* total_bytes);
+B2K_API int32_t b2k_job_t1_decode(b2k_device_job* j, float* ms);/* from the job's own coded blocks */
+B2K_API int32_t b2k_job_inverse(b2k_device_job* j, float* ms);  /* inverse DWT+MCT into image */
+B2K_API int32_t b2k_job_download(b2k_device_job* j, int32_t* const* planes, const uint32_t* strides);
+/* copy the coefficient planes (Mallat layout per tile, image-shaped, int32 or float bits) */
+B2K_API int32_t b2k_job_download_coeffs(b2k_device_job* j, int32_t* const* planes, const uint32_t* strides);
+B2K_API int32_t b2k_job_upload_coeffs(b2k_device_job* j, const int32_t* const* planes, const uint32_t* strides);
+/* fetch coded blocks of the last b2k_job_t1_encode as a host result */
+B2K_API int32_t b2k_job_fetch_result(b2k_device_job* j, b2k_result** out);
+B2K_API uint64_t b2k_job_num_blocks(const b2k_device_job* j);
+/* launches issued by this library since engine creation (bench.py "gpu_launches") */
+B2K_API uint64_t b2k_launch_count(void);
+/* per-kernel timing of the last forward()/inverse(): ms of the level-1 kernel and algorithmic
+ * bytes it moved (for the roofline line of bench.py) */
+B2K_API int32_t b2k_job_last_kernel_stats(const b2k_device_job* j, int which, float* ms, uint64_t* alg_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GROK_B200_H */
