@@ -1,0 +1,309 @@
+"""GPU parity tests (-m gpu): the CUDA engine, called through the C ABI, against the oracle on the
+same seeded inputs -- bit-exact for the reversible path (integer / byte work), and for the
+irreversible path bit-exact against the oracle's fp32 restatement plus the reference's own
+accelerator tolerances against the source (GrkPluginMemoryTest.cpp L39-52)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import grok_b200 as G
+import oracle_lib as O
+import oracle_pipeline as P
+
+pytestmark = pytest.mark.gpu
+
+GEOMS = [
+    dict(width=512, height=512, numcomps=1, prec=8),                                   # BASELINE config 1
+    dict(width=2048, height=1024, numcomps=3, prec=12, tile=(1024, 1024)),              # config 2 tiles
+    dict(width=333, height=217, numcomps=3, prec=12, numres=4, origin=(3, 5)),          # odd origin
+    dict(width=100, height=75, numcomps=4, prec=16, numres=3, tile=(61, 40), cblk=(32, 32)),  # config 4 shape, ragged tiles
+    dict(width=61, height=9, numcomps=1, prec=8, numres=6),                             # levels run out of samples
+    dict(width=64, height=64, numcomps=3, prec=10, numres=3, tile=(1, 64)),             # 1-pixel-wide tiles
+    dict(width=40, height=33, numcomps=1, prec=12, numres=2, tile=(7, 1), cblk=(4, 4)), # 1-pixel-high tiles
+    dict(width=300, height=200, numcomps=3, prec=8, numres=5, tile=(128, 128), origin=(129, 65), tile_origin=(1, 1),
+         cblk=(16, 128)),
+]
+
+
+def _compare_blocks(cp, res, coefs):
+    blks = P.enumerate_all(cp)
+    rects = P.tile_rects(cp)
+    assert len(blks) == res.num_blocks
+    for i, (t, c, b) in enumerate(blks):
+        if b.x1 == b.x0 or b.y1 == b.y0:
+            assert res.blocks[i]["length"] == 0
+            continue
+        want = P.encode_block(cp, coefs, rects[t], c, b)
+        assert np.array_equal(want, res.block_bytes(i)), "code block %d (res %d orient %d)" % (i, b.resno, b.orient)
+
+
+@pytest.mark.parametrize("args", GEOMS)
+def test_reversible_stage_parity(engine, args):
+    cp = G.make_coding(**args)
+    planes = P.synthetic_image(args["width"], args["height"], args["numcomps"], args["prec"], seed=42,
+                               origin=args.get("origin", (0, 0)))
+    ref = P.forward(cp, planes)
+    job = engine.job(cp)
+    job.upload(planes)
+    job.forward()
+    got = [np.zeros_like(p) for p in planes]
+    job.download_coeffs(got)
+    for g, r in zip(got, ref):
+        assert np.array_equal(g, r)                      # DC shift + RCT + 5/3, every level
+    job.t1_encode()
+    res = job.fetch_result()
+    _compare_blocks(cp, res, ref)                        # HT cleanup bytes, block by block
+    for p in got:
+        p[:] = -1
+    job.upload_coeffs(got)                               # poison, then decode back
+    job.t1_decode()
+    job.download_coeffs(got)
+    for g, r in zip(got, ref):
+        assert np.array_equal(g, r)
+    job.inverse()
+    rec = [np.zeros_like(p) for p in planes]
+    job.download(rec)
+    for g, r in zip(rec, planes):
+        assert np.array_equal(g, r)                      # lossless
+    res.free()
+    job.close()
+
+
+@pytest.mark.parametrize("kind", ["zero", "max_checkerboard", "min_max_stripes", "noise_full_range"])
+def test_adversarial_content(engine, kind):
+    """SURVEY.md 8d adversarial row, from the reference's own tests: all-zero, max-amplitude
+    checkerboard, stripes, full-range noise."""
+    w, h, prec = 200, 136, 12
+    cp = G.make_coding(w, h, 3, prec, numres=5, tile=(128, 128))
+    y, x = np.mgrid[0:h, 0:w]
+    rng = np.random.default_rng(3)
+    if kind == "zero":
+        planes = [np.zeros((h, w), np.int32) for _ in range(3)]
+    elif kind == "max_checkerboard":
+        planes = [(((x + y + c) & 1) * 4095).astype(np.int32) for c in range(3)]
+    elif kind == "min_max_stripes":
+        planes = [(((x >> c) & 1) * 4095).astype(np.int32) for c in range(3)]
+    else:
+        planes = [rng.integers(0, 4096, (h, w)).astype(np.int32) for _ in range(3)]
+    res = engine.encode(cp, planes)
+    _compare_blocks(cp, res, P.forward(cp, planes))
+    out = [np.zeros_like(p) for p in planes]
+    engine.decode(cp, res.blocks.copy(), res.bytes.copy(), out)
+    for a, b in zip(out, planes):
+        assert np.array_equal(a, b)
+    res.free()
+
+
+def test_host_api_strided_planes_and_sharding(engine):
+    """Row stride larger than the width (64-byte aligned strides, gpu_plugin_shared.h L540-544) and
+    tile sharding (tile_mod/tile_rem): two half jobs produce exactly the blocks of the full job."""
+    cp = G.make_coding(700, 300, 3, 12, numres=4, tile=(256, 128))
+    planes = P.synthetic_image(700, 300, 3, 12, seed=5)
+    padded = [np.zeros((300, 704), np.int32) for _ in range(3)]
+    for p, q in zip(padded, planes):
+        p[:, :700] = q
+    views = [p[:, :700] for p in padded]
+    full = engine.encode(cp, views)
+    fb, fbytes = full.blocks.copy(), full.bytes.copy()
+    full.free()
+    for rem in (0, 1):
+        part = engine.encode(cp, views, tile_mod=2, tile_rem=rem)
+        sel = np.nonzero(fb["tile"] % 2 == rem)[0]
+        assert len(sel) == part.num_blocks
+        for j, i in enumerate(sel):
+            a = fbytes[int(fb[i]["offset"]):int(fb[i]["offset"]) + int(fb[i]["length"])]
+            assert np.array_equal(a, part.block_bytes(j))
+        part.free()
+
+
+def test_irreversible_path(engine):
+    """BASELINE config 3 shape (ICT + 9/7 + quantisation + HT, one tile, 5 levels, 64x64 blocks) at a
+    size the oracle handles: forward coefficients and coded bytes bit-exact vs the oracle's fp32
+    restatement; decode within the reference's accelerator tolerances vs the source:
+    lossy 12-bit: <= 16 codes, PSNR > 50 dB (GrkPluginMemoryTest.cpp L39-52)."""
+    w, h = 640, 384
+    cp = G.make_coding(w, h, 3, 12, numres=6, irreversible=True)
+    planes = P.synthetic_image(w, h, 3, 12, seed=20260925)
+    ref = P.forward(cp, planes)
+    job = engine.job(cp)
+    job.upload(planes)
+    job.forward()
+    got = [np.zeros_like(p) for p in planes]
+    job.download_coeffs(got)
+    for c, (g, r) in enumerate(zip(got, ref)):
+        assert np.array_equal(g, r), "9/7 + ICT coefficients of component %d are not bit-identical" % c
+    job.t1_encode()
+    res = job.fetch_result()
+    _compare_blocks(cp, res, ref)
+    job.t1_decode()
+    job.download_coeffs(got)
+    # dequantised coefficients: bit-exact vs the oracle's decode of the same bytes
+    rects = P.tile_rects(cp)
+    for i, (t, c, b) in enumerate(P.enumerate_all(cp)):
+        if b.x1 == b.x0 or b.y1 == b.y0:
+            continue
+        win = P.decode_block(cp, res.block_bytes(i), c, b)
+        sub = got[c][b.buf_y:b.buf_y + win.shape[0], b.buf_x:b.buf_x + win.shape[1]]
+        assert np.array_equal(sub, win)
+    job.inverse()
+    rec = [np.zeros_like(p) for p in planes]
+    job.download(rec)
+    ref_rec = P.inverse(cp, got)
+    for g, r, s in zip(rec, ref_rec, planes):
+        assert np.abs(g - r).max() <= 1          # device vs host inverse wavelet: <= 2 codes (GrkPluginBatchMemoryTest.cpp L35-45)
+        err = (g - s).astype(np.float64)
+        assert np.abs(err).max() <= 16
+        psnr = 10 * np.log10(4095.0 ** 2 / max(1e-12, (err ** 2).mean()))
+        assert psnr > 50.0
+    res.free()
+    job.close()
+
+
+def test_config2_full_size_properties(engine):
+    """BASELINE config 2 at full size (8192x8192x3, 12 bit, 1024 tiles): size-independent
+    properties -- lossless encode->decode round trip through the host API, block table sanity --
+    plus byte parity with the oracle on two whole tiles."""
+    W = H = 8192
+    cp = G.make_coding(W, H, 3, 12, numres=6, tile=(1024, 1024))
+    rng = np.random.default_rng(20260924)
+    # cheap full-size synthetic: per-tile copies of one generated tile with a per-tile offset
+    base = P.synthetic_image(1024, 1024, 3, 12, seed=20260924)
+    planes = [np.empty((H, W), np.int32) for _ in range(3)]
+    for ty in range(8):
+        for tx in range(8):
+            off = int(rng.integers(0, 512))
+            for c in range(3):
+                planes[c][ty * 1024:(ty + 1) * 1024, tx * 1024:(tx + 1) * 1024] = (base[c] + off) % 4096
+    res = engine.encode(cp, planes)
+    assert res.num_blocks == 49728
+    lens = res.blocks["length"].astype(np.int64)
+    assert lens.sum() == res.num_bytes and (lens > 0).all()
+    assert np.array_equal(res.blocks["offset"], np.concatenate([[0], np.cumsum(lens)[:-1]]))
+    # oracle parity on tiles 0 and 37
+    for t in (0, 37):
+        ty, tx = divmod(t, 8)
+        sub = [np.ascontiguousarray(p[ty * 1024:(ty + 1) * 1024, tx * 1024:(tx + 1) * 1024]) for p in planes]
+        cpt = G.make_coding(1024, 1024, 3, 12, numres=6, origin=(tx * 1024, ty * 1024))
+        coefs = P.forward(cpt, sub)
+        idx = np.nonzero(res.blocks["tile"] == t)[0]
+        blks = P.enumerate_all(cpt)
+        assert len(idx) == len(blks)
+        for i, (_, c, b) in zip(idx, blks):
+            want = P.encode_block(cpt, coefs, (tx * 1024, ty * 1024, 0, 0), c, b)
+            assert np.array_equal(want, res.block_bytes(int(i)))
+    out = [np.zeros_like(p) for p in planes]
+    engine.decode(cp, res.blocks.copy(), res.bytes.copy(), out)
+    for a, b in zip(out, planes):
+        assert np.array_equal(a, b)
+    res.free()
+
+
+# ---- the stock plugin symbols ----------------------------------------------------------------
+class GpupImageComp(C.Structure):
+    _fields_ = [("x0", C.c_uint32), ("y0", C.c_uint32), ("w", C.c_uint32), ("stride", C.c_uint32), ("h", C.c_uint32),
+                ("dx", C.c_uint8), ("dy", C.c_uint8), ("prec", C.c_uint8), ("sgnd", C.c_bool),
+                ("data", C.POINTER(C.c_int32)), ("owns_data", C.c_bool)]
+
+
+class GpupImage(C.Structure):
+    _fields_ = [("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32),
+                ("numcomps", C.c_uint16), ("color_space", C.c_int32), ("comps", C.POINTER(GpupImageComp))]
+
+
+class GpupPass(C.Structure):
+    _fields_ = [("distortionDecrease", C.c_double), ("rate", C.c_size_t), ("length", C.c_size_t)]
+
+
+class GpupCodeBlock(C.Structure):
+    _fields_ = [("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32),
+                ("contextStream", C.c_void_p), ("numPix", C.c_uint32), ("compressedData", C.POINTER(C.c_uint8)),
+                ("compressedDataLength", C.c_uint32), ("numBitPlanes", C.c_uint8), ("numPasses", C.c_size_t),
+                ("passes", GpupPass * G.GPUP_MAX_PASSES), ("sortedIndex", C.c_uint)]
+
+
+class GpupPrecinct(C.Structure):
+    _fields_ = [("numBlocks", C.c_uint64), ("blocks", C.POINTER(C.POINTER(GpupCodeBlock)))]
+
+
+class GpupBand(C.Structure):
+    _fields_ = [("orientation", C.c_uint8), ("numPrecincts", C.c_uint64),
+                ("precincts", C.POINTER(C.POINTER(GpupPrecinct))), ("stepsize", C.c_float)]
+
+
+class GpupResolution(C.Structure):
+    _fields_ = [("level", C.c_size_t), ("numBands", C.c_size_t), ("band", C.POINTER(C.POINTER(GpupBand)))]
+
+
+class GpupTileComponent(C.Structure):
+    _fields_ = [("numResolutions", C.c_size_t), ("resolutions", C.POINTER(C.POINTER(GpupResolution)))]
+
+
+class GpupTile(C.Structure):
+    _fields_ = [("decompress_flags", C.c_uint32), ("numComponents", C.c_size_t),
+                ("tileComponents", C.POINTER(C.POINTER(GpupTileComponent)))]
+
+
+def test_stock_gpup_encode_mem(engine):
+    """The unmodified host path: gpup_encode_mem(params, image, &tile) on config 1 (single tile),
+    tree walked in Grok's order (plugin_bridge.cpp L62-111) and compared with the oracle."""
+    assert C.sizeof(GpupCodeBlock) == 1672
+    lib = G.lib()
+    w = h = 512
+    cp = G.make_coding(w, h, 1, 8, numres=6)
+    planes = P.synthetic_image(w, h, 1, 8, seed=1234)
+    params = (C.c_uint8 * 12696)()
+    # fields at the offsets of gpup_compress_params (checked by tests/test_host.py against the header)
+    def put(off, val, typ):
+        typ.from_buffer(params, off).value = val
+    import re, subprocess, os
+    probe = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "grok_b200.h"
+#define O(f) printf(#f " %zu\n", offsetof(gpup_compress_params, f));
+int main(void){ O(numlayers) O(csty) O(numgbits) O(numresolution) O(cblockw_init) O(cblockh_init) O(cblk_sty) O(irreversible) O(roi_compno) O(mct) return 0; }'''
+    exe = "/tmp/b2k_off_%d" % os.getpid()
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(os.path.dirname(G._HERE), "include"), "-o", exe],
+                   input=probe.encode(), check=True)
+    off = dict((k, int(v)) for k, v in (l.split() for l in subprocess.check_output([exe]).decode().splitlines()))
+    put(off["numlayers"], 1, C.c_uint16)
+    put(off["numgbits"], 1, C.c_uint8)
+    put(off["numresolution"], 6, C.c_uint8)
+    put(off["cblockw_init"], 64, C.c_uint32)
+    put(off["cblockh_init"], 64, C.c_uint32)
+    put(off["cblk_sty"], 0x40, C.c_uint8)
+    put(off["roi_compno"], -1, C.c_int32)
+    comp = GpupImageComp(0, 0, w, w, h, 1, 1, 8, False, planes[0].ctypes.data_as(C.POINTER(C.c_int32)), False)
+    img = GpupImage(0, 0, w, h, 1, 3, C.pointer(comp))
+    tile = C.POINTER(GpupTile)()
+    lib.gpup_encode_mem.argtypes = [C.c_void_p, C.POINTER(GpupImage), C.POINTER(C.POINTER(GpupTile))]
+    rc = lib.gpup_encode_mem(params, C.byref(img), C.byref(tile))
+    assert rc == 0, lib.b2k_last_error()
+    coefs = P.forward(cp, planes)
+    blks = [x for x in P.enumerate_all(cp)]
+    T = tile.contents
+    assert T.numComponents == 1
+    tc = T.tileComponents[0].contents
+    assert tc.numResolutions == 6
+    k = 0
+    for r in range(6):
+        res = tc.resolutions[r].contents
+        assert res.numBands == (1 if r == 0 else 3)
+        for b in range(res.numBands):
+            band = res.band[b].contents
+            assert band.orientation == (0 if r == 0 else b + 1)
+            for p in range(band.numPrecincts):
+                prc = band.precincts[p].contents
+                for j in range(prc.numBlocks):
+                    cb = prc.blocks[j].contents
+                    _, c, ob = blks[k]
+                    k += 1
+                    assert (cb.x0, cb.y0, cb.x1, cb.y1) == (ob.x0, ob.y0, ob.x1, ob.y1)
+                    assert cb.numPasses == 1 and cb.numBitPlanes == 1
+                    want = P.encode_block(cp, coefs, (0, 0, w, h), 0, ob)
+                    have = np.ctypeslib.as_array(cb.compressedData, shape=(cb.compressedDataLength,))
+                    assert np.array_equal(want, have)
+                    assert cb.passes[0].rate == cb.compressedDataLength - 1
+    assert k == len(blks)
+    lib.gpup_tile_free(tile)
