@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""bench.py -- Mpixels/s of the HTJ2K tile-engine hot path on BASELINE.json's config 2.
+
+Workload (config.workload): 8192x8192, 3 components, 12 bit unsigned, 1024x1024 tiles, 5/3 + RCT,
+6 resolutions, 64x64 code blocks, HT cleanup coding, lossless.  One STEP = encode the image
+(DC shift + RCT + 5-level DWT + HT block coding of 49,728 blocks) and decode it back (HT decode +
+inverse DWT + inverse RCT).  Mpixels/s = image pixels / step time, so every pixel is encoded AND
+decoded once per step.
+
+  value   device-resident: planes already in HBM, coded blocks stay in HBM (b2k_job_* stages)
+  e2e     through the reference-facing C ABI with HOST (pinned) buffers: b2k_encode() then
+          b2k_decode(), host<->device copies inside the timed region
+  roofline  the dominant memory-bound kernel: the fused DC-shift + RCT + level-1 5/3 DWT
+          (k_dwt53_fwd<3>): algorithmic bytes = samples x 8 B (one 4-byte read + one 4-byte
+          write per sample per level) / CUDA-event duration of that launch
+  cpu_baseline  the reference's own kernels (oracle/_ref, built from /root/reference) over the
+          same image on all host threads
+
+`--impl reference` times that CPU path as the step.  N>1 (torchrun): one process per GPU, each
+rank runs the whole workload on its own image ("weak": tiles shard with no data-path
+collective; NCCL only carries the barrier / max-reduction and the coded-size gather).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+W = H = 8192
+NCOMP, PREC, NUMRES, TILE = 3, 12, 6, 1024
+SEED = 20260924
+METRIC = "Mpixels/s encode+decode 8K RGB 12-bit HTJ2K; DWT HBM GB/s vs roofline"
+WORKLOAD = ("8192x8192x3 12-bit HTJ2K lossless (5/3 + RCT), 1024x1024 tiles, 6 resolutions, 64x64 blocks; "
+            "step = encode + decode of the whole image")
+
+
+def make_image():
+    """SURVEY.md 8d config-2 generator (global coordinates), int32 planar."""
+    import oracle_pipeline as P
+    return P.synthetic_image(W, H, NCOMP, PREC, SEED)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_setup(planes):
+    """Block list of one tile + output slots for the oracle/_ref threaded driver."""
+    import oracle_lib as O
+    import oracle_pipeline as P
+    import grok_b200 as G
+    R = O.ref()
+    if R is None:
+        return None
+    cp1 = G.make_coding(TILE, TILE, NCOMP, PREC, numres=NUMRES)
+
+    class Desc(C.Structure):
+        _fields_ = [("comp", C.c_uint32), ("buf_x", C.c_uint32), ("buf_y", C.c_uint32), ("w", C.c_uint32),
+                    ("h", C.c_uint32), ("kmax", C.c_uint32)]
+    blks = [(c, b) for (_, c, b) in P.enumerate_all(cp1) if b.x1 > b.x0 and b.y1 > b.y0]
+    descs = (Desc * len(blks))()
+    for i, (c, b) in enumerate(blks):
+        kmax, _, _ = P.band_params(cp1, b.resno, b.orient)
+        descs[i] = Desc(c, b.buf_x, b.buf_y, b.x1 - b.x0, b.y1 - b.y0, kmax)
+    ntiles = (W // TILE) * (H // TILE)
+    slot = 16384
+    st = dict(R=R, descs=descs, nblocks=len(blks), ntiles=ntiles, slot=slot,
+              coded=np.zeros((ntiles * len(blks), slot), np.uint8), lengths=np.zeros(ntiles * len(blks), np.uint32),
+              ptrs=(C.c_void_p * NCOMP)(*[p.ctypes.data for p in planes]), stride=planes[0].strides[0] // 4,
+              threads=os.cpu_count() or 1)
+    R.ref_bench_encode.restype = C.c_double
+    R.ref_bench_decode.restype = C.c_double
+    R.ref_bench_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int,
+                                   C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+    R.ref_bench_decode.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    return st
+
+
+def cpu_reference_step(st):
+    """One encode+decode of the whole image with the reference's kernels; returns (seconds, info)."""
+    R = st["R"]
+    te = R.ref_bench_encode(st["ptrs"], st["stride"], NCOMP, st["ntiles"], W // TILE, TILE, TILE, PREC, NUMRES,
+                            C.cast(st["descs"], C.c_void_p), st["nblocks"], st["coded"].ctypes.data, st["slot"],
+                            st["lengths"].ctypes.data, st["threads"])
+    dwt = C.c_double()
+    td = R.ref_bench_decode(NCOMP, st["ntiles"], TILE, TILE, PREC, NUMRES, C.cast(st["descs"], C.c_void_p), st["nblocks"],
+                            st["coded"].ctypes.data, st["slot"], st["lengths"].ctypes.data, st["threads"], C.byref(dwt))
+    return te + td, dict(enc_s=te, dec_s=td, coded_bytes=int(st["lengths"].sum()), inv_dwt_ms_per_tilecomp=dwt.value * 1e3)
+
+
+def cpu_model():
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference CPU path is the step (rank 0 only)."""
+    if rank != 0:
+        return
+    planes = make_image()
+    st = cpu_reference_setup(planes)
+    if st is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgrok_ref.so was not built (no reference tree at build time)"}))
+        return
+    for _ in range(args.warmup):
+        cpu_reference_step(st)
+    t0 = time.perf_counter()
+    info = None
+    for _ in range(args.steps):
+        _, info = cpu_reference_step(st)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = W * H / dt / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpixels/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "host": cpu_model()},
+            "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": st["threads"], "kind": "reference",
+                             "sample": "64 of 64 tiles (whole image), reference HT coder + forward DWT kernels and "
+                                       "grk_bench_dwt_53 inverse-DWT hook from oracle/_ref; MCT and T1 pre/post restated",
+                             **{k: v for k, v in info.items()}},
+            "e2e": {"value": val, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import grok_b200 as G
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cp = G.make_coding(W, H, NCOMP, PREC, numres=NUMRES, tile=(TILE, TILE))
+    img = make_image()
+    # pinned host buffers: the image planes Grok would hand over (int32, 64-byte aligned rows) and the output
+    planes = [G.pinned_empty((H, W), np.int32) for _ in range(NCOMP)]
+    out = [G.pinned_empty((H, W), np.int32) for _ in range(NCOMP)]
+    for p, q in zip(planes, img):
+        p[:] = q
+    eng = G.Engine(local)
+    lib = G.lib()
+
+    # ---------------- device-resident: `value` ----------------
+    job = eng.job(cp)
+    job.upload(planes)
+
+    def device_step():
+        a = job.forward()
+        b, nbytes = job.t1_encode()
+        c = job.t1_decode()
+        d = job.inverse()
+        return (a, b, c, d), nbytes
+
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = lib.b2k_launch_count()
+    t0 = time.perf_counter()
+    stage = np.zeros(4)
+    lvl1 = []
+    nbytes = 0
+    for _ in range(args.steps):
+        s, nbytes = device_step()
+        stage += np.array(s)
+        lvl1.append(job.kernel_stats(0))
+    barrier()
+    dt_dev = time.perf_counter() - t0
+    launches = lib.b2k_launch_count() - l0
+    clocks = sampler.stop()
+    job.download(out)
+    assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "device-resident round trip is not lossless"
+    job.close()
+
+    # ---------------- end to end through the C ABI with host buffers: `e2e` ----------------
+    def e2e_step():
+        res = eng.encode(cp, planes)
+        blocks, data = res.blocks, res.bytes
+        eng.decode(cp, blocks, data, out)
+        nb, nbk = res.num_bytes, res.num_blocks
+        res.free()
+        return nb, nbk
+
+    for _ in range(max(1, args.warmup - 1)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nb, nbk = e2e_step()
+    barrier()
+    dt_e2e = time.perf_counter() - t0
+    assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "e2e round trip is not lossless"
+
+    # max over ranks
+    times = torch.tensor([dt_dev, dt_e2e], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([nb], dtype=torch.int64, device="cuda"))  # codestream segment sizes
+    dt_dev, dt_e2e = float(times[0]), float(times[1])
+
+    if rank == 0:
+        pix = W * H * world
+        ms_step = dt_dev / args.steps * 1e3
+        value = pix / (dt_dev / args.steps) / 1e6
+        e2e_val = pix / (dt_e2e / args.steps) / 1e6
+        peak, peak_src = peaks()
+        l1_ms = float(np.mean([m for m, _ in lvl1]))
+        l1_bytes = lvl1[0][1]
+        achieved = l1_bytes / (l1_ms * 1e-3) / 1e9 if l1_ms > 0 else 0.0
+        img_bytes = W * H * NCOMP * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu": "one 8192x8192x3 image (64 tiles) per rank",
+                       "l2": "inputs (805 MB of planes per step) are larger than the 126 MB L2",
+                       "coded_bytes": int(nbytes), "blocks": int(nbk),
+                       "stage_ms": {"fwd_mct_dwt": stage[0] / args.steps, "ht_encode": stage[1] / args.steps,
+                                    "ht_decode": stage[2] / args.steps, "inv_dwt_mct": stage[3] / args.steps}},
+            "e2e": {"value": e2e_val, "unit": "Mpixels/s", "ms_per_step": dt_e2e / args.steps * 1e3,
+                    "h2d_bytes_per_step": int(img_bytes + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes + nb + nbk * 24),
+                    "api": "b2k_encode + b2k_decode (include/grok_b200.h), pinned host planes"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_dwt53_fwd<3> (DC shift + RCT + level-1 5/3, all 64 tiles x 3 comps)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(l1_bytes),
+                         "ms_per_launch": l1_ms, "traffic": TRAFFIC_NCU},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            st = cpu_reference_setup(img)
+            if st is not None:
+                sec, info = cpu_reference_step(st)
+                line["cpu_baseline"] = {"value": W * H / sec / 1e6, "unit": "Mpixels/s", "cores": st["threads"],
+                                        "kind": "reference", "host": cpu_model(),
+                                        "sample": "64 of 64 tiles (whole image, one pass), reference HT coder + forward DWT "
+                                                  "kernels and grk_bench_dwt_53 inverse-DWT hook (oracle/_ref)",
+                                        **info}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "Mpixels/s", "cores": 0, "kind": "reference",
+                                        "sample": "oracle/_ref not built"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_dwt53_fwd<3> launch, from the committed
+# `ncu --set full` capture under profiles/ (None until that capture exists)
+TRAFFIC_NCU = None
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,7 @@
 #include <thread>
 #include <atomic>
 #include <mutex>
+#include <algorithm>
 
 #include "ojph_arch.h"
 #include "ojph_mem.h"
@@ -159,6 +160,200 @@ __attribute__((visibility("default"))) void ref_dwt97_fwd_2d(float* buf, uint32_
                                                              int int_input)
 {
   ref_fwd_2d<float, grk::dwt97>(buf, stride, x0, y0, x1, y1, numres, dcshift, int_input != 0);
+}
+
+} /* extern "C" */
+
+/* =============================================================================================
+ * CPU baseline driver (bench.py --impl reference / cpu_baseline): the reference's kernels over
+ * whole tiles on all host threads, tiles handed out by an atomic counter the way the reference
+ * hands them to Taskflow workers (CodeStreamCompress.cpp L943-966; block list built like
+ * CompressScheduler.cpp L84-139).  What runs per tile:
+ *   encode: row copy into an aligned tile buffer (TileProcessorCompress.cpp L176-240),
+ *           DC shift + RCT (restated from mct.cpp L497-531 -- that TU needs the Tile graph),
+ *           grk::dwt53 multi-level forward (the reference's code), per block the T1 pre-pass
+ *           (restated from CoderOJPH.cpp L121-160) + the reference's dispatched HT encoder;
+ *   decode: the reference's dispatched HT decoder + shift filter (PostDecodeFiltersOJPH.h L48-66),
+ *           inverse RCT (restated from mct.cpp L201-256); the inverse DWT is timed through the
+ *           reference's own single-thread hook grk_bench_dwt_53 (WaveletReverse.h L111-118) on
+ *           every worker, once per tile component.
+ * ========================================================================================== */
+struct ref_block_desc
+{
+  uint32_t comp, buf_x, buf_y, w, h, kmax;
+};
+
+extern "C" double grk_bench_dwt_53(uint32_t width, uint32_t height, uint8_t numres, uint32_t iters);
+
+#include <chrono>
+static double now_s()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" {
+
+/* planes: ncomp image planes (int32, row stride `stride`), the first ntiles tiles of a tw x th
+ * grid with `tiles_per_row` tiles per row are processed.  coded: per (tile, block) output slots of
+ * `slot` bytes; lengths[tile*nblocks + b].  Returns wall seconds. */
+__attribute__((visibility("default"))) double ref_bench_encode(const int32_t* const* planes, uint32_t stride, int ncomp,
+                                                              int ntiles, int tiles_per_row, uint32_t tw, uint32_t th,
+                                                              int prec, int numres, const ref_block_desc* blocks,
+                                                              int nblocks, uint8_t* coded, uint32_t slot,
+                                                              uint32_t* lengths, int nthreads)
+{
+  init_once();
+  std::atomic<int> next{0};
+  const uint32_t tstride = ((tw + 15) / 16) * 16 + 16;
+  const int32_t dc = -(1 << (prec - 1));
+  auto worker = [&]() {
+    std::vector<int32_t*> buf(ncomp);
+    for(int c = 0; c < ncomp; ++c)
+      buf[c] = (int32_t*)aligned_alloc(64, (size_t)tstride * (th + 2) * sizeof(int32_t));
+    std::vector<uint32_t> sm(4096 + 64);
+    for(;;)
+    {
+      const int t = next.fetch_add(1);
+      if(t >= ntiles)
+        break;
+      const uint32_t ox = (uint32_t)(t % tiles_per_row) * tw, oy = (uint32_t)(t / tiles_per_row) * th;
+      for(int c = 0; c < ncomp; ++c)
+        for(uint32_t y = 0; y < th; ++y)
+          memcpy(buf[c] + (size_t)y * tstride, planes[c] + (size_t)(oy + y) * stride + ox, tw * sizeof(int32_t));
+      if(ncomp >= 3)
+      {
+        for(uint32_t y = 0; y < th; ++y)
+        {
+          int32_t *r = buf[0] + (size_t)y * tstride, *g = buf[1] + (size_t)y * tstride, *b = buf[2] + (size_t)y * tstride;
+          for(uint32_t x = 0; x < tw; ++x)
+          {
+            const int32_t rr = r[x] + dc, gg = g[x] + dc, bb = b[x] + dc;
+            r[x] = ((gg + gg) + bb + rr) >> 2;
+            g[x] = bb - gg;
+            b[x] = rr - gg;
+          }
+        }
+      }
+      for(int c = 0; c < ncomp; ++c)
+        ref_fwd_2d<int32_t, grk::dwt53>(buf[c], tstride, ox, oy, ox + tw, oy + th, numres, (ncomp >= 3 && c < 3) ? 0 : -dc, false);
+      for(int k = 0; k < nblocks; ++k)
+      {
+        const ref_block_desc& B = blocks[k];
+        const int shift = 31 - (int)(B.kmax + 1);
+        for(uint32_t y = 0; y < B.h; ++y)
+        {
+          const int32_t* src = buf[B.comp] + (size_t)(B.buf_y + y) * tstride + B.buf_x;
+          for(uint32_t x = 0; x < B.w; ++x)
+          {
+            const int32_t v = src[x];
+            const uint32_t mag = v >= 0 ? (uint32_t)v : (uint32_t)0 - (uint32_t)v;
+            sm[y * B.w + x] = (v >= 0 ? 0u : 0x80000000u) | (mag << shift);
+          }
+        }
+        const int n = ref_ht_encode(-1, sm.data(), B.kmax, B.w, B.h, B.w, coded + ((size_t)t * nblocks + k) * slot, slot);
+        lengths[(size_t)t * nblocks + k] = n > 0 ? (uint32_t)n : 0;
+      }
+    }
+    for(int c = 0; c < ncomp; ++c)
+      free(buf[c]);
+  };
+  const double t0 = now_s();
+  std::vector<std::thread> th_;
+  for(int i = 0; i < nthreads; ++i)
+    th_.emplace_back(worker);
+  for(auto& t : th_)
+    t.join();
+  return now_s() - t0;
+}
+
+__attribute__((visibility("default"))) double ref_bench_decode(int ncomp, int ntiles, uint32_t tw, uint32_t th, int prec,
+                                                              int numres, const ref_block_desc* blocks, int nblocks,
+                                                              const uint8_t* coded, uint32_t slot, const uint32_t* lengths,
+                                                              int nthreads, double* dwt_seconds_per_tilecomp)
+{
+  init_once();
+  std::atomic<int> next{0};
+  const uint32_t tstride = ((tw + 15) / 16) * 16 + 16;
+  const int32_t dc = 1 << (prec - 1), hi = (1 << prec) - 1;
+  std::vector<double> dwt_best(nthreads, 0.0), excess(nthreads, 0.0);
+  auto worker = [&](int wid) {
+    std::vector<int32_t*> buf(ncomp);
+    for(int c = 0; c < ncomp; ++c)
+      buf[c] = (int32_t*)aligned_alloc(64, (size_t)tstride * (th + 2) * sizeof(int32_t));
+    std::vector<uint32_t> dec((size_t)72 * 72 + 64);
+    std::vector<uint8_t> pad(slot + 64);
+    int done = 0;
+    for(;;)
+    {
+      const int t = next.fetch_add(1);
+      if(t >= ntiles)
+        break;
+      for(int k = 0; k < nblocks; ++k)
+      {
+        const ref_block_desc& B = blocks[k];
+        const uint32_t len = lengths[(size_t)t * nblocks + k];
+        const uint32_t dstride = (B.w + 7u) & ~7u;
+        memset(pad.data(), 0, 16);
+        memcpy(pad.data() + 16, coded + ((size_t)t * nblocks + k) * slot, len);
+        memset(pad.data() + 16 + len, 0, 16);
+        ref_ht_decode(-1, pad.data() + 16, dec.data(), B.kmax - 1, 1, len, 0, B.w, B.h, dstride);
+        const uint32_t sh = 31u - B.kmax;
+        for(uint32_t y = 0; y < B.h; ++y)
+        {
+          int32_t* dst = buf[B.comp] + (size_t)(B.buf_y + y) * tstride + B.buf_x;
+          for(uint32_t x = 0; x < B.w; ++x)
+          {
+            const uint32_t v = dec[y * dstride + x];
+            const int32_t m = (int32_t)((v & 0x7FFFFFFFu) >> sh);
+            dst[x] = (v & 0x80000000u) ? -m : m;
+          }
+        }
+      }
+      /* inverse DWT: the reference's own hook, once per tile component */
+      const double h0 = now_s();
+      const double per = grk_bench_dwt_53(tw, th, (uint8_t)numres, (uint32_t)ncomp);
+      /* the hook also allocates and fills its buffers: only ncomp * per belongs to a decode */
+      excess[wid] += (now_s() - h0) - (double)ncomp * (per > 0 ? per : 0);
+      if(per > 0 && (dwt_best[wid] == 0.0 || per < dwt_best[wid]))
+        dwt_best[wid] = per;
+      if(ncomp >= 3)
+        for(uint32_t y = 0; y < th; ++y)
+        {
+          int32_t *a = buf[0] + (size_t)y * tstride, *b = buf[1] + (size_t)y * tstride, *c = buf[2] + (size_t)y * tstride;
+          for(uint32_t x = 0; x < tw; ++x)
+          {
+            const int32_t g = a[x] - ((b[x] + c[x]) >> 2), r = c[x] + g, bl = b[x] + g;
+            a[x] = std::min(std::max(r + dc, 0), hi);
+            b[x] = std::min(std::max(g + dc, 0), hi);
+            c[x] = std::min(std::max(bl + dc, 0), hi);
+          }
+        }
+      ++done;
+    }
+    for(int c = 0; c < ncomp; ++c)
+      free(buf[c]);
+  };
+  const double t0 = now_s();
+  std::vector<std::thread> th_;
+  for(int i = 0; i < nthreads; ++i)
+    th_.emplace_back(worker, i);
+  for(auto& t : th_)
+    t.join();
+  double el = now_s() - t0;
+  {
+    double ex = 0;
+    for(double v : excess) ex += v;
+    el -= ex / nthreads;
+  }
+  if(dwt_seconds_per_tilecomp)
+  {
+    double s = 0;
+    int n = 0;
+    for(double v : dwt_best)
+      if(v > 0) { s += v; ++n; }
+    *dwt_seconds_per_tilecomp = n ? s / n : 0.0;
+  }
+  return el;
 }
 
 } /* extern "C" */
