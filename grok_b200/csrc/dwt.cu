@@ -28,10 +28,8 @@
 
 namespace {
 
-__device__ __forceinline__ int mirror_rel(int t, int n)
+__device__ __noinline__ int mirror_rel_slow(int t, int n)
 {
-  if(t >= 0 && t < n)
-    return t;
   if(n == 1)
     return 0;
   const int period = 2 * (n - 1);
@@ -39,6 +37,17 @@ __device__ __forceinline__ int mirror_rel(int t, int n)
   if(t < 0)
     t += period;
   return t < n ? t : period - t;
+}
+/* whole-sample symmetric extension index; one reflection covers every halo unless the line is
+   shorter than the halo, which takes the (out-of-line) periodic path */
+__device__ __forceinline__ int mirror_rel(int t, int n)
+{
+  if((unsigned)t < (unsigned)n)
+    return t;
+  const int r = t < 0 ? -t : 2 * (n - 1) - t;
+  if((unsigned)r < (unsigned)n)
+    return r;
+  return mirror_rel_slow(t, n);
 }
 
 /* ---- 8-sample row loads ------------------------------------------------------------------ */
@@ -303,6 +312,7 @@ __device__ __forceinline__ void store_band_rows(const DwtLevelDesc& D, const Job
 }
 
 /* ---- horizontal lifting of one row held as 8 values per lane -------------------------------- */
+template <bool DEGEN = true>
 __device__ __forceinline__ void hfwd53(const int (&r)[8], int wn, int (&lo)[4], int (&hi)[4])
 {
   const int en = __shfl_down_sync(0xffffffffu, r[0], 1);
@@ -315,7 +325,7 @@ __device__ __forceinline__ void hfwd53(const int (&r)[8], int wn, int (&lo)[4], 
   lo[1] = r[2] + ((hi[0] + hi[1] + 2) >> 2);
   lo[2] = r[4] + ((hi[1] + hi[2] + 2) >> 2);
   lo[3] = r[6] + ((hi[2] + hi[3] + 2) >> 2);
-  if(wn == 1)
+  if(DEGEN && wn == 1)
   { /* WaveletFwd.cpp L289-300: lone column, doubled when it sits on an odd coordinate */
 #pragma unroll
     for(int i = 0; i < 4; ++i)
@@ -373,17 +383,229 @@ __device__ __forceinline__ void hfwd97(const float (&r)[8], int wn, float invK, 
 }
 
 /* =============================================================================================
- * forward 5/3
+ * staged row fetch for the forward kernels: every lane prefetches ITS OWN 8 samples of the next
+ * row pairs into a private shared-memory slot with cp.async (LDGSTS, 16 bytes per copy, L1
+ * bypass) and reads them back later, so STAGES-1 row pairs (x NC components) are in flight per
+ * warp without holding registers.  No cross-lane traffic -> no barrier; edge lanes (mirrored or
+ * unaligned columns) fill their slot with ordinary loads.
  * =========================================================================================== */
-template <int NC, bool U16>
-__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_fwd(const DwtLevelDesc* __restrict__ descs)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
-  const DwtLevelDesc& D = descs[blockIdx.y];
-  Job J;
-  if(!decode_job(D, J))
-    return;
-  const BandGeom g = band_geom(D);
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
+{
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
+template <int NC, bool U16>
+struct RowStage
+{
+  static constexpr int ROWB = U16 ? 512 : 1024; /* bytes of one warp-row of one component */
+  static constexpr int PAIRB = 2 * NC * ROWB;   /* one row pair, all components */
+  /* 16-byte chunk k of a 32-bit warp-row (lane L owns chunks 2L, 2L+1) is stored at chunk slot
+     k ^ ((k >> 3) & 1): the two 128-bit reads of a lane then hit disjoint banks per quarter warp */
+  static __device__ __forceinline__ int swz(int k) { return k ^ ((k >> 3) & 1); }
+
+  /* fill slot `which` (0 = odd row, 1 = next even row) of a stage with canvas row v.
+     32-bit rows are copied COOPERATIVELY: one cp.async instruction moves 512 contiguous bytes
+     (lane L copies chunks L and L+32), so every 32-byte DRAM sector is requested once.
+     fastmask: ballot of the lanes whose 8 columns are interior and aligned. */
+  static __device__ __forceinline__ void fill(uint8_t* stage, int which, const DwtLevelDesc& D, const Job& J, int v,
+                                              bool fast, unsigned fastmask, const int (&mcol)[8])
+  {
+    const int r = mirror_rel(v - D.v0, J.hn);
+    const int rel = J.ulane - D.u0;
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+      uint8_t* dst = stage + (which * NC + c) * ROWB;
+      if(U16)
+      {
+        const uint16_t* row = reinterpret_cast<const uint16_t*>(D.in[c]) + (size_t)r * D.in_pitch;
+        if(fast)
+          cp_async16(dst + J.lane * 16, row + rel);
+        else if(J.need)
+        {
+          uint32_t w[4];
+#pragma unroll
+          for(int i = 0; i < 4; ++i)
+            w[i] = (uint32_t)__ldg(row + mcol[2 * i]) | ((uint32_t)__ldg(row + mcol[2 * i + 1]) << 16);
+          *reinterpret_cast<uint4*>(dst + J.lane * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      else
+      {
+        const int32_t* row = reinterpret_cast<const int32_t*>(D.in[c]) + (size_t)r * D.in_pitch;
+        const int rel0 = rel - 8 * J.lane; /* lane 0's first column */
+#pragma unroll
+        for(int h = 0; h < 2; ++h)
+        {
+          const int k = J.lane + 32 * h;
+          if((fastmask >> (k >> 1)) & 1u)
+            cp_async16(dst + swz(k) * 16, row + rel0 + 4 * k);
+        }
+        if(J.need && !fast)
+        { /* edge lane: mirrored columns, still asynchronous (4-byte copies) */
+          uint8_t* d0 = dst + swz(2 * J.lane) * 16;
+          uint8_t* d1 = dst + swz(2 * J.lane + 1) * 16;
+#pragma unroll
+          for(int i = 0; i < 4; ++i)
+          {
+            cp_async4(d0 + 4 * i, row + mcol[i]);
+            cp_async4(d1 + 4 * i, row + mcol[4 + i]);
+          }
+        }
+      }
+    }
+  }
+  static __device__ __forceinline__ void read(const uint8_t* stage, int which, const DwtLevelDesc& D, const Job& J,
+                                              int (&out)[NC][8])
+  {
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+      const uint8_t* src = stage + (which * NC + c) * ROWB;
+      if(U16)
+      {
+        const uint4 a = *reinterpret_cast<const uint4*>(src + J.lane * 16);
+        out[c][0] = a.x & 0xFFFF; out[c][1] = a.x >> 16; out[c][2] = a.y & 0xFFFF; out[c][3] = a.y >> 16;
+        out[c][4] = a.z & 0xFFFF; out[c][5] = a.z >> 16; out[c][6] = a.w & 0xFFFF; out[c][7] = a.w >> 16;
+        if(D.in_is_u16 == 2)
+        {
+#pragma unroll
+          for(int i = 0; i < 8; ++i)
+            out[c][i] = (int)(int16_t)out[c][i];
+        }
+      }
+      else
+      {
+        const int4 a = *reinterpret_cast<const int4*>(src + swz(2 * J.lane) * 16),
+                   b = *reinterpret_cast<const int4*>(src + swz(2 * J.lane + 1) * 16);
+        out[c][0] = a.x; out[c][1] = a.y; out[c][2] = a.z; out[c][3] = a.w;
+        out[c][4] = b.x; out[c][5] = b.y; out[c][6] = b.z; out[c][7] = b.w;
+      }
+      /* lanes beyond the right halo hold stale shared memory: nothing they compute is stored */
+    }
+  }
+  /* lane can use 16-byte async copies: its 8 columns are inside the line and 16-byte aligned */
+  static __device__ __forceinline__ bool lane_fast(const DwtLevelDesc& D, const Job& J)
+  {
+    const int rel = J.ulane - D.u0;
+    bool ok = J.need && rel >= 0 && rel + 8 <= J.wn && ((D.in_pitch * (U16 ? 2u : 4u)) & 15u) == 0;
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+      ok = ok && (((reinterpret_cast<uintptr_t>(D.in[c]) + (size_t)rel * (U16 ? 2 : 4)) & 15) == 0);
+    return ok;
+  }
+};
+
+/* integer samples of the finest level -> DC shift (+ RCT): mct.cpp L497-531 */
+template <int NC>
+__device__ __forceinline__ void rct_fwd_inplace(const DwtLevelDesc& D, int (&x)[NC][8])
+{
+  if(!D.first_level)
+    return;
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+  {
+    if(NC == 3)
+    {
+      const int r = x[0][i] + D.shift[0], g = x[NC > 1 ? 1 : 0][i] + D.shift[1], b = x[NC > 2 ? 2 : 0][i] + D.shift[2];
+      x[0][i] = ((g + g) + b + r) >> 2;
+      x[NC > 1 ? 1 : 0][i] = b - g;
+      x[NC > 2 ? 2 : 0][i] = r - g;
+    }
+    else
+      x[0][i] += D.shift[0];
+  }
+}
+
+/* per-lane constants of the sub-band stores */
+struct StoreCtx
+{
+  unsigned mlo, mhi;
+  bool vec_ll, vec_lo, vec_hi; /* all four samples valid and the 16-byte store is aligned */
+  int col_ll, col_lo, col_hi; /* column of the lane's first low sample in the LL plane / in the
+                                 Mallat buffer, and of its first high sample */
+};
+__device__ __forceinline__ StoreCtx store_ctx(const DwtLevelDesc& D, const Job& J, const BandGeom& g)
+{
+  StoreCtx s;
+  s.mlo = s.mhi = 0;
+  if(J.owner)
+  {
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+    {
+      const int ue = J.ulane + 2 * i;
+      if(ue >= D.u0 && ue < D.u1)
+        s.mlo |= 1u << i;
+      if(ue + 1 >= D.u0 && ue + 1 < D.u1)
+        s.mhi |= 1u << i;
+    }
+  }
+  const int k0 = J.ulane >> 1;
+  s.col_ll = k0 - g.x0l;
+  s.col_lo = k0 - g.x0l;
+  s.col_hi = g.snx + k0 - g.x0h;
+  /* row pitches are multiples of 4 elements (engine allocates 128-byte multiples) */
+  const bool pitch_ok = ((D.ll_pitch | D.c_pitch) & 3u) == 0;
+  s.vec_ll = pitch_ok && s.mlo == 0xF && (((reinterpret_cast<uintptr_t>(D.out_ll[0]) >> 2) + (unsigned)s.col_ll) & 3u) == 0;
+  s.vec_lo = pitch_ok && s.mlo == 0xF && (((reinterpret_cast<uintptr_t>(D.out_c[0]) >> 2) + (unsigned)s.col_lo) & 3u) == 0;
+  s.vec_hi = pitch_ok && s.mhi == 0xF && (((reinterpret_cast<uintptr_t>(D.out_c[0]) >> 2) + (unsigned)s.col_hi) & 3u) == 0;
+  return s;
+}
+__device__ __forceinline__ void store4v(int32_t* __restrict__ p, const int (&v)[4], unsigned mask, bool vec)
+{
+  if(vec)
+    *reinterpret_cast<int4*>(p) = make_int4(v[0], v[1], v[2], v[3]);
+  else
+  {
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+      if(mask & (1u << i))
+        p[i] = v[i];
+  }
+}
+__device__ __forceinline__ void store_rows_fast(const DwtLevelDesc& D, const BandGeom& g, const StoreCtx& S, int c, int j,
+                                                bool vhigh, const int (&lo)[4], const int (&hi)[4])
+{
+  const int v = 2 * j + (vhigh ? 1 : 0);
+  if(v < D.v0 || v >= D.v1 || (S.mlo | S.mhi) == 0)
+    return;
+  /* all components of a descriptor share the alignment of component 0 (planes are equally laid out) */
+  if(!vhigh)
+  {
+    const int r = j - g.y0l;
+    store4v(reinterpret_cast<int32_t*>(D.out_ll[c]) + (r * (int)D.ll_pitch + S.col_ll), lo, S.mlo, S.vec_ll);
+    store4v(reinterpret_cast<int32_t*>(D.out_c[c]) + (r * (int)D.c_pitch + S.col_hi), hi, S.mhi, S.vec_hi);
+  }
+  else
+  {
+    const int r = g.sny + j - g.y0h;
+    int32_t* crow = reinterpret_cast<int32_t*>(D.out_c[c]) + r * (int)D.c_pitch;
+    store4v(crow + S.col_lo, lo, S.mlo, S.vec_lo);
+    store4v(crow + S.col_hi, hi, S.mhi, S.vec_hi);
+  }
+}
+
+
+/* a tile component one sample wide or high at this level: straightforward, unpipelined path
+   (WaveletFwd.cpp L146-156, L289-300 special cases live here, not in the hot loop) */
+template <int NC, bool U16>
+__device__ __noinline__ void fwd53_degenerate_job(const DwtLevelDesc* __restrict__ dptr, const Job J)
+{
+  const DwtLevelDesc& D = *dptr; /* re-read from global memory: this path is cold */
+  const BandGeom g = band_geom(D);
   int E[NC][8], DP[NC][8];
   {
     int A[NC][8], B[NC][8];
@@ -401,7 +623,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_fwd(const DwtL
     int O[NC][8], E2[NC][8];
     fetch53<NC, U16>(D, J, 2 * j + 1, O);
     fetch53<NC, U16>(D, J, 2 * j + 2, E2);
-#pragma unroll
+#pragma unroll 1
     for(int c = 0; c < NC; ++c)
     {
       int s[8], d[8];
@@ -411,7 +633,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_fwd(const DwtL
         d[i] = O[c][i] - ((E[c][i] + E2[c][i]) >> 1);
         s[i] = E[c][i] + ((DP[c][i] + d[i] + 2) >> 2);
         if(J.hn == 1)
-        { /* WaveletFwd.cpp L146-156 */
+        {
           s[i] = E[c][i];
           d[i] = O[c][i] << 1;
         }
@@ -419,12 +641,107 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_fwd(const DwtL
         E[c][i] = E2[c][i];
       }
       int lo[4], hi[4];
-      hfwd53(s, J.wn, lo, hi);
+      hfwd53<true>(s, J.wn, lo, hi);
       store_band_rows(D, J, g, c, j, false, lo, hi);
-      hfwd53(d, J.wn, lo, hi);
+      hfwd53<true>(d, J.wn, lo, hi);
       store_band_rows(D, J, g, c, j, true, lo, hi);
     }
   }
+}
+
+/* =============================================================================================
+ * forward 5/3
+ * =========================================================================================== */
+template <int NC, bool U16, int STAGES>
+__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_fwd(const DwtLevelDesc* __restrict__ descs)
+{
+  extern __shared__ __align__(16) uint8_t smem_dwt[];
+  typedef RowStage<NC, U16> RS;
+  const DwtLevelDesc D = descs[blockIdx.y]; /* by value: fields live in (uniform) registers, not re-read after every store */
+  Job J;
+  if(!decode_job(D, J))
+    return;
+  if(J.hn == 1 || J.wn == 1)
+  {
+    fwd53_degenerate_job<NC, U16>(descs + blockIdx.y, J);
+    return;
+  }
+  const BandGeom g = band_geom(D);
+  const StoreCtx SC = store_ctx(D, J, g);
+  uint8_t* wsm = smem_dwt + (size_t)(threadIdx.x >> 5) * STAGES * RS::PAIRB;
+  const bool fast = RS::lane_fast(D, J);
+  const unsigned fastmask = __ballot_sync(0xffffffffu, fast);
+  int mcol[8]; /* mirrored column of each of the lane's samples: only edge lanes use them */
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+    mcol[i] = mirror_rel(J.ulane - D.u0 + i, J.wn);
+
+  /* pairs t = jbeg-1 .. jend-1 : rows (2t+1, 2t+2); the even row before them is fetched directly */
+  const int tfirst = J.jbeg - 1, tlast = J.jend - 1;
+  int tfill = tfirst;
+#pragma unroll
+  for(int s = 0; s < STAGES - 1; ++s)
+  {
+    if(tfill <= tlast)
+    {
+      uint8_t* st = wsm + (size_t)((tfill - tfirst) % STAGES) * RS::PAIRB;
+      RS::fill(st, 0, D, J, 2 * tfill + 1, fast, fastmask, mcol);
+      RS::fill(st, 1, D, J, 2 * tfill + 2, fast, fastmask, mcol);
+    }
+    cp_async_commit();
+    ++tfill;
+  }
+  int E[NC][8], DP[NC][8];
+  fetch53<NC, U16>(D, J, 2 * tfirst, E);
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+      DP[c][i] = 0;
+
+  for(int t = tfirst; t <= tlast; ++t)
+  {
+    __syncwarp(); /* every lane has read the stage that is refilled next */
+    if(tfill <= tlast)
+    {
+      uint8_t* st = wsm + (size_t)((tfill - tfirst) % STAGES) * RS::PAIRB;
+      RS::fill(st, 0, D, J, 2 * tfill + 1, fast, fastmask, mcol);
+      RS::fill(st, 1, D, J, 2 * tfill + 2, fast, fastmask, mcol);
+    }
+    cp_async_commit();
+    ++tfill;
+    cp_async_wait<STAGES - 1>();
+    __syncwarp(); /* rows were copied cooperatively */
+    const uint8_t* st = wsm + (size_t)((t - tfirst) % STAGES) * RS::PAIRB;
+    int O[NC][8], E2[NC][8];
+    RS::read(st, 0, D, J, O);
+    RS::read(st, 1, D, J, E2);
+    rct_fwd_inplace<NC>(D, O);
+    rct_fwd_inplace<NC>(D, E2);
+    const bool emit = t >= J.jbeg;
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+      int s[8], d[8];
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+      {
+        d[i] = O[c][i] - ((E[c][i] + E2[c][i]) >> 1);
+        s[i] = E[c][i] + ((DP[c][i] + d[i] + 2) >> 2);
+        DP[c][i] = d[i];
+        E[c][i] = E2[c][i];
+      }
+      if(emit)
+      { /* warp-uniform */
+        int lo[4], hi[4];
+        hfwd53<false>(s, J.wn, lo, hi);
+        store_rows_fast(D, g, SC, c, t, false, lo, hi);
+        hfwd53<false>(d, J.wn, lo, hi);
+        store_rows_fast(D, g, SC, c, t, true, lo, hi);
+      }
+    }
+  }
+  cp_async_wait<0>();
 }
 
 /* =============================================================================================
@@ -433,7 +750,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_fwd(const DwtL
 template <int NC, bool U16>
 __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_fwd(const DwtLevelDesc* __restrict__ descs)
 {
-  const DwtLevelDesc& D = descs[blockIdx.y];
+  const DwtLevelDesc D = descs[blockIdx.y]; /* by value: fields live in (uniform) registers, not re-read after every store */
   Job J;
   if(!decode_job(D, J))
     return;
@@ -688,7 +1005,7 @@ __device__ __forceinline__ void store_rows97(const DwtLevelDesc& D, const Job& J
 template <int NC>
 __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtLevelDesc* __restrict__ descs)
 {
-  const DwtLevelDesc& D = descs[blockIdx.y];
+  const DwtLevelDesc D = descs[blockIdx.y]; /* by value: fields live in (uniform) registers, not re-read after every store */
   Job J;
   if(!decode_job(D, J))
     return;
@@ -749,7 +1066,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtL
 template <int NC>
 __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_inv(const DwtLevelDesc* __restrict__ descs)
 {
-  const DwtLevelDesc& D = descs[blockIdx.y];
+  const DwtLevelDesc D = descs[blockIdx.y]; /* by value: fields live in (uniform) registers, not re-read after every store */
   Job J;
   if(!decode_job(D, J))
     return;
@@ -811,6 +1128,20 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_inv(const DwtL
 
 } /* namespace */
 
+constexpr int FWD_STAGES = 3;
+template <int NC, bool U16, int STAGES>
+static void launch_fwd53(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
+{
+  const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * RowStage<NC, U16>::PAIRB;
+  static bool once = false;
+  if(!once)
+  {
+    cudaFuncSetAttribute(k_dwt53_fwd<NC, U16, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    once = true;
+  }
+  k_dwt53_fwd<NC, U16, STAGES><<<grid, block, smem, st>>>(d);
+}
+
 void b2k_launch_dwt_fwd(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, bool irreversible, bool in_u16,
                         cudaStream_t st)
 {
@@ -821,13 +1152,13 @@ void b2k_launch_dwt_fwd(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, 
   {
     if(nc == 3)
     {
-      if(in_u16) k_dwt53_fwd<3, true><<<grid, block, 0, st>>>(d);
-      else k_dwt53_fwd<3, false><<<grid, block, 0, st>>>(d);
+      if(in_u16) launch_fwd53<3, true, FWD_STAGES>(grid, block, st, d);
+      else launch_fwd53<3, false, FWD_STAGES>(grid, block, st, d);
     }
     else
     {
-      if(in_u16) k_dwt53_fwd<1, true><<<grid, block, 0, st>>>(d);
-      else k_dwt53_fwd<1, false><<<grid, block, 0, st>>>(d);
+      if(in_u16) launch_fwd53<1, true, FWD_STAGES>(grid, block, st, d);
+      else launch_fwd53<1, false, FWD_STAGES>(grid, block, st, d);
     }
   }
   else
