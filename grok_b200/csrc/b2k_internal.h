@@ -45,7 +45,7 @@ struct HtBlockDesc
   uint32_t slot_cap;   /* bytes reserved in the scratch slot */
   uint64_t slot_off;   /* byte offset of the scratch slot (encode) / of the coded bytes (decode) */
   uint32_t length;     /* decode: coded length */
-  uint32_t pad2;
+  uint32_t rec_off;    /* decode: first entry of this block in the per-quad record scratch */
 };
 
 struct HtBlockOut /* written by the encoder kernel */
@@ -63,6 +63,6 @@ void b2k_launch_ht_encode(const HtBlockDesc* d_blocks, HtBlockOut* d_out, uint8_
 void b2k_launch_ht_gather(const HtBlockDesc* d_blocks, const HtBlockOut* d_out, const uint64_t* d_offsets,
                           const uint8_t* d_scratch, uint8_t* d_bytes, uint32_t nblocks, cudaStream_t st);
 void b2k_launch_scan_lengths(const HtBlockOut* d_out, uint64_t* d_offsets, uint32_t nblocks, cudaStream_t st);
-void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t nblocks, uint32_t max_w,
-                          int* d_err, cudaStream_t st);
+void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
+                          uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st);
 void b2k_count_launch(void);

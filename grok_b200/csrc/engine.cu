@@ -103,6 +103,9 @@ struct b2k_device_job
   std::vector<HtBlockDesc> h_enc_desc, h_dec_desc;
   HtBlockOut* d_out = nullptr;
   uint64_t* d_offsets = nullptr;
+  uint32_t* d_recs = nullptr;     /* decode: per-quad records between the two decode phases */
+  HtBlockOut* d_dec_status = nullptr;
+  uint64_t total_quads = 0;
   uint8_t* d_scratch = nullptr;
   uint64_t scratch_bytes = 0;
   uint8_t* d_bytes = nullptr;
@@ -342,6 +345,8 @@ static int build_block_plan(b2k_device_job* J)
     d.slot_cap = slot_capacity(d.w, d.h, bq.kmax);
     d.slot_off = off;
     off += d.slot_cap;
+    d.rec_off = (uint32_t)J->total_quads;
+    J->total_quads += (uint64_t)((d.w + 1) / 2) * ((d.h + 1) / 2);
     J->max_cblk_w = std::max<uint32_t>(J->max_cblk_w, d.w);
     J->h_enc_desc.push_back(d);
     J->coded_index.push_back(i);
@@ -356,6 +361,8 @@ static int build_block_plan(b2k_device_job* J)
     CUDA_TRY(cudaMalloc(&J->d_out, n * sizeof(HtBlockOut)));
     CUDA_TRY(cudaMalloc(&J->d_offsets, (n + 1) * sizeof(uint64_t)));
     CUDA_TRY(cudaMalloc(&J->d_scratch, J->scratch_bytes + 64));
+    CUDA_TRY(cudaMalloc(&J->d_recs, (J->total_quads + 64) * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&J->d_dec_status, n * sizeof(HtBlockOut)));
     CUDA_TRY(cudaHostAlloc(&J->h_out, n * sizeof(HtBlockOut), cudaHostAllocDefault));
     CUDA_TRY(cudaHostAlloc(&J->h_offsets, (n + 1) * sizeof(uint64_t), cudaHostAllocDefault));
   }
@@ -434,6 +441,8 @@ extern "C" void b2k_job_destroy(b2k_device_job* J)
   cudaFree(J->d_out);
   cudaFree(J->d_offsets);
   cudaFree(J->d_scratch);
+  cudaFree(J->d_recs);
+  cudaFree(J->d_dec_status);
   cudaFree(J->d_bytes);
   cudaFree(J->d_err);
   cudaFreeHost(J->h_out);
@@ -662,7 +671,7 @@ extern "C" int32_t b2k_job_t1_decode(b2k_device_job* J, float* ms)
   CUDA_TRY(cudaStreamSynchronize(st)); /* h_dec_desc is pageable */
   CUDA_TRY(cudaMemsetAsync(J->d_err, 0, sizeof(int), st));
   CUDA_TRY(cudaEventRecord(J->ev[0], st));
-  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, n, J->max_cblk_w, J->d_err, st);
+  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, J->d_recs, J->d_dec_status, n, J->max_cblk_w, J->d_err, st);
   CUDA_TRY(cudaEventRecord(J->ev[1], st));
   CUDA_TRY(cudaEventSynchronize(J->ev[1]));
   CUDA_TRY(cudaGetLastError());
@@ -893,7 +902,7 @@ extern "C" int32_t b2k_decode(b2k_engine* e, const b2k_coding* cp, const b2k_blo
   if(int prc = prepare_decode(J, blocks, num_blocks, st)) return prc;
   CUDA_TRY(cudaMemsetAsync(J->d_err, 0, sizeof(int), st));
   CUDA_TRY(cudaStreamSynchronize(st)); /* descriptors staged from pageable memory */
-  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, (uint32_t)J->h_enc_desc.size(), J->max_cblk_w, J->d_err, st);
+  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, J->d_recs, J->d_dec_status, (uint32_t)J->h_enc_desc.size(), J->max_cblk_w, J->d_err, st);
   if(enqueue_inverse(J, st)) return -1;
   if(copy_planes(J, J->img, (void* const*)planes, strides, false, st)) return -1;
   CUDA_TRY(cudaEventRecord(J->ev[1], st));

@@ -142,70 +142,49 @@ __device__ __forceinline__ T warp_excl_scan_d(T v, int lane, T& total)
   return x - v;
 }
 
-/* record per quad: rho[3:0] | e_k[7:4] | e_1[11:8] | u[17:12] */
-__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
-    k_ht_decode(const HtBlockDesc* __restrict__ blocks, const uint8_t* __restrict__ bytes, uint32_t nblocks,
-                uint32_t line_entries, int* __restrict__ err)
+/* =============================================================================================
+ * Phase A -- MEL + CxtVLC + UVLC parse, ONE THREAD PER CODE BLOCK.
+ * Context-adaptive variable-length codes cannot be parsed in parallel inside a block, but blocks
+ * are independent: 32 blocks per warp keep every lane busy (a warp-per-block version of this
+ * loop runs the same instruction stream with 1/32 of the lanes doing useful work).
+ * Output: one record per quad in global scratch, rho[3:0] | e_k[7:4] | e_1[11:8] | u[17:12],
+ * consumed by phase B (k_ht_decode_magsgn, warp per block).
+ * =========================================================================================== */
+__global__ void __launch_bounds__(128)
+    k_ht_decode_vlc(const HtBlockDesc* __restrict__ blocks, const uint8_t* __restrict__ bytes, uint32_t* __restrict__ recs,
+                    HtBlockOut* __restrict__ status, uint32_t nblocks)
 {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint16_t* tbl0 = reinterpret_cast<uint16_t*>(smem_raw);
-  uint16_t* tbl1 = tbl0 + 1024;
-  uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw + 2 * 1024 * sizeof(uint16_t));
-  uint32_t* recs_all = rings + B2K_WARPS_PER_CTA * MS_RING_WORDS;
-  uint16_t* lines_all = reinterpret_cast<uint16_t*>(recs_all + (size_t)B2K_WARPS_PER_CTA * 2 * line_entries);
+  __shared__ uint16_t tbl0[1024], tbl1[1024];
   for(int i = threadIdx.x; i < 1024; i += blockDim.x)
   {
     tbl0[i] = HT_DEC_VLC0[i];
     tbl1[i] = HT_DEC_VLC1[i];
   }
   __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bidx = blockIdx.x * B2K_WARPS_PER_CTA + warp;
+  const uint32_t bidx = blockIdx.x * blockDim.x + threadIdx.x;
   if(bidx >= nblocks)
     return;
   const HtBlockDesc B = blocks[bidx];
-  uint32_t* ring = rings + warp * MS_RING_WORDS;
-  uint32_t* rec[2] = {recs_all + (size_t)warp * 2 * line_entries, recs_all + (size_t)warp * 2 * line_entries + line_entries};
-  uint16_t* line[2] = {lines_all + (size_t)warp * 2 * line_entries, lines_all + (size_t)warp * 2 * line_entries + line_entries};
-
   const int w = B.w, h = B.h, nq = (w + 1) >> 1;
-  const int kmax = B.kmax;
-  int32_t* coef = reinterpret_cast<int32_t*>(B.coef);
-
-  /* zero-length block (not included in any packet): all coefficients are zero */
   const uint32_t lcup = B.length;
-  bool bad = false;
-  const int mmsbs = (int)B.mmsbs;
-  int scup = 0;
   const uint8_t* data = bytes + B.slot_off;
+  HtBlockOut st;
+  st.ms_len = 0; st.mel_len = 0; st.vlc_len = 0; st.total = 0;
+  int scup = 0;
   if(lcup >= 2)
   {
     scup = ((int)__ldg(data + lcup - 1) << 4) + (int)(__ldg(data + lcup - 2) & 0xF);
-    if(scup < 2 || scup > (int)lcup || scup > 4079 || mmsbs > 29)
-      bad = true;
+    if(scup < 2 || scup > (int)lcup || scup > 4079 || B.mmsbs > 29)
+      st.total = 2; /* malformed */
   }
-  if(lcup < 2 || bad)
+  else
+    st.total = lcup == 0 ? 1 : 2; /* 1: empty block (all zero), 2: malformed */
+  if(st.total)
   {
-    for(int y = 0; y < h; ++y)
-      for(int x = lane; x < w; x += 32)
-        coef[(size_t)y * B.pitch + x] = 0;
-    if(lane == 0 && (bad || lcup == 1))
-      atomicAdd(err, 1);
+    status[bidx] = st;
     return;
   }
-  const int p = 30 - mmsbs;
-  const uint32_t mmsbp2 = (uint32_t)mmsbs + 2u;
-  const int post_shift = 31 - kmax;
-
-  for(int i = lane; i < MS_RING_WORDS; i += 32)
-    ring[i] = 0;
-  for(uint32_t i = lane; i < 2 * line_entries; i += 32)
-  {
-    rec[0][i] = 0;
-    line[0][i] = 0;
-  }
-  __syncwarp();
+  st.ms_len = lcup - (uint32_t)scup;
 
   MelR mel = {data + lcup - scup, scup - 1, 0, 0, 0, 0, 0, 0, 0};
   VlcR vlc = {data, (int)lcup - 3, (int)lcup - scup, 0, 0, 0};
@@ -215,18 +194,15 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
     vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1 : 0);
     vlc.unstuff = (d | 0xF) > 0x8F;
   }
-  /* MagSgn ring feeder state */
-  const int ms_size = (int)lcup - scup;
-  int ms_pos = 0;            /* next byte of the segment to feed */
-  uint32_t ms_head = 0, ms_tail = 0;
-  bool ms_prevff = false;
+  uint32_t* rec = recs + B.rec_off;
+  /* significance of the previous quad row's bottom samples: bit q of bl / br = rho&2 / rho&8 */
+  uint32_t pbl[16], pbr[16], cbl[16], cbr[16];
+#pragma unroll
+  for(int i = 0; i < 16; ++i)
+    pbl[i] = pbr[i] = cbl[i] = cbr[i] = 0;
 
-  for(int y = 0; y < h && !bad; y += 2)
+  for(int y = 0; y < h; y += 2)
   {
-    const int cur = (y >> 1) & 1;
-    uint32_t* rcur = rec[cur];
-    const uint32_t* rprev = rec[cur ^ 1];
-    /* ---------------- (a) serial MEL / VLC / UVLC parse of this quad row ---------------- */
     int rho_left = 0;
     for(int q0 = 0; q0 < nq; q0 += 2)
     {
@@ -239,10 +215,10 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
         if(y == 0)
           cq = (rho_left >> 1) | (rho_left & 1);
         else
-        { /* records are stored at index q+1; index 0 and nq+1 stay zero */
-          const uint32_t pl = rprev[q], pc = rprev[q + 1], pr = rprev[q + 2];
-          const int a = (int)((pl & 8) | (pc & 2)), b = (int)((pc & 8) | (pr & 2));
-          cq = (a ? 1 : 0) | ((rho_left & 0xC) ? 2 : 0) | (b ? 4 : 0);
+        {
+          const int a = (q > 0 ? (int)((pbr[(q - 1) >> 5] >> ((q - 1) & 31)) & 1u) : 0) | (int)((pbl[q >> 5] >> (q & 31)) & 1u);
+          const int b = (int)((pbr[q >> 5] >> (q & 31)) & 1u) | (q + 1 < nq ? (int)((pbl[(q + 1) >> 5] >> ((q + 1) & 31)) & 1u) : 0);
+          cq = a | ((rho_left & 0xC) ? 2 : 0) | (b << 2);
         }
         uint32_t t = (y ? tbl1 : tbl0)[(cq << 7) | (vlc_peek(vlc) & 0x7F)];
         if(cq == 0 && !mel_symbol(mel))
@@ -253,6 +229,8 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
         uoff[j] = (t >> 12) & 1;
         vlc_skip(vlc, (int)(t >> 13));
         rho_left = rho[j];
+        if(rho[j] & 2) cbl[q >> 5] |= 1u << (q & 31);
+        if(rho[j] & 8) cbr[q >> 5] |= 1u << (q & 31);
       }
       if(y == 0 && uoff[0] && uoff[1])
       {
@@ -311,16 +289,75 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
             vlc_skip(vlc, l);
           }
       }
-      if(lane == 0)
-      {
-        rcur[q0 + 1] = (uint32_t)(rho[0] | (ek[0] << 4) | (e1[0] << 8) | (u[0] << 12));
-        if(npair == 2)
-          rcur[q0 + 2] = (uint32_t)(rho[1] | (ek[1] << 4) | (e1[1] << 8) | (u[1] << 12));
-      }
+      rec[q0] = (uint32_t)(rho[0] | (ek[0] << 4) | (e1[0] << 8) | (u[0] << 12));
+      if(npair == 2)
+        rec[q0 + 1] = (uint32_t)(rho[1] | (ek[1] << 4) | (e1[1] << 8) | (u[1] << 12));
     }
-    __syncwarp();
+    rec += nq;
+#pragma unroll
+    for(int i = 0; i < 16; ++i)
+    {
+      pbl[i] = cbl[i];
+      pbr[i] = cbr[i];
+      cbl[i] = cbr[i] = 0;
+    }
+  }
+  status[bidx] = st;
+}
 
-    /* ---------------- (b) MagSgn parse of this quad row, 32 quads per step ---------------- */
+/* record per quad: rho[3:0] | e_k[7:4] | e_1[11:8] | u[17:12] */
+__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
+    k_ht_decode_magsgn(const HtBlockDesc* __restrict__ blocks, const uint8_t* __restrict__ bytes,
+                       const uint32_t* __restrict__ recs, const HtBlockOut* __restrict__ status, uint32_t nblocks,
+                       uint32_t line_entries, int* __restrict__ err)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
+  uint16_t* lines_all = reinterpret_cast<uint16_t*>(rings + B2K_WARPS_PER_CTA * MS_RING_WORDS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bidx = blockIdx.x * B2K_WARPS_PER_CTA + warp;
+  if(bidx >= nblocks)
+    return;
+  const HtBlockDesc B = blocks[bidx];
+  const HtBlockOut st = status[bidx];
+  uint32_t* ring = rings + warp * MS_RING_WORDS;
+  uint16_t* line[2] = {lines_all + (size_t)warp * 2 * line_entries, lines_all + (size_t)warp * 2 * line_entries + line_entries};
+
+  const int w = B.w, h = B.h, nq = (w + 1) >> 1;
+  const int kmax = B.kmax;
+  int32_t* coef = reinterpret_cast<int32_t*>(B.coef);
+  bool bad = st.total == 2;
+  if(st.total)
+  { /* empty (not in any packet) or malformed: all coefficients zero */
+    for(int y = 0; y < h; ++y)
+      for(int x = lane; x < w; x += 32)
+        coef[(size_t)y * B.pitch + x] = 0;
+    if(lane == 0 && bad)
+      atomicAdd(err, 1);
+    return;
+  }
+  const uint8_t* data = bytes + B.slot_off;
+  const int mmsbs = (int)B.mmsbs;
+  const int p = 30 - mmsbs;
+  const uint32_t mmsbp2 = (uint32_t)mmsbs + 2u;
+  const int post_shift = 31 - kmax;
+
+  for(int i = lane; i < MS_RING_WORDS; i += 32)
+    ring[i] = 0;
+  for(uint32_t i = lane; i < 2 * line_entries; i += 32)
+    line[0][i] = 0;
+  __syncwarp();
+
+  const int ms_size = (int)st.ms_len;
+  int ms_pos = 0;
+  uint32_t ms_head = 0, ms_tail = 0;
+  bool ms_prevff = false;
+  const uint32_t* rec = recs + B.rec_off;
+
+  for(int y = 0; y < h && !bad; y += 2)
+  {
+    const int cur = (y >> 1) & 1;
     const uint16_t* labove = line[cur ^ 1];
     uint16_t* lcur = line[cur];
     for(int qb = 0; qb < nq; qb += 32)
@@ -357,7 +394,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
 
       const int q = qb + lane, x = 2 * q;
       const bool qv = q < nq;
-      const uint32_t r = qv ? rcur[q + 1] : 0u;
+      const uint32_t r = qv ? __ldg(rec + q) : 0u;
       const int rho = r & 0xF, ekq = (r >> 4) & 0xF, e1q = (r >> 8) & 0xF, uq = (int)(r >> 12);
       int kappa = 1;
       if(y > 0 && qv)
@@ -380,7 +417,6 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
       }
       uint32_t total;
       const uint32_t off = warp_excl_scan_d<uint32_t>((uint32_t)mlen, lane, total);
-      /* fetch up to 128 bits at ms_head + off */
       const uint32_t pos = ms_head + off;
       const uint32_t wi = pos >> 5;
       const int sh = pos & 31;
@@ -399,12 +435,10 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
       {
         const int xx = x + (i >> 1), yy = y + (i & 1);
         uint32_t outv = 0;
-        float outf = 0.f;
         if(m[i] > 0 || (((rho >> i) & 1) && (x + (i >> 1)) < w && !bad))
         {
           const int mi = m[i];
           const uint32_t msv = (uint32_t)blo;
-          /* consume mi bits */
           if(mi)
           {
             blo = (blo >> mi) | (bhi << (64 - mi));
@@ -424,7 +458,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
           }
           else
           {
-            outf = __fmul_rn((float)(int32_t)(mag & 0x7FFFFFFFu), B.quant);
+            float outf = __fmul_rn((float)(int32_t)(mag & 0x7FFFFFFFu), B.quant);
             if(sgn)
               outf = -outf;
             outv = __float_as_uint(outf);
@@ -435,7 +469,6 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
       }
       if(qv)
         lcur[q + 1] = (uint16_t)(ebot[0] | (ebot[1] << 8));
-      /* release consumed ring words */
       {
         const uint32_t nh = ms_head + total;
         __syncwarp();
@@ -446,6 +479,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
       bad = __any_sync(0xffffffffu, bad);
       __syncwarp();
     }
+    rec += nq;
   }
   if(bad)
   {
@@ -460,21 +494,18 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
 
 } /* namespace */
 
-void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t nblocks, uint32_t max_w,
-                          int* d_err, cudaStream_t st)
+void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
+                          uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st)
 {
   if(!nblocks)
     return;
+  k_ht_decode_vlc<<<(nblocks + 127) / 128, 128, 0, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks);
+  b2k_count_launch();
   const uint32_t line_entries = ((max_w + 1) / 2 + 4 + 1) & ~1u;
-  const size_t smem = 2 * 1024 * sizeof(uint16_t) + (size_t)B2K_WARPS_PER_CTA * MS_RING_WORDS * sizeof(uint32_t) +
-                      (size_t)B2K_WARPS_PER_CTA * 2 * line_entries * (sizeof(uint32_t) + sizeof(uint16_t));
-  static bool attr_set = false;
-  if(!attr_set)
-  {
-    cudaFuncSetAttribute(k_ht_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
-  }
+  const size_t smem = (size_t)B2K_WARPS_PER_CTA * MS_RING_WORDS * sizeof(uint32_t) +
+                      (size_t)B2K_WARPS_PER_CTA * 2 * line_entries * sizeof(uint16_t);
   const uint32_t grid = (nblocks + B2K_WARPS_PER_CTA - 1) / B2K_WARPS_PER_CTA;
-  k_ht_decode<<<grid, B2K_WARPS_PER_CTA * 32, smem, st>>>(d_blocks, d_bytes, nblocks, line_entries, d_err);
+  k_ht_decode_magsgn<<<grid, B2K_WARPS_PER_CTA * 32, smem, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks, line_entries,
+                                                                d_err);
   b2k_count_launch();
 }
