@@ -48,7 +48,7 @@ void b2k_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed)
 struct b2k_engine
 {
   int device = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, h2d_stream = nullptr;
   cudaDeviceProp prop{};
 };
 
@@ -81,6 +81,7 @@ struct LevelLaunch
   DwtLevelDesc* d_descs = nullptr;
   int nc = 1, max_jobs = 0;
   uint64_t alg_bytes = 0; /* one read + one write of every sample of the level */
+  std::vector<uint32_t> tile_first; /* descs of selected tile ti are [tile_first[ti], tile_first[ti+1]) */
 };
 
 struct b2k_device_job
@@ -94,13 +95,18 @@ struct b2k_device_job
   std::vector<BandQuant> quant;
   std::vector<b2k_block> blocks;       /* every block, enumeration order */
   std::vector<uint32_t> coded_index;   /* blocks with area, index into `blocks` */
+  std::vector<float> dec_quant;        /* per coded block: decoder step / 2^(31-Kmax) */
+  std::vector<uint32_t> coded_first;   /* coded blocks of selected tile ti are [coded_first[ti], coded_first[ti+1]) */
+  std::vector<uint32_t> chunk_tile;    /* pipeline chunks: selected tiles [chunk_tile[k], chunk_tile[k+1]) */
+  cudaEvent_t chunk_ev[32]{};
   uint32_t max_cblk_w = 0;
 
   Planes img, coef, ll[2];
   std::vector<LevelLaunch> fwd, inv;   /* launch order */
   HtBlockDesc* d_enc_desc = nullptr;
   HtBlockDesc* d_dec_desc = nullptr;
-  std::vector<HtBlockDesc> h_enc_desc, h_dec_desc;
+  std::vector<HtBlockDesc> h_enc_desc;
+  HtBlockDesc* h_dec_desc = nullptr;   /* pinned staging */
   HtBlockOut* d_out = nullptr;
   uint64_t* d_offsets = nullptr;
   uint32_t* d_recs = nullptr;     /* decode: per-quad records between the two decode phases */
@@ -148,6 +154,7 @@ extern "C" int32_t b2k_engine_create(int32_t device, b2k_engine** out)
   CUDA_TRY(cudaGetDeviceProperties(&eng->prop, device));
   CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&eng->h2d_stream, cudaStreamNonBlocking));
   *out = eng;
   return 0;
 }
@@ -161,6 +168,8 @@ extern "C" void b2k_engine_destroy(b2k_engine* e)
     cudaStreamDestroy(e->stream);
   if(e->copy_stream)
     cudaStreamDestroy(e->copy_stream);
+  if(e->h2d_stream)
+    cudaStreamDestroy(e->h2d_stream);
   delete e;
 }
 
@@ -245,6 +254,8 @@ static int build_dwt_plan(b2k_device_job* J)
       sglL.nc = 1;
       for(size_t ti = 0; ti < J->tiles.size(); ++ti)
       {
+        mctL.tile_first.push_back((uint32_t)mctL.descs.size());
+        sglL.tile_first.push_back((uint32_t)sglL.descs.size());
         const Rect tc = J->tile_rects[ti];
         const Rect r = resolution_rect(tc, cp.numres, resno);
         if(r.empty())
@@ -289,6 +300,8 @@ static int build_dwt_plan(b2k_device_job* J)
           c += nc;
         }
       }
+      mctL.tile_first.push_back((uint32_t)mctL.descs.size());
+      sglL.tile_first.push_back((uint32_t)sglL.descs.size());
       if(dir == 0)
       {
         if(!mctL.descs.empty()) out.push_back(std::move(mctL));
@@ -327,11 +340,16 @@ static int build_block_plan(b2k_device_job* J)
   for(size_t ti = 0; ti < J->tiles.size(); ++ti)
     rect_of[J->tiles[ti]] = J->tile_rects[ti];
   uint64_t off = 0;
+  std::vector<uint32_t> sel_of(J->grid.nx * J->grid.ny, 0);
+  for(size_t ti = 0; ti < J->tiles.size(); ++ti)
+    sel_of[J->tiles[ti]] = (uint32_t)ti;
+  J->coded_first.assign(J->tiles.size() + 1, 0);
   for(uint32_t i = 0; i < J->blocks.size(); ++i)
   {
     const b2k_block& b = J->blocks[i];
     if(b.x1 <= b.x0 || b.y1 <= b.y0)
       continue;
+    J->coded_first[sel_of[b.tile] + 1] = (uint32_t)J->h_enc_desc.size() + 1;
     const Rect& tr = rect_of[b.tile];
     const BandQuant& bq = J->quant[band_quant_index(b.resno, b.orient)];
     HtBlockDesc d{};
@@ -349,9 +367,19 @@ static int build_block_plan(b2k_device_job* J)
     J->total_quads += (uint64_t)((d.w + 1) / 2) * ((d.h + 1) / 2);
     J->max_cblk_w = std::max<uint32_t>(J->max_cblk_w, d.w);
     J->h_enc_desc.push_back(d);
+    J->dec_quant.push_back(bq.step_dec / (float)(1u << (31 - bq.kmax)));
     J->coded_index.push_back(i);
   }
   J->scratch_bytes = off;
+  for(size_t ti = 1; ti <= J->tiles.size(); ++ti) /* tiles without coded blocks inherit the running count */
+    J->coded_first[ti] = std::max(J->coded_first[ti], J->coded_first[ti - 1]);
+  {
+    const uint32_t nt = (uint32_t)J->tiles.size();
+    const uint32_t nchunks = std::max(1u, std::min(8u, nt));
+    J->chunk_tile.clear();
+    for(uint32_t k = 0; k <= nchunks; ++k)
+      J->chunk_tile.push_back((uint32_t)((uint64_t)k * nt / nchunks));
+  }
   const size_t n = J->h_enc_desc.size();
   if(n)
   {
@@ -364,6 +392,7 @@ static int build_block_plan(b2k_device_job* J)
     CUDA_TRY(cudaMalloc(&J->d_recs, (J->total_quads + 64) * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&J->d_dec_status, n * sizeof(HtBlockOut)));
     CUDA_TRY(cudaHostAlloc(&J->h_out, n * sizeof(HtBlockOut), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&J->h_dec_desc, n * sizeof(HtBlockDesc), cudaHostAllocDefault));
     CUDA_TRY(cudaHostAlloc(&J->h_offsets, (n + 1) * sizeof(uint64_t), cudaHostAllocDefault));
   }
   CUDA_TRY(cudaMalloc(&J->d_err, sizeof(int)));
@@ -420,6 +449,8 @@ extern "C" int32_t b2k_job_create(b2k_engine* e, const b2k_coding* cp, uint32_t 
   }
   for(cudaEvent_t& ev : J->ev)
     CUDA_TRY(cudaEventCreate(&ev));
+  for(cudaEvent_t& ev : J->chunk_ev)
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   *out = J;
   return 0;
 }
@@ -446,8 +477,12 @@ extern "C" void b2k_job_destroy(b2k_device_job* J)
   cudaFree(J->d_bytes);
   cudaFree(J->d_err);
   cudaFreeHost(J->h_out);
+  cudaFreeHost(J->h_dec_desc);
   cudaFreeHost(J->h_offsets);
   for(cudaEvent_t& ev : J->ev)
+    if(ev)
+      cudaEventDestroy(ev);
+  for(cudaEvent_t& ev : J->chunk_ev)
     if(ev)
       cudaEventDestroy(ev);
   delete J;
@@ -457,12 +492,20 @@ extern "C" uint64_t b2k_job_num_blocks(const b2k_device_job* J) { return J ? J->
 
 /* ---- host <-> device plane copies, per selected tile ---------------------------------------- */
 static int copy_planes(b2k_device_job* J, const Planes& P, void* const* host, const uint32_t* strides, bool to_device,
-                       cudaStream_t st)
+                       cudaStream_t st, size_t t0 = 0, size_t t1 = (size_t)-1)
 {
   const b2k_coding& cp = J->cp;
-  for(size_t ti = 0; ti < J->tiles.size(); ++ti)
+  t1 = std::min(t1, J->tiles.size());
+  for(size_t ti = t0; ti < t1;)
   {
-    const Rect r = J->tile_rects[ti];
+    /* merge horizontally adjacent selected tiles of one tile row into a single rectangle */
+    Rect r = J->tile_rects[ti];
+    size_t tj = ti + 1;
+    while(tj < t1 && J->tile_rects[tj].y0 == r.y0 && J->tile_rects[tj].y1 == r.y1 && J->tile_rects[tj].x0 == r.x1)
+    {
+      r.x1 = J->tile_rects[tj].x1;
+      ++tj;
+    }
     for(int c = 0; c < cp.numcomps; ++c)
     {
       int32_t* dev = P.at(c, r.x0, r.y0);
@@ -474,6 +517,7 @@ static int copy_planes(b2k_device_job* J, const Planes& P, void* const* host, co
         CUDA_TRY(cudaMemcpy2DAsync(hst, (size_t)strides[c] * 4, dev, (size_t)P.pitch * 4, (size_t)r.w() * 4, r.h(),
                                    cudaMemcpyDeviceToHost, st));
     }
+    ti = tj;
   }
   return 0;
 }
@@ -512,14 +556,18 @@ extern "C" int32_t b2k_job_upload_coeffs(b2k_device_job* J, const int32_t* const
 }
 
 /* ---- stages ----------------------------------------------------------------------------------- */
-static int enqueue_forward(b2k_device_job* J, cudaStream_t st, bool time_level1)
+static int enqueue_forward(b2k_device_job* J, cudaStream_t st, bool time_level1, size_t t0 = 0, size_t t1 = (size_t)-1)
 {
+  t1 = std::min(t1, J->tiles.size());
   bool first = true;
   for(LevelLaunch& L : J->fwd)
   {
+    const uint32_t d0 = L.tile_first[t0], d1 = L.tile_first[t1];
     if(first && time_level1)
       CUDA_TRY(cudaEventRecord(J->ev[4], st));
-    b2k_launch_dwt_fwd(L.d_descs, (int)L.descs.size(), L.max_jobs, L.nc, J->cp.irreversible, J->img_is_u16 && L.descs[0].first_level, st);
+    if(d1 > d0)
+      b2k_launch_dwt_fwd(L.d_descs + d0, (int)(d1 - d0), L.max_jobs, L.nc, J->cp.irreversible,
+                         J->img_is_u16 && L.descs[0].first_level, st);
     if(first && time_level1)
     {
       CUDA_TRY(cudaEventRecord(J->ev[5], st));
@@ -531,10 +579,26 @@ static int enqueue_forward(b2k_device_job* J, cudaStream_t st, bool time_level1)
   return 0;
 }
 
-static int enqueue_inverse(b2k_device_job* J, cudaStream_t st)
+static int enqueue_inverse(b2k_device_job* J, cudaStream_t st, size_t t0 = 0, size_t t1 = (size_t)-1)
 {
+  t1 = std::min(t1, J->tiles.size());
   for(LevelLaunch& L : J->inv)
-    b2k_launch_dwt_inv(L.d_descs, (int)L.descs.size(), L.max_jobs, L.nc, J->cp.irreversible, st);
+  {
+    const uint32_t d0 = L.tile_first[t0], d1 = L.tile_first[t1];
+    if(d1 > d0)
+      b2k_launch_dwt_inv(L.d_descs + d0, (int)(d1 - d0), L.max_jobs, L.nc, J->cp.irreversible, st);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+/* block coder over the coded blocks of selected tiles [t0, t1) */
+static int enqueue_t1_blocks(b2k_device_job* J, cudaStream_t st, size_t t0, size_t t1)
+{
+  t1 = std::min(t1, J->tiles.size());
+  const uint32_t b0 = J->coded_first[t0], b1 = J->coded_first[t1];
+  if(b1 > b0)
+    b2k_launch_ht_encode(J->d_enc_desc + b0, J->d_out + b0, J->d_scratch, b1 - b0, J->max_cblk_w, st);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -616,20 +680,20 @@ extern "C" int32_t b2k_job_t1_encode(b2k_device_job* J, float* ms, uint64_t* tot
   return 0;
 }
 
-/* decode descriptors from (length, offset, numbps) per coded block */
-static int prepare_decode(b2k_device_job* J, const b2k_block* blocks, uint64_t num_blocks, cudaStream_t st)
+/* decode descriptors from (length, offset, numbps) per coded block, for coded blocks [k0, k1) */
+static int prepare_decode(b2k_device_job* J, const b2k_block* blocks, uint64_t num_blocks, cudaStream_t st, size_t k0 = 0,
+                          size_t k1 = (size_t)-1)
 {
   const size_t n = J->h_enc_desc.size();
-  J->h_dec_desc.resize(n);
+  k1 = std::min(k1, n);
   if(num_blocks != J->blocks.size())
   {
     g_err = "block count does not match this coding's enumeration";
     return -1;
   }
-  for(size_t k = 0; k < n; ++k)
+  for(size_t k = k0; k < k1; ++k)
   {
     const b2k_block& b = blocks[J->coded_index[k]];
-    const BandQuant& bq = J->quant[band_quant_index(b.resno, b.orient)];
     HtBlockDesc d = J->h_enc_desc[k];
     d.length = b.length;
     d.slot_off = b.offset;
@@ -639,12 +703,12 @@ static int prepare_decode(b2k_device_job* J, const b2k_block* blocks, uint64_t n
       return 1;
     }
     const int nb = b.length ? b.numbps : 0;
-    d.mmsbs = (uint8_t)std::max(0, (int)bq.kmax - nb);
-    d.quant = bq.step_dec / (float)(1u << (31 - bq.kmax)); /* PostDecodeFiltersOJPH.h L103 */
+    d.mmsbs = (uint8_t)std::max(0, (int)d.kmax - nb);
+    d.quant = J->dec_quant[k]; /* stepsize / 2^(31-Kmax), PostDecodeFiltersOJPH.h L103 */
     J->h_dec_desc[k] = d;
   }
-  if(n)
-    CUDA_TRY(cudaMemcpyAsync(J->d_dec_desc, J->h_dec_desc.data(), n * sizeof(HtBlockDesc), cudaMemcpyHostToDevice, st));
+  if(k1 > k0)
+    CUDA_TRY(cudaMemcpyAsync(J->d_dec_desc + k0, J->h_dec_desc + k0, (k1 - k0) * sizeof(HtBlockDesc), cudaMemcpyHostToDevice, st));
   return 0;
 }
 
@@ -668,7 +732,6 @@ extern "C" int32_t b2k_job_t1_decode(b2k_device_job* J, float* ms)
     b.numpasses = 1;
   }
   if(int rc = prepare_decode(J, blk.data(), blk.size(), st)) return rc;
-  CUDA_TRY(cudaStreamSynchronize(st)); /* h_dec_desc is pageable */
   CUDA_TRY(cudaMemsetAsync(J->d_err, 0, sizeof(int), st));
   CUDA_TRY(cudaEventRecord(J->ev[0], st));
   b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, J->d_recs, J->d_dec_status, n, J->max_cblk_w, J->d_err, st);
@@ -841,12 +904,25 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
     return rc;
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = e->stream;
+  /* software pipeline over tile chunks: chunk k+1 crosses PCIe on the copy stream while chunk k
+     is transformed and block-coded on the compute stream */
+  cudaStream_t cs = e->copy_stream;
   CUDA_TRY(cudaEventRecord(J->ev[0], st));
-  if(copy_planes(J, J->img, planes, strides, true, st)) return -1;
-  CUDA_TRY(cudaEventRecord(J->ev[1], st));
-  if(enqueue_forward(J, st, true)) return -1;
+  CUDA_TRY(cudaStreamWaitEvent(cs, J->ev[0], 0));
+  const size_t nchunks = J->chunk_tile.size() - 1;
+  for(size_t k = 0; k < nchunks; ++k)
+  {
+    const size_t t0 = J->chunk_tile[k], t1 = J->chunk_tile[k + 1];
+    if(copy_planes(J, J->img, planes, strides, true, cs, t0, t1)) return -1;
+    CUDA_TRY(cudaEventRecord(J->chunk_ev[k], cs));
+    CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[k], 0));
+    if(k == nchunks - 1)
+      CUDA_TRY(cudaEventRecord(J->ev[1], st)); /* all planes on the device */
+    if(enqueue_forward(J, st, k == 0, t0, t1)) return -1;
+    if(enqueue_t1_blocks(J, st, t0, t1)) return -1;
+  }
   CUDA_TRY(cudaEventRecord(J->ev[2], st));
-  if(enqueue_t1_encode(J, st)) return -1;
+  b2k_launch_scan_lengths(J->d_out, J->d_offsets, (uint32_t)J->h_enc_desc.size(), st);
   if(finish_t1_encode(J, st)) return -1;
   CUDA_TRY(cudaEventRecord(J->ev[3], st));
   b2k_result* R = nullptr;
@@ -897,14 +973,63 @@ extern "C" int32_t b2k_decode(b2k_engine* e, const b2k_coding* cp, const b2k_blo
     CUDA_TRY(cudaMalloc(&J->d_bytes, J->bytes_cap));
   }
   CUDA_TRY(cudaEventRecord(J->ev[0], st));
-  if(num_bytes)
-    CUDA_TRY(cudaMemcpyAsync(J->d_bytes, bytes, num_bytes, cudaMemcpyHostToDevice, st));
-  if(int prc = prepare_decode(J, blocks, num_blocks, st)) return prc;
   CUDA_TRY(cudaMemsetAsync(J->d_err, 0, sizeof(int), st));
-  CUDA_TRY(cudaStreamSynchronize(st)); /* descriptors staged from pageable memory */
-  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, J->d_recs, J->d_dec_status, (uint32_t)J->h_enc_desc.size(), J->max_cblk_w, J->d_err, st);
-  if(enqueue_inverse(J, st)) return -1;
-  if(copy_planes(J, J->img, (void* const*)planes, strides, false, st)) return -1;
+  cudaStream_t cs = e->copy_stream;
+  const size_t nchunks = J->chunk_tile.size() - 1;
+  CUDA_TRY(cudaStreamWaitEvent(cs, J->ev[0], 0));
+  CUDA_TRY(cudaStreamWaitEvent(e->h2d_stream, J->ev[0], 0));
+  /* Pipeline over tile chunks.  Host: build chunk k's descriptors while the device works on chunk
+     k-1.  PCIe in: chunk k's coded bytes (one contiguous range when the arena is in block order,
+     which ours always is; otherwise the whole arena goes up once).  Compute: block decode +
+     inverse transform.  PCIe out: chunk k-1's pixels -- both directions stay busy. */
+  bool all_uploaded = false;
+  uint64_t prev_end = 0;
+  for(size_t k = 0; k < nchunks; ++k)
+  {
+    const size_t t0 = J->chunk_tile[k], t1 = J->chunk_tile[k + 1];
+    const uint32_t b0 = J->coded_first[t0], b1 = J->coded_first[t1];
+    if(int prc = prepare_decode(J, blocks, num_blocks, st, b0, b1)) return prc;
+    uint64_t lo = UINT64_MAX, hi = 0;
+    for(uint32_t b = b0; b < b1; ++b)
+    {
+      const HtBlockDesc& d = J->h_dec_desc[b];
+      if(!d.length)
+        continue;
+      lo = std::min<uint64_t>(lo, d.slot_off);
+      hi = std::max<uint64_t>(hi, d.slot_off + d.length);
+    }
+    if(hi > num_bytes)
+    {
+      g_err = "block offsets exceed the byte arena";
+      return -1;
+    }
+    if(!all_uploaded && lo != UINT64_MAX)
+    {
+      if(lo < prev_end)
+      { /* arena not in block order: upload what is left in one go */
+        CUDA_TRY(cudaMemcpyAsync(J->d_bytes + prev_end, bytes + prev_end, num_bytes - prev_end, cudaMemcpyHostToDevice, st));
+        if(prev_end > 0)
+          CUDA_TRY(cudaMemcpyAsync(J->d_bytes, bytes, prev_end, cudaMemcpyHostToDevice, st));
+        all_uploaded = true;
+      }
+      else
+      {
+        CUDA_TRY(cudaMemcpyAsync(J->d_bytes + lo, bytes + lo, hi - lo, cudaMemcpyHostToDevice, e->h2d_stream));
+        CUDA_TRY(cudaEventRecord(J->chunk_ev[16 + (k & 7)], e->h2d_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[16 + (k & 7)], 0));
+        prev_end = hi;
+      }
+    }
+    if(b1 > b0)
+      b2k_launch_ht_decode(J->d_dec_desc + b0, J->d_bytes, J->d_recs, J->d_dec_status + b0, b1 - b0, J->max_cblk_w,
+                           J->d_err, st);
+    if(enqueue_inverse(J, st, t0, t1)) return -1;
+    CUDA_TRY(cudaEventRecord(J->chunk_ev[k], st));
+    CUDA_TRY(cudaStreamWaitEvent(cs, J->chunk_ev[k], 0));
+    if(copy_planes(J, J->img, (void* const*)planes, strides, false, cs, t0, t1)) return -1;
+  }
+  CUDA_TRY(cudaEventRecord(J->chunk_ev[nchunks], cs));
+  CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[nchunks], 0));
   CUDA_TRY(cudaEventRecord(J->ev[1], st));
   CUDA_TRY(cudaEventSynchronize(J->ev[1]));
   CUDA_TRY(cudaGetLastError());
