@@ -61,7 +61,7 @@ void b2k_launch_dwt_inv(const DwtLevelDesc* d_descs, int ndesc, int max_jobs, in
 void b2k_launch_ht_encode(const HtBlockDesc* d_blocks, HtBlockOut* d_out, uint8_t* d_scratch, uint32_t nblocks,
                           uint32_t max_w, cudaStream_t st);
 void b2k_launch_ht_gather(const HtBlockDesc* d_blocks, const HtBlockOut* d_out, const uint64_t* d_offsets,
-                          const uint8_t* d_scratch, uint8_t* d_bytes, uint32_t nblocks, cudaStream_t st);
+                          const uint8_t* d_scratch, uint8_t* d_bytes, uint32_t nblocks, uint64_t cap, cudaStream_t st);
 void b2k_launch_scan_lengths(const HtBlockOut* d_out, uint64_t* d_offsets, uint32_t nblocks, cudaStream_t st);
 void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
                           uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st);

@@ -388,6 +388,7 @@ static int build_block_plan(b2k_device_job* J)
     CUDA_TRY(cudaMalloc(&J->d_dec_desc, n * sizeof(HtBlockDesc)));
     CUDA_TRY(cudaMalloc(&J->d_out, n * sizeof(HtBlockOut)));
     CUDA_TRY(cudaMalloc(&J->d_offsets, (n + 1) * sizeof(uint64_t)));
+    CUDA_TRY(cudaMemset(J->d_offsets, 0, (n + 1) * sizeof(uint64_t))); /* offsets[0] stays 0: the scan's base */
     CUDA_TRY(cudaMalloc(&J->d_scratch, J->scratch_bytes + 64));
     CUDA_TRY(cudaMalloc(&J->d_recs, (J->total_quads + 64) * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&J->d_dec_status, n * sizeof(HtBlockOut)));
@@ -627,7 +628,7 @@ static int finish_t1_encode(b2k_device_job* J, cudaStream_t st)
     CUDA_TRY(cudaMalloc(&J->d_bytes, J->bytes_cap));
   }
   J->bytes_used = total;
-  b2k_launch_ht_gather(J->d_enc_desc, J->d_out, J->d_offsets, J->d_scratch, J->d_bytes, n, st);
+  b2k_launch_ht_gather(J->d_enc_desc, J->d_out, J->d_offsets, J->d_scratch, J->d_bytes, n, J->bytes_cap, st);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -808,7 +809,7 @@ static void pool_put(uint8_t* p)
   cudaFreeHost(p);
 }
 
-static int fetch_result(b2k_device_job* J, cudaStream_t st, b2k_result** out)
+static int fetch_result(b2k_device_job* J, cudaStream_t st, b2k_result** out, uint8_t* host_bytes = nullptr)
 {
   const uint32_t n = (uint32_t)J->h_enc_desc.size();
   b2k_result* R = new b2k_result();
@@ -818,7 +819,7 @@ static int fetch_result(b2k_device_job* J, cudaStream_t st, b2k_result** out)
   memcpy(R->blocks, J->blocks.data(), sizeof(b2k_block) * J->blocks.size());
   R->num_bytes = J->bytes_used;
   R->num_tiles = (uint32_t)J->tiles.size();
-  R->bytes = pool_get(std::max<uint64_t>(64, J->bytes_used));
+  R->bytes = host_bytes ? host_bytes : pool_get(std::max<uint64_t>(64, J->bytes_used));
   if(!R->bytes)
   {
     g_err = "cudaHostAlloc(result bytes) failed";
@@ -826,7 +827,8 @@ static int fetch_result(b2k_device_job* J, cudaStream_t st, b2k_result** out)
     delete R;
     return -1;
   }
-  CUDA_TRY(cudaMemcpyAsync(R->bytes, J->d_bytes, J->bytes_used, cudaMemcpyDeviceToHost, st));
+  if(!host_bytes)
+    CUDA_TRY(cudaMemcpyAsync(R->bytes, J->d_bytes, J->bytes_used, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(J->h_out, J->d_out, n * sizeof(HtBlockOut), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(J->h_offsets, J->d_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -920,13 +922,78 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
       CUDA_TRY(cudaEventRecord(J->ev[1], st)); /* all planes on the device */
     if(enqueue_forward(J, st, k == 0, t0, t1)) return -1;
     if(enqueue_t1_blocks(J, st, t0, t1)) return -1;
+    if(J->bytes_cap > 0 && nchunks > 1)
+    {
+      const uint32_t b0 = J->coded_first[t0], b1 = J->coded_first[t1];
+      if(b1 > b0)
+      {
+        b2k_launch_scan_lengths(J->d_out + b0, J->d_offsets + b0, b1 - b0, st);
+        b2k_launch_ht_gather(J->d_enc_desc + b0, J->d_out + b0, J->d_offsets + b0, J->d_scratch, J->d_bytes, b1 - b0,
+                             J->bytes_cap, st);
+      }
+      CUDA_TRY(cudaMemcpyAsync(&J->h_offsets[b1], J->d_offsets + b1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaEventRecord(J->chunk_ev[24 + (k & 7)], st));
+    }
   }
   CUDA_TRY(cudaEventRecord(J->ev[2], st));
-  b2k_launch_scan_lengths(J->d_out, J->d_offsets, (uint32_t)J->h_enc_desc.size(), st);
-  if(finish_t1_encode(J, st)) return -1;
-  CUDA_TRY(cudaEventRecord(J->ev[3], st));
   b2k_result* R = nullptr;
-  if(int frc = fetch_result(J, st, &R)) return frc;
+  const uint32_t nb_all = (uint32_t)J->h_enc_desc.size();
+  bool streamed = false;
+  if(J->bytes_cap > 0 && nchunks > 1)
+  {
+    /* the arena size of the previous call is the estimate: scan + compact + return every chunk's
+       bytes while later chunks are still arriving (the D2H direction of PCIe is otherwise idle) */
+    uint8_t* hb = pool_get(J->bytes_cap);
+    if(!hb)
+    {
+      g_err = "cudaHostAlloc(result bytes) failed";
+      return -1;
+    }
+    cudaStream_t ds = e->h2d_stream; /* third stream: device-to-host here */
+    streamed = true;
+    uint64_t total = 0;
+    bool overflow = false;
+    for(size_t k = 0; k < nchunks; ++k)
+    {
+      const uint32_t b0 = J->coded_first[J->chunk_tile[k]], b1 = J->coded_first[J->chunk_tile[k + 1]];
+      CUDA_TRY(cudaEventSynchronize(J->chunk_ev[24 + (k & 7)]));
+      const uint64_t lo = k == 0 ? 0 : J->h_offsets[b0], hi = J->h_offsets[b1];
+      total = hi;
+      if(hi > J->bytes_cap)
+        overflow = true;
+      else if(hi > lo)
+      {
+        CUDA_TRY(cudaStreamWaitEvent(ds, J->chunk_ev[24 + (k & 7)], 0));
+        CUDA_TRY(cudaMemcpyAsync(hb + lo, J->d_bytes + lo, hi - lo, cudaMemcpyDeviceToHost, ds));
+      }
+    }
+    CUDA_TRY(cudaEventRecord(J->chunk_ev[23], ds));
+    CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[23], 0));
+    J->bytes_used = total;
+    if(overflow)
+    { /* estimate too small: grow, compact everything again from the scratch slots, plain copy */
+      pool_put(hb);
+      CUDA_TRY(cudaStreamSynchronize(st));
+      cudaFree(J->d_bytes);
+      J->bytes_cap = total + total / 8 + 4096;
+      CUDA_TRY(cudaMalloc(&J->d_bytes, J->bytes_cap));
+      b2k_launch_ht_gather(J->d_enc_desc, J->d_out, J->d_offsets, J->d_scratch, J->d_bytes, nb_all, J->bytes_cap, st);
+      CUDA_TRY(cudaEventRecord(J->ev[3], st));
+      if(int frc = fetch_result(J, st, &R)) return frc;
+    }
+    else
+    {
+      CUDA_TRY(cudaEventRecord(J->ev[3], st));
+      if(int frc = fetch_result(J, st, &R, hb)) return frc;
+    }
+  }
+  if(!streamed)
+  {
+    b2k_launch_scan_lengths(J->d_out, J->d_offsets, nb_all, st);
+    if(finish_t1_encode(J, st)) return -1;
+    CUDA_TRY(cudaEventRecord(J->ev[3], st));
+    if(int frc = fetch_result(J, st, &R)) return frc;
+  }
   CUDA_TRY(cudaEventRecord(J->ev[6], st));
   CUDA_TRY(cudaEventSynchronize(J->ev[6]));
   float a = 0, b = 0, c = 0, d = 0;

@@ -597,7 +597,7 @@ __global__ void k_scan_lengths(const HtBlockOut* __restrict__ outs, uint64_t* __
   __shared__ uint64_t partial[1024];
   __shared__ uint64_t carry;
   if(threadIdx.x == 0)
-    carry = 0;
+    carry = offsets[0]; /* running base: 0 for the first range, the previous range's end otherwise */
   __syncthreads();
   for(uint32_t base = 0; base < n; base += 1024)
   {
@@ -631,15 +631,15 @@ __global__ void k_scan_lengths(const HtBlockOut* __restrict__ outs, uint64_t* __
 /* compaction: MagSgn|MEL from the slot head, VLC from the slot tail (warp per block) */
 __global__ void k_ht_gather(const HtBlockDesc* __restrict__ blocks, const HtBlockOut* __restrict__ outs,
                             const uint64_t* __restrict__ offsets, const uint8_t* __restrict__ scratch,
-                            uint8_t* __restrict__ bytes, uint32_t nblocks)
+                            uint8_t* __restrict__ bytes, uint32_t nblocks, uint64_t cap)
 {
   const uint32_t bidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if(bidx >= nblocks)
     return;
   const HtBlockOut o = outs[bidx];
-  if(o.total == 0xFFFFFFFFu)
-    return;
+  if(o.total == 0xFFFFFFFFu || offsets[bidx] + o.total > cap)
+    return; /* arena too small: the host notices from the offsets and re-gathers */
   const uint8_t* slot = scratch + blocks[bidx].slot_off;
   uint8_t* dst = bytes + offsets[bidx];
   const uint32_t front = o.ms_len + o.mel_len;
@@ -678,11 +678,11 @@ void b2k_launch_scan_lengths(const HtBlockOut* d_out, uint64_t* d_offsets, uint3
 }
 
 void b2k_launch_ht_gather(const HtBlockDesc* d_blocks, const HtBlockOut* d_out, const uint64_t* d_offsets,
-                          const uint8_t* d_scratch, uint8_t* d_bytes, uint32_t nblocks, cudaStream_t st)
+                          const uint8_t* d_scratch, uint8_t* d_bytes, uint32_t nblocks, uint64_t cap, cudaStream_t st)
 {
   if(!nblocks)
     return;
   const uint32_t threads = 256, wpb = threads / 32;
-  k_ht_gather<<<(nblocks + wpb - 1) / wpb, threads, 0, st>>>(d_blocks, d_out, d_offsets, d_scratch, d_bytes, nblocks);
+  k_ht_gather<<<(nblocks + wpb - 1) / wpb, threads, 0, st>>>(d_blocks, d_out, d_offsets, d_scratch, d_bytes, nblocks, cap);
   b2k_count_launch();
 }
