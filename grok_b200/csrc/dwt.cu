@@ -1002,13 +1002,11 @@ __device__ __forceinline__ void store_rows97(const DwtLevelDesc& D, const Job& J
   }
 }
 
+/* a resolution one sample wide or high: straightforward, unpipelined path (cold) */
 template <int NC>
-__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtLevelDesc* __restrict__ descs)
+__device__ __noinline__ void inv53_degenerate_job(const DwtLevelDesc* __restrict__ dptr, const Job J)
 {
-  const DwtLevelDesc D = descs[blockIdx.y]; /* by value: fields live in (uniform) registers, not re-read after every store */
-  Job J;
-  if(!decode_job(D, J))
-    return;
+  const DwtLevelDesc& D = *dptr;
   const BandGeom g = band_geom(D);
   int DV[NC][8], EP[NC][8];
 #pragma unroll
@@ -1061,6 +1059,237 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtL
       store_rows53<NC>(D, J, 2 * (t - 1) + 1, Or);
     }
   }
+}
+
+
+/* staged band-row fetch for the inverse kernels: per row pair four band rows (LL|HL, LH|HH) x NC,
+   each lane owning 4 consecutive samples (16 bytes) of each -> one cp.async per lane per band row,
+   512 contiguous bytes per instruction, private slots (no barrier) */
+template <int NC>
+struct BandStage
+{
+  static constexpr int ROWB = 512;
+  static constexpr int PAIRB = 4 * NC * ROWB;
+  struct Lane
+  {
+    bool need;
+    bool fast[4];   /* LL, HL, LH, HH source: 4 samples interior and 16-byte aligned */
+    int col[4];     /* band-relative column of the lane's first sample (low, high) per source */
+    int mlo[4], mhi[4]; /* mirrored band-relative columns for edge lanes */
+  };
+  static __device__ __forceinline__ void setup(const DwtLevelDesc& D, const Job& J, const BandGeom& g, Lane& L)
+  {
+    const int k0 = J.ulane >> 1;
+    L.need = J.need;
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+    {
+      const int ul = D.u0 + mirror_rel(2 * (k0 + i) - D.u0, J.wn), uh = D.u0 + mirror_rel(2 * (k0 + i) + 1 - D.u0, J.wn);
+      L.mlo[i] = (ul >> 1) - g.x0l;
+      L.mhi[i] = (uh >> 1) - g.x0h;
+    }
+    const bool in_lo = 2 * k0 >= D.u0 && 2 * k0 + 6 < D.u1, in_hi = 2 * k0 + 1 >= D.u0 && 2 * k0 + 7 < D.u1;
+    const int clo = k0 - g.x0l, chi = k0 - g.x0h;
+    L.col[0] = clo; L.col[1] = g.snx + chi; L.col[2] = clo; L.col[3] = g.snx + chi;
+    const bool pitch_ok = ((D.ll_pitch | D.c_pitch) & 3u) == 0;
+    L.fast[0] = J.need && pitch_ok && in_lo && (((reinterpret_cast<uintptr_t>(D.out_ll[0]) >> 2) + (unsigned)clo) & 3u) == 0;
+    L.fast[1] = J.need && pitch_ok && in_hi && (((reinterpret_cast<uintptr_t>(D.out_c[0]) >> 2) + (unsigned)(g.snx + chi)) & 3u) == 0;
+    L.fast[2] = J.need && pitch_ok && in_lo && (((reinterpret_cast<uintptr_t>(D.out_c[0]) >> 2) + (unsigned)clo) & 3u) == 0;
+    L.fast[3] = L.fast[1];
+  }
+  /* band rows of pair t into the stage */
+  static __device__ __forceinline__ void fill(uint8_t* stage, const DwtLevelDesc& D, const Job& J, const BandGeom& g,
+                                              const Lane& L, int t)
+  {
+    if(!L.need)
+      return;
+    const int jl = ((D.v0 + mirror_rel(2 * t - D.v0, J.hn)) >> 1), jh = ((D.v0 + mirror_rel(2 * t + 1 - D.v0, J.hn)) >> 1);
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+      const int32_t* src[4];
+      src[0] = reinterpret_cast<const int32_t*>(D.out_ll[c]) + (jl - g.y0l) * (int)D.ll_pitch;
+      src[1] = reinterpret_cast<const int32_t*>(D.out_c[c]) + (jl - g.y0l) * (int)D.c_pitch;
+      src[2] = reinterpret_cast<const int32_t*>(D.out_c[c]) + (g.sny + jh - g.y0h) * (int)D.c_pitch;
+      src[3] = src[2];
+#pragma unroll
+      for(int b = 0; b < 4; ++b)
+      {
+        uint8_t* dst = stage + (b * NC + c) * ROWB + J.lane * 16;
+        if(L.fast[b])
+          cp_async16(dst, src[b] + L.col[b]);
+        else
+        {
+          const int base = (b & 1) ? g.snx : 0;
+#pragma unroll
+          for(int i = 0; i < 4; ++i)
+            cp_async4(dst + 4 * i, src[b] + base + ((b & 1) ? L.mhi[i] : L.mlo[i]));
+        }
+      }
+    }
+  }
+  static __device__ __forceinline__ void read(const uint8_t* stage, const Job& J, int b, int c, int (&v)[4])
+  {
+    const int4 a = *reinterpret_cast<const int4*>(stage + (b * NC + c) * ROWB + J.lane * 16);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  }
+};
+
+/* per-lane constants of the reconstructed-row stores */
+struct OutCtx
+{
+  unsigned m;
+  bool vec;
+  int col;
+};
+__device__ __forceinline__ OutCtx out_ctx(const DwtLevelDesc& D, const Job& J)
+{
+  OutCtx o;
+  o.m = 0;
+  if(J.owner)
+  {
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+      if(J.ulane + i >= D.u0 && J.ulane + i < D.u1)
+        o.m |= 1u << i;
+  }
+  o.col = J.ulane - D.u0;
+  o.vec = o.m == 0xFF && (D.in_pitch & 3u) == 0 && (((reinterpret_cast<uintptr_t>(D.in[0]) >> 2) + (unsigned)o.col) & 3u) == 0;
+  return o;
+}
+template <int NC>
+__device__ __forceinline__ void store_rows53_fast(const DwtLevelDesc& D, const OutCtx& O, int v, int (&x)[NC][8])
+{
+  if(v < D.v0 || v >= D.v1 || O.m == 0)
+    return;
+  if(D.first_level)
+  {
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+    {
+      if(NC == 3)
+      { /* mct.cpp L201-256 */
+        const int y = x[0][i], u = x[NC > 1 ? 1 : 0][i], w = x[NC > 2 ? 2 : 0][i];
+        const int gg = y - ((u + w) >> 2);
+        x[0][i] = w + gg;
+        x[NC > 1 ? 1 : 0][i] = gg;
+        x[NC > 2 ? 2 : 0][i] = u + gg;
+      }
+#pragma unroll
+      for(int c = 0; c < NC; ++c)
+        x[c][i] = min(max(x[c][i] - D.shift[c], D.lo[c]), D.hi[c]);
+    }
+  }
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+  {
+    int32_t* p = reinterpret_cast<int32_t*>(const_cast<void*>(D.in[c])) + ((v - D.v0) * (int)D.in_pitch + O.col);
+    if(O.vec)
+    {
+      reinterpret_cast<int4*>(p)[0] = make_int4(x[c][0], x[c][1], x[c][2], x[c][3]);
+      reinterpret_cast<int4*>(p)[1] = make_int4(x[c][4], x[c][5], x[c][6], x[c][7]);
+    }
+    else
+    {
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+        if(O.m & (1u << i))
+          p[i] = x[c][i];
+    }
+  }
+}
+
+template <bool DEGEN = true>
+__device__ __forceinline__ void hinv53t(const int (&lo)[4], const int (&hi)[4], int (&r)[8])
+{
+  const int dm = __shfl_up_sync(0xffffffffu, hi[3], 1);
+  int e[5];
+  e[0] = lo[0] - ((dm + hi[0] + 2) >> 2);
+  e[1] = lo[1] - ((hi[0] + hi[1] + 2) >> 2);
+  e[2] = lo[2] - ((hi[1] + hi[2] + 2) >> 2);
+  e[3] = lo[3] - ((hi[2] + hi[3] + 2) >> 2);
+  e[4] = __shfl_down_sync(0xffffffffu, e[0], 1);
+#pragma unroll
+  for(int i = 0; i < 4; ++i)
+  {
+    r[2 * i] = e[i];
+    r[2 * i + 1] = hi[i] + ((e[i] + e[i + 1]) >> 1);
+  }
+}
+
+template <int NC, int STAGES>
+__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtLevelDesc* __restrict__ descs)
+{
+  extern __shared__ __align__(16) uint8_t smem_dwt[];
+  typedef BandStage<NC> BS;
+  const DwtLevelDesc D = descs[blockIdx.y]; /* by value: fields live in (uniform) registers */
+  Job J;
+  if(!decode_job(D, J))
+    return;
+  if(J.hn == 1 || J.wn == 1)
+  {
+    inv53_degenerate_job<NC>(descs + blockIdx.y, J);
+    return;
+  }
+  const BandGeom g = band_geom(D);
+  typename BS::Lane L;
+  BS::setup(D, J, g, L);
+  const OutCtx OC = out_ctx(D, J);
+  uint8_t* wsm = smem_dwt + (size_t)(threadIdx.x >> 5) * STAGES * BS::PAIRB;
+
+  const int tfirst = J.jbeg - 1, tlast = J.jend;
+  int tfill = tfirst;
+#pragma unroll
+  for(int s = 0; s < STAGES - 1; ++s)
+  {
+    if(tfill <= tlast)
+      BS::fill(wsm + (size_t)((tfill - tfirst) % STAGES) * BS::PAIRB, D, J, g, L, tfill);
+    cp_async_commit();
+    ++tfill;
+  }
+  int DV[NC][8], EP[NC][8];
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+      DV[c][i] = EP[c][i] = 0;
+
+  for(int t = tfirst; t <= tlast; ++t)
+  {
+    if(tfill <= tlast)
+      BS::fill(wsm + (size_t)((tfill - tfirst) % STAGES) * BS::PAIRB, D, J, g, L, tfill);
+    cp_async_commit();
+    ++tfill;
+    cp_async_wait<STAGES - 1>();
+    const uint8_t* st = wsm + (size_t)((t - tfirst) % STAGES) * BS::PAIRB;
+    int Er[NC][8], Or[NC][8];
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+      int lo[4], hi[4], sv[8], dv[8];
+      BS::read(st, J, 0, c, lo);
+      BS::read(st, J, 1, c, hi);
+      hinv53t<false>(lo, hi, sv);
+      BS::read(st, J, 2, c, lo);
+      BS::read(st, J, 3, c, hi);
+      hinv53t<false>(lo, hi, dv);
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+      {
+        const int e = sv[i] - ((DV[c][i] + dv[i] + 2) >> 2);
+        Or[c][i] = DV[c][i] + ((EP[c][i] + e) >> 1);
+        Er[c][i] = EP[c][i];
+        EP[c][i] = e;
+        DV[c][i] = dv[i];
+      }
+    }
+    if(t - 1 >= J.jbeg)
+    {
+      store_rows53_fast<NC>(D, OC, 2 * (t - 1), Er);
+      store_rows53_fast<NC>(D, OC, 2 * (t - 1) + 1, Or);
+    }
+  }
+  cp_async_wait<0>();
 }
 
 template <int NC>
@@ -1177,6 +1406,19 @@ void b2k_launch_dwt_fwd(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, 
   b2k_count_launch();
 }
 
+template <int NC, int STAGES>
+static void launch_inv53(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
+{
+  const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * BandStage<NC>::PAIRB;
+  static bool once = false;
+  if(!once)
+  {
+    cudaFuncSetAttribute(k_dwt53_inv<NC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    once = true;
+  }
+  k_dwt53_inv<NC, STAGES><<<grid, block, smem, st>>>(d);
+}
+
 void b2k_launch_dwt_inv(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, bool irreversible, cudaStream_t st)
 {
   if(ndesc <= 0 || max_jobs <= 0)
@@ -1184,8 +1426,8 @@ void b2k_launch_dwt_inv(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, 
   dim3 grid((max_jobs + B2K_WARPS_PER_CTA - 1) / B2K_WARPS_PER_CTA, ndesc), block(B2K_WARPS_PER_CTA * 32);
   if(!irreversible)
   {
-    if(nc == 3) k_dwt53_inv<3><<<grid, block, 0, st>>>(d);
-    else k_dwt53_inv<1><<<grid, block, 0, st>>>(d);
+    if(nc == 3) launch_inv53<3, FWD_STAGES>(grid, block, st, d);
+    else launch_inv53<1, FWD_STAGES>(grid, block, st, d);
   }
   else
   {
