@@ -300,13 +300,34 @@ def main():
     clocks = sampler.stop()   # clocks / throttle reasons over both timed regions
     assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "e2e round trip is not lossless"
 
+    # ---------------- same, 16-bit sample containers (b2k_encode16 / b2k_decode16) ----------------
+    p16 = [G.pinned_empty((H, W), np.uint16) for _ in range(NCOMP)]
+    o16 = [G.pinned_empty((H, W), np.uint16) for _ in range(NCOMP)]
+    for p, q in zip(p16, img):
+        p[:] = q
+
+    def e2e16_step():
+        res = eng.encode(cp, p16)
+        eng.decode(cp, res.blocks, res.bytes, o16)
+        res.free()
+
+    for _ in range(2):
+        e2e16_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e16_step()
+    barrier()
+    dt_e2e16 = time.perf_counter() - t0
+    assert all(np.array_equal(a, b) for a, b in zip(o16, p16)), "16-bit e2e round trip is not lossless"
+
     # max over ranks
-    times = torch.tensor([dt_dev, dt_e2e], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dt_dev, dt_e2e, dt_e2e16], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
         dist.all_gather(sizes, torch.tensor([nb], dtype=torch.int64, device="cuda"))  # codestream segment sizes
-    dt_dev, dt_e2e = float(times[0]), float(times[1])
+    dt_dev, dt_e2e, dt_e2e16 = float(times[0]), float(times[1]), float(times[2])
 
     if rank == 0:
         pix = W * H * world
@@ -329,7 +350,10 @@ def main():
                                     "ht_decode": stage[2] / args.steps, "inv_dwt_mct": stage[3] / args.steps}},
             "e2e": {"value": e2e_val, "unit": "Mpixels/s", "ms_per_step": dt_e2e / args.steps * 1e3,
                     "h2d_bytes_per_step": int(img_bytes + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes + nb + nbk * 24),
-                    "api": "b2k_encode + b2k_decode (include/grok_b200.h), pinned host planes"},
+                    "api": "b2k_encode + b2k_decode (include/grok_b200.h), pinned host int32 planes (the gpup_image layout)"},
+            "e2e_u16": {"value": pix / (dt_e2e16 / args.steps) / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_e2e16 / args.steps * 1e3,
+                        "h2d_bytes_per_step": int(img_bytes // 2 + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes // 2 + nb + nbk * 24),
+                        "api": "b2k_encode16 + b2k_decode16: same path, 16-bit sample containers (cf. gpup_batch_memory_submit_planes)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_dwt53_fwd<3> (DC shift + RCT + level-1 5/3, all 64 tiles x 3 comps)",

@@ -57,7 +57,7 @@ assert BLOCK_DTYPE.itemsize == C.sizeof(Block), (BLOCK_DTYPE.itemsize, C.sizeof(
 # every symbol include/grok_b200.h declares
 EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "gpup_encode_mem", "gpup_tile_free",
            "b2k_engine_create", "b2k_engine_destroy", "b2k_last_error", "b2k_host_alloc", "b2k_host_free",
-           "b2k_encode", "b2k_encode16", "b2k_result_free", "b2k_decode", "b2k_enumerate",
+           "b2k_encode", "b2k_encode16", "b2k_result_free", "b2k_decode", "b2k_decode16", "b2k_enumerate",
            "b2k_result_to_gpup_tile", "b2k_job_create", "b2k_job_destroy", "b2k_job_upload", "b2k_job_forward",
            "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_inverse", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
@@ -84,9 +84,11 @@ def lib():
     L.b2k_host_alloc.restype = vp
     L.b2k_host_free.argtypes = [vp]
     L.b2k_encode.argtypes = [vp, C.POINTER(Coding), pp, C.POINTER(u32), u32, u32, C.POINTER(C.POINTER(Result))]
+    L.b2k_encode16.argtypes = L.b2k_encode.argtypes
     L.b2k_result_free.argtypes = [C.POINTER(Result)]
     L.b2k_decode.argtypes = [vp, C.POINTER(Coding), vp, u64, vp, u64, pp, C.POINTER(u32), u32, u32,
                              C.POINTER(C.c_double)]
+    L.b2k_decode16.argtypes = L.b2k_decode.argtypes
     L.b2k_enumerate.argtypes = [C.POINTER(Coding), u32, u32, vp, u64]
     L.b2k_enumerate.restype = C.c_int64
     L.b2k_result_to_gpup_tile.argtypes = [C.POINTER(Coding), C.POINTER(Result), u32]
@@ -199,10 +201,12 @@ class Engine:
             self._h = C.c_void_p()
 
     def encode(self, cp, planes, tile_mod=1, tile_rem=0):
-        """planes: list of 2-D int32 arrays (row stride may exceed width)."""
+        """planes: list of 2-D int32 arrays (row stride may exceed width), or uint16 / int16 arrays
+        (16-bit containers, b2k_encode16)."""
         ptrs, strides = _plane_ptrs(planes)
         out = C.POINTER(Result)()
-        _check(lib().b2k_encode(self._h, C.byref(cp), ptrs, strides, tile_mod, tile_rem, C.byref(out)), "b2k_encode")
+        fn = "b2k_encode16" if planes[0].itemsize == 2 else "b2k_encode"
+        _check(getattr(lib(), fn)(self._h, C.byref(cp), ptrs, strides, tile_mod, tile_rem, C.byref(out)), fn)
         return EncodeResult(out)
 
     def decode(self, cp, blocks, data, out_planes, tile_mod=1, tile_rem=0):
@@ -210,8 +214,9 @@ class Engine:
         blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
         data = np.ascontiguousarray(data, dtype=np.uint8)
         ms = C.c_double()
-        _check(lib().b2k_decode(self._h, C.byref(cp), blocks.ctypes.data, len(blocks), data.ctypes.data, len(data),
-                                ptrs, strides, tile_mod, tile_rem, C.byref(ms)), "b2k_decode")
+        fn = "b2k_decode16" if out_planes[0].itemsize == 2 else "b2k_decode"
+        _check(getattr(lib(), fn)(self._h, C.byref(cp), blocks.ctypes.data, len(blocks), data.ctypes.data, len(data),
+                                  ptrs, strides, tile_mod, tile_rem, C.byref(ms)), fn)
         return ms.value
 
     def job(self, cp, tile_mod=1, tile_rem=0):

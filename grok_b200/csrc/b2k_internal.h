@@ -26,8 +26,9 @@ struct DwtLevelDesc
   int32_t lo[3], hi[3];/* inverse: clamp range after the shift is restored */
   uint16_t nstrips, nsegs, strip_w, pairs_per_seg;
   uint8_t first_level; /* 1: samples are integers from the image (apply shift / MCT) */
-  uint8_t in_is_u16;
-  uint8_t pad[2];
+  uint8_t in_is_u16;   /* finest level only: 0 = 32-bit samples, 1 = uint16, 2 = int16 containers */
+  uint8_t comp0;       /* first component this descriptor covers */
+  uint8_t pad;
 };
 
 /* ---- one code block for the HT coder kernels ------------------------------------------------
@@ -56,7 +57,7 @@ struct HtBlockOut /* written by the encoder kernel */
 /* kernel launchers (dwt.cu, ht_enc.cu, ht_dec.cu) */
 void b2k_launch_dwt_fwd(const DwtLevelDesc* d_descs, int ndesc, int max_jobs, int nc, bool irreversible,
                         bool in_u16, cudaStream_t st);
-void b2k_launch_dwt_inv(const DwtLevelDesc* d_descs, int ndesc, int max_jobs, int nc, bool irreversible,
+void b2k_launch_dwt_inv(const DwtLevelDesc* d_descs, int ndesc, int max_jobs, int nc, bool irreversible, bool out_u16,
                         cudaStream_t st);
 void b2k_launch_ht_encode(const HtBlockDesc* d_blocks, HtBlockOut* d_out, uint8_t* d_scratch, uint32_t nblocks,
                           uint32_t max_w, cudaStream_t st);
@@ -65,4 +66,12 @@ void b2k_launch_ht_gather(const HtBlockDesc* d_blocks, const HtBlockOut* d_out, 
 void b2k_launch_scan_lengths(const HtBlockOut* d_out, uint64_t* d_offsets, uint32_t nblocks, cudaStream_t st);
 void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
                           uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st);
+void b2k_launch_ht_decode_vlc(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
+                              uint32_t nblocks, cudaStream_t st);
+void b2k_launch_ht_decode_magsgn(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, const uint32_t* d_recs,
+                                 const HtBlockOut* d_status, uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st);
+void b2k_launch_widen16(const uint16_t* src, uint32_t spitch, int32_t* dst, uint32_t dpitch, uint32_t w, uint32_t h, int sgnd,
+                        cudaStream_t st);
+void b2k_launch_narrow16(const int32_t* src, uint32_t spitch, uint16_t* dst, uint32_t dpitch, uint32_t w, uint32_t h,
+                         cudaStream_t st);
 void b2k_count_launch(void);

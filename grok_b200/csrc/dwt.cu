@@ -1142,6 +1142,7 @@ struct OutCtx
   bool vec;
   int col;
 };
+template <bool OUT16 = false>
 __device__ __forceinline__ OutCtx out_ctx(const DwtLevelDesc& D, const Job& J)
 {
   OutCtx o;
@@ -1154,10 +1155,13 @@ __device__ __forceinline__ OutCtx out_ctx(const DwtLevelDesc& D, const Job& J)
         o.m |= 1u << i;
   }
   o.col = J.ulane - D.u0;
-  o.vec = o.m == 0xFF && (D.in_pitch & 3u) == 0 && (((reinterpret_cast<uintptr_t>(D.in[0]) >> 2) + (unsigned)o.col) & 3u) == 0;
+  if(OUT16)
+    o.vec = o.m == 0xFF && (D.in_pitch & 7u) == 0 && (((reinterpret_cast<uintptr_t>(D.in[0]) >> 1) + (unsigned)o.col) & 7u) == 0;
+  else
+    o.vec = o.m == 0xFF && (D.in_pitch & 3u) == 0 && (((reinterpret_cast<uintptr_t>(D.in[0]) >> 2) + (unsigned)o.col) & 3u) == 0;
   return o;
 }
-template <int NC>
+template <int NC, bool OUT16 = false>
 __device__ __forceinline__ void store_rows53_fast(const DwtLevelDesc& D, const OutCtx& O, int v, int (&x)[NC][8])
 {
   if(v < D.v0 || v >= D.v1 || O.m == 0)
@@ -1183,6 +1187,21 @@ __device__ __forceinline__ void store_rows53_fast(const DwtLevelDesc& D, const O
 #pragma unroll
   for(int c = 0; c < NC; ++c)
   {
+    if(OUT16)
+    { /* 16-bit sample containers: the clamped value fits, two's complement for signed data */
+      uint16_t* q = reinterpret_cast<uint16_t*>(const_cast<void*>(D.in[c])) + ((v - D.v0) * (int)D.in_pitch + O.col);
+      if(O.vec)
+        *reinterpret_cast<uint4*>(q) = make_uint4((x[c][0] & 0xFFFF) | (x[c][1] << 16), (x[c][2] & 0xFFFF) | (x[c][3] << 16),
+                                                  (x[c][4] & 0xFFFF) | (x[c][5] << 16), (x[c][6] & 0xFFFF) | (x[c][7] << 16));
+      else
+      {
+#pragma unroll
+        for(int i = 0; i < 8; ++i)
+          if(O.m & (1u << i))
+            q[i] = (uint16_t)x[c][i];
+      }
+      continue;
+    }
     int32_t* p = reinterpret_cast<int32_t*>(const_cast<void*>(D.in[c])) + ((v - D.v0) * (int)D.in_pitch + O.col);
     if(O.vec)
     {
@@ -1217,7 +1236,7 @@ __device__ __forceinline__ void hinv53t(const int (&lo)[4], const int (&hi)[4], 
   }
 }
 
-template <int NC, int STAGES>
+template <int NC, int STAGES, bool OUT16>
 __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtLevelDesc* __restrict__ descs)
 {
   extern __shared__ __align__(16) uint8_t smem_dwt[];
@@ -1226,7 +1245,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtL
   Job J;
   if(!decode_job(D, J))
     return;
-  if(J.hn == 1 || J.wn == 1)
+  if((J.hn == 1 || J.wn == 1) && !OUT16)
   {
     inv53_degenerate_job<NC>(descs + blockIdx.y, J);
     return;
@@ -1234,7 +1253,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtL
   const BandGeom g = band_geom(D);
   typename BS::Lane L;
   BS::setup(D, J, g, L);
-  const OutCtx OC = out_ctx(D, J);
+  const OutCtx OC = out_ctx<OUT16>(D, J);
   uint8_t* wsm = smem_dwt + (size_t)(threadIdx.x >> 5) * STAGES * BS::PAIRB;
 
   const int tfirst = J.jbeg - 1, tlast = J.jend;
@@ -1285,8 +1304,8 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtL
     }
     if(t - 1 >= J.jbeg)
     {
-      store_rows53_fast<NC>(D, OC, 2 * (t - 1), Er);
-      store_rows53_fast<NC>(D, OC, 2 * (t - 1) + 1, Or);
+      store_rows53_fast<NC, OUT16>(D, OC, 2 * (t - 1), Er);
+      store_rows53_fast<NC, OUT16>(D, OC, 2 * (t - 1) + 1, Or);
     }
   }
   cp_async_wait<0>();
@@ -1355,7 +1374,74 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_inv(const DwtL
   }
 }
 
+/* 16-bit sample containers <-> the engine's 32-bit planes: one rectangle (a merged tile row) per
+   launch, 8 samples per thread, 128-bit accesses.  Costs 6 B/sample of HBM traffic -- noise next to
+   the PCIe transfer it halves. */
+__global__ void k_widen16(const uint16_t* __restrict__ src, uint32_t spitch, int32_t* __restrict__ dst, uint32_t dpitch,
+                          uint32_t w, uint32_t h, int sgnd)
+{
+  const uint32_t x8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8, y = blockIdx.y;
+  if(x8 >= w || y >= h)
+    return;
+  const uint16_t* s = src + (size_t)y * spitch + x8;
+  int32_t* d = dst + (size_t)y * dpitch + x8;
+  if(x8 + 8 <= w && ((reinterpret_cast<uintptr_t>(s) & 15) == 0) && ((reinterpret_cast<uintptr_t>(d) & 15) == 0))
+  {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(s));
+    int v[8] = {(int)(a.x & 0xFFFF), (int)(a.x >> 16), (int)(a.y & 0xFFFF), (int)(a.y >> 16),
+                (int)(a.z & 0xFFFF), (int)(a.z >> 16), (int)(a.w & 0xFFFF), (int)(a.w >> 16)};
+    if(sgnd)
+    {
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+        v[i] = (int)(int16_t)v[i];
+    }
+    reinterpret_cast<int4*>(d)[0] = make_int4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<int4*>(d)[1] = make_int4(v[4], v[5], v[6], v[7]);
+  }
+  else
+    for(uint32_t i = 0; i < 8 && x8 + i < w; ++i)
+      d[i] = sgnd ? (int)(int16_t)s[i] : (int)s[i];
+}
+__global__ void k_narrow16(const int32_t* __restrict__ src, uint32_t spitch, uint16_t* __restrict__ dst, uint32_t dpitch,
+                           uint32_t w, uint32_t h)
+{
+  const uint32_t x8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8, y = blockIdx.y;
+  if(x8 >= w || y >= h)
+    return;
+  const int32_t* s = src + (size_t)y * spitch + x8;
+  uint16_t* d = dst + (size_t)y * dpitch + x8;
+  if(x8 + 8 <= w && ((reinterpret_cast<uintptr_t>(s) & 15) == 0) && ((reinterpret_cast<uintptr_t>(d) & 15) == 0))
+  {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(s)), b = __ldg(reinterpret_cast<const int4*>(s) + 1);
+    *reinterpret_cast<uint4*>(d) = make_uint4((a.x & 0xFFFF) | (a.y << 16), (a.z & 0xFFFF) | (a.w << 16),
+                                              (b.x & 0xFFFF) | (b.y << 16), (b.z & 0xFFFF) | (b.w << 16));
+  }
+  else
+    for(uint32_t i = 0; i < 8 && x8 + i < w; ++i)
+      d[i] = (uint16_t)s[i];
+}
+
 } /* namespace */
+
+void b2k_launch_widen16(const uint16_t* src, uint32_t spitch, int32_t* dst, uint32_t dpitch, uint32_t w, uint32_t h, int sgnd,
+                        cudaStream_t st)
+{
+  if(!w || !h)
+    return;
+  dim3 grid((w + 8 * 128 - 1) / (8 * 128), h), block(128);
+  k_widen16<<<grid, block, 0, st>>>(src, spitch, dst, dpitch, w, h, sgnd);
+  b2k_count_launch();
+}
+void b2k_launch_narrow16(const int32_t* src, uint32_t spitch, uint16_t* dst, uint32_t dpitch, uint32_t w, uint32_t h,
+                         cudaStream_t st)
+{
+  if(!w || !h)
+    return;
+  dim3 grid((w + 8 * 128 - 1) / (8 * 128), h), block(128);
+  k_narrow16<<<grid, block, 0, st>>>(src, spitch, dst, dpitch, w, h);
+  b2k_count_launch();
+}
 
 constexpr int FWD_STAGES = 3;
 template <int NC, bool U16, int STAGES>
@@ -1406,28 +1492,37 @@ void b2k_launch_dwt_fwd(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, 
   b2k_count_launch();
 }
 
-template <int NC, int STAGES>
+template <int NC, int STAGES, bool OUT16>
 static void launch_inv53(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
 {
   const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * BandStage<NC>::PAIRB;
   static bool once = false;
   if(!once)
   {
-    cudaFuncSetAttribute(k_dwt53_inv<NC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_dwt53_inv<NC, STAGES, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     once = true;
   }
-  k_dwt53_inv<NC, STAGES><<<grid, block, smem, st>>>(d);
+  k_dwt53_inv<NC, STAGES, OUT16><<<grid, block, smem, st>>>(d);
 }
 
-void b2k_launch_dwt_inv(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, bool irreversible, cudaStream_t st)
+void b2k_launch_dwt_inv(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, bool irreversible, bool out_u16,
+                        cudaStream_t st)
 {
   if(ndesc <= 0 || max_jobs <= 0)
     return;
   dim3 grid((max_jobs + B2K_WARPS_PER_CTA - 1) / B2K_WARPS_PER_CTA, ndesc), block(B2K_WARPS_PER_CTA * 32);
   if(!irreversible)
   {
-    if(nc == 3) launch_inv53<3, FWD_STAGES>(grid, block, st, d);
-    else launch_inv53<1, FWD_STAGES>(grid, block, st, d);
+    if(out_u16)
+    { /* finest level straight into 16-bit containers (widths of 1 are not supported there: the engine checks) */
+      if(nc == 3) launch_inv53<3, FWD_STAGES, true>(grid, block, st, d);
+      else launch_inv53<1, FWD_STAGES, true>(grid, block, st, d);
+    }
+    else
+    {
+      if(nc == 3) launch_inv53<3, FWD_STAGES, false>(grid, block, st, d);
+      else launch_inv53<1, FWD_STAGES, false>(grid, block, st, d);
+    }
   }
   else
   {

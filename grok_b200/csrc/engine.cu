@@ -49,6 +49,7 @@ struct b2k_engine
 {
   int device = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr, h2d_stream = nullptr;
+  cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr}; /* latency-bound side kernels run concurrently here */
   cudaDeviceProp prop{};
 };
 
@@ -75,6 +76,15 @@ static int alloc_planes(Planes& p, int n, uint32_t cx0, uint32_t cy0, uint32_t c
   return 0;
 }
 
+struct Planes16
+{
+  uint16_t* base = nullptr;
+  uint32_t pitch = 0, rows = 0, X0 = 0, Y0 = 0;
+  int n = 0;
+  size_t plane_elems() const { return (size_t)pitch * rows; }
+  uint16_t* at(int c, uint32_t x, uint32_t y) const { return base + (size_t)c * plane_elems() + (size_t)(y - Y0) * pitch + (x - X0); }
+};
+
 struct LevelLaunch
 {
   std::vector<DwtLevelDesc> descs;
@@ -98,11 +108,13 @@ struct b2k_device_job
   std::vector<float> dec_quant;        /* per coded block: decoder step / 2^(31-Kmax) */
   std::vector<uint32_t> coded_first;   /* coded blocks of selected tile ti are [coded_first[ti], coded_first[ti+1]) */
   std::vector<uint32_t> chunk_tile;    /* pipeline chunks: selected tiles [chunk_tile[k], chunk_tile[k+1]) */
-  cudaEvent_t chunk_ev[32]{};
+  cudaEvent_t chunk_ev[48]{};
   uint32_t max_cblk_w = 0;
 
   Planes img, coef, ll[2];
+  Planes16 img16;                      /* 16-bit sample containers (b2k_encode16 / b2k_decode16), lazily */
   std::vector<LevelLaunch> fwd, inv;   /* launch order */
+  std::vector<LevelLaunch> fwd16, inv16; /* finest-level launches re-pointed at img16 (parallel to fwd / inv) */
   HtBlockDesc* d_enc_desc = nullptr;
   HtBlockDesc* d_dec_desc = nullptr;
   std::vector<HtBlockDesc> h_enc_desc;
@@ -155,6 +167,8 @@ extern "C" int32_t b2k_engine_create(int32_t device, b2k_engine** out)
   CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&eng->h2d_stream, cudaStreamNonBlocking));
+  for(cudaStream_t& a : eng->aux)
+    CUDA_TRY(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
   *out = eng;
   return 0;
 }
@@ -170,6 +184,9 @@ extern "C" void b2k_engine_destroy(b2k_engine* e)
     cudaStreamDestroy(e->copy_stream);
   if(e->h2d_stream)
     cudaStreamDestroy(e->h2d_stream);
+  for(cudaStream_t a : e->aux)
+    if(a)
+      cudaStreamDestroy(a);
   delete e;
 }
 
@@ -268,6 +285,7 @@ static int build_dwt_plan(b2k_device_job* J)
           d.u0 = (int32_t)r.x0; d.v0 = (int32_t)r.y0; d.u1 = (int32_t)r.x1; d.v1 = (int32_t)r.y1;
           d.first_level = lvl == 1;
           d.in_is_u16 = 0;
+          d.comp0 = (uint8_t)c;
           const uint32_t llx = (r.x0 + 1) >> 1, lly = (r.y0 + 1) >> 1;
           for(int k = 0; k < nc; ++k)
           {
@@ -463,6 +481,9 @@ extern "C" void b2k_job_destroy(b2k_device_job* J)
   cudaSetDevice(J->eng->device);
   cudaStreamSynchronize(J->eng->stream);
   cudaFree(J->img.base);
+  cudaFree(J->img16.base);
+  for(LevelLaunch& L : J->fwd16) cudaFree(L.d_descs);
+  for(LevelLaunch& L : J->inv16) cudaFree(L.d_descs);
   cudaFree(J->coef.base);
   cudaFree(J->ll[0].base);
   cudaFree(J->ll[1].base);
@@ -556,19 +577,107 @@ extern "C" int32_t b2k_job_upload_coeffs(b2k_device_job* J, const int32_t* const
   return 0;
 }
 
+
+/* ---- 16-bit sample containers ---------------------------------------------------------------- */
+static int ensure_u16(b2k_device_job* J)
+{
+  if(J->img16.base)
+    return 0;
+  const b2k_coding& cp = J->cp;
+  Planes16& P = J->img16;
+  P.n = cp.numcomps;
+  P.X0 = cp.x0 & ~63u;
+  P.Y0 = cp.y0;
+  P.pitch = ((cp.x1 - P.X0) + 7u) & ~7u; /* no slack: a full-width tile row is one contiguous block */
+  P.rows = (cp.y1 - cp.y0) + 2;
+  CUDA_TRY(cudaMalloc(&P.base, (size_t)P.n * P.plane_elems() * sizeof(uint16_t)));
+  CUDA_TRY(cudaMemset(P.base, 0, (size_t)P.n * P.plane_elems() * sizeof(uint16_t)));
+  return 0;
+}
+
+/* widen (after H2D) or narrow (before D2H) the rectangles of selected tiles [t0, t1) */
+static int convert_planes16(b2k_device_job* J, bool widen, cudaStream_t st, size_t t0, size_t t1)
+{
+  const b2k_coding& cp = J->cp;
+  t1 = std::min(t1, J->tiles.size());
+  for(size_t ti = t0; ti < t1;)
+  {
+    Rect r = J->tile_rects[ti];
+    size_t tj = ti + 1;
+    while(tj < t1 && J->tile_rects[tj].y0 == r.y0 && J->tile_rects[tj].y1 == r.y1 && J->tile_rects[tj].x0 == r.x1)
+    {
+      r.x1 = J->tile_rects[tj].x1;
+      ++tj;
+    }
+    for(int c = 0; c < cp.numcomps; ++c)
+    {
+      if(widen)
+        b2k_launch_widen16(J->img16.at(c, r.x0, r.y0), J->img16.pitch, J->img.at(c, r.x0, r.y0), J->img.pitch, r.w(), r.h(),
+                           cp.sgnd, st);
+      else
+        b2k_launch_narrow16(J->img.at(c, r.x0, r.y0), J->img.pitch, J->img16.at(c, r.x0, r.y0), J->img16.pitch, r.w(), r.h(), st);
+    }
+    ti = tj;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int copy_planes16(b2k_device_job* J, void* const* host, const uint32_t* strides, bool to_device, cudaStream_t st,
+                         size_t t0, size_t t1)
+{
+  const b2k_coding& cp = J->cp;
+  const Planes16& P = J->img16;
+  t1 = std::min(t1, J->tiles.size());
+  for(size_t ti = t0; ti < t1;)
+  {
+    Rect r = J->tile_rects[ti];
+    size_t tj = ti + 1;
+    while(tj < t1 && J->tile_rects[tj].y0 == r.y0 && J->tile_rects[tj].y1 == r.y1 && J->tile_rects[tj].x0 == r.x1)
+    {
+      r.x1 = J->tile_rects[tj].x1;
+      ++tj;
+    }
+    for(int c = 0; c < cp.numcomps; ++c)
+    {
+      uint16_t* dev = P.at(c, r.x0, r.y0);
+      uint16_t* hst = reinterpret_cast<uint16_t*>(host[c]) + (size_t)(r.y0 - cp.y0) * strides[c] + (r.x0 - cp.x0);
+      if(strides[c] == P.pitch && r.w() == P.pitch)
+      { /* contiguous on both sides: one linear copy */
+        if(to_device)
+          CUDA_TRY(cudaMemcpyAsync(dev, hst, (size_t)r.w() * r.h() * 2, cudaMemcpyHostToDevice, st));
+        else
+          CUDA_TRY(cudaMemcpyAsync(hst, dev, (size_t)r.w() * r.h() * 2, cudaMemcpyDeviceToHost, st));
+        continue;
+      }
+      if(to_device)
+        CUDA_TRY(cudaMemcpy2DAsync(dev, (size_t)P.pitch * 2, hst, (size_t)strides[c] * 2, (size_t)r.w() * 2, r.h(),
+                                   cudaMemcpyHostToDevice, st));
+      else
+        CUDA_TRY(cudaMemcpy2DAsync(hst, (size_t)strides[c] * 2, dev, (size_t)P.pitch * 2, (size_t)r.w() * 2, r.h(),
+                                   cudaMemcpyDeviceToHost, st));
+    }
+    ti = tj;
+  }
+  return 0;
+}
+
 /* ---- stages ----------------------------------------------------------------------------------- */
-static int enqueue_forward(b2k_device_job* J, cudaStream_t st, bool time_level1, size_t t0 = 0, size_t t1 = (size_t)-1)
+static int enqueue_forward(b2k_device_job* J, cudaStream_t st, bool time_level1, size_t t0 = 0, size_t t1 = (size_t)-1,
+                           bool use16 = false)
 {
   t1 = std::min(t1, J->tiles.size());
   bool first = true;
-  for(LevelLaunch& L : J->fwd)
+  for(size_t li = 0; li < J->fwd.size(); ++li)
   {
+    const bool l16 = false;
+    (void)use16;
+    LevelLaunch& L = J->fwd[li];
     const uint32_t d0 = L.tile_first[t0], d1 = L.tile_first[t1];
     if(first && time_level1)
       CUDA_TRY(cudaEventRecord(J->ev[4], st));
     if(d1 > d0)
-      b2k_launch_dwt_fwd(L.d_descs + d0, (int)(d1 - d0), L.max_jobs, L.nc, J->cp.irreversible,
-                         J->img_is_u16 && L.descs[0].first_level, st);
+      b2k_launch_dwt_fwd(L.d_descs + d0, (int)(d1 - d0), L.max_jobs, L.nc, J->cp.irreversible, l16, st);
     if(first && time_level1)
     {
       CUDA_TRY(cudaEventRecord(J->ev[5], st));
@@ -580,14 +689,17 @@ static int enqueue_forward(b2k_device_job* J, cudaStream_t st, bool time_level1,
   return 0;
 }
 
-static int enqueue_inverse(b2k_device_job* J, cudaStream_t st, size_t t0 = 0, size_t t1 = (size_t)-1)
+static int enqueue_inverse(b2k_device_job* J, cudaStream_t st, size_t t0 = 0, size_t t1 = (size_t)-1, bool use16 = false)
 {
   t1 = std::min(t1, J->tiles.size());
-  for(LevelLaunch& L : J->inv)
+  for(size_t li = 0; li < J->inv.size(); ++li)
   {
+    const bool l16 = false;
+    (void)use16;
+    LevelLaunch& L = J->inv[li];
     const uint32_t d0 = L.tile_first[t0], d1 = L.tile_first[t1];
     if(d1 > d0)
-      b2k_launch_dwt_inv(L.d_descs + d0, (int)(d1 - d0), L.max_jobs, L.nc, J->cp.irreversible, st);
+      b2k_launch_dwt_inv(L.d_descs + d0, (int)(d1 - d0), L.max_jobs, L.nc, J->cp.irreversible, l16, st);
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -895,7 +1007,7 @@ static b2k_device_job* cached_job(b2k_engine* e, const b2k_coding* cp, uint32_t 
 }
 
 static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* planes, const uint32_t* strides,
-                             uint32_t mod, uint32_t rem, b2k_result** out)
+                             uint32_t mod, uint32_t rem, b2k_result** out, bool u16)
 {
   if(!e || !cp || !planes || !strides || !out)
     return -1;
@@ -905,6 +1017,9 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
   if(rc)
     return rc;
   CUDA_TRY(cudaSetDevice(e->device));
+  if(u16)
+    if(int urc = ensure_u16(J))
+      return urc;
   cudaStream_t st = e->stream;
   /* software pipeline over tile chunks: chunk k+1 crosses PCIe on the copy stream while chunk k
      is transformed and block-coded on the compute stream */
@@ -915,11 +1030,13 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
   for(size_t k = 0; k < nchunks; ++k)
   {
     const size_t t0 = J->chunk_tile[k], t1 = J->chunk_tile[k + 1];
-    if(copy_planes(J, J->img, planes, strides, true, cs, t0, t1)) return -1;
+    if(u16 ? copy_planes16(J, planes, strides, true, cs, t0, t1) : copy_planes(J, J->img, planes, strides, true, cs, t0, t1))
+      return -1;
     CUDA_TRY(cudaEventRecord(J->chunk_ev[k], cs));
     CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[k], 0));
     if(k == nchunks - 1)
       CUDA_TRY(cudaEventRecord(J->ev[1], st)); /* all planes on the device */
+    if(u16 && convert_planes16(J, true, st, t0, t1)) return -1;
     if(enqueue_forward(J, st, k == 0, t0, t1)) return -1;
     if(enqueue_t1_blocks(J, st, t0, t1)) return -1;
     if(J->bytes_cap > 0 && nchunks > 1)
@@ -1010,19 +1127,37 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
 extern "C" int32_t b2k_encode(b2k_engine* e, const b2k_coding* cp, const int32_t* const* planes, const uint32_t* strides,
                               uint32_t tile_mod, uint32_t tile_rem, b2k_result** out)
 {
-  return encode_common(e, cp, (void* const*)planes, strides, tile_mod, tile_rem, out);
+  return encode_common(e, cp, (void* const*)planes, strides, tile_mod, tile_rem, out, false);
 }
 
-extern "C" int32_t b2k_encode16(b2k_engine*, const b2k_coding*, const uint16_t* const*, const uint32_t*, uint32_t, uint32_t,
-                                b2k_result**)
+extern "C" int32_t b2k_encode16(b2k_engine* e, const b2k_coding* cp, const uint16_t* const* planes, const uint32_t* strides,
+                                uint32_t tile_mod, uint32_t tile_rem, b2k_result** out)
 {
-  g_err = "b2k_encode16: 16-bit containers are not wired up yet";
-  return 1;
+  return encode_common(e, cp, (void* const*)planes, strides, tile_mod, tile_rem, out, true);
 }
+
+static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks, uint64_t num_blocks,
+                             const uint8_t* bytes, uint64_t num_bytes, void* const* planes, const uint32_t* strides,
+                             uint32_t tile_mod, uint32_t tile_rem, double* ms_total, bool u16);
 
 extern "C" int32_t b2k_decode(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks, uint64_t num_blocks,
                               const uint8_t* bytes, uint64_t num_bytes, int32_t* const* planes, const uint32_t* strides,
                               uint32_t tile_mod, uint32_t tile_rem, double* ms_total)
+{
+  return decode_common(e, cp, blocks, num_blocks, bytes, num_bytes, (void* const*)planes, strides, tile_mod, tile_rem,
+                       ms_total, false);
+}
+extern "C" int32_t b2k_decode16(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks, uint64_t num_blocks,
+                                const uint8_t* bytes, uint64_t num_bytes, uint16_t* const* planes, const uint32_t* strides,
+                                uint32_t tile_mod, uint32_t tile_rem, double* ms_total)
+{
+  return decode_common(e, cp, blocks, num_blocks, bytes, num_bytes, (void* const*)planes, strides, tile_mod, tile_rem,
+                       ms_total, true);
+}
+
+static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks, uint64_t num_blocks,
+                             const uint8_t* bytes, uint64_t num_bytes, void* const* planes, const uint32_t* strides,
+                             uint32_t tile_mod, uint32_t tile_rem, double* ms_total, bool u16)
 {
   if(!e || !cp || !blocks || !planes || !strides)
     return -1;
@@ -1032,6 +1167,9 @@ extern "C" int32_t b2k_decode(b2k_engine* e, const b2k_coding* cp, const b2k_blo
   if(rc)
     return rc;
   CUDA_TRY(cudaSetDevice(e->device));
+  if(u16)
+    if(int urc = ensure_u16(J))
+      return urc;
   cudaStream_t st = e->stream;
   if(num_bytes + 64 > J->bytes_cap)
   {
@@ -1055,7 +1193,9 @@ extern "C" int32_t b2k_decode(b2k_engine* e, const b2k_coding* cp, const b2k_blo
   {
     const size_t t0 = J->chunk_tile[k], t1 = J->chunk_tile[k + 1];
     const uint32_t b0 = J->coded_first[t0], b1 = J->coded_first[t1];
-    if(int prc = prepare_decode(J, blocks, num_blocks, st, b0, b1)) return prc;
+    /* descriptors travel on the upload stream with the chunk's bytes, so the side-stream parse of
+       chunk k+1 depends on nothing the main stream is still doing for chunk k */
+    if(int prc = prepare_decode(J, blocks, num_blocks, e->h2d_stream, b0, b1)) return prc;
     uint64_t lo = UINT64_MAX, hi = 0;
     for(uint32_t b = b0; b < b1; ++b)
     {
@@ -1074,26 +1214,36 @@ extern "C" int32_t b2k_decode(b2k_engine* e, const b2k_coding* cp, const b2k_blo
     {
       if(lo < prev_end)
       { /* arena not in block order: upload what is left in one go */
-        CUDA_TRY(cudaMemcpyAsync(J->d_bytes + prev_end, bytes + prev_end, num_bytes - prev_end, cudaMemcpyHostToDevice, st));
-        if(prev_end > 0)
-          CUDA_TRY(cudaMemcpyAsync(J->d_bytes, bytes, prev_end, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(J->d_bytes + prev_end, bytes + prev_end, num_bytes - prev_end, cudaMemcpyHostToDevice,
+                                 e->h2d_stream));
         all_uploaded = true;
       }
       else
       {
         CUDA_TRY(cudaMemcpyAsync(J->d_bytes + lo, bytes + lo, hi - lo, cudaMemcpyHostToDevice, e->h2d_stream));
-        CUDA_TRY(cudaEventRecord(J->chunk_ev[16 + (k & 7)], e->h2d_stream));
-        CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[16 + (k & 7)], 0));
         prev_end = hi;
       }
     }
+    CUDA_TRY(cudaEventRecord(J->chunk_ev[16 + (k & 7)], e->h2d_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[16 + (k & 7)], 0));
     if(b1 > b0)
-      b2k_launch_ht_decode(J->d_dec_desc + b0, J->d_bytes, J->d_recs, J->d_dec_status + b0, b1 - b0, J->max_cblk_w,
-                           J->d_err, st);
+    {
+      /* phase A (serial VLC/MEL parse, one thread per block) is latency-bound and leaves the SMs
+         nearly empty: run the chunks' parses concurrently on side streams, ahead of the main stream */
+      cudaStream_t ax = e->aux[k & 3];
+      CUDA_TRY(cudaStreamWaitEvent(ax, J->chunk_ev[16 + (k & 7)], 0)); /* this chunk's descriptors + bytes are up */
+      b2k_launch_ht_decode_vlc(J->d_dec_desc + b0, J->d_bytes, J->d_recs, J->d_dec_status + b0, b1 - b0, ax);
+      CUDA_TRY(cudaEventRecord(J->chunk_ev[24 + (k & 7)], ax));
+      CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[24 + (k & 7)], 0));
+      b2k_launch_ht_decode_magsgn(J->d_dec_desc + b0, J->d_bytes, J->d_recs, J->d_dec_status + b0, b1 - b0, J->max_cblk_w,
+                                  J->d_err, st);
+    }
     if(enqueue_inverse(J, st, t0, t1)) return -1;
+    if(u16 && convert_planes16(J, false, st, t0, t1)) return -1;
     CUDA_TRY(cudaEventRecord(J->chunk_ev[k], st));
     CUDA_TRY(cudaStreamWaitEvent(cs, J->chunk_ev[k], 0));
-    if(copy_planes(J, J->img, (void* const*)planes, strides, false, cs, t0, t1)) return -1;
+    if(u16 ? copy_planes16(J, planes, strides, false, cs, t0, t1) : copy_planes(J, J->img, planes, strides, false, cs, t0, t1))
+      return -1;
   }
   CUDA_TRY(cudaEventRecord(J->chunk_ev[nchunks], cs));
   CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[nchunks], 0));

@@ -494,13 +494,22 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
 
 } /* namespace */
 
-void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
-                          uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st)
+void b2k_launch_ht_decode_vlc(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
+                              uint32_t nblocks, cudaStream_t st)
 {
   if(!nblocks)
     return;
-  k_ht_decode_vlc<<<(nblocks + 127) / 128, 128, 0, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks);
+  /* 32 threads per CTA: the kernel is a serial chain per thread, so spread the blocks over as many
+     SMs as possible instead of packing 4 warps onto one */
+  k_ht_decode_vlc<<<(nblocks + 31) / 32, 32, 0, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks);
   b2k_count_launch();
+}
+
+void b2k_launch_ht_decode_magsgn(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, const uint32_t* d_recs,
+                                 const HtBlockOut* d_status, uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st)
+{
+  if(!nblocks)
+    return;
   const uint32_t line_entries = ((max_w + 1) / 2 + 4 + 1) & ~1u;
   const size_t smem = (size_t)B2K_WARPS_PER_CTA * MS_RING_WORDS * sizeof(uint32_t) +
                       (size_t)B2K_WARPS_PER_CTA * 2 * line_entries * sizeof(uint16_t);
@@ -508,4 +517,11 @@ void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, u
   k_ht_decode_magsgn<<<grid, B2K_WARPS_PER_CTA * 32, smem, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks, line_entries,
                                                                 d_err);
   b2k_count_launch();
+}
+
+void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
+                          uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st)
+{
+  b2k_launch_ht_decode_vlc(d_blocks, d_bytes, d_recs, d_status, nblocks, st);
+  b2k_launch_ht_decode_magsgn(d_blocks, d_bytes, d_recs, d_status, nblocks, max_w, d_err, st);
 }

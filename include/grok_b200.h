@@ -351,6 +351,11 @@ B2K_API int32_t b2k_decode(b2k_engine* e, const b2k_coding* cp, const b2k_block*
                            uint64_t num_blocks, const uint8_t* bytes, uint64_t num_bytes,
                            int32_t* const* planes, const uint32_t* strides, uint32_t tile_mod,
                            uint32_t tile_rem, double* ms_total);
+/* same, pixels returned in 16-bit containers (reversible path) */
+B2K_API int32_t b2k_decode16(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks,
+                             uint64_t num_blocks, const uint8_t* bytes, uint64_t num_bytes,
+                             uint16_t* const* planes, const uint32_t* strides, uint32_t tile_mod,
+                             uint32_t tile_rem, double* ms_total);
 
 /* Geometry only (host): enumerate the blocks of the selected tiles, lengths zero.  Returns the
  * count; fills at most cap entries. */

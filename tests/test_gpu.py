@@ -307,3 +307,25 @@ int main(void){ O(numlayers) O(csty) O(numgbits) O(numresolution) O(cblockw_init
                     assert cb.passes[0].rate == cb.compressedDataLength - 1
     assert k == len(blks)
     lib.gpup_tile_free(tile)
+
+
+@pytest.mark.parametrize("sgnd", [False, True])
+def test_16bit_containers(engine, sgnd):
+    """b2k_encode16 / b2k_decode16 (cf. gpup_batch_memory_submit_planes: 16-bit sample containers):
+    identical code blocks to the 32-bit entry point, lossless round trip into 16-bit planes."""
+    w, h, prec = 600, 300, 12
+    cp = G.make_coding(w, h, 3, prec, sgnd=sgnd, numres=5, tile=(256, 128), origin=(8, 0))
+    planes = P.synthetic_image(w, h, 3, prec, seed=77)
+    if sgnd:
+        planes = [p - 2048 for p in planes]
+    p16 = [p.astype(np.int16 if sgnd else np.uint16) for p in planes]
+    a = engine.encode(cp, planes)
+    b = engine.encode(cp, p16)
+    assert a.num_blocks == b.num_blocks and np.array_equal(a.blocks["length"], b.blocks["length"])
+    assert np.array_equal(a.bytes, b.bytes)
+    out = [np.zeros_like(p) for p in p16]
+    engine.decode(cp, b.blocks.copy(), b.bytes.copy(), out)
+    for x, y in zip(out, p16):
+        assert np.array_equal(x, y)
+    a.free()
+    b.free()
