@@ -711,7 +711,7 @@ static int enqueue_t1_blocks(b2k_device_job* J, cudaStream_t st, size_t t0, size
   t1 = std::min(t1, J->tiles.size());
   const uint32_t b0 = J->coded_first[t0], b1 = J->coded_first[t1];
   if(b1 > b0)
-    b2k_launch_ht_encode(J->d_enc_desc + b0, J->d_out + b0, J->d_scratch, b1 - b0, J->max_cblk_w, st);
+    b2k_launch_ht_encode(J->d_enc_desc + b0, J->d_out + b0, J->d_scratch, b1 - b0, J->max_cblk_w, J->cp.irreversible, st);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -719,7 +719,7 @@ static int enqueue_t1_blocks(b2k_device_job* J, cudaStream_t st, size_t t0, size
 static int enqueue_t1_encode(b2k_device_job* J, cudaStream_t st)
 {
   const uint32_t n = (uint32_t)J->h_enc_desc.size();
-  b2k_launch_ht_encode(J->d_enc_desc, J->d_out, J->d_scratch, n, J->max_cblk_w, st);
+  b2k_launch_ht_encode(J->d_enc_desc, J->d_out, J->d_scratch, n, J->max_cblk_w, J->cp.irreversible, st);
   b2k_launch_scan_lengths(J->d_out, J->d_offsets, n, st);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1232,7 +1232,7 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
          nearly empty: run the chunks' parses concurrently on side streams, ahead of the main stream */
       cudaStream_t ax = e->aux[k & 3];
       CUDA_TRY(cudaStreamWaitEvent(ax, J->chunk_ev[16 + (k & 7)], 0)); /* this chunk's descriptors + bytes are up */
-      b2k_launch_ht_decode_vlc(J->d_dec_desc + b0, J->d_bytes, J->d_recs, J->d_dec_status + b0, b1 - b0, ax);
+      b2k_launch_ht_decode_vlc(J->d_dec_desc + b0, J->d_bytes, J->d_recs, J->d_dec_status + b0, b1 - b0, J->max_cblk_w, ax);
       CUDA_TRY(cudaEventRecord(J->chunk_ev[24 + (k & 7)], ax));
       CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[24 + (k & 7)], 0));
       b2k_launch_ht_decode_magsgn(J->d_dec_desc + b0, J->d_bytes, J->d_recs, J->d_dec_status + b0, b1 - b0, J->max_cblk_w,

@@ -150,6 +150,56 @@ __device__ __forceinline__ T warp_excl_scan_d(T v, int lane, T& total)
  * Output: one record per quad in global scratch, rho[3:0] | e_k[7:4] | e_1[11:8] | u[17:12],
  * consumed by phase B (k_ht_decode_magsgn, warp per block).
  * =========================================================================================== */
+/* refill so that at least 32 un-stuffed bits are buffered: one quad pair consumes at most
+   7+7 (CxtVLC) + 3+3+5+5 (UVLC) + 1 = 31 bits, so the parse of a pair needs no further checks */
+__device__ __forceinline__ void vlc_fill32(VlcR& v)
+{
+  while(v.bits < 32)
+  {
+    uint32_t b = 0;
+    if(v.pos >= v.lo)
+      b = __ldg(v.d + v.pos);
+    v.pos--;
+    const int nb = 8 - ((v.unstuff && ((b & 0x7F) == 0x7F)) ? 1 : 0);
+    v.tmp |= (uint64_t)b << v.bits;
+    v.bits += nb;
+    v.unstuff = b > 0x8F;
+  }
+}
+__device__ __forceinline__ uint32_t vlc_head(const VlcR& v) { return (uint32_t)v.tmp; }
+
+/* significance of the previous / current quad row's bottom samples, one bit per quad.
+   WIDE = false: blocks at most 64 samples wide (32 quads) -> plain registers. */
+template <bool WIDE>
+struct SigRows
+{
+  uint32_t pbl[WIDE ? 16 : 1], pbr[WIDE ? 16 : 1], cbl[WIDE ? 16 : 1], cbr[WIDE ? 16 : 1];
+  __device__ __forceinline__ void clear()
+  {
+#pragma unroll
+    for(int i = 0; i < (WIDE ? 16 : 1); ++i)
+      pbl[i] = pbr[i] = cbl[i] = cbr[i] = 0;
+  }
+  __device__ __forceinline__ int prev_bl(int q) const { return (int)((pbl[WIDE ? (q >> 5) : 0] >> (q & 31)) & 1u); }
+  __device__ __forceinline__ int prev_br(int q) const { return (int)((pbr[WIDE ? (q >> 5) : 0] >> (q & 31)) & 1u); }
+  __device__ __forceinline__ void set(int q, int rho)
+  {
+    cbl[WIDE ? (q >> 5) : 0] |= (uint32_t)((rho >> 1) & 1) << (q & 31);
+    cbr[WIDE ? (q >> 5) : 0] |= (uint32_t)((rho >> 3) & 1) << (q & 31);
+  }
+  __device__ __forceinline__ void next_row()
+  {
+#pragma unroll
+    for(int i = 0; i < (WIDE ? 16 : 1); ++i)
+    {
+      pbl[i] = cbl[i];
+      pbr[i] = cbr[i];
+      cbl[i] = cbr[i] = 0;
+    }
+  }
+};
+
+template <bool WIDE>
 __global__ void __launch_bounds__(128)
     k_ht_decode_vlc(const HtBlockDesc* __restrict__ blocks, const uint8_t* __restrict__ bytes, uint32_t* __restrict__ recs,
                     HtBlockOut* __restrict__ status, uint32_t nblocks)
@@ -195,112 +245,125 @@ __global__ void __launch_bounds__(128)
     vlc.unstuff = (d | 0xF) > 0x8F;
   }
   uint32_t* rec = recs + B.rec_off;
-  /* significance of the previous quad row's bottom samples: bit q of bl / br = rho&2 / rho&8 */
-  uint32_t pbl[16], pbr[16], cbl[16], cbr[16];
-#pragma unroll
-  for(int i = 0; i < 16; ++i)
-    pbl[i] = pbr[i] = cbl[i] = cbr[i] = 0;
+  SigRows<WIDE> sig;
+  sig.clear();
 
   for(int y = 0; y < h; y += 2)
   {
+    const uint16_t* tbl = y ? tbl1 : tbl0;
     int rho_left = 0;
     for(int q0 = 0; q0 < nq; q0 += 2)
     {
-      const int npair = (q0 + 1 < nq) ? 2 : 1;
-      int rho[2] = {0, 0}, uoff[2] = {0, 0}, ek[2] = {0, 0}, e1[2] = {0, 0}, u[2] = {0, 0};
-      for(int j = 0; j < npair; ++j)
+      vlc_fill32(vlc);
+      const bool has1 = q0 + 1 < nq;
+      /* ---- CxtVLC of the two quads ---- */
+      int cq0, cq1 = 0;
+      if(y == 0)
+        cq0 = (rho_left >> 1) | (rho_left & 1);
+      else
+        cq0 = ((q0 > 0 ? sig.prev_br(q0 - 1) : 0) | sig.prev_bl(q0)) | ((rho_left & 0xC) ? 2 : 0) |
+              ((sig.prev_br(q0) | (has1 ? sig.prev_bl(q0 + 1) : 0)) << 2);
+      uint32_t t0 = tbl[(cq0 << 7) | (vlc_head(vlc) & 0x7F)];
+      if(cq0 == 0 && !mel_symbol(mel))
+        t0 = 0;
+      vlc_skip(vlc, (int)(t0 >> 13));
+      const int rho0 = t0 & 0xF;
+      sig.set(q0, rho0);
+      uint32_t t1 = 0;
+      int rho1 = 0;
+      if(has1)
       {
-        const int q = q0 + j;
-        int cq;
         if(y == 0)
-          cq = (rho_left >> 1) | (rho_left & 1);
+          cq1 = (rho0 >> 1) | (rho0 & 1);
         else
-        {
-          const int a = (q > 0 ? (int)((pbr[(q - 1) >> 5] >> ((q - 1) & 31)) & 1u) : 0) | (int)((pbl[q >> 5] >> (q & 31)) & 1u);
-          const int b = (int)((pbr[q >> 5] >> (q & 31)) & 1u) | (q + 1 < nq ? (int)((pbl[(q + 1) >> 5] >> ((q + 1) & 31)) & 1u) : 0);
-          cq = a | ((rho_left & 0xC) ? 2 : 0) | (b << 2);
-        }
-        uint32_t t = (y ? tbl1 : tbl0)[(cq << 7) | (vlc_peek(vlc) & 0x7F)];
-        if(cq == 0 && !mel_symbol(mel))
-          t = 0;
-        rho[j] = t & 0xF;
-        ek[j] = (t >> 4) & 0xF;
-        e1[j] = (t >> 8) & 0xF;
-        uoff[j] = (t >> 12) & 1;
-        vlc_skip(vlc, (int)(t >> 13));
-        rho_left = rho[j];
-        if(rho[j] & 2) cbl[q >> 5] |= 1u << (q & 31);
-        if(rho[j] & 8) cbr[q >> 5] |= 1u << (q & 31);
+          cq1 = (sig.prev_br(q0) | sig.prev_bl(q0 + 1)) | ((rho0 & 0xC) ? 2 : 0) |
+                ((sig.prev_br(q0 + 1) | (q0 + 2 < nq ? sig.prev_bl(q0 + 2) : 0)) << 2);
+        t1 = tbl[(cq1 << 7) | (vlc_head(vlc) & 0x7F)];
+        if(cq1 == 0 && !mel_symbol(mel))
+          t1 = 0;
+        vlc_skip(vlc, (int)(t1 >> 13));
+        rho1 = t1 & 0xF;
+        sig.set(q0 + 1, rho1);
+        rho_left = rho1;
       }
-      if(y == 0 && uoff[0] && uoff[1])
+      else
+        rho_left = rho0;
+      /* ---- UVLC (T.814 7.3.6) ---- */
+      const int uoff0 = (t0 >> 12) & 1, uoff1 = (t1 >> 12) & 1;
+      int u0 = 0, u1 = 0;
+      if(uoff0 | uoff1)
       {
         int len;
-        if(mel_symbol(mel))
+        if(y == 0 && uoff0 && uoff1)
         {
-          const int p0 = uvlc_prefix(vlc_peek(vlc), len);
-          vlc_skip(vlc, len);
-          const int p1 = uvlc_prefix(vlc_peek(vlc), len);
-          vlc_skip(vlc, len);
-          const int l0 = uvlc_suflen(p0), l1 = uvlc_suflen(p1);
-          u[0] = 2 + p0 + (int)(vlc_peek(vlc) & ((1u << l0) - 1u));
-          vlc_skip(vlc, l0);
-          u[1] = 2 + p1 + (int)(vlc_peek(vlc) & ((1u << l1) - 1u));
-          vlc_skip(vlc, l1);
-        }
-        else
-        {
-          const int p0 = uvlc_prefix(vlc_peek(vlc), len);
-          vlc_skip(vlc, len);
-          if(p0 > 2)
+          if(mel_symbol(mel))
           {
-            u[1] = 1 + (int)(vlc_peek(vlc) & 1u);
-            vlc_skip(vlc, 1);
-            const int l0 = uvlc_suflen(p0);
-            u[0] = p0 + (int)(vlc_peek(vlc) & ((1u << l0) - 1u));
+            const int p0 = uvlc_prefix(vlc_head(vlc), len);
+            vlc_skip(vlc, len);
+            const int p1 = uvlc_prefix(vlc_head(vlc), len);
+            vlc_skip(vlc, len);
+            const int l0 = uvlc_suflen(p0), l1 = uvlc_suflen(p1);
+            u0 = 2 + p0 + (int)(vlc_head(vlc) & ((1u << l0) - 1u));
             vlc_skip(vlc, l0);
+            u1 = 2 + p1 + (int)(vlc_head(vlc) & ((1u << l1) - 1u));
+            vlc_skip(vlc, l1);
           }
           else
           {
-            const int p1 = uvlc_prefix(vlc_peek(vlc), len);
+            const int p0 = uvlc_prefix(vlc_head(vlc), len);
             vlc_skip(vlc, len);
-            const int l1 = uvlc_suflen(p1);
-            u[0] = p0;
-            u[1] = p1 + (int)(vlc_peek(vlc) & ((1u << l1) - 1u));
-            vlc_skip(vlc, l1);
+            if(p0 > 2)
+            {
+              u1 = 1 + (int)(vlc_head(vlc) & 1u);
+              vlc_skip(vlc, 1);
+              const int l0 = uvlc_suflen(p0);
+              u0 = p0 + (int)(vlc_head(vlc) & ((1u << l0) - 1u));
+              vlc_skip(vlc, l0);
+            }
+            else
+            {
+              const int p1 = uvlc_prefix(vlc_head(vlc), len);
+              vlc_skip(vlc, len);
+              const int l1 = uvlc_suflen(p1);
+              u0 = p0;
+              u1 = p1 + (int)(vlc_head(vlc) & ((1u << l1) - 1u));
+              vlc_skip(vlc, l1);
+            }
+          }
+        }
+        else
+        {
+          int pf0 = 0, pf1 = 0;
+          if(uoff0)
+          {
+            pf0 = uvlc_prefix(vlc_head(vlc), len);
+            vlc_skip(vlc, len);
+          }
+          if(uoff1)
+          {
+            pf1 = uvlc_prefix(vlc_head(vlc), len);
+            vlc_skip(vlc, len);
+          }
+          if(uoff0)
+          {
+            const int l = uvlc_suflen(pf0);
+            u0 = pf0 + (int)(vlc_head(vlc) & ((1u << l) - 1u));
+            vlc_skip(vlc, l);
+          }
+          if(uoff1)
+          {
+            const int l = uvlc_suflen(pf1);
+            u1 = pf1 + (int)(vlc_head(vlc) & ((1u << l) - 1u));
+            vlc_skip(vlc, l);
           }
         }
       }
-      else
-      {
-        int len, pf[2] = {0, 0};
-#pragma unroll
-        for(int j = 0; j < 2; ++j)
-          if(uoff[j])
-          {
-            pf[j] = uvlc_prefix(vlc_peek(vlc), len);
-            vlc_skip(vlc, len);
-          }
-#pragma unroll
-        for(int j = 0; j < 2; ++j)
-          if(uoff[j])
-          {
-            const int l = uvlc_suflen(pf[j]);
-            u[j] = pf[j] + (int)(vlc_peek(vlc) & ((1u << l) - 1u));
-            vlc_skip(vlc, l);
-          }
-      }
-      rec[q0] = (uint32_t)(rho[0] | (ek[0] << 4) | (e1[0] << 8) | (u[0] << 12));
-      if(npair == 2)
-        rec[q0 + 1] = (uint32_t)(rho[1] | (ek[1] << 4) | (e1[1] << 8) | (u[1] << 12));
+      rec[q0] = (t0 & 0xFFFu) | ((uint32_t)u0 << 12); /* rho | e_k<<4 | e_1<<8 | u<<12 */
+      if(has1)
+        rec[q0 + 1] = (t1 & 0xFFFu) | ((uint32_t)u1 << 12);
     }
     rec += nq;
-#pragma unroll
-    for(int i = 0; i < 16; ++i)
-    {
-      pbl[i] = cbl[i];
-      pbr[i] = cbr[i];
-      cbl[i] = cbr[i] = 0;
-    }
+    sig.next_row();
   }
   status[bidx] = st;
 }
@@ -495,13 +558,16 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
 } /* namespace */
 
 void b2k_launch_ht_decode_vlc(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
-                              uint32_t nblocks, cudaStream_t st)
+                              uint32_t nblocks, uint32_t max_w, cudaStream_t st)
 {
   if(!nblocks)
     return;
   /* 32 threads per CTA: the kernel is a serial chain per thread, so spread the blocks over as many
      SMs as possible instead of packing 4 warps onto one */
-  k_ht_decode_vlc<<<(nblocks + 31) / 32, 32, 0, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks);
+  if(max_w > 64)
+    k_ht_decode_vlc<true><<<(nblocks + 31) / 32, 32, 0, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks);
+  else
+    k_ht_decode_vlc<false><<<(nblocks + 31) / 32, 32, 0, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks);
   b2k_count_launch();
 }
 
@@ -522,6 +588,6 @@ void b2k_launch_ht_decode_magsgn(const HtBlockDesc* d_blocks, const uint8_t* d_b
 void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
                           uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st)
 {
-  b2k_launch_ht_decode_vlc(d_blocks, d_bytes, d_recs, d_status, nblocks, st);
+  b2k_launch_ht_decode_vlc(d_blocks, d_bytes, d_recs, d_status, nblocks, max_w, st);
   b2k_launch_ht_decode_magsgn(d_blocks, d_bytes, d_recs, d_status, nblocks, max_w, d_err, st);
 }

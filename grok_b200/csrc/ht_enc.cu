@@ -66,7 +66,9 @@ __device__ __forceinline__ void ring_put(uint32_t* ring, int ring_words, uint32_
       atomicOr(&ring[(w + i) & (ring_words - 1)], v[i]);
 }
 
-/* 15 bits starting at absolute bit position pos; bits at or beyond `tail` read as `fill` */
+/* 15 bits starting at absolute bit position pos; bits at or beyond `tail` read as `fill`
+   (MASK = false: the caller guarantees pos + 15 <= tail) */
+template <bool MASK = true>
 __device__ __forceinline__ uint32_t ring_get15(const uint32_t* ring, int ring_words, uint32_t pos, uint32_t tail,
                                                uint32_t fill)
 {
@@ -75,7 +77,7 @@ __device__ __forceinline__ uint32_t ring_get15(const uint32_t* ring, int ring_wo
   const uint32_t lo = ring[w & (ring_words - 1)], hi = ring[(w + 1) & (ring_words - 1)];
   uint32_t v = __funnelshift_r(lo, hi, sh) & 0x7FFFu;
   const int avail = (int)(tail - pos);
-  if(avail < 15)
+  if(MASK && avail < 15)
   {
     const uint32_t keep = avail <= 0 ? 0u : ((1u << avail) - 1u);
     v = (v & keep) | ((fill ? 0x7FFFu : 0u) & ~keep);
@@ -87,6 +89,8 @@ __device__ __forceinline__ uint32_t ring_get15(const uint32_t* ring, int ring_wo
 __device__ __forceinline__ void ring_release(uint32_t* ring, int ring_words, uint32_t old_head, uint32_t new_head, int lane)
 {
   const uint32_t w0 = old_head >> 5, w1 = new_head >> 5;
+  if(w1 == w0)
+    return;
   for(uint32_t w = w0 + lane; w < w1; w += 32)
     ring[w & (ring_words - 1)] = 0;
 }
@@ -97,9 +101,11 @@ __device__ __forceinline__ void ring_release(uint32_t* ring, int ring_words, uin
  * final: pad the tail with 1s and emit the last partial byte too (ms_terminate L516-535; the
  * caller drops a trailing 0xFF).
  * ------------------------------------------------------------------------------------------- */
+template <bool FINAL>
 __device__ __forceinline__ int ms_drain32(uint32_t* ring, uint32_t& head, uint32_t tail, bool& last_ff, uint8_t* out,
-                                          bool final, int lane, uint32_t& last_byte)
+                                          int lane, uint32_t& last_byte)
 {
+  const bool final = FINAL;
   unsigned ffmask = 0;
   uint32_t byte = 0, start = 0;
   int nbits = 8;
@@ -110,7 +116,8 @@ __device__ __forceinline__ int ms_drain32(uint32_t* ring, uint32_t& head, uint32
     nbits = ((prevff >> lane) & 1u) ? 7 : 8;
     const int stuffed_before = __popc(prevff & lanemask_lt()) ; /* 7-bit bytes among lanes < i */
     start = head + 8u * lane - (uint32_t)stuffed_before;
-    const uint32_t raw = ring_get15(ring, MS_RING_WORDS, start, tail, 1u);
+    /* non-final drains run with >= 256 bits queued, but lane 31's window can still poke past the tail */
+    const uint32_t raw = ring_get15<true>(ring, MS_RING_WORDS, start, tail, 1u);
     byte = raw & (nbits == 7 ? 0x7Fu : 0xFFu);
     const unsigned nf = __ballot_sync(0xffffffffu, byte == 0xFFu);
     if(nf == ffmask)
@@ -131,10 +138,7 @@ __device__ __forceinline__ int ms_drain32(uint32_t* ring, uint32_t& head, uint32
     last_byte = __shfl_sync(0xffffffffu, byte, nb - 1);
     last_ff = (last_byte == 0xFFu);
   }
-  __syncwarp();
-  ring_release(ring, MS_RING_WORDS, head, new_head < tail ? new_head : tail, lane);
-  head = new_head;
-  __syncwarp();
+  head = new_head; /* consumed ring words are zeroed by the caller, once per step (ring_release) */
   return nb;
 }
 
@@ -178,10 +182,7 @@ __device__ __forceinline__ int vlc_drain32(uint32_t* ring, uint32_t& head, uint3
   const uint32_t new_head = nb ? __shfl_sync(0xffffffffu, endpos, nb - 1) : head;
   if(nb)
     prev_byte = __shfl_sync(0xffffffffu, byte, nb - 1);
-  __syncwarp();
-  ring_release(ring, VLC_RING_WORDS, head, new_head, lane);
   head = new_head;
-  __syncwarp();
   return nb;
 }
 
@@ -235,14 +236,16 @@ __device__ __forceinline__ void mel_one(Mel& m, uint8_t* buf, int lane)
   m.thr = 1 << mel_exp(m.k);
 }
 
-/* UVLC codeword (uvlc_tbl, L196-256) as one bit string, prefix first: returns length */
+/* UVLC codeword (uvlc_tbl, L196-256): prefix[2:0] | prefix_len<<3 | suffix<<6 | suffix_len<<11 for
+   u = 0..32 (u==0: nothing; 1: "1"; 2: "01"; 3,4: "001"+1 bit; 5..32: "000"+5 bits) */
+__constant__ uint16_t UVLC_LUT[33] = {0x0000, 0x0009, 0x0012, 0x081C, 0x085C, 0x2818, 0x2858, 0x2898, 0x28D8, 0x2918, 0x2958, 0x2998, 0x29D8, 0x2A18, 0x2A58, 0x2A98, 0x2AD8, 0x2B18, 0x2B58, 0x2B98, 0x2BD8, 0x2C18, 0x2C58, 0x2C98, 0x2CD8, 0x2D18, 0x2D58, 0x2D98, 0x2DD8, 0x2E18, 0x2E58, 0x2E98, 0x2ED8};
 __device__ __forceinline__ void uvlc_bits(int u, uint32_t& pre, int& prel, uint32_t& suf, int& sufl)
 {
-  if(u == 0) { pre = 0; prel = 0; suf = 0; sufl = 0; }
-  else if(u == 1) { pre = 1; prel = 1; suf = 0; sufl = 0; }
-  else if(u == 2) { pre = 2; prel = 2; suf = 0; sufl = 0; }
-  else if(u <= 4) { pre = 4; prel = 3; suf = (uint32_t)(u - 3); sufl = 1; }
-  else { pre = 0; prel = 3; suf = (uint32_t)(u - 5); sufl = 5; }
+  const uint32_t t = UVLC_LUT[u > 32 ? 32 : u];
+  pre = t & 7u;
+  prel = (int)((t >> 3) & 7u);
+  suf = (t >> 6) & 31u;
+  sufl = (int)(t >> 11);
 }
 
 template <typename T>
@@ -260,6 +263,7 @@ __device__ __forceinline__ T warp_excl_scan(T v, int lane, T& total)
   return x - v;
 }
 
+template <bool IRREV>
 __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
     k_ht_encode(const HtBlockDesc* __restrict__ blocks, HtBlockOut* __restrict__ outs, uint8_t* __restrict__ scratch,
                 uint32_t nblocks, uint32_t line_entries)
@@ -315,12 +319,31 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
 
   const float fscale = (float)(1u << shift);
 
-  for(int y = 0; y < h; y += 2)
+  /* flattened (quad row, 32-quad chunk) steps so the NEXT step's four samples are already in flight
+     while this step is coded */
+  const int nch = (nq + 31) >> 5, nsteps = ((h + 1) >> 1) * nch;
+  auto fetch = [&](int step, uint32_t (&raw)[4]) {
+    const int yy0 = 2 * (step / nch), xq = 2 * ((step % nch) * 32 + lane);
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+    {
+      const int xx = xq + (i >> 1), yy = yy0 + (i & 1);
+      raw[i] = 0;
+      if(step < nsteps && xx < w && yy < h)
+        raw[i] = __ldg(reinterpret_cast<const uint32_t*>(B.coef) + ((size_t)yy * B.pitch + xx));
+    }
+  };
+  uint32_t cur[4], nxt[4];
+  fetch(0, cur);
+  int rho_carry = 0;
+  for(int step = 0; step < nsteps; ++step)
   {
+    const int y = 2 * (step / nch), q0 = (step % nch) * 32;
     const uint16_t* labove = line[(y >> 1) & 1];
     uint16_t* lcur = line[((y >> 1) & 1) ^ 1];
-    int rho_carry = 0;
-    for(int q0 = 0; q0 < nq; q0 += 32)
+    if(q0 == 0)
+      rho_carry = 0;
+    fetch(step + 1, nxt);
     {
       const int q = q0 + lane, x = 2 * q;
       const bool qv = q < nq;
@@ -331,36 +354,33 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
 #pragma unroll
       for(int i = 0; i < 4; ++i)
       {
-        const int xx = x + (i >> 1), yy = y + (i & 1);
         e[i] = 0;
         sv[i] = 0;
-        if(qv && xx < w && yy < h)
+        uint32_t mu, sgn;
+        if(!IRREV)
         {
-          uint32_t mu, sgn;
-          if(!B.irreversible)
-          {
-            const int32_t v = reinterpret_cast<const int32_t*>(B.coef)[(size_t)yy * B.pitch + xx];
-            sgn = (uint32_t)v >> 31;
-            mu = (uint32_t)(v < 0 ? -v : v);
-            /* bits of |v| above Kmax are shifted out by the reference's `mag << shift; t + t` */
-            mu &= (1u << (kmax + 1)) - 1u;
-          }
-          else
-          { /* CoderOJPH.cpp L166-180 */
-            const float f = reinterpret_cast<const float*>(B.coef)[(size_t)yy * B.pitch + xx];
-            const int32_t t = __float2int_rz(__fmul_rn(__fmul_rn(f, B.quant), fscale));
-            sgn = (uint32_t)t >> 31;
-            const uint32_t m = (uint32_t)(t < 0 ? -t : t);
-            mu = ((m + m) >> shift) >> 1;
-          }
-          if(mu)
-          {
-            rho |= 1 << i;
-            e[i] = 32 - __clz(2 * mu - 1);
-            emax = max(emax, e[i]);
-            sv[i] = 2 * (mu - 1) + sgn;
-          }
+          const int32_t v = (int32_t)cur[i];
+          sgn = (uint32_t)v >> 31;
+          mu = (uint32_t)(v < 0 ? -v : v);
+          /* bits of |v| above Kmax are shifted out by the reference's `mag << shift; t + t` */
+          mu &= (1u << (kmax + 1)) - 1u;
         }
+        else
+        { /* CoderOJPH.cpp L166-180 */
+          const float f = __uint_as_float(cur[i]);
+          const int32_t t = __float2int_rz(__fmul_rn(__fmul_rn(f, B.quant), fscale));
+          sgn = (uint32_t)t >> 31;
+          const uint32_t m = (uint32_t)(t < 0 ? -t : t);
+          mu = ((m + m) >> shift) >> 1;
+        }
+        if(mu)
+        {
+          rho |= 1 << i;
+          e[i] = 32 - __clz(2 * mu - 1);
+          emax = max(emax, e[i]);
+          sv[i] = 2 * (mu - 1) + sgn;
+        }
+        cur[i] = nxt[i];
       }
       /* ---- neighbours ---- */
       int rho_left = __shfl_up_sync(0xffffffffu, rho, 1);
@@ -415,10 +435,6 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
           mlen += m;
         }
       }
-      uint32_t ms_total;
-      const uint32_t ms_off = warp_excl_scan<uint32_t>((uint32_t)mlen, lane, ms_total);
-      ring_put(S.ms_ring, MS_RING_WORDS, ms_tail + ms_off, mlo, mhi, mlen);
-      ms_tail += ms_total;
 
       /* ---- VLC bits of the quad pair (even lane builds them) ---- */
       const uint32_t cwd1 = __shfl_down_sync(0xffffffffu, cwd, 1);
@@ -473,10 +489,14 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
         vbits |= s0 << vlen; vlen += sl0;
         vbits |= s1 << vlen; vlen += sl1;
       }
-      uint32_t v_total;
-      const uint32_t v_off = warp_excl_scan<uint32_t>((uint32_t)vlen, lane, v_total);
-      ring_put(S.vlc_ring, VLC_RING_WORDS, vlc_tail + v_off, (uint64_t)vbits, 0ull, vlen);
-      vlc_tail += v_total;
+      /* one warp scan places both bit strings: MagSgn length (< 2^16 per step) in the low half,
+         VLC length (<= 16*30) in the high half */
+      uint32_t both_total;
+      const uint32_t both_off = warp_excl_scan<uint32_t>((uint32_t)mlen | ((uint32_t)vlen << 16), lane, both_total);
+      ring_put(S.ms_ring, MS_RING_WORDS, ms_tail + (both_off & 0xFFFFu), mlo, mhi, mlen);
+      ms_tail += both_total & 0xFFFFu;
+      ring_put(S.vlc_ring, VLC_RING_WORDS, vlc_tail + (both_off >> 16), (uint64_t)vbits, 0ull, vlen);
+      vlc_tail += both_total >> 16;
 
       /* ---- MEL events, in coding order: quad 2p, quad 2p+1, pair p (L664-665, L750-751) ---- */
       {
@@ -516,18 +536,24 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
       }
       __syncwarp();
 
-      /* ---- drain full 32-byte windows ---- */
-      while(ms_tail - ms_head >= 256u)
-        ms_out += (uint32_t)ms_drain32(S.ms_ring, ms_head, ms_tail, ms_lastff, slot + ms_out, false, lane, ms_lastbyte);
-      while(vlc_tail - vlc_head >= 256u)
-        vlc_out += (uint32_t)vlc_drain32(S.vlc_ring, vlc_head, vlc_tail, vlc_prev, slot_last - vlc_out, lane);
+      /* ---- drain full 32-byte windows, then zero the ring words that were consumed ---- */
+      {
+        const uint32_t h0 = ms_head, v0 = vlc_head;
+        while(ms_tail - ms_head >= 256u)
+          ms_out += (uint32_t)ms_drain32<false>(S.ms_ring, ms_head, ms_tail, ms_lastff, slot + ms_out, lane, ms_lastbyte);
+        while(vlc_tail - vlc_head >= 256u)
+          vlc_out += (uint32_t)vlc_drain32(S.vlc_ring, vlc_head, vlc_tail, vlc_prev, slot_last - vlc_out, lane);
+        __syncwarp();
+        ring_release(S.ms_ring, MS_RING_WORDS, h0, ms_head, lane);
+        ring_release(S.vlc_ring, VLC_RING_WORDS, v0, vlc_head, lane);
+        __syncwarp();
+      }
     }
-    __syncwarp();
   }
 
   /* ---- terminate MagSgn (ms_terminate L516-535) ---- */
   while(ms_head < ms_tail)
-    ms_out += (uint32_t)ms_drain32(S.ms_ring, ms_head, ms_tail, ms_lastff, slot + ms_out, true, lane, ms_lastbyte);
+    ms_out += (uint32_t)ms_drain32<true>(S.ms_ring, ms_head, ms_tail, ms_lastff, slot + ms_out, lane, ms_lastbyte);
   if(ms_out > 0 && ms_lastff)
     ms_out--; /* a final 0xFF is not written (padded partial byte) or is taken back (L533-534) */
 
@@ -653,7 +679,7 @@ __global__ void k_ht_gather(const HtBlockDesc* __restrict__ blocks, const HtBloc
 } /* namespace */
 
 void b2k_launch_ht_encode(const HtBlockDesc* d_blocks, HtBlockOut* d_out, uint8_t* d_scratch, uint32_t nblocks,
-                          uint32_t max_w, cudaStream_t st)
+                          uint32_t max_w, bool irreversible, cudaStream_t st)
 {
   if(!nblocks)
     return;
@@ -663,11 +689,15 @@ void b2k_launch_ht_encode(const HtBlockDesc* d_blocks, HtBlockOut* d_out, uint8_
   static bool attr_set = false;
   if(!attr_set)
   {
-    cudaFuncSetAttribute(k_ht_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_ht_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_ht_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_set = true;
   }
   const uint32_t grid = (nblocks + B2K_WARPS_PER_CTA - 1) / B2K_WARPS_PER_CTA;
-  k_ht_encode<<<grid, B2K_WARPS_PER_CTA * 32, smem, st>>>(d_blocks, d_out, d_scratch, nblocks, line_entries);
+  if(irreversible)
+    k_ht_encode<true><<<grid, B2K_WARPS_PER_CTA * 32, smem, st>>>(d_blocks, d_out, d_scratch, nblocks, line_entries);
+  else
+    k_ht_encode<false><<<grid, B2K_WARPS_PER_CTA * 32, smem, st>>>(d_blocks, d_out, d_scratch, nblocks, line_entries);
   b2k_count_launch();
 }
 
