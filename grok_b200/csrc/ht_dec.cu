@@ -425,33 +425,50 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
     uint16_t* lcur = line[cur];
     for(int qb = 0; qb < nq; qb += 32)
     {
-      /* keep at least 4096 un-stuffed bits (or the rest of the segment + 1-fill) in the ring */
+      /* keep at least 4096 un-stuffed bits (or the rest of the segment + 1-fill) in the ring:
+         128 segment bytes per round, 4 per lane, read as two aligned words (frwd_read L628-669:
+         a byte after 0xFF carries 7 bits, 0xFF is fed once the segment is exhausted) */
       while(ms_tail - ms_head < 4096u)
       {
-        uint32_t b = 0xFF;
-        if(ms_pos + lane < ms_size)
-          b = __ldg(data + ms_pos + lane);
-        const unsigned ff = __ballot_sync(0xffffffffu, b == 0xFFu);
-        const unsigned prevff = (ff << 1) | (ms_prevff ? 1u : 0u);
-        const int nb = ((prevff >> lane) & 1u) ? 7 : 8;
-        const uint32_t pos = ms_tail + 8u * lane - (uint32_t)__popc(prevff & lanemask_lt_d());
-        const uint32_t val = b & (nb == 7 ? 0x7Fu : 0xFFu);
+        const uint8_t* pb = data + ms_pos + 4 * lane;
+        uint32_t val = 0xFFFFFFFFu;
+        if(ms_pos + 4 * lane < ms_size)
+        {
+          const uintptr_t a = reinterpret_cast<uintptr_t>(pb) & ~(uintptr_t)3;
+          const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(a)), w1 = __ldg(reinterpret_cast<const uint32_t*>(a) + 1);
+          val = __funnelshift_r(w0, w1, 8 * (int)(reinterpret_cast<uintptr_t>(pb) & 3));
+          const int left = ms_size - (ms_pos + 4 * lane);
+          if(left < 4)
+            val |= 0xFFFFFFFFu << (8 * left);
+        }
+        const unsigned lastff = __ballot_sync(0xffffffffu, (val >> 24) == 0xFFu);
+        bool f = lane == 0 ? ms_prevff : (((lastff >> (lane - 1)) & 1u) != 0);
+        uint64_t acc = 0;
+        int nb = 0;
+#pragma unroll
+        for(int j = 0; j < 4; ++j)
+        {
+          const uint32_t b = (val >> (8 * j)) & 0xFFu;
+          acc |= (uint64_t)(b & (f ? 0x7Fu : 0xFFu)) << nb;
+          nb += f ? 7 : 8;
+          f = (b == 0xFFu);
+        }
+        uint32_t tot;
+        const uint32_t off = warp_excl_scan_d<uint32_t>((uint32_t)nb, lane, tot);
+        const uint32_t pos = ms_tail + off;
         {
           const int sh = pos & 31;
           const uint32_t wi = pos >> 5;
-          const uint32_t lo = val << sh;
+          const uint64_t sft = acc << sh;
+          const uint32_t lo = (uint32_t)sft, hi = (uint32_t)(sft >> 32);
           if(lo)
             atomicOr(&ring[wi & (MS_RING_WORDS - 1)], lo);
-          if(sh + nb > 32)
-          {
-            const uint32_t hi = val >> (32 - sh);
-            if(hi)
-              atomicOr(&ring[(wi + 1) & (MS_RING_WORDS - 1)], hi);
-          }
+          if(hi)
+            atomicOr(&ring[(wi + 1) & (MS_RING_WORDS - 1)], hi);
         }
-        ms_tail += 256u - (uint32_t)__popc(prevff);
-        ms_prevff = (ff >> 31) & 1u;
-        ms_pos += 32;
+        ms_tail += tot;
+        ms_prevff = (lastff >> 31) & 1u;
+        ms_pos += 128;
         __syncwarp();
       }
 

@@ -143,6 +143,47 @@ __device__ __forceinline__ int ms_drain32(uint32_t* ring, uint32_t& head, uint32
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * Drain exactly 128 bytes of the forward MagSgn stream, 4 bytes per lane (requires >= 1024 raw bits
+ * queued).  A lane walks its own four bytes serially (a byte after 0xFF carries 7 bits); how many
+ * stuffed bytes sit in the lanes below -- which shifts the lane's window one bit each -- is
+ * resolved with the same speculate-and-fix iteration on ballots as the 32-byte drain.
+ * ------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void ms_drain128(const uint32_t* ring, uint32_t& head, bool& last_ff, uint8_t* out, int lane)
+{
+  unsigned m1 = 0, m2 = 0, lf = 0; /* lanes with >=1 / >=2 seven-bit bytes; lanes whose 4th byte is 0xFF */
+  uint32_t word = 0;
+  for(int it = 0; it < 34; ++it)
+  {
+    const unsigned below = lanemask_lt();
+    const uint32_t start = head + 32u * lane - (uint32_t)(__popc(m1 & below) + __popc(m2 & below));
+    const bool pff = lane == 0 ? last_ff : (((lf >> (lane - 1)) & 1u) != 0);
+    const uint32_t wi = start >> 5;
+    const int sh = start & 31;
+    uint32_t raw = __funnelshift_r(ring[wi & (MS_RING_WORDS - 1)], ring[(wi + 1) & (MS_RING_WORDS - 1)], sh);
+    int sev = 0;
+    bool f = pff;
+    word = 0;
+#pragma unroll
+    for(int j = 0; j < 4; ++j)
+    {
+      const uint32_t b = raw & (f ? 0x7Fu : 0xFFu);
+      raw >>= f ? 7 : 8;
+      sev += f ? 1 : 0;
+      f = (b == 0xFFu);
+      word |= b << (8 * j);
+    }
+    const unsigned n1 = __ballot_sync(0xffffffffu, sev >= 1), n2 = __ballot_sync(0xffffffffu, sev >= 2),
+                   nf = __ballot_sync(0xffffffffu, f);
+    if(n1 == m1 && n2 == m2 && nf == lf)
+      break;
+    m1 = n1; m2 = n2; lf = nf;
+  }
+  *reinterpret_cast<uint32_t*>(out + 4 * lane) = word;
+  head += 1024u - (uint32_t)(__popc(m1) + __popc(m2));
+  last_ff = (lf >> 31) & 1u;
+}
+
+/* ---------------------------------------------------------------------------------------------
  * Drain up to 32 bytes of the backward VLC stream (vlc_encode L378-410): a byte that follows one
  * > 0x8F and whose first 7 bits are all ones is emitted as 0x7F and carries 7 bits.  Only
  * complete bytes are written; byte k of the stream goes to out_last[-k].
@@ -539,8 +580,11 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
       /* ---- drain full 32-byte windows, then zero the ring words that were consumed ---- */
       {
         const uint32_t h0 = ms_head, v0 = vlc_head;
-        while(ms_tail - ms_head >= 256u)
-          ms_out += (uint32_t)ms_drain32<false>(S.ms_ring, ms_head, ms_tail, ms_lastff, slot + ms_out, lane, ms_lastbyte);
+        while(ms_tail - ms_head >= 1024u)
+        {
+          ms_drain128(S.ms_ring, ms_head, ms_lastff, slot + ms_out, lane);
+          ms_out += 128u;
+        }
         while(vlc_tail - vlc_head >= 256u)
           vlc_out += (uint32_t)vlc_drain32(S.vlc_ring, vlc_head, vlc_tail, vlc_prev, slot_last - vlc_out, lane);
         __syncwarp();
