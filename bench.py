@@ -162,6 +162,26 @@ def cpu_reference_step(st):
     return te + td, dict(enc_s=te, dec_s=td, coded_bytes=int(st["lengths"].sum()), inv_dwt_ms_per_tilecomp=dwt.value * 1e3)
 
 
+def bind_to_gpu_numa_node(local):
+    """Best effort: run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off,
+    so host<->device copies do not cross the socket interconnect.  Returns the node or None."""
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def cpu_model():
     try:
         for l in open("/proc/cpuinfo"):
@@ -225,6 +245,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -343,7 +364,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu": "one 8192x8192x3 image (64 tiles) per rank",
+            "config": {"workload": WORKLOAD, "per_gpu": "one 8192x8192x3 image (64 tiles) per rank", "numa_node": numa,
                        "l2": "inputs (805 MB of planes per step) are larger than the 126 MB L2",
                        "coded_bytes": int(nbytes), "blocks": int(nbk),
                        "stage_ms": {"fwd_mct_dwt": stage[0] / args.steps, "ht_encode": stage[1] / args.steps,
@@ -362,6 +383,10 @@ def main():
                          "ms_per_launch": l1_ms, "traffic": TRAFFIC_NCU},
         }
         if world == 1 and not args.no_cpu_baseline:
+            try:
+                os.sched_setaffinity(0, range(os.cpu_count()))   # the CPU arm gets every core back
+            except Exception:
+                pass
             st = cpu_reference_setup(img)
             if st is not None:
                 sec, info = min((cpu_reference_step(st) for _ in range(2)), key=lambda r: r[0])  # warm + best of 2

@@ -747,13 +747,11 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_fwd(const DwtL
 /* =============================================================================================
  * forward 9/7: vertical pipeline  d1[t] -> s1[t] -> d2[t-1] -> s2[t-1]   
  * =========================================================================================== */
+/* unpipelined path for lines of one sample (cold) */
 template <int NC, bool U16>
-__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_fwd(const DwtLevelDesc* __restrict__ descs)
+__device__ __noinline__ void fwd97_degenerate_job(const DwtLevelDesc* __restrict__ dptr, const Job J)
 {
-  const DwtLevelDesc D = descs[blockIdx.y]; /* by value: fields live in (uniform) registers, not re-read after every store */
-  Job J;
-  if(!decode_job(D, J))
-    return;
+  const DwtLevelDesc& D = *dptr;
   const BandGeom g = band_geom(D);
   const float invK = (float)(1.0 / 1.230174105);
   const float deltaS = __fmul_rn(F97_DELTA, invK);
@@ -806,6 +804,145 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_fwd(const DwtL
         store_band_rows(D, J, g, c, t - 1, true, lo, hi);
     }
   }
+}
+
+
+/* float samples of a staged row: finest level = integers from the image (+DC shift, +ICT,
+   mct.cpp L584-636), other levels = float bits */
+template <int NC>
+__device__ __forceinline__ void ict_fwd_convert(const DwtLevelDesc& D, const int (&raw)[NC][8], float (&out)[NC][8])
+{
+  if(D.first_level)
+  {
+    const float a_r = 0.299f, a_g = 0.587f, a_b = 0.114f;
+    const float cb = __fdiv_rn(0.5f, __fsub_rn(1.0f, a_b)), cr = __fdiv_rn(0.5f, __fsub_rn(1.0f, a_r));
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+    {
+      if(NC == 3)
+      {
+        const float r = (float)(raw[0][i] + D.shift[0]), g = (float)(raw[NC > 1 ? 1 : 0][i] + D.shift[1]),
+                    b = (float)(raw[NC > 2 ? 2 : 0][i] + D.shift[2]);
+        const float y = __fadd_rn(__fadd_rn(__fmul_rn(a_r, r), __fmul_rn(a_g, g)), __fmul_rn(a_b, b));
+        out[0][i] = y;
+        out[NC > 1 ? 1 : 0][i] = __fmul_rn(cb, __fsub_rn(b, y));
+        out[NC > 2 ? 2 : 0][i] = __fmul_rn(cr, __fsub_rn(r, y));
+      }
+      else
+        out[0][i] = (float)(raw[0][i] + D.shift[0]);
+    }
+  }
+  else
+  {
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+        out[c][i] = __int_as_float(raw[c][i]);
+  }
+}
+
+template <int NC, bool U16, int STAGES>
+__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_fwd(const DwtLevelDesc* __restrict__ descs)
+{
+  extern __shared__ __align__(16) uint8_t smem_dwt[];
+  typedef RowStage<NC, U16> RS;
+  const DwtLevelDesc D = descs[blockIdx.y]; /* by value */
+  Job J;
+  if(!decode_job(D, J))
+    return;
+  if(J.hn == 1 || J.wn == 1)
+  {
+    fwd97_degenerate_job<NC, U16>(descs + blockIdx.y, J);
+    return;
+  }
+  const BandGeom g = band_geom(D);
+  const StoreCtx SC = store_ctx(D, J, g);
+  uint8_t* wsm = smem_dwt + (size_t)(threadIdx.x >> 5) * STAGES * RS::PAIRB;
+  const bool fast = RS::lane_fast(D, J);
+  const unsigned fastmask = __ballot_sync(0xffffffffu, fast);
+  int mcol[8];
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+    mcol[i] = mirror_rel(J.ulane - D.u0 + i, J.wn);
+  const float invK = (float)(1.0 / 1.230174105);
+  const float deltaS = __fmul_rn(F97_DELTA, invK);
+
+  /* pairs t = jbeg-2 .. jend : rows (2t+1, 2t+2); output pair t-1 from t = jbeg+1 on */
+  const int tfirst = J.jbeg - 2, tlast = J.jend;
+  int tfill = tfirst;
+#pragma unroll
+  for(int s = 0; s < STAGES - 1; ++s)
+  {
+    if(tfill <= tlast)
+    {
+      uint8_t* st = wsm + (size_t)((tfill - tfirst) % STAGES) * RS::PAIRB;
+      RS::fill(st, 0, D, J, 2 * tfill + 1, fast, fastmask, mcol);
+      RS::fill(st, 1, D, J, 2 * tfill + 2, fast, fastmask, mcol);
+    }
+    cp_async_commit();
+    ++tfill;
+  }
+  float Ev[NC][8], D1[NC][8], S1[NC][8], D2[NC][8];
+  fetch97<NC, U16>(D, J, 2 * tfirst, Ev);
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+      D1[c][i] = S1[c][i] = D2[c][i] = 0.f;
+
+  for(int t = tfirst; t <= tlast; ++t)
+  {
+    __syncwarp();
+    if(tfill <= tlast)
+    {
+      uint8_t* st = wsm + (size_t)((tfill - tfirst) % STAGES) * RS::PAIRB;
+      RS::fill(st, 0, D, J, 2 * tfill + 1, fast, fastmask, mcol);
+      RS::fill(st, 1, D, J, 2 * tfill + 2, fast, fastmask, mcol);
+    }
+    cp_async_commit();
+    ++tfill;
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    const uint8_t* st = wsm + (size_t)((t - tfirst) % STAGES) * RS::PAIRB;
+    float O[NC][8], E2[NC][8];
+    {
+      int raw[NC][8];
+      RS::read(st, 0, D, J, raw);
+      ict_fwd_convert<NC>(D, raw, O);
+      RS::read(st, 1, D, J, raw);
+      ict_fwd_convert<NC>(D, raw, E2);
+    }
+    const bool emit = (t - 1) >= J.jbeg;
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+      float lowrow[8], highrow[8];
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+      {
+        const float d1 = fmaf(Ev[c][i] + E2[c][i], F97_ALPHA, O[c][i]);
+        const float s1 = fmaf(D1[c][i] + d1, F97_BETA, Ev[c][i]);
+        const float d2 = __fmul_rn(fmaf(S1[c][i] + s1, F97_GAMMA, D1[c][i]), F97_K);
+        const float s2 = __fmul_rn(fmaf(D2[c][i] + d2, deltaS, S1[c][i]), invK);
+        lowrow[i] = s2;
+        highrow[i] = d2;
+        D2[c][i] = d2;
+        D1[c][i] = d1;
+        S1[c][i] = s1;
+        Ev[c][i] = E2[c][i];
+      }
+      if(emit)
+      { /* warp-uniform */
+        int lo[4], hi[4];
+        hfwd97(lowrow, 2, invK, deltaS, lo, hi);
+        store_rows_fast(D, g, SC, c, t - 1, false, lo, hi);
+        hfwd97(highrow, 2, invK, deltaS, lo, hi);
+        store_rows_fast(D, g, SC, c, t - 1, true, lo, hi);
+      }
+    }
+  }
+  cp_async_wait<0>();
 }
 
 /* =============================================================================================
@@ -1311,13 +1448,11 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtL
   cp_async_wait<0>();
 }
 
+/* unpipelined path for lines of one sample (cold) */
 template <int NC>
-__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_inv(const DwtLevelDesc* __restrict__ descs)
+__device__ __noinline__ void inv97_degenerate_job(const DwtLevelDesc* __restrict__ dptr, const Job J)
 {
-  const DwtLevelDesc D = descs[blockIdx.y]; /* by value: fields live in (uniform) registers, not re-read after every store */
-  Job J;
-  if(!decode_job(D, J))
-    return;
+  const DwtLevelDesc& D = *dptr;
   const BandGeom g = band_geom(D);
   const float K = 1.230174105f, twice_invK = 1.625732422f;
   /* state: d0[t-1], s1[t-1], d1[t-2], s2[t-2] */
@@ -1372,6 +1507,144 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_inv(const DwtL
       store_rows97<NC>(D, J, 2 * (t - 2) + 1, Or);
     }
   }
+}
+
+
+template <int NC>
+__device__ __forceinline__ void store_rows97_fast(const DwtLevelDesc& D, const OutCtx& O, int v, float (&x)[NC][8])
+{
+  if(v < D.v0 || v >= D.v1 || O.m == 0)
+    return;
+  int o[NC][8];
+  if(D.first_level)
+  {
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+    {
+      float f[NC];
+      if(NC == 3)
+      { /* mct.cpp L318-391 */
+        const float y = x[0][i], u = x[NC > 1 ? 1 : 0][i], w = x[NC > 2 ? 2 : 0][i];
+        f[0] = __fadd_rn(y, __fmul_rn(w, 1.402f));
+        f[NC > 1 ? 1 : 0] = __fsub_rn(__fsub_rn(y, __fmul_rn(u, 0.34413f)), __fmul_rn(w, 0.71414f));
+        f[NC > 2 ? 2 : 0] = __fadd_rn(y, __fmul_rn(u, 1.772f));
+      }
+      else
+        f[0] = x[0][i];
+#pragma unroll
+      for(int c = 0; c < NC; ++c)
+        o[c][i] = min(max(__float2int_rn(f[c]) - D.shift[c], D.lo[c]), D.hi[c]);
+    }
+  }
+  else
+  {
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+        o[c][i] = __float_as_int(x[c][i]);
+  }
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+  {
+    int32_t* p = reinterpret_cast<int32_t*>(const_cast<void*>(D.in[c])) + ((v - D.v0) * (int)D.in_pitch + O.col);
+    if(O.vec)
+    {
+      reinterpret_cast<int4*>(p)[0] = make_int4(o[c][0], o[c][1], o[c][2], o[c][3]);
+      reinterpret_cast<int4*>(p)[1] = make_int4(o[c][4], o[c][5], o[c][6], o[c][7]);
+    }
+    else
+    {
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+        if(O.m & (1u << i))
+          p[i] = o[c][i];
+    }
+  }
+}
+
+template <int NC, int STAGES>
+__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_inv(const DwtLevelDesc* __restrict__ descs)
+{
+  extern __shared__ __align__(16) uint8_t smem_dwt[];
+  typedef BandStage<NC> BS;
+  const DwtLevelDesc D = descs[blockIdx.y]; /* by value */
+  Job J;
+  if(!decode_job(D, J))
+    return;
+  if(J.hn == 1 || J.wn == 1)
+  {
+    inv97_degenerate_job<NC>(descs + blockIdx.y, J);
+    return;
+  }
+  const BandGeom g = band_geom(D);
+  typename BS::Lane L;
+  BS::setup(D, J, g, L);
+  const OutCtx OC = out_ctx<false>(D, J);
+  uint8_t* wsm = smem_dwt + (size_t)(threadIdx.x >> 5) * STAGES * BS::PAIRB;
+  const float K = 1.230174105f, twice_invK = 1.625732422f;
+
+  const int tfirst = J.jbeg - 2, tlast = J.jend + 1;
+  int tfill = tfirst;
+#pragma unroll
+  for(int s = 0; s < STAGES - 1; ++s)
+  {
+    if(tfill <= tlast)
+      BS::fill(wsm + (size_t)((tfill - tfirst) % STAGES) * BS::PAIRB, D, J, g, L, tfill);
+    cp_async_commit();
+    ++tfill;
+  }
+  /* state: d0[t-1], s1[t-1], d1[t-2], s2[t-2] */
+  float D0[NC][8], S1[NC][8], D1[NC][8], S2[NC][8];
+#pragma unroll
+  for(int c = 0; c < NC; ++c)
+#pragma unroll
+    for(int i = 0; i < 8; ++i)
+      D0[c][i] = S1[c][i] = D1[c][i] = S2[c][i] = 0.f;
+
+  for(int t = tfirst; t <= tlast; ++t)
+  {
+    if(tfill <= tlast)
+      BS::fill(wsm + (size_t)((tfill - tfirst) % STAGES) * BS::PAIRB, D, J, g, L, tfill);
+    cp_async_commit();
+    ++tfill;
+    cp_async_wait<STAGES - 1>();
+    const uint8_t* st = wsm + (size_t)((t - tfirst) % STAGES) * BS::PAIRB;
+    float Er[NC][8], Or[NC][8];
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+      int lo[4], hi[4];
+      float sv[8], dv[8];
+      BS::read(st, J, 0, c, lo);
+      BS::read(st, J, 1, c, hi);
+      hinv97(lo, hi, 2, sv);
+      BS::read(st, J, 2, c, lo);
+      BS::read(st, J, 3, c, hi);
+      hinv97(lo, hi, 2, dv);
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+      {
+        const float s0 = __fmul_rn(sv[i], K), d0 = __fmul_rn(dv[i], twice_invK);
+        const float s1 = fmaf(D0[c][i] + d0, -0.443506852f, s0);
+        const float d1 = fmaf(S1[c][i] + s1, -0.882911075f, D0[c][i]);
+        const float s2 = fmaf(D1[c][i] + d1, 0.052980118f, S1[c][i]);
+        const float d2 = fmaf(S2[c][i] + s2, 1.586134342f, D1[c][i]);
+        Er[c][i] = S2[c][i];
+        Or[c][i] = d2;
+        D0[c][i] = d0;
+        S1[c][i] = s1;
+        D1[c][i] = d1;
+        S2[c][i] = s2;
+      }
+    }
+    if(t - 2 >= J.jbeg)
+    {
+      store_rows97_fast<NC>(D, OC, 2 * (t - 2), Er);
+      store_rows97_fast<NC>(D, OC, 2 * (t - 2) + 1, Or);
+    }
+  }
+  cp_async_wait<0>();
 }
 
 /* 16-bit sample containers <-> the engine's 32-bit planes: one rectangle (a merged tile row) per
@@ -1457,6 +1730,19 @@ static void launch_fwd53(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelD
   k_dwt53_fwd<NC, U16, STAGES><<<grid, block, smem, st>>>(d);
 }
 
+template <int NC, bool U16, int STAGES>
+static void launch_fwd97(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
+{
+  const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * RowStage<NC, U16>::PAIRB;
+  static bool once = false;
+  if(!once)
+  {
+    cudaFuncSetAttribute(k_dwt97_fwd<NC, U16, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    once = true;
+  }
+  k_dwt97_fwd<NC, U16, STAGES><<<grid, block, smem, st>>>(d);
+}
+
 void b2k_launch_dwt_fwd(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, bool irreversible, bool in_u16,
                         cudaStream_t st)
 {
@@ -1480,13 +1766,13 @@ void b2k_launch_dwt_fwd(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, 
   {
     if(nc == 3)
     {
-      if(in_u16) k_dwt97_fwd<3, true><<<grid, block, 0, st>>>(d);
-      else k_dwt97_fwd<3, false><<<grid, block, 0, st>>>(d);
+      if(in_u16) launch_fwd97<3, true, FWD_STAGES>(grid, block, st, d);
+      else launch_fwd97<3, false, FWD_STAGES>(grid, block, st, d);
     }
     else
     {
-      if(in_u16) k_dwt97_fwd<1, true><<<grid, block, 0, st>>>(d);
-      else k_dwt97_fwd<1, false><<<grid, block, 0, st>>>(d);
+      if(in_u16) launch_fwd97<1, true, FWD_STAGES>(grid, block, st, d);
+      else launch_fwd97<1, false, FWD_STAGES>(grid, block, st, d);
     }
   }
   b2k_count_launch();
@@ -1503,6 +1789,19 @@ static void launch_inv53(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelD
     once = true;
   }
   k_dwt53_inv<NC, STAGES, OUT16><<<grid, block, smem, st>>>(d);
+}
+
+template <int NC, int STAGES>
+static void launch_inv97(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
+{
+  const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * BandStage<NC>::PAIRB;
+  static bool once = false;
+  if(!once)
+  {
+    cudaFuncSetAttribute(k_dwt97_inv<NC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    once = true;
+  }
+  k_dwt97_inv<NC, STAGES><<<grid, block, smem, st>>>(d);
 }
 
 void b2k_launch_dwt_inv(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, bool irreversible, bool out_u16,
@@ -1526,8 +1825,8 @@ void b2k_launch_dwt_inv(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, 
   }
   else
   {
-    if(nc == 3) k_dwt97_inv<3><<<grid, block, 0, st>>>(d);
-    else k_dwt97_inv<1><<<grid, block, 0, st>>>(d);
+    if(nc == 3) launch_inv97<3, FWD_STAGES>(grid, block, st, d);
+    else launch_inv97<1, FWD_STAGES>(grid, block, st, d);
   }
   b2k_count_launch();
 }
