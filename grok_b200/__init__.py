@@ -121,7 +121,7 @@ def _check(rc, what):
 
 
 def make_coding(width, height, numcomps=1, prec=8, sgnd=False, numres=6, tile=None, cblk=(64, 64), irreversible=False,
-                mct=None, numgbits=1, origin=(0, 0), tile_origin=None):
+                mct=None, numgbits=1, origin=(0, 0), tile_origin=None, precincts=None):
     """Convenience constructor; defaults follow grk_compress for an HT (.jph) output:
     6 resolutions (CodeStream.h L43), 64x64 blocks (L40), one guard bit (GrkCompress.cpp L849)."""
     cp = Coding()
@@ -138,6 +138,10 @@ def make_coding(width, height, numcomps=1, prec=8, sgnd=False, numres=6, tile=No
     for r in range(33):
         cp.prcw_exp[r] = 15
         cp.prch_exp[r] = 15
+    if precincts:  # [(w, h)] per resolution, coarsest first; the last entry repeats
+        for r in range(numres):
+            pw, ph = precincts[min(r, len(precincts) - 1)]
+            cp.prcw_exp[r], cp.prch_exp[r] = int(np.log2(pw)), int(np.log2(ph))
     return cp
 
 

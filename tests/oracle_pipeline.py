@@ -134,7 +134,7 @@ def enumerate_all(cp, tiles=None):
     for t, (x0, y0, x1, y1) in enumerate(tile_rects(cp)):
         if tiles is not None and t not in tiles:
             continue
-        blks = O.enumerate_blocks((x0, y0, x1, y1), cp.numres, cp.cblkw_exp, cp.cblkh_exp)
+        blks = O.enumerate_blocks((x0, y0, x1, y1), cp.numres, cp.cblkw_exp, cp.cblkh_exp, list(cp.prcw_exp), list(cp.prch_exp))
         for c in range(cp.numcomps):
             for b in blks:
                 out.append((t, c, b))

@@ -23,6 +23,8 @@ GEOMS = [
     dict(width=40, height=33, numcomps=1, prec=12, numres=2, tile=(7, 1), cblk=(4, 4)), # 1-pixel-high tiles
     dict(width=300, height=200, numcomps=3, prec=8, numres=5, tile=(128, 128), origin=(129, 65), tile_origin=(1, 1),
          cblk=(16, 128)),
+    dict(width=700, height=500, numcomps=3, prec=12, numres=5, tile=(512, 256), origin=(5, 11), precincts=[(128, 128)]),  # many precincts
+    dict(width=260, height=140, numcomps=3, prec=16, sgnd=True, numres=4, numgbits=2),                                   # signed 16 bit, 2 guard bits
 ]
 
 
@@ -43,6 +45,8 @@ def test_reversible_stage_parity(engine, args):
     cp = G.make_coding(**args)
     planes = P.synthetic_image(args["width"], args["height"], args["numcomps"], args["prec"], seed=42,
                                origin=args.get("origin", (0, 0)))
+    if args.get("sgnd"):
+        planes = [p - (1 << (args["prec"] - 1)) for p in planes]
     ref = P.forward(cp, planes)
     job = engine.job(cp)
     job.upload(planes)

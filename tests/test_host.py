@@ -80,6 +80,9 @@ int main(void){ printf("%zu %zu %zu %zu\n", sizeof(b2k_coding), sizeof(b2k_block
     dict(width=7, height=5, numcomps=1, prec=8, numres=6),
     dict(width=1000, height=600, numcomps=3, prec=10, numres=5, tile=(256, 256), origin=(17, 9), tile_origin=(5, 3),
          cblk=(16, 128)),
+    dict(width=700, height=500, numcomps=3, prec=12, numres=5, tile=(512, 256), origin=(5, 11), precincts=[(128, 128)]),
+    dict(width=513, height=300, numcomps=1, prec=10, numres=4, precincts=[(32, 64), (64, 32), (128, 128), (256, 256)],
+         cblk=(64, 64)),
 ])
 def test_geometry_matches_oracle(args):
     cp = G.make_coding(**args)
