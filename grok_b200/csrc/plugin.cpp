@@ -210,7 +210,9 @@ extern "C" gpup_tile* b2k_result_to_gpup_tile(const b2k_coding* cp, const b2k_re
   return T;
 }
 
-static void free_tree(gpup_tile* T)
+void b2k_plugin_free_tree(gpup_tile* T);
+static void free_tree(gpup_tile* T) { b2k_plugin_free_tree(T); }
+void b2k_plugin_free_tree(gpup_tile* T)
 {
   if(!T)
     return;
@@ -242,6 +244,15 @@ static void free_tree(gpup_tile* T)
   }
   free(T->tileComponents);
   free(T);
+}
+
+/* the engine the stock entry points share (created by plugin_init, or lazily on first use) */
+b2k_engine* b2k_plugin_engine(void)
+{
+  std::lock_guard<std::mutex> lock(g_mu);
+  if(!g_engine && b2k_engine_create(g_device, &g_engine) != 0)
+    return nullptr;
+  return g_engine;
 }
 
 extern "C" int32_t gpup_encode_mem(gpup_compress_params* params, gpup_image* image, gpup_tile** out)

@@ -333,3 +333,55 @@ def test_16bit_containers(engine, sgnd):
         assert np.array_equal(x, y)
     a.free()
     b.free()
+
+
+def _mock_host():
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = "/tmp/b2k_mock_host_%d.so" % os.getpid()
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-I", os.path.join(os.path.dirname(here), "grok_b200", "csrc"),
+                    os.path.join(here, "mock_host.cpp"), "-o", so], check=True)
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("irreversible", [False, True])
+def test_stock_plugin_decompress_protocol(engine, irreversible):
+    """plugin_decompress(): the HEADER -> T2 -> POST_T1 -> CLEAN callback protocol against a mock of
+    Grok's host side (tests/mock_host.cpp) fed with this engine's own coded blocks.  Reversible: pixels
+    equal the source; irreversible: equal to b2k_decode's.  A block claiming refinement passes must be
+    handed back as "not handled" (1), never mis-decoded."""
+    w, h = 320, 200
+    cp = G.make_coding(w, h, 3, 12, numres=5, irreversible=irreversible)
+    planes = P.synthetic_image(w, h, 3, 12, seed=99)
+    res = engine.encode(cp, planes)
+    blocks, data = res.blocks.copy(), res.bytes.copy()
+    res.free()
+    ref_out = [np.zeros_like(p) for p in planes]
+    engine.decode(cp, blocks, data, ref_out)
+    steps = []
+    for c in range(3):
+        for r in range(cp.numres):
+            for b in range(1 if r == 0 else 3):
+                steps.append(P.band_params(cp, r, 0 if r == 0 else b + 1)[2])
+    steps = np.array(steps, np.float32)
+    M = _mock_host()
+    lib = G.lib()
+    fn = C.cast(lib.plugin_decompress, C.c_void_p)
+    out = [np.zeros((h, w), np.int32) for _ in range(3)]
+    outp = (C.c_void_p * 3)(*[o.ctypes.data for o in out])
+    strides = (C.c_uint32 * 3)(w, w, w)
+    phases = C.c_int(0)
+    M.mock_host_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_int, C.POINTER(C.c_int)]
+    rc = M.mock_host_run(fn, C.byref(cp), blocks.ctypes.data, len(blocks), data.ctypes.data, steps.ctypes.data, outp, strides, 0,
+                         C.byref(phases))
+    assert rc == 0 and phases.value == 15, (rc, phases.value, lib.b2k_last_error())
+    for a, b, s in zip(out, ref_out, planes):
+        assert np.array_equal(a, b)
+        if not irreversible:
+            assert np.array_equal(a, s)
+    rc = M.mock_host_run(fn, C.byref(cp), blocks.ctypes.data, len(blocks), data.ctypes.data, steps.ctypes.data, outp, strides, 1,
+                         C.byref(phases))
+    assert rc == 1 and (phases.value & 4) == 0   # declined before POST_T1, CLEAN still delivered
+    assert phases.value & 8

@@ -163,3 +163,36 @@ def test_tile_sharding_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_plugin_decode_callback_struct_matches_reference():
+    """PluginDecodeCallbackInfo (std::string members: C++ ABI, plugin_interface.h L78-115) restated in
+    grok_b200/csrc/plugin_decode_abi.h: same size and member offsets as the reference's own header."""
+    probe = r'''
+#include <cstdio>
+#include <cstddef>
+%s
+int main(){ printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu\n", sizeof(PluginDecodeCallbackInfo), offsetof(PluginDecodeCallbackInfo, inputFile),
+  offsetof(PluginDecodeCallbackInfo, header_info), offsetof(PluginDecodeCallbackInfo, image), offsetof(PluginDecodeCallbackInfo, tile),
+  offsetof(PluginDecodeCallbackInfo, decompress_flags), offsetof(PluginDecodeCallbackInfo, codestream)); return 0; }'''
+
+    def run(include, flags):
+        exe = "/tmp/b2k_abi_dec_%d" % os.getpid()
+        subprocess.run(["g++", "-std=c++20", "-w", "-x", "c++", "-", "-o", exe] + flags, input=(probe % include).encode(), check=True)
+        return [int(v) for v in subprocess.check_output([exe]).split()]
+
+    mine = run('#include "plugin_decode_abi.h"', ["-I", os.path.join(ROOT, "grok_b200", "csrc")])
+    assert mine == [488, 16, 104, 416, 432, 444, 464]   # measured from the reference header (g++ 13, x86-64)
+    ref = "/root/reference/src/lib/core"
+    if os.path.isdir(ref):
+        theirs = run('#include "plugin_interface.h"\nusing namespace grk;',
+                     ["-I", ref + "/plugin", "-I", ref + "/plugin/gpup", "-I", ref, "-I", ref + "/util",
+                      "-I", os.path.join(ROOT, "oracle", "ref_shim")])
+        assert theirs == mine
+
+
+def test_stock_symbols_exported():
+    lib = G.lib()
+    for s in ("minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "gpup_encode_mem", "gpup_tile_free",
+              "plugin_decompress"):
+        assert hasattr(lib, s), s
