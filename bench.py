@@ -271,11 +271,8 @@ def main():
     job.upload(planes)
 
     def device_step():
-        a = job.forward()
-        b, nbytes = job.t1_encode()
-        c = job.t1_decode()
-        d = job.inverse()
-        return (a, b, c, d), nbytes
+        _, st4, nbytes = job.roundtrip()   # fwd -> HT encode -> HT decode -> inverse, one synchronisation
+        return tuple(st4), nbytes
 
     sampler = ClockSampler(local)
     sampler.start()

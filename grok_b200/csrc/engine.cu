@@ -122,6 +122,7 @@ struct b2k_device_job
   HtBlockOut* d_out = nullptr;
   uint64_t* d_offsets = nullptr;
   uint32_t* d_recs = nullptr;     /* decode: per-quad records between the two decode phases */
+  float* d_dec_quant = nullptr;
   HtBlockOut* d_dec_status = nullptr;
   uint64_t total_quads = 0;
   uint8_t* d_scratch = nullptr;
@@ -410,6 +411,8 @@ static int build_block_plan(b2k_device_job* J)
     CUDA_TRY(cudaMalloc(&J->d_scratch, J->scratch_bytes + 64));
     CUDA_TRY(cudaMalloc(&J->d_recs, (J->total_quads + 64) * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&J->d_dec_status, n * sizeof(HtBlockOut)));
+    CUDA_TRY(cudaMalloc(&J->d_dec_quant, n * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(J->d_dec_quant, J->dec_quant.data(), n * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaHostAlloc(&J->h_out, n * sizeof(HtBlockOut), cudaHostAllocDefault));
     CUDA_TRY(cudaHostAlloc(&J->h_dec_desc, n * sizeof(HtBlockDesc), cudaHostAllocDefault));
     CUDA_TRY(cudaHostAlloc(&J->h_offsets, (n + 1) * sizeof(uint64_t), cudaHostAllocDefault));
@@ -495,6 +498,7 @@ extern "C" void b2k_job_destroy(b2k_device_job* J)
   cudaFree(J->d_offsets);
   cudaFree(J->d_scratch);
   cudaFree(J->d_recs);
+  cudaFree(J->d_dec_quant);
   cudaFree(J->d_dec_status);
   cudaFree(J->d_bytes);
   cudaFree(J->d_err);
@@ -825,35 +829,89 @@ static int prepare_decode(b2k_device_job* J, const b2k_block* blocks, uint64_t n
   return 0;
 }
 
+static int enqueue_t1_decode_own(b2k_device_job* J, cudaStream_t st)
+{
+  const uint32_t n = (uint32_t)J->h_enc_desc.size();
+  b2k_launch_build_dec_desc(J->d_enc_desc, J->d_out, J->d_offsets, J->d_dec_quant, J->d_dec_desc, n, st);
+  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, J->d_recs, J->d_dec_status, n, J->max_cblk_w, J->d_err, st);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int32_t b2k_job_t1_decode(b2k_device_job* J, float* ms)
 {
   if(!J) return -1;
   CUDA_TRY(cudaSetDevice(J->eng->device));
   cudaStream_t st = J->eng->stream;
-  const uint32_t n = (uint32_t)J->h_enc_desc.size();
-  /* lengths/offsets of the job's own last encode */
-  CUDA_TRY(cudaMemcpyAsync(J->h_out, J->d_out, n * sizeof(HtBlockOut), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(J->h_offsets, J->d_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  std::vector<b2k_block> blk = J->blocks;
-  for(uint32_t k = 0; k < n; ++k)
-  {
-    b2k_block& b = blk[J->coded_index[k]];
-    b.length = J->h_out[k].total;
-    b.offset = J->h_offsets[k];
-    b.numbps = 1;
-    b.numpasses = 1;
-  }
-  if(int rc = prepare_decode(J, blk.data(), blk.size(), st)) return rc;
   CUDA_TRY(cudaMemsetAsync(J->d_err, 0, sizeof(int), st));
   CUDA_TRY(cudaEventRecord(J->ev[0], st));
-  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, J->d_recs, J->d_dec_status, n, J->max_cblk_w, J->d_err, st);
+  if(enqueue_t1_decode_own(J, st)) return -1;
   CUDA_TRY(cudaEventRecord(J->ev[1], st));
   CUDA_TRY(cudaEventSynchronize(J->ev[1]));
-  CUDA_TRY(cudaGetLastError());
   float t = 0;
   CUDA_TRY(cudaEventElapsedTime(&t, J->ev[0], J->ev[1]));
   if(ms) *ms = t;
+  int herr = 0;
+  CUDA_TRY(cudaMemcpy(&herr, J->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if(herr)
+  {
+    g_err = "HT decoder rejected " + std::to_string(herr) + " block(s)";
+    return -2;
+  }
+  return 0;
+}
+
+/* One device-resident round trip, enqueued back to back with a single synchronisation at the end:
+   forward (DC shift + MCT + DWT) -> block encode -> scan + compact -> block decode -> inverse.
+   stage_ms[4] (optional) = forward, encode (incl. scan/compact), decode, inverse from CUDA events. */
+extern "C" int32_t b2k_job_roundtrip(b2k_device_job* J, float* ms_total, float* stage_ms, uint64_t* total_bytes)
+{
+  if(!J) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  cudaStream_t st = J->eng->stream;
+  const uint32_t n = (uint32_t)J->h_enc_desc.size();
+  if(J->bytes_cap == 0)
+  { /* first use: size the arena (one synchronising pass) */
+    float t;
+    uint64_t b;
+    if(int rc = b2k_job_forward(J, &t)) return rc;
+    if(int rc = b2k_job_t1_encode(J, &t, &b)) return rc;
+  }
+  CUDA_TRY(cudaMemsetAsync(J->d_err, 0, sizeof(int), st));
+  CUDA_TRY(cudaEventRecord(J->ev[0], st));
+  if(enqueue_forward(J, st, true)) return -1;
+  CUDA_TRY(cudaEventRecord(J->ev[1], st));
+  if(enqueue_t1_encode(J, st)) return -1;
+  b2k_launch_ht_gather(J->d_enc_desc, J->d_out, J->d_offsets, J->d_scratch, J->d_bytes, n, J->bytes_cap, st);
+  CUDA_TRY(cudaMemcpyAsync(&J->h_offsets[n], J->d_offsets + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(J->ev[2], st));
+  if(enqueue_t1_decode_own(J, st)) return -1;
+  CUDA_TRY(cudaEventRecord(J->ev[3], st));
+  if(enqueue_inverse(J, st)) return -1;
+  CUDA_TRY(cudaEventRecord(J->ev[6], st));
+  CUDA_TRY(cudaEventSynchronize(J->ev[6]));
+  CUDA_TRY(cudaGetLastError());
+  if(J->h_offsets[n] > J->bytes_cap)
+  { /* arena estimate too small (content changed): grow and let the caller repeat */
+    cudaFree(J->d_bytes);
+    J->bytes_cap = J->h_offsets[n] + J->h_offsets[n] / 8 + 4096;
+    CUDA_TRY(cudaMalloc(&J->d_bytes, J->bytes_cap));
+    g_err = "coded size grew past the arena: arena resized, call again";
+    return 2;
+  }
+  J->bytes_used = J->h_offsets[n];
+  float t[5] = {0, 0, 0, 0, 0};
+  cudaEventElapsedTime(&t[0], J->ev[0], J->ev[1]);
+  cudaEventElapsedTime(&t[1], J->ev[1], J->ev[2]);
+  cudaEventElapsedTime(&t[2], J->ev[2], J->ev[3]);
+  cudaEventElapsedTime(&t[3], J->ev[3], J->ev[6]);
+  cudaEventElapsedTime(&t[4], J->ev[0], J->ev[6]);
+  cudaEventElapsedTime(&J->last_level1_ms, J->ev[4], J->ev[5]);
+  if(ms_total) *ms_total = t[4];
+  if(stage_ms)
+    for(int i = 0; i < 4; ++i)
+      stage_ms[i] = t[i];
+  if(total_bytes) *total_bytes = J->bytes_used;
   int herr = 0;
   CUDA_TRY(cudaMemcpy(&herr, J->d_err, sizeof(int), cudaMemcpyDeviceToHost));
   if(herr)

@@ -378,6 +378,9 @@ B2K_API int32_t b2k_job_forward(b2k_device_job* j, float* ms);  /* DC shift+MCT+
 B2K_API int32_t b2k_job_t1_encode(b2k_device_job* j, float* ms, uint64_t* total_bytes);
 B2K_API int32_t b2k_job_t1_decode(b2k_device_job* j, float* ms);/* from the job's own coded blocks */
 B2K_API int32_t b2k_job_inverse(b2k_device_job* j, float* ms);  /* inverse DWT+MCT into image */
+/* all four stages enqueued back to back, one synchronisation; stage_ms[4] optional; returns 2 once if the
+ * coded size outgrew the arena (arena resized: call again) */
+B2K_API int32_t b2k_job_roundtrip(b2k_device_job* j, float* ms_total, float* stage_ms, uint64_t* total_bytes);
 B2K_API int32_t b2k_job_download(b2k_device_job* j, int32_t* const* planes, const uint32_t* strides);
 /* copy the coefficient planes (Mallat layout per tile, image-shaped, int32 or float bits) */
 B2K_API int32_t b2k_job_download_coeffs(b2k_device_job* j, int32_t* const* planes, const uint32_t* strides);
