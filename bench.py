@@ -306,6 +306,7 @@ def main():
         res.free()
         return nb, nbk
 
+    host_threads = G.set_host_threads(-1)
     for _ in range(max(1, args.warmup - 1)):
         e2e_step()
     barrier()
@@ -317,6 +318,19 @@ def main():
     sampler.end()
     clocks = sampler.stop()   # clocks / throttle reasons over both timed regions
     assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "e2e round trip is not lossless"
+
+    # ---------------- same call with host packing off: the int32 planes cross PCIe as they are ----------------
+    G.set_host_threads(0)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(3, args.steps // 2)):
+        e2e_step()
+    barrier()
+    dt_e2e32 = (time.perf_counter() - t0) / max(3, args.steps // 2)
+    assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "e2e (no host packing) round trip is not lossless"
+    G.set_host_threads(-1)
 
     # ---------------- same, 16-bit sample containers (b2k_encode16 / b2k_decode16) ----------------
     p16 = [G.pinned_empty((H, W), np.uint16) for _ in range(NCOMP)]
@@ -340,12 +354,12 @@ def main():
     assert all(np.array_equal(a, b) for a, b in zip(o16, p16)), "16-bit e2e round trip is not lossless"
 
     # max over ranks
-    times = torch.tensor([dt_dev, dt_e2e, dt_e2e16], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dt_dev, dt_e2e, dt_e2e16, dt_e2e32], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
         dist.all_gather(sizes, torch.tensor([nb], dtype=torch.int64, device="cuda"))  # codestream segment sizes
-    dt_dev, dt_e2e, dt_e2e16 = float(times[0]), float(times[1]), float(times[2])
+    dt_dev, dt_e2e, dt_e2e16, dt_e2e32 = float(times[0]), float(times[1]), float(times[2]), float(times[3])
 
     if rank == 0:
         pix = W * H * world
@@ -367,8 +381,14 @@ def main():
                        "stage_ms": {"fwd_mct_dwt": stage[0] / args.steps, "ht_encode": stage[1] / args.steps,
                                     "ht_decode": stage[2] / args.steps, "inv_dwt_mct": stage[3] / args.steps}},
             "e2e": {"value": e2e_val, "unit": "Mpixels/s", "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "h2d_bytes_per_step": int(img_bytes + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes + nb + nbk * 24),
-                    "api": "b2k_encode + b2k_decode (include/grok_b200.h), pinned host int32 planes (the gpup_image layout)"},
+                    "h2d_bytes_per_step": int((img_bytes // 2 if host_threads else img_bytes) + nb + nbk * 64),
+                    "d2h_bytes_per_step": int((img_bytes // 2 if host_threads else img_bytes) + nb + nbk * 24),
+                    "host_threads": host_threads,
+                    "api": "b2k_encode + b2k_decode (include/grok_b200.h), host int32 planes (the gpup_image layout); samples "
+                           "<= 16 bit cross PCIe in 16-bit containers, narrowed/widened per chunk by host_threads host threads"},
+            "e2e_i32_direct": {"value": pix / dt_e2e32 / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_e2e32 * 1e3,
+                               "h2d_bytes_per_step": int(img_bytes + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes + nb + nbk * 24),
+                               "api": "same calls with b2k_set_host_threads(0): pinned int32 planes copied as they are"},
             "e2e_u16": {"value": pix / (dt_e2e16 / args.steps) / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_e2e16 / args.steps * 1e3,
                         "h2d_bytes_per_step": int(img_bytes // 2 + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes // 2 + nb + nbk * 24),
                         "api": "b2k_encode16 + b2k_decode16: same path, 16-bit sample containers (cf. gpup_batch_memory_submit_planes)"},
@@ -404,7 +424,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_dwt53_fwd<3> launch, from the committed
 # `ncu --set full` capture under profiles/ (None until that capture exists)
-TRAFFIC_NCU = None
+TRAFFIC_NCU = 1639977216   # profiles/r01f_dwt53_fwd_ncu_full_summary.txt: 878.94 MB read + 761.03 MB written
 
 if __name__ == "__main__":
     main()

@@ -62,7 +62,7 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_result_to_gpup_tile", "b2k_job_create", "b2k_job_destroy", "b2k_job_upload", "b2k_job_forward",
            "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
-           "b2k_launch_count", "b2k_job_last_kernel_stats"]
+           "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads"]
 
 _lib = None
 
@@ -108,6 +108,8 @@ def lib():
     L.b2k_job_num_blocks.argtypes = [vp]
     L.b2k_job_num_blocks.restype = u64
     L.b2k_launch_count.restype = u64
+    L.b2k_set_host_threads.argtypes = [C.c_int32]
+    L.b2k_set_host_threads.restype = C.c_int32
     L.b2k_job_last_kernel_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(u64)]
     _lib = L
     return L
@@ -152,6 +154,11 @@ def _plane_ptrs(planes):
     arr = (C.c_void_p * n)(*[p.ctypes.data for p in planes])
     strides = (C.c_uint32 * n)(*[p.strides[0] // p.itemsize for p in planes])
     return arr, strides
+
+
+def set_host_threads(n):
+    """Host threads that narrow/widen int32 planes to 16-bit PCIe containers (0 = off, <0 = default)."""
+    return int(lib().b2k_set_host_threads(int(n)))
 
 
 def pinned_empty(shape, dtype):

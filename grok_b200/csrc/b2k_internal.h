@@ -77,3 +77,15 @@ void b2k_launch_widen16(const uint16_t* src, uint32_t spitch, int32_t* dst, uint
 void b2k_launch_narrow16(const int32_t* src, uint32_t spitch, uint16_t* dst, uint32_t dpitch, uint32_t w, uint32_t h,
                          cudaStream_t st);
 void b2k_count_launch(void);
+
+/* host_pack.cpp: container conversion on a small host thread pool (int32 planes <-> pinned 16-bit staging) */
+struct b2k_host_rect
+{
+  const void* src;
+  void* dst;
+  size_t src_stride, dst_stride; /* in elements */
+  size_t w, h;
+};
+void b2k_host_convert(const b2k_host_rect* rects, size_t nrects, bool widen, bool sgnd);
+void b2k_host_set_threads(int n); /* 0 disables host packing, <0 restores the default */
+int b2k_host_threads(void);

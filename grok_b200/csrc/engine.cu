@@ -18,6 +18,7 @@
  */
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -137,6 +138,8 @@ struct b2k_device_job
   float last_level1_ms = 0.f, last_inv_level1_ms = 0.f;
   uint64_t level1_alg_bytes = 0;
   bool img_is_u16 = false;
+  uint16_t* h_stage16 = nullptr;  /* pinned 16-bit staging for the int32 entry points (host_pack.cpp) */
+  uint64_t stage16_elems = 0;
 };
 
 /* -------------------------------------------------------------------------------------------- */
@@ -198,6 +201,12 @@ extern "C" void* b2k_host_alloc(size_t bytes)
     return nullptr;
   return p;
 }
+extern "C" int32_t b2k_set_host_threads(int32_t n)
+{
+  b2k_host_set_threads(n);
+  return b2k_host_threads();
+}
+
 extern "C" void b2k_host_free(void* p)
 {
   if(p)
@@ -505,6 +514,7 @@ extern "C" void b2k_job_destroy(b2k_device_job* J)
   cudaFreeHost(J->h_out);
   cudaFreeHost(J->h_dec_desc);
   cudaFreeHost(J->h_offsets);
+  cudaFreeHost(J->h_stage16);
   for(cudaEvent_t& ev : J->ev)
     if(ev)
       cudaEventDestroy(ev);
@@ -664,6 +674,67 @@ static int copy_planes16(b2k_device_job* J, void* const* host, const uint32_t* s
     ti = tj;
   }
   return 0;
+}
+
+/* int32 entry points with samples of <= 16 bits: the PCIe legs carry 16-bit containers, converted
+   chunk by chunk on host threads (host_pack.cpp) while the neighbouring chunk is on the bus */
+static bool host_pack_wanted(const b2k_device_job* J)
+{
+  const b2k_coding& cp = J->cp;
+  const uint64_t samples = (uint64_t)(cp.x1 - cp.x0) * (cp.y1 - cp.y0) * cp.numcomps;
+  return cp.prec <= 16 && samples >= (1u << 22) && J->chunk_tile.size() > 2 && b2k_host_threads() > 0;
+}
+static int ensure_stage16(b2k_device_job* J)
+{
+  if(J->h_stage16)
+    return 0;
+  const b2k_coding& cp = J->cp;
+  J->stage16_elems = (uint64_t)(cp.x1 - cp.x0) * (cp.y1 - cp.y0);
+  CUDA_TRY(cudaHostAlloc(&J->h_stage16, J->stage16_elems * cp.numcomps * sizeof(uint16_t), cudaHostAllocDefault));
+  return 0;
+}
+/* staging planes are image-shaped, stride = image width */
+static void stage16_views(const b2k_device_job* J, void** planes, uint32_t* strides)
+{
+  for(int c = 0; c < J->cp.numcomps; ++c)
+  {
+    planes[c] = J->h_stage16 + (uint64_t)c * J->stage16_elems;
+    strides[c] = J->cp.x1 - J->cp.x0;
+  }
+}
+static void host_convert_chunk(const b2k_device_job* J, void* const* user, const uint32_t* strides, bool widen, size_t t0,
+                               size_t t1)
+{
+  const b2k_coding& cp = J->cp;
+  const uint32_t W = cp.x1 - cp.x0;
+  std::vector<b2k_host_rect> rects;
+  t1 = std::min(t1, J->tiles.size());
+  for(size_t ti = t0; ti < t1;)
+  {
+    Rect r = J->tile_rects[ti];
+    size_t tj = ti + 1;
+    while(tj < t1 && J->tile_rects[tj].y0 == r.y0 && J->tile_rects[tj].y1 == r.y1 && J->tile_rects[tj].x0 == r.x1)
+    {
+      r.x1 = J->tile_rects[tj].x1;
+      ++tj;
+    }
+    for(int c = 0; c < cp.numcomps; ++c)
+    {
+      int32_t* u = reinterpret_cast<int32_t*>(user[c]) + (size_t)(r.y0 - cp.y0) * strides[c] + (r.x0 - cp.x0);
+      uint16_t* s = J->h_stage16 + (uint64_t)c * J->stage16_elems + (size_t)(r.y0 - cp.y0) * W + (r.x0 - cp.x0);
+      if(widen)
+        rects.push_back({s, u, W, strides[c], r.w(), r.h()});
+      else
+        rects.push_back({u, s, strides[c], W, r.w(), r.h()});
+    }
+    ti = tj;
+  }
+  static const bool dbg = getenv("B2K_DEBUG_TIMING") != nullptr;
+  const auto t_a = std::chrono::steady_clock::now();
+  b2k_host_convert(rects.data(), rects.size(), widen, cp.sgnd != 0);
+  if(dbg)
+    fprintf(stderr, "[b2k] host %s tiles [%zu,%zu): %.3f ms\n", widen ? "widen" : "narrow", t0, t1,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count());
 }
 
 /* ---- stages ----------------------------------------------------------------------------------- */
@@ -1075,6 +1146,19 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
   if(rc)
     return rc;
   CUDA_TRY(cudaSetDevice(e->device));
+  void* const* user_planes = planes;
+  const uint32_t* user_strides = strides;
+  void* stage_planes[4];
+  uint32_t stage_strides[4];
+  const bool pack = !u16 && host_pack_wanted(J);
+  if(pack)
+  {
+    if(ensure_stage16(J)) return -1;
+    stage16_views(J, stage_planes, stage_strides);
+    planes = stage_planes;
+    strides = stage_strides;
+    u16 = true;
+  }
   if(u16)
     if(int urc = ensure_u16(J))
       return urc;
@@ -1088,6 +1172,8 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
   for(size_t k = 0; k < nchunks; ++k)
   {
     const size_t t0 = J->chunk_tile[k], t1 = J->chunk_tile[k + 1];
+    if(pack)
+      host_convert_chunk(J, user_planes, user_strides, false, t0, t1); /* overlaps chunk k-1's H2D */
     if(u16 ? copy_planes16(J, planes, strides, true, cs, t0, t1) : copy_planes(J, J->img, planes, strides, true, cs, t0, t1))
       return -1;
     CUDA_TRY(cudaEventRecord(J->chunk_ev[k], cs));
@@ -1225,6 +1311,19 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
   if(rc)
     return rc;
   CUDA_TRY(cudaSetDevice(e->device));
+  void* const* user_planes = planes;
+  const uint32_t* user_strides = strides;
+  void* stage_planes[4];
+  uint32_t stage_strides[4];
+  const bool pack = !u16 && host_pack_wanted(J);
+  if(pack)
+  {
+    if(ensure_stage16(J)) return -1;
+    stage16_views(J, stage_planes, stage_strides);
+    planes = stage_planes;
+    strides = stage_strides;
+    u16 = true;
+  }
   if(u16)
     if(int urc = ensure_u16(J))
       return urc;
@@ -1302,7 +1401,15 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
     CUDA_TRY(cudaStreamWaitEvent(cs, J->chunk_ev[k], 0));
     if(u16 ? copy_planes16(J, planes, strides, false, cs, t0, t1) : copy_planes(J, J->img, planes, strides, false, cs, t0, t1))
       return -1;
+    if(pack)
+      CUDA_TRY(cudaEventRecord(J->chunk_ev[40 + (k & 7)], cs));
   }
+  if(pack) /* widen chunk k into the caller's planes while chunk k+1 is still coming down */
+    for(size_t k = 0; k < nchunks; ++k)
+    {
+      CUDA_TRY(cudaEventSynchronize(J->chunk_ev[40 + (k & 7)]));
+      host_convert_chunk(J, user_planes, user_strides, true, J->chunk_tile[k], J->chunk_tile[k + 1]);
+    }
   CUDA_TRY(cudaEventRecord(J->chunk_ev[nchunks], cs));
   CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[nchunks], 0));
   CUDA_TRY(cudaEventRecord(J->ev[1], st));

@@ -1,0 +1,339 @@
+/*
+ * grok_b200/csrc/host_pack.cpp -- host-side sample-container conversion for the PCIe legs.
+ *
+ * Grok hands the plugin 32-bit sample planes (grk_image_comp::data, grok.h; gpup_image_comp in
+ * plugin/gpup/gpu_plugin_shared.h L34-48) although JPEG 2000 samples of up to 16 bits fit half
+ * of that.  PCIe is the end-to-end bound of b2k_encode / b2k_decode, so the int32
+ * entry points narrow each pipeline chunk into a pinned 16-bit staging buffer on a small pool of
+ * host threads while the previous chunk crosses the bus, and widen on the way back.  A host that
+ * already owns pinned 16-bit planes calls b2k_encode16 / b2k_decode16 and skips this file.
+ *
+ * Pure host code: no CUDA, no reference code.  Nothing here touches coefficient values -- it is
+ * a container change (truncate to 16 bits / zero- or sign-extend), so parity is unaffected.
+ */
+#include "b2k_internal.h"
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include <pthread.h>
+#include <sched.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace
+{
+
+/* fork-join pool: parallel_for(n, fn) runs fn(i) for i in [0, n) on the workers plus the caller */
+class HostPool
+{
+public:
+  explicit HostPool(int nthreads) : stop_(false), gen_(0), next_(0), n_(0), pending_(0)
+  {
+    const std::vector<int> cpus = spread_cpus();
+    for(int i = 0; i < nthreads - 1; ++i)
+    {
+      workers_.emplace_back([this] { loop(); });
+      if(!cpus.empty())
+      { /* one worker per physical core first: two bandwidth-bound threads on SMT siblings gain nothing */
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET(cpus[(size_t)(i + 1) % cpus.size()], &set);
+        pthread_setaffinity_np(workers_.back().native_handle(), sizeof(set), &set);
+      }
+    }
+  }
+  ~HostPool()
+  {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for(auto& t : workers_)
+      t.join();
+  }
+  int size() const { return (int)workers_.size() + 1; }
+  void parallel_for(size_t n, const std::function<void(size_t)>& fn)
+  {
+    if(n == 0)
+      return;
+    if(workers_.empty() || n == 1)
+    {
+      for(size_t i = 0; i < n; ++i)
+        fn(i);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      n_ = n;
+      next_.store(0, std::memory_order_relaxed);
+      pending_.store((int)workers_.size(), std::memory_order_relaxed);
+      ++gen_;
+    }
+    cv_.notify_all();
+    drain();
+    /* wait until every worker has left this generation (fn must stay alive until then) */
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [this] { return pending_.load(std::memory_order_acquire) == 0; });
+    fn_ = nullptr;
+  }
+
+private:
+  /* CPUs this process may use, ordered so that distinct physical cores come first (B2K_HOST_PIN=0: no pinning) */
+  static std::vector<int> spread_cpus()
+  {
+    std::vector<int> out;
+    const char* pin = getenv("B2K_HOST_PIN");
+    if(pin && atoi(pin) == 0)
+      return out;
+    cpu_set_t set;
+    if(sched_getaffinity(0, sizeof(set), &set) != 0)
+      return out;
+    std::vector<std::pair<long, int>> first, rest; /* (package << 16 | core, cpu) */
+    std::vector<long> seen;
+    for(int cpu = 0; cpu < CPU_SETSIZE; ++cpu)
+    {
+      if(!CPU_ISSET(cpu, &set))
+        continue;
+      long core = cpu, pkg = 0;
+      char path[128];
+      snprintf(path, sizeof(path), "/sys/devices/system/cpu/cpu%d/topology/core_id", cpu);
+      if(FILE* f = fopen(path, "r"))
+      {
+        if(fscanf(f, "%ld", &core) != 1) core = cpu;
+        fclose(f);
+      }
+      snprintf(path, sizeof(path), "/sys/devices/system/cpu/cpu%d/topology/physical_package_id", cpu);
+      if(FILE* f = fopen(path, "r"))
+      {
+        if(fscanf(f, "%ld", &pkg) != 1) pkg = 0;
+        fclose(f);
+      }
+      const long key = (pkg << 16) | core;
+      bool dup = false;
+      for(long k : seen)
+        dup |= (k == key);
+      if(dup)
+        rest.push_back({key, cpu});
+      else
+      {
+        seen.push_back(key);
+        first.push_back({key, cpu});
+      }
+    }
+    for(auto& p : first) out.push_back(p.second);
+    for(auto& p : rest) out.push_back(p.second);
+    return out;
+  }
+  void drain()
+  {
+    for(;;)
+    {
+      const size_t i = next_.fetch_add(1, std::memory_order_relaxed);
+      if(i >= n_)
+        break;
+      (*fn_)(i);
+    }
+  }
+  void loop()
+  {
+    uint64_t seen = 0;
+    for(;;)
+    {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if(stop_)
+          return;
+      }
+      drain();
+      if(pending_.fetch_sub(1, std::memory_order_acq_rel) == 1)
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        done_cv_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  bool stop_;
+  uint64_t gen_;
+  const std::function<void(size_t)>* fn_ = nullptr;
+  std::atomic<size_t> next_;
+  size_t n_;
+  std::atomic<int> pending_;
+};
+
+std::mutex g_pool_mu;
+HostPool* g_pool = nullptr;
+int g_threads = -1; /* -1: not decided yet; 0: host packing disabled */
+
+int default_threads()
+{
+  if(const char* s = getenv("B2K_HOST_THREADS"))
+    return std::max(0, atoi(s));
+  cpu_set_t set;
+  int avail = (int)std::thread::hardware_concurrency();
+  if(sched_getaffinity(0, sizeof(set), &set) == 0)
+    avail = CPU_COUNT(&set);
+  /* a container change is bandwidth work: a couple of dozen cores saturate one socket's DRAM */
+  return std::max(1, std::min(avail, 24));
+}
+
+HostPool* pool()
+{
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if(g_threads < 0)
+    g_threads = default_threads();
+  if(g_threads == 0)
+    return nullptr;
+  if(!g_pool || g_pool->size() != g_threads)
+  {
+    delete g_pool;
+    g_pool = new HostPool(g_threads);
+  }
+  return g_pool;
+}
+
+/* ---- row kernels -------------------------------------------------------------------------------- */
+void narrow_row_scalar(const int32_t* s, uint16_t* d, size_t n)
+{
+  for(size_t i = 0; i < n; ++i)
+    d[i] = (uint16_t)s[i];
+}
+void widen_row_scalar(const uint16_t* s, int32_t* d, size_t n, bool sgnd)
+{
+  if(sgnd)
+    for(size_t i = 0; i < n; ++i)
+      d[i] = (int16_t)s[i];
+  else
+    for(size_t i = 0; i < n; ++i)
+      d[i] = s[i];
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void narrow_row_avx2(const int32_t* s, uint16_t* d, size_t n)
+{
+  size_t i = 0;
+  while(i < n && ((uintptr_t)(d + i) & 31)) /* align the streaming stores */
+  {
+    d[i] = (uint16_t)s[i];
+    ++i;
+  }
+  const __m256i m = _mm256_set1_epi32(0xFFFF);
+  for(; i + 16 <= n; i += 16)
+  {
+    const __m256i a = _mm256_and_si256(_mm256_loadu_si256((const __m256i*)(s + i)), m);
+    const __m256i b = _mm256_and_si256(_mm256_loadu_si256((const __m256i*)(s + i + 8)), m);
+    const __m256i p = _mm256_permute4x64_epi64(_mm256_packus_epi32(a, b), 0xD8);
+    _mm256_stream_si256((__m256i*)(d + i), p);
+  }
+  for(; i < n; ++i)
+    d[i] = (uint16_t)s[i];
+}
+__attribute__((target("avx2"))) void widen_row_avx2(const uint16_t* s, int32_t* d, size_t n, bool sgnd)
+{
+  size_t i = 0;
+  while(i < n && ((uintptr_t)(d + i) & 31))
+  {
+    d[i] = sgnd ? (int32_t)(int16_t)s[i] : (int32_t)s[i];
+    ++i;
+  }
+  if(sgnd)
+    for(; i + 8 <= n; i += 8)
+      _mm256_stream_si256((__m256i*)(d + i), _mm256_cvtepi16_epi32(_mm_loadu_si128((const __m128i*)(s + i))));
+  else
+    for(; i + 8 <= n; i += 8)
+      _mm256_stream_si256((__m256i*)(d + i), _mm256_cvtepu16_epi32(_mm_loadu_si128((const __m128i*)(s + i))));
+  for(; i < n; ++i)
+    d[i] = sgnd ? (int32_t)(int16_t)s[i] : (int32_t)s[i];
+}
+bool have_avx2()
+{
+  static const bool v = __builtin_cpu_supports("avx2");
+  return v;
+}
+#endif
+
+constexpr size_t ROWS_PER_TASK = 8;
+
+} // namespace
+
+void b2k_host_set_threads(int n)
+{
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_threads = n < 0 ? default_threads() : n;
+}
+
+int b2k_host_threads(void)
+{
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if(g_threads < 0)
+    g_threads = default_threads();
+  return g_threads;
+}
+
+void b2k_host_convert(const b2k_host_rect* rects, size_t nrects, bool widen, bool sgnd)
+{
+  /* one fork-join over every rectangle of the chunk: tasks are groups of ROWS_PER_TASK rows */
+  std::vector<size_t> first(nrects + 1, 0);
+  for(size_t r = 0; r < nrects; ++r)
+    first[r + 1] = first[r] + (rects[r].h + ROWS_PER_TASK - 1) / ROWS_PER_TASK;
+  auto body = [&](size_t t) {
+    size_t r = 0;
+    while(t >= first[r + 1])
+      ++r;
+    const b2k_host_rect& R = rects[r];
+    const size_t y0 = (t - first[r]) * ROWS_PER_TASK, y1 = std::min(R.h, y0 + ROWS_PER_TASK);
+    for(size_t y = y0; y < y1; ++y)
+    {
+      if(widen)
+      {
+        const uint16_t* s = (const uint16_t*)R.src + y * R.src_stride;
+        int32_t* d = (int32_t*)R.dst + y * R.dst_stride;
+#if defined(__x86_64__)
+        if(have_avx2())
+        {
+          widen_row_avx2(s, d, R.w, sgnd);
+          continue;
+        }
+#endif
+        widen_row_scalar(s, d, R.w, sgnd);
+      }
+      else
+      {
+        const int32_t* s = (const int32_t*)R.src + y * R.src_stride;
+        uint16_t* d = (uint16_t*)R.dst + y * R.dst_stride;
+#if defined(__x86_64__)
+        if(have_avx2())
+        {
+          narrow_row_avx2(s, d, R.w);
+          continue;
+        }
+#endif
+        narrow_row_scalar(s, d, R.w);
+      }
+    }
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
+  };
+  HostPool* P = pool();
+  if(P)
+    P->parallel_for(first[nrects], body);
+  else
+    for(size_t t = 0; t < first[nrects]; ++t)
+      body(t);
+}

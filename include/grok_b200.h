@@ -333,6 +333,12 @@ B2K_API const char* b2k_last_error(void);
  * to grk_image when the plugin is loaded) */
 B2K_API void* b2k_host_alloc(size_t bytes);
 B2K_API void b2k_host_free(void* p);
+/* b2k_encode / b2k_decode carry samples of <= 16 bits over PCIe in 16-bit containers: each
+ * pipeline chunk is narrowed (widened) between the caller's int32 planes and a pinned staging
+ * buffer by `n` host threads while its neighbour is on the bus.  n = 0 turns that off (the int32
+ * planes are then copied as they are and should be pinned), n < 0 restores the default
+ * (min(cores the process may run on, 24); env B2K_HOST_THREADS).  Returns the value in force. */
+B2K_API int32_t b2k_set_host_threads(int32_t n);
 
 /* Encode every tile of the image for which (tile_index % tile_mod) == tile_rem (tile_mod=1:
  * all tiles).  planes[c] = int32 samples, row stride strides[c] elements, origin (x0,y0). */

@@ -196,3 +196,14 @@ def test_stock_symbols_exported():
     for s in ("minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "gpup_encode_mem", "gpup_tile_free",
               "plugin_decompress"):
         assert hasattr(lib, s), s
+
+
+def test_host_pack_container_conversion(tmp_path):
+    """host_pack.cpp (int32 planes <-> pinned 16-bit PCIe containers on a host thread pool): exact
+    truncation / zero- and sign-extension over ragged widths, strides and 1/3/8 threads, nothing
+    written outside the rows.  Built straight from the product source, no GPU involved."""
+    exe = str(tmp_path / "host_pack_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", "/usr/local/cuda/include", os.path.join(ROOT, "tests", "host_pack_check.cpp"),
+                    os.path.join(ROOT, "grok_b200", "csrc", "host_pack.cpp"), "-o", exe, "-lpthread"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
