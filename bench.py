@@ -62,13 +62,17 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, indices, enabled=True):
+        """one nvidia-smi process for all the job's GPUs, on rank 0 only (eight pollers contend in the driver)"""
+        self.index, self.proc, self.lines = ",".join(str(i) for i in indices), None, []
         self.mark0 = self.mark1 = None
+        self.enabled = enabled
 
     def start(self):
+        if not self.enabled:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
@@ -94,6 +98,8 @@ class ClockSampler:
         self.mark1 = len(self.lines)
 
     def stop(self):
+        if not self.enabled:
+            return None
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -162,24 +168,44 @@ def cpu_reference_step(st):
     return te + td, dict(enc_s=te, dec_s=td, coded_bytes=int(st["lengths"].sum()), inv_dwt_ms_per_tilecomp=dwt.value * 1e3)
 
 
-def bind_to_gpu_numa_node(local):
+def bind_to_gpu_numa_node(local, nlocal=1):
     """Best effort: run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off,
-    so host<->device copies do not cross the socket interconnect.  Returns the node or None."""
+    so host<->device copies do not cross the socket interconnect.  Ranks whose GPUs share a node split that
+    node's physical cores between them (each keeps both SMT siblings of its cores), so their host threads do
+    not land on one another.  Returns (node, cpus given to this rank) or (None, 0)."""
     try:
         import torch
-        prop = torch.cuda.get_device_properties(local)
-        bus = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+
+        def node_of(dev):
+            prop = torch.cuda.get_device_properties(dev)
+            bus = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+            return int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+
+        node = node_of(local)
         if node < 0:
-            return None
-        cpus = set()
+            return None, 0
+        cpus = []
         for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
             lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        os.sched_setaffinity(0, cpus)
-        return node
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        ndev = min(nlocal, torch.cuda.device_count())
+        peers = [d for d in range(ndev) if node_of(d) == node]
+        if len(peers) > 1 and local in peers:
+            cores = {}
+            for c in cpus:
+                try:
+                    key = int(open("/sys/devices/system/cpu/cpu%d/topology/core_id" % c).read())
+                except Exception:
+                    key = c
+                cores.setdefault(key, []).append(c)
+            keys = sorted(cores)
+            i, n = peers.index(local), len(peers)
+            mine = keys[i * len(keys) // n:(i + 1) * len(keys) // n]
+            cpus = [c for k in mine for c in cores[k]] or cpus
+        os.sched_setaffinity(0, set(cpus))
+        return node, len(cpus)
     except Exception:
-        return None
+        return None, 0
 
 
 def cpu_model():
@@ -245,7 +271,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    numa = bind_to_gpu_numa_node(local)
+    numa, ncpus = bind_to_gpu_numa_node(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -274,7 +300,7 @@ def main():
         _, st4, nbytes = job.roundtrip()   # fwd -> HT encode -> HT decode -> inverse, one synchronisation
         return tuple(st4), nbytes
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(range(int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))) if world > 1 else [local], enabled=(rank == 0))
     sampler.start()
     for _ in range(args.warmup):
         device_step()
@@ -306,9 +332,10 @@ def main():
         res.free()
         return nb, nbk
 
-    host_threads = G.set_host_threads(-1)
-    for _ in range(max(1, args.warmup - 1)):
+    host_threads = G.set_host_threads(-1)   # default policy: the engine times packed vs direct on its first calls
+    for _ in range(max(6, args.warmup)):
         e2e_step()
+    pack_mode = G.host_pack_last()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -375,15 +402,15 @@ def main():
             "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu": "one 8192x8192x3 image (64 tiles) per rank", "numa_node": numa,
+            "config": {"workload": WORKLOAD, "per_gpu": "one 8192x8192x3 image (64 tiles) per rank", "numa_node": numa, "cpus_per_rank": ncpus,
                        "l2": "inputs (805 MB of planes per step) are larger than the 126 MB L2",
                        "coded_bytes": int(nbytes), "blocks": int(nbk),
                        "stage_ms": {"fwd_mct_dwt": stage[0] / args.steps, "ht_encode": stage[1] / args.steps,
                                     "ht_decode": stage[2] / args.steps, "inv_dwt_mct": stage[3] / args.steps}},
             "e2e": {"value": e2e_val, "unit": "Mpixels/s", "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "h2d_bytes_per_step": int((img_bytes // 2 if host_threads else img_bytes) + nb + nbk * 64),
-                    "d2h_bytes_per_step": int((img_bytes // 2 if host_threads else img_bytes) + nb + nbk * 24),
-                    "host_threads": host_threads,
+                    "h2d_bytes_per_step": int((img_bytes // 2 if pack_mode[0] == 1 else img_bytes) + nb + nbk * 64),
+                    "d2h_bytes_per_step": int((img_bytes // 2 if pack_mode[1] == 1 else img_bytes) + nb + nbk * 24),
+                    "host_threads": host_threads, "host_pack": {"encode": pack_mode[0], "decode": pack_mode[1]},
                     "api": "b2k_encode + b2k_decode (include/grok_b200.h), host int32 planes (the gpup_image layout); samples "
                            "<= 16 bit cross PCIe in 16-bit containers, narrowed/widened per chunk by host_threads host threads"},
             "e2e_i32_direct": {"value": pix / dt_e2e32 / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_e2e32 * 1e3,

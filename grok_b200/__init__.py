@@ -62,7 +62,7 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_result_to_gpup_tile", "b2k_job_create", "b2k_job_destroy", "b2k_job_upload", "b2k_job_forward",
            "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
-           "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads"]
+           "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last"]
 
 _lib = None
 
@@ -110,6 +110,8 @@ def lib():
     L.b2k_launch_count.restype = u64
     L.b2k_set_host_threads.argtypes = [C.c_int32]
     L.b2k_set_host_threads.restype = C.c_int32
+    L.b2k_host_pack_last.argtypes = [C.c_int32]
+    L.b2k_host_pack_last.restype = C.c_int32
     L.b2k_job_last_kernel_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(u64)]
     _lib = L
     return L
@@ -159,6 +161,11 @@ def _plane_ptrs(planes):
 def set_host_threads(n):
     """Host threads that narrow/widen int32 planes to 16-bit PCIe containers (0 = off, <0 = default)."""
     return int(lib().b2k_set_host_threads(int(n)))
+
+
+def host_pack_last():
+    """(encode, decode): 1 if the last int32 call went through 16-bit host packing, 0 direct, -1 none yet."""
+    return int(lib().b2k_host_pack_last(0)), int(lib().b2k_host_pack_last(1))
 
 
 def pinned_empty(shape, dtype):

@@ -33,6 +33,8 @@ using namespace b2k;
 
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_pack_policy{-1}; /* host packing: -1 auto (PackTuner), 0 never, 1 always */
+static std::atomic<int> g_last_pack[2]{{-1}, {-1}};
 void b2k_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 #define CUDA_TRY(expr)                                                                             \
@@ -95,6 +97,53 @@ struct LevelLaunch
   std::vector<uint32_t> tile_first; /* descs of selected tile ti are [tile_first[ti], tile_first[ti+1]) */
 };
 
+/* Whether the int32 entry points should narrow to 16-bit containers on the host is a property of the
+   machine at that moment: it halves the PCIe bytes but triples the host DRAM traffic, so it wins while
+   PCIe is the bound (one or two GPUs per socket, or unpinned caller memory) and loses once several
+   ranks share a socket's DRAM.  Default policy: time both ways on the first calls, keep the faster,
+   look at the other one again every 128 calls. */
+struct PackTuner
+{
+  int calls = 0;
+  double best[2] = {1e30, 1e30}; /* [0] direct, [1] packed: best wall ms seen while probing */
+  double recent = 0;             /* EMA of the chosen mode */
+  int choice = -1;
+  bool probing_other = false;
+  bool next_mode()
+  {
+    if(choice < 0)
+      return (calls & 1) == 0; /* packed, direct, packed, direct */
+    probing_other = (calls % 128) == 127;
+    return probing_other ? !choice : (choice != 0);
+  }
+  void record(bool packed, double ms)
+  {
+    ++calls;
+    if(choice < 0)
+    {
+      if(calls > 1 || !packed) /* the very first packed call allocates the staging buffer */
+        best[packed ? 1 : 0] = std::min(best[packed ? 1 : 0], ms);
+      if(calls >= 5)
+      {
+        choice = best[1] < best[0] ? 1 : 0;
+        recent = best[choice];
+      }
+      return;
+    }
+    if(probing_other)
+    {
+      if(ms < 0.9 * recent)
+      {
+        choice = packed ? 1 : 0;
+        recent = ms;
+      }
+      probing_other = false;
+      return;
+    }
+    recent = 0.9 * recent + 0.1 * ms;
+  }
+};
+
 struct b2k_device_job
 {
   b2k_engine* eng = nullptr;
@@ -140,6 +189,7 @@ struct b2k_device_job
   bool img_is_u16 = false;
   uint16_t* h_stage16 = nullptr;  /* pinned 16-bit staging for the int32 entry points (host_pack.cpp) */
   uint64_t stage16_elems = 0;
+  PackTuner tune_enc, tune_dec;
 };
 
 /* -------------------------------------------------------------------------------------------- */
@@ -204,8 +254,11 @@ extern "C" void* b2k_host_alloc(size_t bytes)
 extern "C" int32_t b2k_set_host_threads(int32_t n)
 {
   b2k_host_set_threads(n);
+  g_pack_policy.store(n < 0 ? -1 : n == 0 ? 0 : 1);
   return b2k_host_threads();
 }
+
+extern "C" int32_t b2k_host_pack_last(int32_t decode) { return g_last_pack[decode ? 1 : 0].load(); }
 
 extern "C" void b2k_host_free(void* p)
 {
@@ -678,12 +731,13 @@ static int copy_planes16(b2k_device_job* J, void* const* host, const uint32_t* s
 
 /* int32 entry points with samples of <= 16 bits: the PCIe legs carry 16-bit containers, converted
    chunk by chunk on host threads (host_pack.cpp) while the neighbouring chunk is on the bus */
-static bool host_pack_wanted(const b2k_device_job* J)
+static bool host_pack_eligible(const b2k_device_job* J)
 {
   const b2k_coding& cp = J->cp;
   const uint64_t samples = (uint64_t)(cp.x1 - cp.x0) * (cp.y1 - cp.y0) * cp.numcomps;
   return cp.prec <= 16 && samples >= (1u << 22) && J->chunk_tile.size() > 2 && b2k_host_threads() > 0;
 }
+
 static int ensure_stage16(b2k_device_job* J)
 {
   if(J->h_stage16)
@@ -1150,7 +1204,11 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
   const uint32_t* user_strides = strides;
   void* stage_planes[4];
   uint32_t stage_strides[4];
-  const bool pack = !u16 && host_pack_wanted(J);
+  const bool tuned = !u16 && host_pack_eligible(J) && g_pack_policy.load() < 0;
+  const bool pack = !u16 && host_pack_eligible(J) && (tuned ? J->tune_enc.next_mode() : g_pack_policy.load() > 0);
+  const auto wall0 = std::chrono::steady_clock::now();
+  if(!u16)
+    g_last_pack[0].store(pack ? 1 : 0);
   if(pack)
   {
     if(ensure_stage16(J)) return -1;
@@ -1264,6 +1322,8 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
   cudaEventElapsedTime(&d, J->ev[3], J->ev[6]);
   cudaEventElapsedTime(&J->last_level1_ms, J->ev[4], J->ev[5]);
   R->ms_h2d = a; R->ms_dwt = b; R->ms_t1 = c; R->ms_d2h = d; R->ms_total = a + b + c + d;
+  if(tuned)
+    J->tune_enc.record(pack, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
   *out = R;
   return 0;
 }
@@ -1315,7 +1375,11 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
   const uint32_t* user_strides = strides;
   void* stage_planes[4];
   uint32_t stage_strides[4];
-  const bool pack = !u16 && host_pack_wanted(J);
+  const bool tuned = !u16 && host_pack_eligible(J) && g_pack_policy.load() < 0;
+  const bool pack = !u16 && host_pack_eligible(J) && (tuned ? J->tune_dec.next_mode() : g_pack_policy.load() > 0);
+  const auto wall0 = std::chrono::steady_clock::now();
+  if(!u16)
+    g_last_pack[1].store(pack ? 1 : 0);
   if(pack)
   {
     if(ensure_stage16(J)) return -1;
@@ -1418,6 +1482,8 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
   float t = 0;
   cudaEventElapsedTime(&t, J->ev[0], J->ev[1]);
   if(ms_total) *ms_total = t;
+  if(tuned)
+    J->tune_dec.record(pack, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
   int herr = 0;
   CUDA_TRY(cudaMemcpy(&herr, J->d_err, sizeof(int), cudaMemcpyDeviceToHost));
   if(herr)

@@ -333,12 +333,18 @@ B2K_API const char* b2k_last_error(void);
  * to grk_image when the plugin is loaded) */
 B2K_API void* b2k_host_alloc(size_t bytes);
 B2K_API void b2k_host_free(void* p);
-/* b2k_encode / b2k_decode carry samples of <= 16 bits over PCIe in 16-bit containers: each
+/* b2k_encode / b2k_decode can carry samples of <= 16 bits over PCIe in 16-bit containers: each
  * pipeline chunk is narrowed (widened) between the caller's int32 planes and a pinned staging
- * buffer by `n` host threads while its neighbour is on the bus.  n = 0 turns that off (the int32
- * planes are then copied as they are and should be pinned), n < 0 restores the default
- * (min(cores the process may run on, 24); env B2K_HOST_THREADS).  Returns the value in force. */
+ * buffer by host threads while its neighbour is on the bus.  That halves the PCIe bytes and costs
+ * host DRAM bandwidth, so whether it pays depends on the machine and on what else runs on it.
+ *   n < 0 (default): min(cores the process may run on, 24) threads (env B2K_HOST_THREADS); each
+ *          job times both ways on its first calls and keeps the faster one;
+ *   n = 0: never (int32 planes are copied as they are and should be pinned);
+ *   n > 0: always, with n threads (also the way to feed unpinned planes).
+ * Returns the thread count in force.  b2k_host_pack_last(decode) tells which way the last
+ * b2k_encode (0) / b2k_decode (1) went: 1 packed, 0 direct, -1 none yet. */
 B2K_API int32_t b2k_set_host_threads(int32_t n);
+B2K_API int32_t b2k_host_pack_last(int32_t decode);
 
 /* Encode every tile of the image for which (tile_index % tile_mod) == tile_rem (tile_mod=1:
  * all tiles).  planes[c] = int32 samples, row stride strides[c] elements, origin (x0,y0). */

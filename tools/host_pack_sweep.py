@@ -7,7 +7,7 @@ import grok_b200 as G
 import oracle_pipeline as P
 sys.path.insert(0, ROOT)
 import bench
-numa = bench.bind_to_gpu_numa_node(0)
+numa = bench.bind_to_gpu_numa_node(0)[0]
 print("numa", numa, "cpus", len(os.sched_getaffinity(0)))
 W = H = 8192
 cp = G.make_coding(W, H, 3, 12, numres=6, tile=(1024, 1024))
