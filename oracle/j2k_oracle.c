@@ -1200,3 +1200,240 @@ ORC_API int orc_ht_decode(const uint8_t* data, uint32_t lcup, uint32_t missing_m
   free(rho_prev); free(rho_cur); free(vn_prev); free(vn_cur);
   return rc;
 }
+
+/* ================================================================================================
+ * HT refinement passes (ITU-T T.814 SigProp + MagRef), the part of T1OJPH::decompress the reference
+ * runs when a code block carries 2 or 3 passes: ojph_block_decoder32.cpp L1318-1616.
+ *
+ * The reference works on 4x4 nibble-packed significance words; this restatement keeps per-sample
+ * state and the scan order only:
+ *   stripes of 4 rows, inside a stripe groups of 4 columns, inside a group column by column,
+ *   top to bottom.  sigma = significant after the cleanup pass (cleanup LSB plane p); the passes
+ *   add bit-plane p-1.
+ *   SigProp: a sample that is not in sigma is a member when any of its 8 neighbours is in sigma or
+ *     became significant earlier in this pass; neighbours outside the block do not exist, and in
+ *     stripe-causal mode neither do those in the stripe below (L1404-1407).  Each member costs one
+ *     bit (1 = significant at plane p-1); the sign bits of a group's new samples follow the
+ *     group's last membership bit (L1437-1543).  Forward stream, LSB first, a byte after 0xFF
+ *     carries 7 bits (frwd_read<0>, L609-654); zeros once the segment is used up.
+ *   MagRef: every sample in sigma (not the ones SigProp added) costs one bit = bit p-1 of its
+ *     magnitude, same scan except that groups do not matter (L1562-1612).  Backward stream from
+ *     the segment's last byte, LSB first, a byte whose 7 low bits are all ones and whose successor
+ *     (in reading order: predecessor) was > 0x8F carries 7 bits, starting as if that were the case
+ *     (rev_read_mrp / rev_init_mrp, L453-541).
+ * Decoded magnitudes keep the reference's bin-centre convention: a half bit at plane p-2.
+ * The encoder below is test infrastructure only (the reference's own encoder never emits these
+ * passes); tests pin it by decoding its output with the reference decoder (oracle/_ref).
+ * ============================================================================================== */
+typedef struct { uint8_t* buf; int pos, cap, nbits, limit; uint32_t tmp; } spp_w;
+static void spp_put(spp_w* s, int bit)
+{
+  s->tmp |= (uint32_t)(bit & 1) << s->nbits;
+  if(++s->nbits == s->limit)
+  {
+    if(s->pos < s->cap) s->buf[s->pos] = (uint8_t)s->tmp;
+    s->pos++;
+    s->limit = (s->tmp == 0xFF) ? 7 : 8;
+    s->tmp = 0; s->nbits = 0;
+  }
+}
+static void spp_flush(spp_w* s)
+{
+  if(s->nbits)
+  {
+    uint32_t last = s->tmp;
+    if(s->pos < s->cap) s->buf[s->pos] = (uint8_t)last;
+    s->pos++;
+    s->tmp = 0; s->nbits = 0;
+    s->limit = (last == 0xFF) ? 7 : 8;
+  }
+  if(s->limit == 7)
+  { /* never end a forward segment on 0xFF: what follows may be > 0x8F */
+    if(s->pos < s->cap) s->buf[s->pos] = 0;
+    s->pos++;
+    s->limit = 8;
+  }
+}
+typedef struct { uint8_t* buf; int pos, cap, nbits; uint32_t tmp; int prev_gt8f; } mrp_w; /* buf filled in writing order */
+static void mrp_emit(mrp_w* m)
+{
+  if(m->pos < m->cap) m->buf[m->pos] = (uint8_t)m->tmp;
+  m->pos++;
+  m->prev_gt8f = m->tmp > 0x8F;
+  m->tmp = 0; m->nbits = 0;
+}
+static void mrp_put(mrp_w* m, int bit)
+{
+  m->tmp |= (uint32_t)(bit & 1) << m->nbits;
+  ++m->nbits;
+  if(m->nbits == 7 && m->prev_gt8f && m->tmp == 0x7F) { mrp_emit(m); return; }
+  if(m->nbits == 8) mrp_emit(m);
+}
+
+static int refine_neighbour(const uint8_t* sig, uint32_t w, uint32_t h, uint32_t x, uint32_t y, uint32_t y_limit)
+{
+  for(int dy = -1; dy <= 1; ++dy)
+    for(int dx = -1; dx <= 1; ++dx)
+    {
+      if(!dx && !dy) continue;
+      const int xx = (int)x + dx, yy = (int)y + dy;
+      if(xx < 0 || yy < 0 || xx >= (int)w || yy >= (int)h || yy >= (int)y_limit) continue;
+      if(sig[(size_t)yy * w + xx]) return 1;
+    }
+  return 0;
+}
+
+/* buf as for orc_ht_encode; the cleanup pass is assumed coded with the same missing_msbs (plane p =
+ * 30 - missing_msbs, p >= 2).  num_passes 2 (SigProp) or 3 (SigProp + MagRef).  Writes the refinement
+ * segment (SigProp bytes, then MagRef bytes) and returns its length, -1 if it does not fit. */
+ORC_API int orc_ht_encode_refine(const uint32_t* buf, uint32_t missing_msbs, uint32_t num_passes, uint32_t width,
+                                 uint32_t height, uint32_t stride, int stripe_causal, uint8_t* out, uint32_t out_cap)
+{
+  if(missing_msbs > 28 || num_passes < 2 || num_passes > 3) return -1;
+  const uint32_t p = 30 - missing_msbs;
+  uint8_t* sig = (uint8_t*)calloc((size_t)width * height, 1);   /* sigma, then sigma + new */
+  uint8_t* cup = (uint8_t*)calloc((size_t)width * height, 1);
+  const int cap = (int)(width * height / 4 + 64);
+  uint8_t* sbuf = (uint8_t*)malloc((size_t)cap);
+  uint8_t* mbuf = (uint8_t*)malloc((size_t)cap);
+  spp_w sp = {sbuf, 0, cap, 0, 8, 0};
+  mrp_w mr = {mbuf, 0, cap, 0, 0, 1};
+  for(uint32_t y = 0; y < height; ++y)
+    for(uint32_t x = 0; x < width; ++x)
+      cup[(size_t)y * width + x] = sig[(size_t)y * width + x] = ((buf[(size_t)y * stride + x] & 0x7FFFFFFFu) >> p) != 0;
+  for(uint32_t y0 = 0; y0 < height; y0 += 4)
+  {
+    const uint32_t y_limit = stripe_causal ? y0 + 4 : height;
+    for(uint32_t gx = 0; gx < width; gx += 4)
+    {
+      int signs[16], ns = 0;
+      for(uint32_t x = gx; x < gx + 4 && x < width; ++x)
+        for(uint32_t y = y0; y < y0 + 4 && y < height; ++y)
+        {
+          if(cup[(size_t)y * width + x]) continue;
+          if(!refine_neighbour(sig, width, height, x, y, y_limit)) continue;
+          const uint32_t v = buf[(size_t)y * stride + x];
+          const int bit = (int)(((v & 0x7FFFFFFFu) >> (p - 1)) & 1);
+          spp_put(&sp, bit);
+          if(bit)
+          {
+            sig[(size_t)y * width + x] = 1;
+            signs[ns++] = (int)(v >> 31);
+          }
+        }
+      for(int i = 0; i < ns; ++i) spp_put(&sp, signs[i]);
+    }
+  }
+  spp_flush(&sp);
+  if(num_passes == 3)
+  {
+    for(uint32_t y0 = 0; y0 < height; y0 += 4)
+      for(uint32_t x = 0; x < width; ++x)
+        for(uint32_t y = y0; y < y0 + 4 && y < height; ++y)
+          if(cup[(size_t)y * width + x])
+            mrp_put(&mr, (int)(((buf[(size_t)y * stride + x] & 0x7FFFFFFFu) >> (p - 1)) & 1));
+    if(mr.nbits) mrp_emit(&mr);
+  }
+  int total = sp.pos + mr.pos;
+  int rc = -1;
+  if(sp.pos <= cap && mr.pos <= cap)
+  {
+    if(total == 0) { sbuf[0] = 0; sp.pos = 1; total = 1; } /* a refinement segment cannot be empty */
+    if((uint32_t)total <= out_cap)
+    {
+      memcpy(out, sbuf, (size_t)sp.pos);
+      for(int i = 0; i < mr.pos; ++i) out[total - 1 - i] = mbuf[i];
+      rc = total;
+    }
+  }
+  free(sig); free(cup); free(sbuf); free(mbuf);
+  return rc;
+}
+
+typedef struct { const uint8_t* data; int size, pos, unstuff; uint64_t tmp; int bits; } spp_r;
+static int spp_get(spp_r* s)
+{
+  if(!s->bits)
+  {
+    const uint32_t b = s->pos < s->size ? s->data[s->pos] : 0;
+    s->pos++;
+    s->tmp = b;
+    s->bits = 8 - s->unstuff;
+    s->unstuff = (b == 0xFF);
+  }
+  const int v = (int)(s->tmp & 1);
+  s->tmp >>= 1; s->bits--;
+  return v;
+}
+typedef struct { const uint8_t* last; int size, pos, unstuff; uint64_t tmp; int bits; } mrp_r;
+static int mrp_get(mrp_r* m)
+{
+  if(!m->bits)
+  {
+    const uint32_t b = m->pos < m->size ? *(m->last - m->pos) : 0;
+    m->pos++;
+    m->tmp = b;
+    m->bits = 8 - ((m->unstuff && (b & 0x7F) == 0x7F) ? 1 : 0);
+    m->unstuff = b > 0x8F;
+  }
+  const int v = (int)(m->tmp & 1);
+  m->tmp >>= 1; m->bits--;
+  return v;
+}
+
+/* Full block decode: cleanup (orc_ht_decode) + SigProp (+ MagRef).  `data` holds the cleanup segment
+ * (lcup bytes) followed by the refinement segment (len2 bytes).  Mirrors the reference's leniency:
+ * len2 == 0 or p == 1 drop the refinement passes (L752-758, L790-803); more than 3 passes fail. */
+ORC_API int orc_ht_decode_passes(const uint8_t* data, uint32_t lcup, uint32_t len2, uint32_t num_passes,
+                                 uint32_t missing_msbs, uint32_t width, uint32_t height, uint32_t stride,
+                                 int stripe_causal, uint32_t* out)
+{
+  if(num_passes > 3) return -1;
+  if(num_passes > 1 && len2 == 0) num_passes = 1;
+  if(missing_msbs == 29) num_passes = 1;
+  const int rc = orc_ht_decode(data, lcup, missing_msbs, width, height, stride, out);
+  if(rc || num_passes <= 1) return rc;
+  const uint32_t p = 30 - missing_msbs;
+  uint8_t* sig = (uint8_t*)calloc((size_t)width * height, 1);
+  uint8_t* cup = (uint8_t*)calloc((size_t)width * height, 1);
+  for(uint32_t y = 0; y < height; ++y)
+    for(uint32_t x = 0; x < width; ++x)
+      cup[(size_t)y * width + x] = sig[(size_t)y * width + x] = out[(size_t)y * stride + x] != 0;
+  spp_r sp = {data + lcup, (int)len2, 0, 0, 0, 0};
+  for(uint32_t y0 = 0; y0 < height; y0 += 4)
+  {
+    const uint32_t y_limit = stripe_causal ? y0 + 4 : height;
+    for(uint32_t gx = 0; gx < width; gx += 4)
+    {
+      uint32_t nx[16], ny[16];
+      int nn = 0;
+      for(uint32_t x = gx; x < gx + 4 && x < width; ++x)
+        for(uint32_t y = y0; y < y0 + 4 && y < height; ++y)
+        {
+          if(cup[(size_t)y * width + x]) continue;
+          if(!refine_neighbour(sig, width, height, x, y, y_limit)) continue;
+          if(spp_get(&sp))
+          {
+            sig[(size_t)y * width + x] = 1;
+            nx[nn] = x; ny[nn] = y; ++nn;
+          }
+        }
+      for(int i = 0; i < nn; ++i)
+        out[(size_t)ny[i] * stride + nx[i]] = ((uint32_t)spp_get(&sp) << 31) | (3u << (p - 2));
+    }
+  }
+  if(num_passes > 2)
+  {
+    mrp_r mr = {data + lcup + len2 - 1, (int)len2, 0, 1, 0, 0};
+    for(uint32_t y0 = 0; y0 < height; y0 += 4)
+      for(uint32_t x = 0; x < width; ++x)
+        for(uint32_t y = y0; y < y0 + 4 && y < height; ++y)
+          if(cup[(size_t)y * width + x])
+          {
+            const uint32_t bit = (uint32_t)mrp_get(&mr);
+            out[(size_t)y * stride + x] ^= ((1u - bit) << (p - 1)) | (1u << (p - 2));
+          }
+  }
+  free(sig); free(cup);
+  return 0;
+}

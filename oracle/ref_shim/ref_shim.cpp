@@ -110,6 +110,17 @@ __attribute__((visibility("default"))) int ref_ht_decode(int variant, uint8_t* d
   return g_dec[variant](data, out, missing_msbs, num_passes, len1, len2, w, h, stride, false) ? 0 : -1;
 }
 
+/* same, with the stripe-causal flag of the code-block style (CoderOJPH.cpp L248) */
+__attribute__((visibility("default"))) int ref_ht_decode_vsc(int variant, uint8_t* data, uint32_t* out, uint32_t missing_msbs,
+                                                             uint32_t num_passes, uint32_t len1, uint32_t len2,
+                                                             uint32_t w, uint32_t h, uint32_t stride, int stripe_causal)
+{
+  init_once();
+  if(variant < 0) variant = g_best_dec;
+  if(variant > 2 || !g_dec[variant]) return -2;
+  return g_dec[variant](data, out, missing_msbs, num_passes, len1, len2, w, h, stride, stripe_causal != 0) ? 0 : -1;
+}
+
 static inline uint32_t cdp2(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a + ((1ull << b) - 1)) >> b); }
 
 __attribute__((visibility("default"))) int ref_dwt_lanes(void) { return (int)(hwy::VectorBytes() / 4); }

@@ -7,6 +7,10 @@ fixtures are committed so the GPU box (no reference tree) can check against them
                    produce for them (all variants agree; asserted here) + what
                    ojph_decode_codeblock32 returns for those bytes.
   dwt_cases.npz  : tile components + grk::dwt53 / grk::dwt97 multi-level forward outputs.
+  ht_refine.npz  : code blocks with 2 and 3 coding passes: the reference's encoder never writes SigProp /
+                   MagRef, so the streams come from the oracle's test-only refinement encoder on top of the
+                   reference-identical cleanup bytes; the fixture holds what ojph_decode_codeblock32 /
+                   _ssse3 / _avx2 (all agree; asserted here) make of them, plain and stripe-causal.
 """
 import os
 import sys
@@ -55,6 +59,35 @@ def main():
     blocks["count"] = np.int32(n)
     np.savez_compressed(os.path.join(HERE, "ht_blocks.npz"), **blocks)
 
+    ref = {}
+    rng2 = np.random.default_rng(20260925)
+    n = 0
+    for (w, h) in shapes:
+        for dens in (0.03, 0.3, 1.0):
+            M = int(rng2.integers(8, 28))         # missing MSBs of the cleanup pass; its LSB plane is p = 30 - M
+            p = 30 - M
+            nb = int(rng2.integers(1, p + 3))
+            mag = rng2.integers(0, 1 << nb, (h, w)).astype(np.uint64) * (rng2.random((h, w)) < dens)
+            mag = np.minimum(mag, (1 << (31 - (p - 1))) - 1)
+            v = (mag << np.uint64(p - 1)).astype(np.uint32)
+            sm = np.where(v != 0, v | (rng2.integers(0, 2, (h, w)).astype(np.uint32) << 31), 0).astype(np.uint32)
+            cup = O.ref_ht_encode(sm, M, 0)
+            for causal in (False, True):
+                for npass in (2, 3):
+                    seg = O.ht_encode_refine(sm, M, npass, causal)
+                    data = np.concatenate([cup, seg])
+                    outs = [O.ref_ht_decode(data, M, w, h, variant=vv, num_passes=npass, len2=len(seg), causal=causal) for vv in (0, 1, 2)]
+                    assert all(rc == 0 for rc, _ in outs)
+                    assert all(np.array_equal(outs[0][1], o) for _, o in outs), "reference decoder variants disagree"
+                    ref["data%03d" % n] = data
+                    ref["meta%03d" % n] = np.array([w, h, M, npass, len(seg), int(causal)], np.int32)
+                    ref["dec%03d" % n] = outs[0][1]
+                    n += 1
+    ref["count"] = np.int32(n)
+    np.savez_compressed(os.path.join(HERE, "ht_refine.npz"), **ref)
+    nref = n
+    n = int(blocks["count"])
+
     cases = {}
     geoms = [(0, 0, 64, 64, 4), (3, 5, 61, 47, 3), (1, 0, 17, 33, 6), (0, 1, 128, 9, 5), (7, 7, 1, 20, 3), (2, 3, 40, 1, 2),
              (0, 0, 5, 5, 6)]
@@ -73,7 +106,7 @@ def main():
         cases["dwt97_%d" % i] = f[:h, :w].copy()
     cases["count"] = np.int32(len(geoms))
     np.savez_compressed(os.path.join(HERE, "dwt_cases.npz"), **cases)
-    print("wrote", n, "HT blocks and", len(geoms), "DWT cases")
+    print("wrote", n, "HT blocks,", nref, "refinement blocks and", len(geoms), "DWT cases")
 
 
 if __name__ == "__main__":

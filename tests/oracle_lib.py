@@ -102,6 +102,28 @@ def ht_decode(data, missing_msbs, w, h):
     return rc, out
 
 
+def ht_encode_refine(sgnmag, missing_msbs, num_passes, causal=False, cap=8192):
+    """SigProp (+ MagRef) segment for a block whose cleanup pass was coded with the same missing_msbs."""
+    a = np.ascontiguousarray(sgnmag, dtype=np.uint32)
+    h, w = a.shape
+    out = np.zeros(cap, np.uint8)
+    L = lib()
+    L.orc_ht_encode_refine.argtypes = [_u32p] + [C.c_uint32] * 5 + [C.c_int, _u8p, C.c_uint32]
+    n = L.orc_ht_encode_refine(a, missing_msbs, num_passes, w, h, w, int(causal), out, cap)
+    assert n >= 0, "oracle refinement encoder overflow"
+    return out[:n].copy()
+
+
+def ht_decode_passes(data, len2, num_passes, missing_msbs, w, h, causal=False):
+    """cleanup + refinement segments (len2 = bytes of the latter) -> sign-magnitude words."""
+    d = np.concatenate([np.asarray(data, np.uint8), np.zeros(8, np.uint8)])
+    out = np.zeros((h, w), np.uint32)
+    L = lib()
+    L.orc_ht_decode_passes.argtypes = [_u8p] + [C.c_uint32] * 7 + [C.c_int, _u32p]
+    rc = L.orc_ht_decode_passes(d, len(data) - len2, len2, num_passes, missing_msbs, w, h, w, int(causal), out)
+    return rc, out
+
+
 def ref_ht_encode(sgnmag, missing_msbs, variant=-1, cap=24576):
     a = np.ascontiguousarray(sgnmag, dtype=np.uint32)
     h, w = a.shape
@@ -116,13 +138,15 @@ def ref_ht_encode(sgnmag, missing_msbs, variant=-1, cap=24576):
     return out[:n].copy()
 
 
-def ref_ht_decode(data, missing_msbs, w, h, variant=-1, num_passes=1, len2=0):
+def ref_ht_decode(data, missing_msbs, w, h, variant=-1, num_passes=1, len2=0, causal=False):
     stride = (w + 7) & ~7
     buf = np.zeros(len(data) + 64, np.uint8)
     buf[16:16 + len(data)] = data
     out = np.zeros((h + 2, stride), np.uint32)
-    rc = ref().ref_ht_decode(variant, buf.ctypes.data + 16, out, missing_msbs, num_passes,
-                             len(data) - len2, len2, w, h, stride)
+    R = ref()
+    R.ref_ht_decode_vsc.argtypes = [C.c_int, C.c_void_p, _u32p] + [C.c_uint32] * 7 + [C.c_int]
+    rc = R.ref_ht_decode_vsc(variant, buf.ctypes.data + 16, out, missing_msbs, num_passes,
+                             len(data) - len2, len2, w, h, stride, int(causal))
     return rc, out[:h, :w].copy()
 
 

@@ -173,3 +173,53 @@ def test_whole_tile_oracle_pipeline_round_trip():
     assert np.array_equal(rebuilt[0], coefs[0])
     out = P.inverse(cp, rebuilt)
     assert np.array_equal(out[0], planes[0])
+
+
+def test_ht_refinement_passes_match_reference_golden():
+    """SigProp / MagRef (2- and 3-pass blocks, plain and stripe-causal): the oracle's restatement decodes
+    the fixture streams to exactly what ojph_decode_codeblock32 returned for them, and the oracle's
+    test-only refinement encoder still reproduces those streams from the decoded planes' source."""
+    g = np.load(os.path.join(GOLD, "ht_refine.npz"))
+    seen = set()
+    for i in range(int(g["count"])):
+        w, h, M, npass, len2, causal = (int(v) for v in g["meta%03d" % i])
+        data = g["data%03d" % i]
+        rc, dec = O.ht_decode_passes(data, len2, npass, M, w, h, causal=bool(causal))
+        assert rc == 0
+        assert np.array_equal(dec, g["dec%03d" % i]), i
+        seen.add((npass, causal))
+        # bin-centre convention after all three passes: every decoded sample carries the half bit at plane
+        # p-2 and nothing below it (L1499, L1596-1599)
+        p = 30 - M
+        nz = dec != 0
+        if npass == 3:
+            assert np.all(((dec[nz] >> (p - 2)) & 1) == 1)
+        assert np.all((dec[nz] & ((1 << (p - 2)) - 1)) == 0)
+    assert seen == {(2, 0), (2, 1), (3, 0), (3, 1)}
+
+
+@pytest.mark.skipif(O.ref() is None, reason="oracle/_ref not built (no reference tree here)")
+def test_ht_refinement_vs_reference_live():
+    rng = np.random.default_rng(77)
+    for trial in range(60):
+        w, h = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        M = int(rng.integers(8, 28))
+        p = 30 - M
+        nb = int(rng.integers(1, p + 3))
+        mag = rng.integers(0, 1 << nb, (h, w)).astype(np.uint64) * (rng.random((h, w)) < rng.choice([0.05, 0.4, 1.0]))
+        mag = np.minimum(mag, (1 << (31 - (p - 1))) - 1)
+        v = (mag << np.uint64(p - 1)).astype(np.uint32)
+        sm = np.where(v != 0, v | (rng.integers(0, 2, (h, w)).astype(np.uint32) << 31), 0).astype(np.uint32)
+        cup = O.ht_encode(sm, M)
+        for npass in (2, 3):
+            for causal in (False, True):
+                seg = O.ht_encode_refine(sm, M, npass, causal)
+                data = np.concatenate([cup, seg])
+                rc1, a = O.ht_decode_passes(data, len(seg), npass, M, w, h, causal=causal)
+                rc2, b = O.ref_ht_decode(data, M, w, h, variant=-1, num_passes=npass, len2=len(seg), causal=causal)
+                assert rc1 == 0 and rc2 == 0 and np.array_equal(a, b), (trial, npass, causal)
+                if npass == 3:   # cleanup-significant samples are exact down to plane p-1
+                    m = sm & 0x7FFFFFFF
+                    cs = (m >> p) != 0
+                    want = ((m >> (p - 1)) << (p - 1)) | (1 << (p - 2)) | (sm & 0x80000000)
+                    assert np.array_equal(a[cs], want[cs])
