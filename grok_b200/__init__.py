@@ -27,7 +27,7 @@ class Coding(C.Structure):
                 ("numcomps", C.c_uint16), ("prec", C.c_uint8), ("sgnd", C.c_uint8),
                 ("numres", C.c_uint8), ("cblkw_exp", C.c_uint8), ("cblkh_exp", C.c_uint8),
                 ("irreversible", C.c_uint8), ("mct", C.c_uint8), ("numgbits", C.c_uint8),
-                ("prcw_exp", C.c_uint8 * 33), ("prch_exp", C.c_uint8 * 33)]
+                ("prcw_exp", C.c_uint8 * 33), ("prch_exp", C.c_uint8 * 33), ("cblk_sty", C.c_uint8)]
 
 
 class Block(C.Structure):
@@ -37,7 +37,7 @@ class Block(C.Structure):
                 ("precno", C.c_uint32), ("cblkno", C.c_uint32),
                 ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32),
                 ("buf_x", C.c_uint32), ("buf_y", C.c_uint32), ("length", C.c_uint32),
-                ("offset", C.c_uint64), ("stepsize", C.c_float)]
+                ("offset", C.c_uint64), ("stepsize", C.c_float), ("length2", C.c_uint32)]
 
 
 class Result(C.Structure):
@@ -51,7 +51,7 @@ class Result(C.Structure):
 BLOCK_DTYPE = np.dtype([("tile", "<u4"), ("comp", "<u2"), ("resno", "u1"), ("band_index", "u1"), ("orient", "u1"),
                         ("kmax", "u1"), ("numbps", "u1"), ("numpasses", "u1"), ("precno", "<u4"), ("cblkno", "<u4"),
                         ("x0", "<u4"), ("y0", "<u4"), ("x1", "<u4"), ("y1", "<u4"), ("buf_x", "<u4"), ("buf_y", "<u4"),
-                        ("length", "<u4"), ("offset", "<u8"), ("stepsize", "<f4"), ("pad2", "<u4")])
+                        ("length", "<u4"), ("offset", "<u8"), ("stepsize", "<f4"), ("length2", "<u4")])
 assert BLOCK_DTYPE.itemsize == C.sizeof(Block), (BLOCK_DTYPE.itemsize, C.sizeof(Block))
 
 # every symbol include/grok_b200.h declares
@@ -60,7 +60,7 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_engine_create", "b2k_engine_destroy", "b2k_last_error", "b2k_host_alloc", "b2k_host_free",
            "b2k_encode", "b2k_encode16", "b2k_result_free", "b2k_decode", "b2k_decode16", "b2k_enumerate",
            "b2k_result_to_gpup_tile", "b2k_job_create", "b2k_job_destroy", "b2k_job_upload", "b2k_job_forward",
-           "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_download",
+           "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
            "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last"]
 
@@ -103,6 +103,7 @@ def lib():
     L.b2k_job_inverse.argtypes = [vp, C.POINTER(C.c_float)]
     L.b2k_job_t1_encode.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u64)]
     L.b2k_job_t1_decode.argtypes = [vp, C.POINTER(C.c_float)]
+    L.b2k_job_t1_decode_blocks.argtypes = [vp, vp, u64, vp, u64, C.POINTER(C.c_float)]
     L.b2k_job_roundtrip.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
     L.b2k_job_fetch_result.argtypes = [vp, C.POINTER(C.POINTER(Result))]
     L.b2k_job_num_blocks.argtypes = [vp]
@@ -290,6 +291,15 @@ class Job:
     def t1_decode(self):
         ms = C.c_float()
         _check(lib().b2k_job_t1_decode(self._h, C.byref(ms)), "b2k_job_t1_decode")
+        return ms.value
+
+    def t1_decode_blocks(self, blocks, data):
+        """Block-decode a caller-supplied block table (BLOCK_DTYPE) + byte arena into the coefficient planes."""
+        blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        ms = C.c_float()
+        _check(lib().b2k_job_t1_decode_blocks(self._h, blocks.ctypes.data, len(blocks), data.ctypes.data, len(data), C.byref(ms)),
+               "b2k_job_t1_decode_blocks")
         return ms.value
 
     def roundtrip(self):

@@ -41,13 +41,15 @@ struct HtBlockDesc
   uint8_t kmax;        /* band maxBitPlanes_ == missing_msbs handed to the encoder */
   uint8_t irreversible;
   uint8_t mmsbs;       /* decode: missing MSBs = Kmax - numbps (DecompressScheduler.cpp L261-263) */
-  uint8_t pad;
+  uint8_t passes;      /* decode: 1 cleanup only, 2 + SigProp, 3 + SigProp + MagRef */
   float quant;         /* encode: inv_step_ht * 2^(30-kmax); decode: stepsize / 2^(31-kmax) */
   uint32_t slot_cap;   /* bytes reserved in the scratch slot */
   uint64_t slot_off;   /* byte offset of the scratch slot (encode) / of the coded bytes (decode) */
   uint32_t length;     /* decode: coded length */
   uint32_t rec_off;    /* decode: first entry of this block in the per-quad record scratch */
+  uint32_t length2;    /* decode: bytes of the refinement segment that follows the cleanup segment */
 };
+static_assert(sizeof(HtBlockDesc) == 56, "HtBlockDesc layout");
 
 struct HtBlockOut /* written by the encoder kernel */
 {
@@ -64,6 +66,8 @@ void b2k_launch_ht_encode(const HtBlockDesc* d_blocks, HtBlockOut* d_out, uint8_
 void b2k_launch_ht_gather(const HtBlockDesc* d_blocks, const HtBlockOut* d_out, const uint64_t* d_offsets,
                           const uint8_t* d_scratch, uint8_t* d_bytes, uint32_t nblocks, uint64_t cap, cudaStream_t st);
 void b2k_launch_scan_lengths(const HtBlockOut* d_out, uint64_t* d_offsets, uint32_t nblocks, cudaStream_t st);
+void b2k_launch_ht_decode_refine(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, const HtBlockOut* d_status,
+                                 uint32_t nblocks, int stripe_causal, cudaStream_t st);
 void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
                           uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st);
 void b2k_launch_ht_decode_vlc(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,

@@ -190,6 +190,7 @@ struct b2k_device_job
   uint16_t* h_stage16 = nullptr;  /* pinned 16-bit staging for the int32 entry points (host_pack.cpp) */
   uint64_t stage16_elems = 0;
   PackTuner tune_enc, tune_dec;
+  bool dec_has_refinement = false; /* the block table of the current decode carries SigProp / MagRef passes */
 };
 
 /* -------------------------------------------------------------------------------------------- */
@@ -939,13 +940,19 @@ static int prepare_decode(b2k_device_job* J, const b2k_block* blocks, uint64_t n
     HtBlockDesc d = J->h_enc_desc[k];
     d.length = b.length;
     d.slot_off = b.offset;
-    if(b.numpasses > 1)
+    if(b.numpasses > 3)
     {
-      g_err = "HT refinement passes (SigProp/MagRef) are not decoded by this engine yet";
+      g_err = "an HT code block with more than 3 coding passes";
       return 1;
     }
     const int nb = b.length ? b.numbps : 0;
     d.mmsbs = (uint8_t)std::max(0, (int)d.kmax - nb);
+    /* ojph_block_decoder32.cpp L752-758, L790-803: no refinement bytes, or a cleanup pass already at
+       bit-plane 1, leave nothing to refine */
+    d.passes = (b.length && b.numpasses > 1 && b.length2 > 0 && d.mmsbs < 29) ? b.numpasses : 1;
+    d.length2 = d.passes > 1 ? b.length2 : 0;
+    if(d.passes > 1)
+      J->dec_has_refinement = true;
     d.quant = J->dec_quant[k]; /* stepsize / 2^(31-Kmax), PostDecodeFiltersOJPH.h L103 */
     J->h_dec_desc[k] = d;
   }
@@ -973,6 +980,53 @@ extern "C" int32_t b2k_job_t1_decode(b2k_device_job* J, float* ms)
   if(enqueue_t1_decode_own(J, st)) return -1;
   CUDA_TRY(cudaEventRecord(J->ev[1], st));
   CUDA_TRY(cudaEventSynchronize(J->ev[1]));
+  float t = 0;
+  CUDA_TRY(cudaEventElapsedTime(&t, J->ev[0], J->ev[1]));
+  if(ms) *ms = t;
+  int herr = 0;
+  CUDA_TRY(cudaMemcpy(&herr, J->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if(herr)
+  {
+    g_err = "HT decoder rejected " + std::to_string(herr) + " block(s)";
+    return -2;
+  }
+  return 0;
+}
+
+/* stage hook: block-decode a caller-supplied block table (what the host's T2 parse produced, or a foreign
+   stream's blocks with SigProp / MagRef passes) into the job's coefficient planes */
+extern "C" int32_t b2k_job_t1_decode_blocks(b2k_device_job* J, const b2k_block* blocks, uint64_t num_blocks,
+                                            const uint8_t* bytes, uint64_t num_bytes, float* ms)
+{
+  if(!J || !blocks || (!bytes && num_bytes)) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  cudaStream_t st = J->eng->stream;
+  if(num_bytes + 64 > J->bytes_cap)
+  {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(J->d_bytes);
+    J->bytes_cap = num_bytes + 4096;
+    CUDA_TRY(cudaMalloc(&J->d_bytes, J->bytes_cap));
+  }
+  J->dec_has_refinement = false;
+  if(int prc = prepare_decode(J, blocks, num_blocks, st)) return prc;
+  const uint32_t n = (uint32_t)J->h_enc_desc.size();
+  for(uint32_t k = 0; k < n; ++k)
+    if((uint64_t)J->h_dec_desc[k].slot_off + J->h_dec_desc[k].length + J->h_dec_desc[k].length2 > num_bytes)
+    {
+      g_err = "block offsets exceed the byte arena";
+      return -1;
+    }
+  CUDA_TRY(cudaMemsetAsync(J->d_err, 0, sizeof(int), st));
+  if(num_bytes)
+    CUDA_TRY(cudaMemcpyAsync(J->d_bytes, bytes, num_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(J->ev[0], st));
+  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, J->d_recs, J->d_dec_status, n, J->max_cblk_w, J->d_err, st);
+  if(J->dec_has_refinement)
+    b2k_launch_ht_decode_refine(J->d_dec_desc, J->d_bytes, J->d_dec_status, n, (J->cp.cblk_sty & 0x08) != 0, st);
+  CUDA_TRY(cudaEventRecord(J->ev[1], st));
+  CUDA_TRY(cudaEventSynchronize(J->ev[1]));
+  CUDA_TRY(cudaGetLastError());
   float t = 0;
   CUDA_TRY(cudaEventElapsedTime(&t, J->ev[0], J->ev[1]));
   if(ms) *ms = t;
@@ -1400,6 +1454,7 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
   }
   CUDA_TRY(cudaEventRecord(J->ev[0], st));
   CUDA_TRY(cudaMemsetAsync(J->d_err, 0, sizeof(int), st));
+  J->dec_has_refinement = false;
   cudaStream_t cs = e->copy_stream;
   const size_t nchunks = J->chunk_tile.size() - 1;
   CUDA_TRY(cudaStreamWaitEvent(cs, J->ev[0], 0));
@@ -1424,7 +1479,7 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
       if(!d.length)
         continue;
       lo = std::min<uint64_t>(lo, d.slot_off);
-      hi = std::max<uint64_t>(hi, d.slot_off + d.length);
+      hi = std::max<uint64_t>(hi, d.slot_off + d.length + d.length2);
     }
     if(hi > num_bytes)
     {
@@ -1458,6 +1513,9 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
       CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[24 + (k & 7)], 0));
       b2k_launch_ht_decode_magsgn(J->d_dec_desc + b0, J->d_bytes, J->d_recs, J->d_dec_status + b0, b1 - b0, J->max_cblk_w,
                                   J->d_err, st);
+      if(J->dec_has_refinement)
+        b2k_launch_ht_decode_refine(J->d_dec_desc + b0, J->d_bytes, J->d_dec_status + b0, b1 - b0,
+                                    (J->cp.cblk_sty & 0x08) != 0, st);
     }
     if(enqueue_inverse(J, st, t0, t1)) return -1;
     if(u16 && convert_planes16(J, false, st, t0, t1)) return -1;

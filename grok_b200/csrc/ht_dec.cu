@@ -5,9 +5,10 @@
  * Replaces (reference, CPU): T1OJPH::decompress            t1/part15/CoderOJPH.cpp L212-262
  *                            ojph_decode_codeblock32        t1/part15/coding/ojph_block_decoder32.cpp L742-1317
  *                            ShiftOJPHFilter/ScaleOJPHFilter t1/part15/PostDecodeFiltersOJPH.h L48-66, L100-119
- * Cleanup pass only (num_passes == 1): that is all Grok's own encoder ever emits
- * (CoderOJPH.cpp L200-205).  SigProp / MagRef refinement of foreign streams is a "next" row
- * (DESIGN.md); a block that carries refinement passes is reported, not mis-decoded.
+ * The cleanup pass is all Grok's own encoder ever emits (CoderOJPH.cpp L200-205) and is the fast
+ * path (k_ht_decode_vlc + k_ht_decode_magsgn).  Blocks of foreign streams that carry SigProp /
+ * MagRef refinement (ojph_block_decoder32.cpp L1318-1616) leave the cleanup kernels as raw
+ * sign-magnitude words and are finished by k_ht_decode_refine, which also dequantises them.
  *
  * Per quad row:  (a) the MEL + CxtVLC + UVLC symbols of the row are decoded serially --
  * context-adaptive variable-length codes have no parallel parse -- by every lane redundantly
@@ -531,7 +532,9 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
           const uint32_t sgn = msv & 1u;
           if(i & 1)
             ebot[i >> 1] = 31 - __clz(v_n | 2u);
-          if(!B.irreversible)
+          if(B.passes > 1)
+            outv = (sgn << 31) | (mag & 0x7FFFFFFFu); /* k_ht_decode_refine finishes and dequantises the block */
+          else if(!B.irreversible)
           {
             const int32_t mv = (int32_t)((mag & 0x7FFFFFFFu) >> post_shift);
             outv = (uint32_t)(sgn ? -mv : mv);
@@ -572,6 +575,237 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
   }
 }
 
+/* ---- SigProp + MagRef ------------------------------------------------------------------------------
+ * One warp per block that carries refinement passes.  Both passes are bit-serial by construction (a
+ * sample's membership depends on what the previous samples of the scan decoded), so lane 0 walks the
+ * scan while the warp does the memory work around it: per stripe of 4 rows the lanes turn the block's
+ * words into significance bitmaps with ballots (coalesced loads), lane 0 decodes the stripe against
+ * those bitmaps, and the lanes write the new / refined samples back (coalesced stores).
+ * Scan, membership and the two bit streams: see oracle/j2k_oracle.c "HT refinement passes", which is
+ * the restatement this kernel is tested against.  Any block width (<= 1024) and height. */
+constexpr int RF_WORDS = 32; /* bitmap words per row: 1024 columns */
+struct RefineRows
+{
+  uint32_t sig[6][RF_WORDS]; /* [0] row above the stripe, [1..4] the stripe, [5] row below (cleanup only) */
+  uint32_t nw[4][RF_WORDS];  /* SigProp: newly significant / MagRef: samples to refine */
+  uint32_t sg[4][RF_WORDS];  /* SigProp: signs of the new samples / MagRef: decoded bit */
+};
+__device__ __forceinline__ uint32_t rf_bit(const uint32_t* row, int x, int w)
+{
+  return (x < 0 || x >= w) ? 0u : ((row[x >> 5] >> (x & 31)) & 1u);
+}
+__device__ __forceinline__ uint32_t rf_window6(const uint32_t* row, int x0, int w)
+{ /* bits of columns x0 .. x0+5 */
+  uint32_t v = 0;
+#pragma unroll
+  for(int i = 0; i < 6; ++i)
+    v |= rf_bit(row, x0 + i, w) << i;
+  return v;
+}
+struct SppR
+{ /* forward reader, zeros after the end (frwd_read<0>, L609-654) */
+  const uint8_t* d;
+  int size, pos, bits, unstuff;
+  uint32_t tmp;
+};
+__device__ __forceinline__ uint32_t spp_get(SppR& s)
+{
+  if(s.bits == 0)
+  {
+    const uint32_t b = s.pos < s.size ? (uint32_t)__ldg(s.d + s.pos) : 0u;
+    s.pos++;
+    s.tmp = b;
+    s.bits = 8 - s.unstuff;
+    s.unstuff = (b == 0xFFu);
+  }
+  const uint32_t v = s.tmp & 1u;
+  s.tmp >>= 1;
+  s.bits--;
+  return v;
+}
+struct MrpR
+{ /* backward reader (rev_read_mrp / rev_init_mrp, L453-541) */
+  const uint8_t* last;
+  int size, pos, bits, unstuff;
+  uint32_t tmp;
+};
+__device__ __forceinline__ uint32_t mrp_get(MrpR& m)
+{
+  if(m.bits == 0)
+  {
+    const uint32_t b = m.pos < m.size ? (uint32_t)__ldg(m.last - m.pos) : 0u;
+    m.pos++;
+    m.tmp = b;
+    m.bits = 8 - ((m.unstuff && (b & 0x7Fu) == 0x7Fu) ? 1 : 0);
+    m.unstuff = b > 0x8Fu;
+  }
+  const uint32_t v = m.tmp & 1u;
+  m.tmp >>= 1;
+  m.bits--;
+  return v;
+}
+
+__global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
+    k_ht_decode_refine(const HtBlockDesc* __restrict__ blocks, const uint8_t* __restrict__ bytes,
+                       const HtBlockOut* __restrict__ status, uint32_t nblocks, int stripe_causal)
+{
+  __shared__ RefineRows rows_all[B2K_WARPS_PER_CTA];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bidx = blockIdx.x * B2K_WARPS_PER_CTA + warp;
+  if(bidx >= nblocks)
+    return;
+  const HtBlockDesc B = blocks[bidx];
+  if(B.passes <= 1 || status[bidx].total != 0) /* cleanup-only blocks are finished; empty / rejected ones are zero */
+    return;
+  RefineRows& R = rows_all[warp];
+  const int w = B.w, h = B.h, nwords = (w + 31) >> 5;
+  const int p = 30 - (int)B.mmsbs;
+  uint32_t* coef = reinterpret_cast<uint32_t*>(B.coef);
+  const uint8_t* seg = bytes + B.slot_off + B.length;
+  const uint32_t newval = 3u << (p - 2);
+
+  /* row y of the block as a "non-zero" bitmap (cleanup significance while SigProp has not reached it) */
+  auto load_row = [&](uint32_t* dst, int y) {
+    for(int xb = 0; xb < nwords * 32; xb += 32)
+    {
+      const int x = xb + lane;
+      const uint32_t v = (y >= 0 && y < h && x < w) ? coef[(size_t)y * B.pitch + x] : 0u;
+      const unsigned m = __ballot_sync(0xffffffffu, (v & 0x7FFFFFFFu) != 0u);
+      if(lane == 0)
+        dst[xb >> 5] = m;
+    }
+  };
+
+  /* ---------------- SigProp ---------------- */
+  SppR sp{seg, (int)B.length2, 0, 0, 0, 0u};
+  for(int i = lane; i < RF_WORDS; i += 32)
+    R.sig[0][i] = 0;
+  for(int y0 = 0; y0 < h; y0 += 4)
+  {
+    for(int k = 1; k <= 5; ++k)
+      load_row(R.sig[k], (k == 5 && stripe_causal) ? -1 : y0 + k - 1);
+    for(int k = 0; k < 4; ++k)
+      for(int i = lane; i < nwords; i += 32)
+      {
+        R.nw[k][i] = 0;
+        R.sg[k][i] = 0;
+      }
+    __syncwarp();
+    if(lane == 0)
+    {
+      const int rows = min(4, h - y0);
+      for(int gx = 0; gx < w; gx += 4)
+      {
+        uint32_t S[6], C[4];
+#pragma unroll
+        for(int k = 0; k < 6; ++k)
+          S[k] = rf_window6(R.sig[k], gx - 1, w);
+#pragma unroll
+        for(int k = 0; k < 4; ++k)
+          C[k] = S[k + 1];
+        uint32_t found = 0; /* bit 4c+r: sample (r, c) of the group became significant */
+        for(int c = 0; c < 4 && gx + c < w; ++c)
+          for(int r = 0; r < rows; ++r)
+          {
+            if((C[r] >> (c + 1)) & 1u)
+              continue;
+            const uint32_t nb = ((S[r] | S[r + 1] | S[r + 2]) >> c) & 7u;
+            if(!nb)
+              continue;
+            if(spp_get(sp))
+            {
+              S[r + 1] |= 1u << (c + 1);
+              found |= 1u << (4 * c + r);
+            }
+          }
+        while(found)
+        {
+          const int i = __ffs(found) - 1;
+          found &= found - 1;
+          const int c = i >> 2, r = i & 3, x = gx + c;
+          const uint32_t bit = 1u << (x & 31);
+          R.sig[r + 1][x >> 5] |= bit;
+          R.nw[r][x >> 5] |= bit;
+          if(spp_get(sp))
+            R.sg[r][x >> 5] |= bit;
+        }
+      }
+    }
+    __syncwarp();
+    for(int r = 0; r < 4 && y0 + r < h; ++r)
+      for(int x = lane; x < w; x += 32)
+        if((R.nw[r][x >> 5] >> (x & 31)) & 1u)
+          coef[(size_t)(y0 + r) * B.pitch + x] = (((R.sg[r][x >> 5] >> (x & 31)) & 1u) << 31) | newval;
+    for(int i = lane; i < nwords; i += 32)
+      R.sig[0][i] = R.sig[4][i]; /* the stripe's last row, new samples included, is the next stripe's row above */
+    __syncwarp();
+  }
+
+  /* ---------------- MagRef ---------------- */
+  if(B.passes > 2)
+  {
+    MrpR mr{seg + B.length2 - 1, (int)B.length2, 0, 0, 1, 0u};
+    for(int y0 = 0; y0 < h; y0 += 4)
+    {
+      for(int k = 0; k < 4; ++k)
+      { /* members: significant after the cleanup pass, i.e. non-zero and not one of SigProp's samples */
+        const int y = y0 + k;
+        for(int xb = 0; xb < nwords * 32; xb += 32)
+        {
+          const int x = xb + lane;
+          const uint32_t v = (y < h && x < w) ? (coef[(size_t)y * B.pitch + x] & 0x7FFFFFFFu) : 0u;
+          const unsigned m = __ballot_sync(0xffffffffu, v != 0u && v != newval);
+          if(lane == 0)
+          {
+            R.nw[k][xb >> 5] = m;
+            R.sg[k][xb >> 5] = 0;
+          }
+        }
+      }
+      __syncwarp();
+      if(lane == 0)
+        for(int x = 0; x < w; ++x)
+#pragma unroll
+          for(int r = 0; r < 4; ++r)
+            if((R.nw[r][x >> 5] >> (x & 31)) & 1u)
+              if(mrp_get(mr))
+                R.sg[r][x >> 5] |= 1u << (x & 31);
+      __syncwarp();
+      for(int r = 0; r < 4 && y0 + r < h; ++r)
+        for(int x = lane; x < w; x += 32)
+          if((R.nw[r][x >> 5] >> (x & 31)) & 1u)
+          {
+            const uint32_t bit = (R.sg[r][x >> 5] >> (x & 31)) & 1u;
+            coef[(size_t)(y0 + r) * B.pitch + x] ^= ((1u - bit) << (p - 1)) | (1u << (p - 2));
+          }
+      __syncwarp();
+    }
+  }
+
+  /* ---------------- dequantise in place (PostDecodeFiltersOJPH.h L48-66 / L100-119) ---------------- */
+  const int post_shift = 31 - (int)B.kmax;
+  for(int y = 0; y < h; ++y)
+    for(int x = lane; x < w; x += 32)
+    {
+      const uint32_t v = coef[(size_t)y * B.pitch + x];
+      const uint32_t mag = v & 0x7FFFFFFFu;
+      uint32_t outv;
+      if(!B.irreversible)
+      {
+        const int32_t mv = (int32_t)(mag >> post_shift);
+        outv = (uint32_t)((v >> 31) ? -mv : mv);
+      }
+      else
+      {
+        float f = __fmul_rn((float)(int32_t)mag, B.quant);
+        if(v >> 31)
+          f = -f;
+        outv = __float_as_uint(f);
+      }
+      coef[(size_t)y * B.pitch + x] = outv;
+    }
+}
+
 } /* namespace */
 
 /* decode descriptors of the engine's OWN last encode, built on the device (device-resident round trip):
@@ -589,6 +823,8 @@ __global__ void k_build_dec_desc(const HtBlockDesc* __restrict__ enc, const HtBl
   d.length = t == 0xFFFFFFFFu ? 0 : t;
   d.slot_off = offsets[i];
   d.mmsbs = (uint8_t)(d.kmax - 1);
+  d.passes = 1;
+  d.length2 = 0;
   d.quant = dec_quant[i];
   dec[i] = d;
 }
@@ -627,6 +863,16 @@ void b2k_launch_ht_decode_magsgn(const HtBlockDesc* d_blocks, const uint8_t* d_b
   const uint32_t grid = (nblocks + B2K_WARPS_PER_CTA - 1) / B2K_WARPS_PER_CTA;
   k_ht_decode_magsgn<<<grid, B2K_WARPS_PER_CTA * 32, smem, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks, line_entries,
                                                                 d_err);
+  b2k_count_launch();
+}
+
+void b2k_launch_ht_decode_refine(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, const HtBlockOut* d_status,
+                                 uint32_t nblocks, int stripe_causal, cudaStream_t st)
+{
+  if(!nblocks)
+    return;
+  const uint32_t grid = (nblocks + B2K_WARPS_PER_CTA - 1) / B2K_WARPS_PER_CTA;
+  k_ht_decode_refine<<<grid, B2K_WARPS_PER_CTA * 32, 0, st>>>(d_blocks, d_bytes, d_status, nblocks, stripe_causal);
   b2k_count_launch();
 }
 

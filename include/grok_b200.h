@@ -294,6 +294,8 @@ typedef struct b2k_coding
   uint8_t mct;                     /* 1: colour transform on components 0..2 */
   uint8_t numgbits;                /* guard bits; Grok's HT CLI forces 1 (GrkCompress.cpp L849) */
   uint8_t prcw_exp[33], prch_exp[33]; /* precinct exponents per resolution (15 = maximal) */
+  uint8_t cblk_sty;                /* code-block style bits (COD); only 0x08 = vertically stripe-causal matters,
+                                      and only to the decoder's SigProp pass (CoderOJPH.cpp L248) */
 } b2k_coding;
 
 /* One coded block as the host's T2 needs it (cf. compress_synch_with_plugin,
@@ -306,13 +308,16 @@ typedef struct b2k_block
   uint8_t kmax;                    /* band->maxBitPlanes_ (TileProcessor.cpp L417-419) */
   uint8_t numbps;                  /* coded bit planes as T2 signals them: Kmax - zero bit planes.
                                       The encoder returns 1 (CoderOJPH.cpp L203-206) */
-  uint8_t numpasses;               /* 1 for every coded block (HT cleanup only), 0 if not coded */
+  uint8_t numpasses;               /* 0 not coded; 1 HT cleanup (all the encoder emits); decode also takes 2
+                                      (+ SigProp) and 3 (+ SigProp + MagRef) from foreign streams */
   uint32_t precno, cblkno;
   uint32_t x0, y0, x1, y1;         /* block rect, band canvas coordinates */
   uint32_t buf_x, buf_y;           /* position inside the tile-component Mallat buffer */
-  uint32_t length;                 /* coded bytes (HT cleanup pass; 1 pass, 1 segment) */
+  uint32_t length;                 /* bytes of the HT cleanup segment */
   uint64_t offset;                 /* byte offset into the result's byte arena */
   float stepsize;                  /* band step size (encoder convention) */
+  uint32_t length2;                /* decode: bytes of the refinement segment (SigProp, MagRef) that follows
+                                      the cleanup segment at offset + length; 0 from the encoder */
 } b2k_block;
 
 typedef struct b2k_result
@@ -397,6 +402,10 @@ B2K_API int32_t b2k_job_download(b2k_device_job* j, int32_t* const* planes, cons
 /* copy the coefficient planes (Mallat layout per tile, image-shaped, int32 or float bits) */
 B2K_API int32_t b2k_job_download_coeffs(b2k_device_job* j, int32_t* const* planes, const uint32_t* strides);
 B2K_API int32_t b2k_job_upload_coeffs(b2k_device_job* j, const int32_t* const* planes, const uint32_t* strides);
+/* block-decode a caller-supplied block table + byte arena (as b2k_decode takes them) into the job's
+ * coefficient planes; 1 = not handled (e.g. more than 3 HT passes), < 0 failure */
+B2K_API int32_t b2k_job_t1_decode_blocks(b2k_device_job* j, const b2k_block* blocks, uint64_t num_blocks,
+                                         const uint8_t* bytes, uint64_t num_bytes, float* ms);
 /* fetch coded blocks of the last b2k_job_t1_encode as a host result */
 B2K_API int32_t b2k_job_fetch_result(b2k_device_job* j, b2k_result** out);
 B2K_API uint64_t b2k_job_num_blocks(const b2k_device_job* j);
