@@ -90,6 +90,8 @@ struct b2k_host_rect
   size_t src_stride, dst_stride; /* in elements */
   size_t w, h;
 };
-void b2k_host_convert(const b2k_host_rect* rects, size_t nrects, bool widen, bool sgnd);
+/* cached_dst: narrow with plain stores (the 16-bit destination is consumed right away) instead of streaming ones */
+void b2k_host_convert(const b2k_host_rect* rects, size_t nrects, bool widen, bool sgnd, bool cached_dst = false);
+void b2k_host_session(bool begin); /* between begin and end the pool's idle workers spin instead of sleeping */
 void b2k_host_set_threads(int n); /* 0 disables host packing, <0 restores the default */
 int b2k_host_threads(void);

@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -102,6 +103,11 @@ struct LevelLaunch
    PCIe is the bound (one or two GPUs per socket, or unpinned caller memory) and loses once several
    ranks share a socket's DRAM.  Default policy: time both ways on the first calls, keep the faster,
    look at the other one again every 128 calls. */
+/* pipeline chunks per call (tile granular) and their events: purpose 0 chunk done on its stream, 1 chunk's
+   upload done, 2 side-stream / scan done, 3 chunk's download done, 4 misc */
+#define B2K_MAX_CHUNKS 32
+#define CEV(purpose, k) ((purpose) * (B2K_MAX_CHUNKS + 1) + (int)(k))
+
 struct PackTuner
 {
   int calls = 0;
@@ -158,7 +164,7 @@ struct b2k_device_job
   std::vector<float> dec_quant;        /* per coded block: decoder step / 2^(31-Kmax) */
   std::vector<uint32_t> coded_first;   /* coded blocks of selected tile ti are [coded_first[ti], coded_first[ti+1]) */
   std::vector<uint32_t> chunk_tile;    /* pipeline chunks: selected tiles [chunk_tile[k], chunk_tile[k+1]) */
-  cudaEvent_t chunk_ev[48]{};
+  cudaEvent_t chunk_ev[5 * (B2K_MAX_CHUNKS + 1)]{}; /* [purpose][chunk], see CEV() */
   uint32_t max_cblk_w = 0;
 
   Planes img, coef, ll[2];
@@ -189,6 +195,12 @@ struct b2k_device_job
   bool img_is_u16 = false;
   uint16_t* h_stage16 = nullptr;  /* pinned 16-bit staging for the int32 entry points (host_pack.cpp) */
   uint64_t stage16_elems = 0;
+  /* ring staging (B2K_STAGE_RING_MB > 0): a few MB-sized pinned slots that are narrowed into / widened out of
+     while still cache-resident, instead of one image-sized staging buffer that round-trips through DRAM */
+  uint16_t* h_ring = nullptr;
+  uint32_t ring_slots = 0;
+  uint64_t ring_slot_elems = 0, ring_elems = 0;
+  cudaEvent_t ring_ev[16]{};
   PackTuner tune_enc, tune_dec;
   bool dec_has_refinement = false; /* the block table of the current decode carries SigProp / MagRef passes */
 };
@@ -457,7 +469,10 @@ static int build_block_plan(b2k_device_job* J)
     J->coded_first[ti] = std::max(J->coded_first[ti], J->coded_first[ti - 1]);
   {
     const uint32_t nt = (uint32_t)J->tiles.size();
-    const uint32_t nchunks = std::max(1u, std::min(8u, nt));
+    uint32_t want = 8;
+    if(const char* ev = getenv("B2K_CHUNKS"))
+      want = (uint32_t)std::max(1, std::min(B2K_MAX_CHUNKS, atoi(ev)));
+    const uint32_t nchunks = std::max(1u, std::min(want, nt));
     J->chunk_tile.clear();
     for(uint32_t k = 0; k <= nchunks; ++k)
       J->chunk_tile.push_back((uint32_t)((uint64_t)k * nt / nchunks));
@@ -569,6 +584,10 @@ extern "C" void b2k_job_destroy(b2k_device_job* J)
   cudaFreeHost(J->h_dec_desc);
   cudaFreeHost(J->h_offsets);
   cudaFreeHost(J->h_stage16);
+  cudaFreeHost(J->h_ring);
+  for(cudaEvent_t& ev : J->ring_ev)
+    if(ev)
+      cudaEventDestroy(ev);
   for(cudaEvent_t& ev : J->ev)
     if(ev)
       cudaEventDestroy(ev);
@@ -790,6 +809,151 @@ static void host_convert_chunk(const b2k_device_job* J, void* const* user, const
   if(dbg)
     fprintf(stderr, "[b2k] host %s tiles [%zu,%zu): %.3f ms\n", widen ? "widen" : "narrow", t0, t1,
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count());
+}
+
+/* ---- ring staging ---------------------------------------------------------------------------- */
+struct StagePiece
+{
+  uint32_t chunk, comp, x0, y0, w, rows; /* canvas coordinates */
+};
+struct RingGeom
+{
+  uint32_t slot_mb, slots;
+};
+/* B2K_RING_ENC / B2K_RING_DEC = "<slot MB>,<slots>" ("0" = image-sized staging instead of a ring) */
+static RingGeom ring_geom(bool decode)
+{
+  static const RingGeom g[2] = {[] {
+                                  RingGeom r{8, 4};
+                                  if(const char* e = getenv("B2K_RING_ENC"))
+                                  {
+                                    r.slot_mb = (uint32_t)std::max(0, atoi(e));
+                                    if(const char* c = strchr(e, ','))
+                                      r.slots = (uint32_t)std::max(2, std::min(16, atoi(c + 1)));
+                                  }
+                                  return r;
+                                }(),
+                                [] {
+                                  RingGeom r{16, 4};
+                                  if(const char* e = getenv("B2K_RING_DEC"))
+                                  {
+                                    r.slot_mb = (uint32_t)std::max(0, atoi(e));
+                                    if(const char* c = strchr(e, ','))
+                                      r.slots = (uint32_t)std::max(2, std::min(16, atoi(c + 1)));
+                                  }
+                                  return r;
+                                }()};
+  return g[decode ? 1 : 0];
+}
+static int ensure_ring(b2k_device_job* J, bool decode)
+{
+  const RingGeom g = ring_geom(decode);
+  const uint64_t min_elems = (uint64_t)(J->cp.x1 - J->cp.x0) * 4;
+  const uint64_t slot_elems = std::max<uint64_t>((uint64_t)g.slot_mb * (1u << 20) / sizeof(uint16_t), min_elems);
+  const uint64_t need = slot_elems * g.slots;
+  if(need > J->ring_elems)
+  {
+    if(J->h_ring)
+      cudaFreeHost(J->h_ring);
+    J->h_ring = nullptr;
+    CUDA_TRY(cudaHostAlloc(&J->h_ring, need * sizeof(uint16_t), cudaHostAllocDefault));
+    J->ring_elems = need;
+  }
+  for(uint32_t i = 0; i < g.slots; ++i)
+    if(!J->ring_ev[i])
+      CUDA_TRY(cudaEventCreateWithFlags(&J->ring_ev[i], cudaEventDisableTiming));
+  J->ring_slots = g.slots;
+  J->ring_slot_elems = slot_elems;
+  return 0;
+}
+static void chunk_pieces(const b2k_device_job* J, uint32_t chunk, std::vector<StagePiece>& out)
+{
+  const b2k_coding& cp = J->cp;
+  const size_t t0 = J->chunk_tile[chunk], t1 = std::min<size_t>(J->chunk_tile[chunk + 1], J->tiles.size());
+  for(size_t ti = t0; ti < t1;)
+  {
+    Rect r = J->tile_rects[ti];
+    size_t tj = ti + 1;
+    while(tj < t1 && J->tile_rects[tj].y0 == r.y0 && J->tile_rects[tj].y1 == r.y1 && J->tile_rects[tj].x0 == r.x1)
+    {
+      r.x1 = J->tile_rects[tj].x1;
+      ++tj;
+    }
+    const uint32_t rows_per = (uint32_t)std::max<uint64_t>(1, J->ring_slot_elems / r.w());
+    for(uint32_t y = r.y0; y < r.y1; y += rows_per)
+      for(uint32_t c = 0; c < cp.numcomps; ++c)
+        out.push_back({chunk, c, r.x0, y, r.w(), std::min(rows_per, r.y1 - y)});
+    ti = tj;
+  }
+}
+/* narrow one chunk piece by piece into the ring and send each piece on its way */
+static int ring_upload_chunk(b2k_device_job* J, void* const* user, const uint32_t* strides, uint32_t chunk, cudaStream_t cs,
+                             uint64_t& counter, const std::function<int()>& between_pieces)
+{
+  const b2k_coding& cp = J->cp;
+  std::vector<StagePiece> pcs;
+  chunk_pieces(J, chunk, pcs);
+  for(const StagePiece& pc : pcs)
+  {
+    const uint32_t slot = (uint32_t)(counter % J->ring_slots);
+    if(counter >= J->ring_slots)
+      CUDA_TRY(cudaEventSynchronize(J->ring_ev[slot])); /* the slot's previous piece has left */
+    uint16_t* sp = J->h_ring + (uint64_t)slot * J->ring_slot_elems;
+    const int32_t* u = reinterpret_cast<const int32_t*>(user[pc.comp]) + (size_t)(pc.y0 - cp.y0) * strides[pc.comp] + (pc.x0 - cp.x0);
+    const b2k_host_rect hr{u, sp, strides[pc.comp], pc.w, pc.w, pc.rows};
+    b2k_host_convert(&hr, 1, false, cp.sgnd != 0, true);
+    uint16_t* dev = J->img16.at(pc.comp, pc.x0, pc.y0);
+    if(J->img16.pitch == pc.w)
+      CUDA_TRY(cudaMemcpyAsync(dev, sp, (size_t)pc.w * pc.rows * 2, cudaMemcpyHostToDevice, cs));
+    else
+      CUDA_TRY(cudaMemcpy2DAsync(dev, (size_t)J->img16.pitch * 2, sp, (size_t)pc.w * 2, (size_t)pc.w * 2, pc.rows,
+                                 cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaEventRecord(J->ring_ev[slot], cs));
+    ++counter;
+    if(between_pieces())
+      return -1;
+  }
+  return 0;
+}
+/* bring every chunk's pixels down through the ring and widen them into the caller's planes; chunk k's pixels are
+   ready on the device when chunk_ev[CEV(0, k)] fires */
+static int ring_download_all(b2k_device_job* J, void* const* user, const uint32_t* strides, cudaStream_t cs)
+{
+  const b2k_coding& cp = J->cp;
+  std::vector<StagePiece> pcs;
+  for(uint32_t k = 0; k + 1 < J->chunk_tile.size(); ++k)
+    chunk_pieces(J, k, pcs);
+  const size_t N = pcs.size(), S = J->ring_slots;
+  auto issue = [&](size_t p) -> int {
+    const StagePiece& pc = pcs[p];
+    const uint32_t slot = (uint32_t)(p % S);
+    uint16_t* sp = J->h_ring + (uint64_t)slot * J->ring_slot_elems;
+    if(p == 0 || pcs[p - 1].chunk != pc.chunk)
+      CUDA_TRY(cudaStreamWaitEvent(cs, J->chunk_ev[CEV(0, pc.chunk)], 0));
+    const uint16_t* dev = J->img16.at(pc.comp, pc.x0, pc.y0);
+    if(J->img16.pitch == pc.w)
+      CUDA_TRY(cudaMemcpyAsync(sp, dev, (size_t)pc.w * pc.rows * 2, cudaMemcpyDeviceToHost, cs));
+    else
+      CUDA_TRY(cudaMemcpy2DAsync(sp, (size_t)pc.w * 2, dev, (size_t)J->img16.pitch * 2, (size_t)pc.w * 2, pc.rows,
+                                 cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaEventRecord(J->ring_ev[slot], cs));
+    return 0;
+  };
+  for(size_t p = 0; p < std::min(S, N); ++p)
+    if(issue(p)) return -1;
+  for(size_t p = 0; p < N; ++p)
+  {
+    const StagePiece& pc = pcs[p];
+    const uint32_t slot = (uint32_t)(p % S);
+    CUDA_TRY(cudaEventSynchronize(J->ring_ev[slot]));
+    const uint16_t* sp = J->h_ring + (uint64_t)slot * J->ring_slot_elems;
+    int32_t* u = reinterpret_cast<int32_t*>(user[pc.comp]) + (size_t)(pc.y0 - cp.y0) * strides[pc.comp] + (pc.x0 - cp.x0);
+    const b2k_host_rect hr{sp, u, pc.w, strides[pc.comp], pc.w, pc.rows};
+    b2k_host_convert(&hr, 1, true, cp.sgnd != 0);
+    if(p + S < N)
+      if(issue(p + S)) return -1;
+  }
+  return 0;
 }
 
 /* ---- stages ----------------------------------------------------------------------------------- */
@@ -1158,16 +1322,26 @@ static void pool_put(uint8_t* p)
   cudaFreeHost(p);
 }
 
-static int fetch_result(b2k_device_job* J, cudaStream_t st, b2k_result** out, uint8_t* host_bytes = nullptr)
+/* the part of a result that does not depend on the device: the block table in enumeration order */
+static b2k_result* result_shell(b2k_device_job* J)
 {
-  const uint32_t n = (uint32_t)J->h_enc_desc.size();
   b2k_result* R = new b2k_result();
   memset(R, 0, sizeof(*R));
   R->num_blocks = J->blocks.size();
   R->blocks = (b2k_block*)malloc(sizeof(b2k_block) * std::max<size_t>(1, J->blocks.size()));
   memcpy(R->blocks, J->blocks.data(), sizeof(b2k_block) * J->blocks.size());
-  R->num_bytes = J->bytes_used;
   R->num_tiles = (uint32_t)J->tiles.size();
+  return R;
+}
+
+/* host_bytes: the caller already brought the byte arena home (chunk by chunk); meta_on_host: also the per-block
+   lengths / offsets (h_out, h_offsets) are on their way on a stream that `st` waits for */
+static int fetch_result(b2k_device_job* J, cudaStream_t st, b2k_result** out, uint8_t* host_bytes = nullptr,
+                        b2k_result* shell = nullptr, bool meta_on_host = false)
+{
+  const uint32_t n = (uint32_t)J->h_enc_desc.size();
+  b2k_result* R = shell ? shell : result_shell(J);
+  R->num_bytes = J->bytes_used;
   R->bytes = host_bytes ? host_bytes : pool_get(std::max<uint64_t>(64, J->bytes_used));
   if(!R->bytes)
   {
@@ -1178,8 +1352,11 @@ static int fetch_result(b2k_device_job* J, cudaStream_t st, b2k_result** out, ui
   }
   if(!host_bytes)
     CUDA_TRY(cudaMemcpyAsync(R->bytes, J->d_bytes, J->bytes_used, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(J->h_out, J->d_out, n * sizeof(HtBlockOut), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(J->h_offsets, J->d_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  if(!meta_on_host)
+  {
+    CUDA_TRY(cudaMemcpyAsync(J->h_out, J->d_out, n * sizeof(HtBlockOut), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(J->h_offsets, J->d_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  }
   CUDA_TRY(cudaStreamSynchronize(st));
   int bad = 0;
   for(uint32_t k = 0; k < n; ++k)
@@ -1221,6 +1398,19 @@ extern "C" void b2k_result_free(b2k_result* r)
 }
 
 /* ---- one-call host paths ---------------------------------------------------------------------- */
+static bool dbg_timing()
+{
+  static const bool v = getenv("B2K_DEBUG_TIMING") != nullptr;
+  return v;
+}
+#define DBG_T(label)                                                                                              \
+  do                                                                                                              \
+  {                                                                                                               \
+    if(dbg_timing())                                                                                              \
+      fprintf(stderr, "[b2k] %-28s %8.3f ms\n", label,                                                            \
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());       \
+  } while(0)
+
 struct JobCache
 {
   std::mutex mu;
@@ -1263,14 +1453,25 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
   const auto wall0 = std::chrono::steady_clock::now();
   if(!u16)
     g_last_pack[0].store(pack ? 1 : 0);
+  const bool ring = pack && ring_geom(false).slot_mb > 0;
+  uint64_t ring_counter = 0;
   if(pack)
   {
-    if(ensure_stage16(J)) return -1;
-    stage16_views(J, stage_planes, stage_strides);
-    planes = stage_planes;
-    strides = stage_strides;
+    if(ring ? ensure_ring(J, false) : ensure_stage16(J)) return -1;
+    if(!ring)
+    {
+      stage16_views(J, stage_planes, stage_strides);
+      planes = stage_planes;
+      strides = stage_strides;
+    }
     u16 = true;
+    b2k_host_session(true);
   }
+  struct SessionEnd
+  {
+    bool on;
+    ~SessionEnd() { if(on) b2k_host_session(false); }
+  } session_end{pack};
   if(u16)
     if(int urc = ensure_u16(J))
       return urc;
@@ -1281,21 +1482,76 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
   CUDA_TRY(cudaEventRecord(J->ev[0], st));
   CUDA_TRY(cudaStreamWaitEvent(cs, J->ev[0], 0));
   const size_t nchunks = J->chunk_tile.size() - 1;
+  /* the arena size of the previous call is the estimate: scan + compact + return every chunk's bytes while later
+     chunks are still arriving (the D2H direction of PCIe is otherwise idle) */
+  const bool streamed = J->bytes_cap > 0 && nchunks > 1;
+  uint8_t* hb = nullptr;
+  if(streamed)
+  {
+    hb = pool_get(J->bytes_cap);
+    if(!hb)
+    {
+      g_err = "cudaHostAlloc(result bytes) failed";
+      return -1;
+    }
+  }
+  cudaStream_t ds = e->h2d_stream; /* third stream: device-to-host here */
+  size_t next_out = 0, enqueued = 0;
+  uint64_t total = 0;
+  bool overflow = false;
+  /* send finished chunks' bytes home; non-blocking while the host still has chunks to feed */
+  auto return_chunks = [&](bool block) -> int {
+    while(next_out < enqueued)
+    {
+      const size_t k = next_out;
+      if(block)
+        CUDA_TRY(cudaEventSynchronize(J->chunk_ev[CEV(2, k)]));
+      else if(cudaEventQuery(J->chunk_ev[CEV(2, k)]) != cudaSuccess)
+        break;
+      const uint32_t b0 = J->coded_first[J->chunk_tile[k]], b1 = J->coded_first[J->chunk_tile[k + 1]];
+      const uint64_t lo = k == 0 ? 0 : J->h_offsets[b0], hi = J->h_offsets[b1];
+      total = hi;
+      if(hi > J->bytes_cap)
+        overflow = true;
+      else if(hi > lo)
+      {
+        CUDA_TRY(cudaStreamWaitEvent(ds, J->chunk_ev[CEV(2, k)], 0));
+        CUDA_TRY(cudaMemcpyAsync(hb + lo, J->d_bytes + lo, hi - lo, cudaMemcpyDeviceToHost, ds));
+      }
+      if(b1 > b0)
+      { /* per-block lengths and offsets of the chunk ride along (h_offsets[b1] is already here) */
+        CUDA_TRY(cudaStreamWaitEvent(ds, J->chunk_ev[CEV(2, k)], 0));
+        CUDA_TRY(cudaMemcpyAsync(J->h_out + b0, J->d_out + b0, (size_t)(b1 - b0) * sizeof(HtBlockOut), cudaMemcpyDeviceToHost, ds));
+        CUDA_TRY(cudaMemcpyAsync(J->h_offsets + b0, J->d_offsets + b0, (size_t)(b1 - b0) * sizeof(uint64_t),
+                                 cudaMemcpyDeviceToHost, ds));
+      }
+      ++next_out;
+    }
+    (void)cudaGetLastError(); /* cudaEventQuery's cudaErrorNotReady is not an error */
+    return 0;
+  };
   for(size_t k = 0; k < nchunks; ++k)
   {
     const size_t t0 = J->chunk_tile[k], t1 = J->chunk_tile[k + 1];
-    if(pack)
-      host_convert_chunk(J, user_planes, user_strides, false, t0, t1); /* overlaps chunk k-1's H2D */
-    if(u16 ? copy_planes16(J, planes, strides, true, cs, t0, t1) : copy_planes(J, J->img, planes, strides, true, cs, t0, t1))
-      return -1;
-    CUDA_TRY(cudaEventRecord(J->chunk_ev[k], cs));
-    CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[k], 0));
+    if(ring)
+    {
+      if(ring_upload_chunk(J, user_planes, user_strides, (uint32_t)k, cs, ring_counter, [&] { return return_chunks(false); })) return -1;
+    }
+    else
+    {
+      if(pack)
+        host_convert_chunk(J, user_planes, user_strides, false, t0, t1); /* overlaps chunk k-1's H2D */
+      if(u16 ? copy_planes16(J, planes, strides, true, cs, t0, t1) : copy_planes(J, J->img, planes, strides, true, cs, t0, t1))
+        return -1;
+    }
+    CUDA_TRY(cudaEventRecord(J->chunk_ev[CEV(0, k)], cs));
+    CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[CEV(0, k)], 0));
     if(k == nchunks - 1)
       CUDA_TRY(cudaEventRecord(J->ev[1], st)); /* all planes on the device */
     if(u16 && convert_planes16(J, true, st, t0, t1)) return -1;
     if(enqueue_forward(J, st, k == 0, t0, t1)) return -1;
     if(enqueue_t1_blocks(J, st, t0, t1)) return -1;
-    if(J->bytes_cap > 0 && nchunks > 1)
+    if(streamed)
     {
       const uint32_t b0 = J->coded_first[t0], b1 = J->coded_first[t1];
       if(b1 > b0)
@@ -1305,43 +1561,22 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
                              J->bytes_cap, st);
       }
       CUDA_TRY(cudaMemcpyAsync(&J->h_offsets[b1], J->d_offsets + b1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaEventRecord(J->chunk_ev[24 + (k & 7)], st));
+      CUDA_TRY(cudaEventRecord(J->chunk_ev[CEV(2, k)], st));
+      enqueued = k + 1;
+      if(return_chunks(false)) return -1;
     }
   }
   CUDA_TRY(cudaEventRecord(J->ev[2], st));
+  DBG_T("encode: chunks enqueued");
   b2k_result* R = nullptr;
   const uint32_t nb_all = (uint32_t)J->h_enc_desc.size();
-  bool streamed = false;
-  if(J->bytes_cap > 0 && nchunks > 1)
+  b2k_result* shell = result_shell(J); /* host work while the device finishes the last chunks */
+  if(streamed)
   {
-    /* the arena size of the previous call is the estimate: scan + compact + return every chunk's
-       bytes while later chunks are still arriving (the D2H direction of PCIe is otherwise idle) */
-    uint8_t* hb = pool_get(J->bytes_cap);
-    if(!hb)
-    {
-      g_err = "cudaHostAlloc(result bytes) failed";
-      return -1;
-    }
-    cudaStream_t ds = e->h2d_stream; /* third stream: device-to-host here */
-    streamed = true;
-    uint64_t total = 0;
-    bool overflow = false;
-    for(size_t k = 0; k < nchunks; ++k)
-    {
-      const uint32_t b0 = J->coded_first[J->chunk_tile[k]], b1 = J->coded_first[J->chunk_tile[k + 1]];
-      CUDA_TRY(cudaEventSynchronize(J->chunk_ev[24 + (k & 7)]));
-      const uint64_t lo = k == 0 ? 0 : J->h_offsets[b0], hi = J->h_offsets[b1];
-      total = hi;
-      if(hi > J->bytes_cap)
-        overflow = true;
-      else if(hi > lo)
-      {
-        CUDA_TRY(cudaStreamWaitEvent(ds, J->chunk_ev[24 + (k & 7)], 0));
-        CUDA_TRY(cudaMemcpyAsync(hb + lo, J->d_bytes + lo, hi - lo, cudaMemcpyDeviceToHost, ds));
-      }
-    }
-    CUDA_TRY(cudaEventRecord(J->chunk_ev[23], ds));
-    CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[23], 0));
+    if(return_chunks(true)) return -1;
+    CUDA_TRY(cudaEventRecord(J->chunk_ev[CEV(4, 0)], ds));
+    CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[CEV(4, 0)], 0));
+    DBG_T("encode: last chunk coded");
     J->bytes_used = total;
     if(overflow)
     { /* estimate too small: grow, compact everything again from the scratch slots, plain copy */
@@ -1352,12 +1587,12 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
       CUDA_TRY(cudaMalloc(&J->d_bytes, J->bytes_cap));
       b2k_launch_ht_gather(J->d_enc_desc, J->d_out, J->d_offsets, J->d_scratch, J->d_bytes, nb_all, J->bytes_cap, st);
       CUDA_TRY(cudaEventRecord(J->ev[3], st));
-      if(int frc = fetch_result(J, st, &R)) return frc;
+      if(int frc = fetch_result(J, st, &R, nullptr, shell)) return frc;
     }
     else
     {
       CUDA_TRY(cudaEventRecord(J->ev[3], st));
-      if(int frc = fetch_result(J, st, &R, hb)) return frc;
+      if(int frc = fetch_result(J, st, &R, hb, shell, true)) return frc;
     }
   }
   if(!streamed)
@@ -1365,10 +1600,12 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
     b2k_launch_scan_lengths(J->d_out, J->d_offsets, nb_all, st);
     if(finish_t1_encode(J, st)) return -1;
     CUDA_TRY(cudaEventRecord(J->ev[3], st));
-    if(int frc = fetch_result(J, st, &R)) return frc;
+    if(int frc = fetch_result(J, st, &R, nullptr, shell)) return frc;
   }
+  DBG_T("encode: result fetched");
   CUDA_TRY(cudaEventRecord(J->ev[6], st));
   CUDA_TRY(cudaEventSynchronize(J->ev[6]));
+  DBG_T("encode: done");
   float a = 0, b = 0, c = 0, d = 0;
   cudaEventElapsedTime(&a, J->ev[0], J->ev[1]);
   cudaEventElapsedTime(&b, J->ev[1], J->ev[2]);
@@ -1434,14 +1671,24 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
   const auto wall0 = std::chrono::steady_clock::now();
   if(!u16)
     g_last_pack[1].store(pack ? 1 : 0);
+  const bool ring = pack && ring_geom(true).slot_mb > 0;
   if(pack)
   {
-    if(ensure_stage16(J)) return -1;
-    stage16_views(J, stage_planes, stage_strides);
-    planes = stage_planes;
-    strides = stage_strides;
+    if(ring ? ensure_ring(J, true) : ensure_stage16(J)) return -1;
+    if(!ring)
+    {
+      stage16_views(J, stage_planes, stage_strides);
+      planes = stage_planes;
+      strides = stage_strides;
+    }
     u16 = true;
+    b2k_host_session(true);
   }
+  struct SessionEnd
+  {
+    bool on;
+    ~SessionEnd() { if(on) b2k_host_session(false); }
+  } session_end{pack};
   if(u16)
     if(int urc = ensure_u16(J))
       return urc;
@@ -1500,17 +1747,17 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
         prev_end = hi;
       }
     }
-    CUDA_TRY(cudaEventRecord(J->chunk_ev[16 + (k & 7)], e->h2d_stream));
-    CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[16 + (k & 7)], 0));
+    CUDA_TRY(cudaEventRecord(J->chunk_ev[CEV(1, k)], e->h2d_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[CEV(1, k)], 0));
     if(b1 > b0)
     {
       /* phase A (serial VLC/MEL parse, one thread per block) is latency-bound and leaves the SMs
          nearly empty: run the chunks' parses concurrently on side streams, ahead of the main stream */
       cudaStream_t ax = e->aux[k & 3];
-      CUDA_TRY(cudaStreamWaitEvent(ax, J->chunk_ev[16 + (k & 7)], 0)); /* this chunk's descriptors + bytes are up */
+      CUDA_TRY(cudaStreamWaitEvent(ax, J->chunk_ev[CEV(1, k)], 0)); /* this chunk's descriptors + bytes are up */
       b2k_launch_ht_decode_vlc(J->d_dec_desc + b0, J->d_bytes, J->d_recs, J->d_dec_status + b0, b1 - b0, J->max_cblk_w, ax);
-      CUDA_TRY(cudaEventRecord(J->chunk_ev[24 + (k & 7)], ax));
-      CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[24 + (k & 7)], 0));
+      CUDA_TRY(cudaEventRecord(J->chunk_ev[CEV(2, k)], ax));
+      CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[CEV(2, k)], 0));
       b2k_launch_ht_decode_magsgn(J->d_dec_desc + b0, J->d_bytes, J->d_recs, J->d_dec_status + b0, b1 - b0, J->max_cblk_w,
                                   J->d_err, st);
       if(J->dec_has_refinement)
@@ -1519,24 +1766,32 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
     }
     if(enqueue_inverse(J, st, t0, t1)) return -1;
     if(u16 && convert_planes16(J, false, st, t0, t1)) return -1;
-    CUDA_TRY(cudaEventRecord(J->chunk_ev[k], st));
-    CUDA_TRY(cudaStreamWaitEvent(cs, J->chunk_ev[k], 0));
+    CUDA_TRY(cudaEventRecord(J->chunk_ev[CEV(0, k)], st));
+    if(ring)
+      continue; /* pixels come down piece by piece below */
+    CUDA_TRY(cudaStreamWaitEvent(cs, J->chunk_ev[CEV(0, k)], 0));
     if(u16 ? copy_planes16(J, planes, strides, false, cs, t0, t1) : copy_planes(J, J->img, planes, strides, false, cs, t0, t1))
       return -1;
     if(pack)
-      CUDA_TRY(cudaEventRecord(J->chunk_ev[40 + (k & 7)], cs));
+      CUDA_TRY(cudaEventRecord(J->chunk_ev[CEV(3, k)], cs));
   }
-  if(pack) /* widen chunk k into the caller's planes while chunk k+1 is still coming down */
+  DBG_T("decode: chunks enqueued");
+  if(ring)
+  {
+    if(ring_download_all(J, user_planes, user_strides, cs)) return -1;
+  }
+  else if(pack) /* widen chunk k into the caller's planes while chunk k+1 is still coming down */
     for(size_t k = 0; k < nchunks; ++k)
     {
-      CUDA_TRY(cudaEventSynchronize(J->chunk_ev[40 + (k & 7)]));
+      CUDA_TRY(cudaEventSynchronize(J->chunk_ev[CEV(3, k)]));
       host_convert_chunk(J, user_planes, user_strides, true, J->chunk_tile[k], J->chunk_tile[k + 1]);
     }
-  CUDA_TRY(cudaEventRecord(J->chunk_ev[nchunks], cs));
-  CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[nchunks], 0));
+  CUDA_TRY(cudaEventRecord(J->chunk_ev[CEV(0, nchunks)], cs));
+  CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[CEV(0, nchunks)], 0));
   CUDA_TRY(cudaEventRecord(J->ev[1], st));
   CUDA_TRY(cudaEventSynchronize(J->ev[1]));
   CUDA_TRY(cudaGetLastError());
+  DBG_T("decode: done");
   float t = 0;
   cudaEventElapsedTime(&t, J->ev[0], J->ev[1]);
   if(ms_total) *ms_total = t;

@@ -14,6 +14,7 @@
 #include "b2k_internal.h"
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -31,11 +32,13 @@
 namespace
 {
 
-/* fork-join pool: parallel_for(n, fn) runs fn(i) for i in [0, n) on the workers plus the caller */
+/* fork-join pool: parallel_for(n, fn) runs fn(i) for i in [0, n) on the workers plus the caller.
+   Inside a session (begin_session / end_session: one b2k_encode / b2k_decode call) idle workers spin on the
+   generation counter instead of sleeping, so a fork-join costs a few microseconds -- the calls issue ~100 of them. */
 class HostPool
 {
 public:
-  explicit HostPool(int nthreads) : stop_(false), gen_(0), next_(0), n_(0), pending_(0)
+  explicit HostPool(int nthreads)
   {
     const std::vector<int> cpus = spread_cpus();
     for(int i = 0; i < nthreads - 1; ++i)
@@ -54,14 +57,16 @@ public:
   {
     {
       std::lock_guard<std::mutex> lk(mu_);
-      stop_ = true;
-      ++gen_;
+      stop_.store(true);
+      gen_.fetch_add(1, std::memory_order_release);
     }
     cv_.notify_all();
     for(auto& t : workers_)
       t.join();
   }
   int size() const { return (int)workers_.size() + 1; }
+  void begin_session() { hot_.fetch_add(1, std::memory_order_relaxed); }
+  void end_session() { hot_.fetch_sub(1, std::memory_order_relaxed); }
   void parallel_for(size_t n, const std::function<void(size_t)>& fn)
   {
     if(n == 0)
@@ -72,23 +77,45 @@ public:
         fn(i);
       return;
     }
+    fn_ = &fn;
+    n_ = n;
+    next_.store(0, std::memory_order_relaxed);
+    pending_.store((int)workers_.size(), std::memory_order_relaxed);
     {
-      std::lock_guard<std::mutex> lk(mu_);
-      fn_ = &fn;
-      n_ = n;
-      next_.store(0, std::memory_order_relaxed);
-      pending_.store((int)workers_.size(), std::memory_order_relaxed);
-      ++gen_;
+      std::lock_guard<std::mutex> lk(mu_); /* pairs with the sleepers' predicate check */
+      gen_.fetch_add(1, std::memory_order_release);
     }
     cv_.notify_all();
     drain();
-    /* wait until every worker has left this generation (fn must stay alive until then) */
-    std::unique_lock<std::mutex> lk(mu_);
-    done_cv_.wait(lk, [this] { return pending_.load(std::memory_order_acquire) == 0; });
+    /* every worker must have left this generation before fn goes out of scope; they are at most one task away */
+    for(int spins = 0; pending_.load(std::memory_order_acquire) != 0;)
+    {
+      cpu_relax();
+      if((++spins & 127) == 0)
+        sched_yield();
+    }
     fn_ = nullptr;
   }
 
 private:
+  /* how long an idle worker polls for the next fork-join of a session before it sleeps (B2K_HOST_SPIN_US) */
+  static int spin_limit()
+  {
+    static const int v = [] {
+      const char* e = getenv("B2K_HOST_SPIN_US");
+      const int us = e ? std::max(0, atoi(e)) : 100;
+      return us * 25; /* ~40 ns per pause */
+    }();
+    return v;
+  }
+  static void cpu_relax()
+  {
+#if defined(__x86_64__)
+    _mm_pause();
+#else
+    std::this_thread::yield();
+#endif
+  }
   /* CPUs this process may use, ordered so that distinct physical cores come first (B2K_HOST_PIN=0: no pinning) */
   static std::vector<int> spread_cpus()
   {
@@ -150,35 +177,72 @@ private:
     uint64_t seen = 0;
     for(;;)
     {
+      uint64_t g;
+      int spins = 0;
+      while((g = gen_.load(std::memory_order_acquire)) == seen)
       {
+        if(hot_.load(std::memory_order_relaxed) > 0 && spins < spin_limit())
+        {
+          cpu_relax();
+          if((++spins & 127) == 0)
+            sched_yield(); /* a spinner must never keep the caller's (or the CUDA runtime's) threads off its core */
+          continue;
+        }
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return gen_ != seen; });
-        seen = gen_;
-        if(stop_)
-          return;
+        cv_.wait_for(lk, std::chrono::milliseconds(hot_.load() > 0 ? 1 : 1000),
+                     [&] { return gen_.load(std::memory_order_acquire) != seen; });
+        spins = 0;
       }
+      if(stop_.load())
+        return;
+      seen = g;
       drain();
-      if(pending_.fetch_sub(1, std::memory_order_acq_rel) == 1)
-      {
-        std::lock_guard<std::mutex> lk(mu_);
-        done_cv_.notify_one();
-      }
+      pending_.fetch_sub(1, std::memory_order_acq_rel);
     }
   }
   std::vector<std::thread> workers_;
   std::mutex mu_;
-  std::condition_variable cv_, done_cv_;
-  bool stop_;
-  uint64_t gen_;
+  std::condition_variable cv_;
+  std::atomic<bool> stop_{false};
+  std::atomic<int> hot_{0};
+  std::atomic<uint64_t> gen_{0};
   const std::function<void(size_t)>* fn_ = nullptr;
-  std::atomic<size_t> next_;
-  size_t n_;
-  std::atomic<int> pending_;
+  std::atomic<size_t> next_{0};
+  size_t n_ = 0;
+  std::atomic<int> pending_{0};
 };
 
 std::mutex g_pool_mu;
 HostPool* g_pool = nullptr;
 int g_threads = -1; /* -1: not decided yet; 0: host packing disabled */
+
+/* CPUs' worth of time this process may use per period, <= 0 if unlimited / unknown (cgroup v2, then v1) */
+double cgroup_cpu_quota()
+{
+  if(FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r"))
+  {
+    char q[64] = {0};
+    long period = 0;
+    const int n = fscanf(f, "%63s %ld", q, &period);
+    fclose(f);
+    if(n == 2 && period > 0 && strcmp(q, "max") != 0)
+      return atof(q) / (double)period;
+    if(n >= 1)
+      return 0;
+  }
+  long quota = -1, period = 0;
+  if(FILE* f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r"))
+  {
+    if(fscanf(f, "%ld", &quota) != 1) quota = -1;
+    fclose(f);
+  }
+  if(FILE* f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r"))
+  {
+    if(fscanf(f, "%ld", &period) != 1) period = 0;
+    fclose(f);
+  }
+  return (quota > 0 && period > 0) ? (double)quota / (double)period : 0;
+}
 
 int default_threads()
 {
@@ -188,6 +252,12 @@ int default_threads()
   int avail = (int)std::thread::hardware_concurrency();
   if(sched_getaffinity(0, sizeof(set), &set) == 0)
     avail = CPU_COUNT(&set);
+  /* a CPU-time quota (cgroup cpu.max, i.e. a container's --cpus) counts before the CPU list does: a pool that
+     burns more than the quota gets the whole process throttled for the rest of the 100 ms period.  Keep three
+     CPUs' worth for the caller, the CUDA runtime's threads and whatever else lives in the container. */
+  const double quota = cgroup_cpu_quota();
+  if(quota > 0)
+    avail = std::min(avail, std::max(1, (int)quota - 3));
   /* a container change is bandwidth work: a couple of dozen cores saturate one socket's DRAM */
   return std::max(1, std::min(avail, 24));
 }
@@ -224,6 +294,19 @@ void widen_row_scalar(const uint16_t* s, int32_t* d, size_t n, bool sgnd)
 }
 
 #if defined(__x86_64__)
+__attribute__((target("avx2"))) void narrow_row_avx2_cached(const int32_t* s, uint16_t* d, size_t n)
+{ /* plain stores: the destination is about to be read by the device while still in cache */
+  size_t i = 0;
+  const __m256i m = _mm256_set1_epi32(0xFFFF);
+  for(; i + 16 <= n; i += 16)
+  {
+    const __m256i a = _mm256_and_si256(_mm256_loadu_si256((const __m256i*)(s + i)), m);
+    const __m256i b = _mm256_and_si256(_mm256_loadu_si256((const __m256i*)(s + i + 8)), m);
+    _mm256_storeu_si256((__m256i*)(d + i), _mm256_permute4x64_epi64(_mm256_packus_epi32(a, b), 0xD8));
+  }
+  for(; i < n; ++i)
+    d[i] = (uint16_t)s[i];
+}
 __attribute__((target("avx2"))) void narrow_row_avx2(const int32_t* s, uint16_t* d, size_t n)
 {
   size_t i = 0;
@@ -285,7 +368,18 @@ int b2k_host_threads(void)
   return g_threads;
 }
 
-void b2k_host_convert(const b2k_host_rect* rects, size_t nrects, bool widen, bool sgnd)
+void b2k_host_session(bool begin)
+{
+  HostPool* P = pool();
+  if(!P)
+    return;
+  if(begin)
+    P->begin_session();
+  else
+    P->end_session();
+}
+
+void b2k_host_convert(const b2k_host_rect* rects, size_t nrects, bool widen, bool sgnd, bool cached_dst)
 {
   /* one fork-join over every rectangle of the chunk: tasks are groups of ROWS_PER_TASK rows */
   std::vector<size_t> first(nrects + 1, 0);
@@ -319,7 +413,10 @@ void b2k_host_convert(const b2k_host_rect* rects, size_t nrects, bool widen, boo
 #if defined(__x86_64__)
         if(have_avx2())
         {
-          narrow_row_avx2(s, d, R.w);
+          if(cached_dst)
+            narrow_row_avx2_cached(s, d, R.w);
+          else
+            narrow_row_avx2(s, d, R.w);
           continue;
         }
 #endif
