@@ -367,7 +367,7 @@ def main():
         return nb, nbk
 
     host_threads = G.set_host_threads(-1)   # default policy: the engine times packed vs direct on its first calls
-    for _ in range(max(6, args.warmup)):
+    for _ in range(max(8, args.warmup)):
         e2e_step()
     pack_mode = G.host_pack_last()
     barrier()

@@ -102,7 +102,7 @@ struct LevelLaunch
    machine at that moment: it halves the PCIe bytes but triples the host DRAM traffic, so it wins while
    PCIe is the bound (one or two GPUs per socket, or unpinned caller memory) and loses once several
    ranks share a socket's DRAM.  Default policy: time both ways on the first calls, keep the faster,
-   look at the other one again every 128 calls. */
+   look at the other one again every 64 calls. */
 /* pipeline chunks per call (tile granular) and their events: purpose 0 chunk done on its stream, 1 chunk's
    upload done, 2 side-stream / scan done, 3 chunk's download done, 4 misc */
 #define B2K_MAX_CHUNKS 32
@@ -118,8 +118,8 @@ struct PackTuner
   bool next_mode()
   {
     if(choice < 0)
-      return (calls & 1) == 0; /* packed, direct, packed, direct */
-    probing_other = (calls % 128) == 127;
+      return (calls & 1) == 0; /* packed, direct, packed, direct, packed, direct */
+    probing_other = (calls % 64) == 63;
     return probing_other ? !choice : (choice != 0);
   }
   void record(bool packed, double ms)
@@ -129,7 +129,7 @@ struct PackTuner
     {
       if(calls > 1 || !packed) /* the very first packed call allocates the staging buffer */
         best[packed ? 1 : 0] = std::min(best[packed ? 1 : 0], ms);
-      if(calls >= 5)
+      if(calls >= 6)
       {
         choice = best[1] < best[0] ? 1 : 0;
         recent = best[choice];

@@ -255,9 +255,19 @@ int default_threads()
   /* a CPU-time quota (cgroup cpu.max, i.e. a container's --cpus) counts before the CPU list does: a pool that
      burns more than the quota gets the whole process throttled for the rest of the 100 ms period.  Keep three
      CPUs' worth for the caller, the CUDA runtime's threads and whatever else lives in the container. */
-  const double quota = cgroup_cpu_quota();
+  double quota = cgroup_cpu_quota();
+  /* one process per GPU launched by torchrun / mpirun share the container and its quota */
+  int peers = 1;
+  for(const char* name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS"})
+    if(const char* e = getenv(name))
+    {
+      peers = std::max(1, atoi(e));
+      break;
+    }
   if(quota > 0)
-    avail = std::min(avail, std::max(1, (int)quota - 3));
+    avail = std::min(avail, std::max(1, (int)(quota / peers) - 3));
+  else if(peers > 1)
+    avail = std::max(1, avail / peers - 1);
   /* a container change is bandwidth work: a couple of dozen cores saturate one socket's DRAM */
   return std::max(1, std::min(avail, 24));
 }
