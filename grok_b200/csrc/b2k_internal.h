@@ -95,3 +95,4 @@ void b2k_host_convert(const b2k_host_rect* rects, size_t nrects, bool widen, boo
 void b2k_host_session(bool begin); /* between begin and end the pool's idle workers spin instead of sleeping */
 void b2k_host_set_threads(int n); /* 0 disables host packing, <0 restores the default */
 int b2k_host_threads(void);
+int b2k_host_local_peers(void);

@@ -1448,7 +1448,9 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
   const uint32_t* user_strides = strides;
   void* stage_planes[4];
   uint32_t stage_strides[4];
-  const bool tuned = !u16 && host_pack_eligible(J) && g_pack_policy.load() < 0;
+  /* several ranks on one host share its DRAM and CPU quota: measured packing loses there,
+     so the automatic policy only considers it for a process that has the host to itself */
+  const bool tuned = !u16 && host_pack_eligible(J) && g_pack_policy.load() < 0 && b2k_host_local_peers() == 1;
   const bool pack = !u16 && host_pack_eligible(J) && (tuned ? J->tune_enc.next_mode() : g_pack_policy.load() > 0);
   const auto wall0 = std::chrono::steady_clock::now();
   if(!u16)
@@ -1666,7 +1668,9 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
   const uint32_t* user_strides = strides;
   void* stage_planes[4];
   uint32_t stage_strides[4];
-  const bool tuned = !u16 && host_pack_eligible(J) && g_pack_policy.load() < 0;
+  /* several ranks on one host share its DRAM and CPU quota: measured packing loses there,
+     so the automatic policy only considers it for a process that has the host to itself */
+  const bool tuned = !u16 && host_pack_eligible(J) && g_pack_policy.load() < 0 && b2k_host_local_peers() == 1;
   const bool pack = !u16 && host_pack_eligible(J) && (tuned ? J->tune_dec.next_mode() : g_pack_policy.load() > 0);
   const auto wall0 = std::chrono::steady_clock::now();
   if(!u16)

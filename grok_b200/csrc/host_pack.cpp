@@ -256,14 +256,7 @@ int default_threads()
      burns more than the quota gets the whole process throttled for the rest of the 100 ms period.  Keep three
      CPUs' worth for the caller, the CUDA runtime's threads and whatever else lives in the container. */
   double quota = cgroup_cpu_quota();
-  /* one process per GPU launched by torchrun / mpirun share the container and its quota */
-  int peers = 1;
-  for(const char* name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS"})
-    if(const char* e = getenv(name))
-    {
-      peers = std::max(1, atoi(e));
-      break;
-    }
+  const int peers = b2k_host_local_peers();
   if(quota > 0)
     avail = std::min(avail, std::max(1, (int)(quota / peers) - 3));
   else if(peers > 1)
@@ -363,6 +356,15 @@ bool have_avx2()
 constexpr size_t ROWS_PER_TASK = 8;
 
 } // namespace
+
+/* processes sharing this host with us, one per GPU, as torchrun / mpirun advertise them (1 if unknown) */
+int b2k_host_local_peers(void)
+{
+  for(const char* name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS"})
+    if(const char* e = getenv(name))
+      return std::max(1, atoi(e));
+  return 1;
+}
 
 void b2k_host_set_threads(int n)
 {
