@@ -1350,6 +1350,11 @@ static int fetch_result(b2k_device_job* J, cudaStream_t st, b2k_result** out, ui
     delete R;
     return -1;
   }
+  struct ResultGuard /* a failing CUDA call below must not leak the result and its pinned arena */
+  {
+    b2k_result* r;
+    ~ResultGuard() { if(r) b2k_result_free(r); }
+  } guard{R};
   if(!host_bytes)
     CUDA_TRY(cudaMemcpyAsync(R->bytes, J->d_bytes, J->bytes_used, cudaMemcpyDeviceToHost, st));
   if(!meta_on_host)
@@ -1375,9 +1380,9 @@ static int fetch_result(b2k_device_job* J, cudaStream_t st, b2k_result** out, ui
   if(bad)
   {
     g_err = std::to_string(bad) + " code block(s) overflowed the coder's buffers";
-    b2k_result_free(R);
     return -2;
   }
+  guard.r = nullptr;
   *out = R;
   return 0;
 }
@@ -1488,6 +1493,11 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
      chunks are still arriving (the D2H direction of PCIe is otherwise idle) */
   const bool streamed = J->bytes_cap > 0 && nchunks > 1;
   uint8_t* hb = nullptr;
+  struct ArenaGuard /* the pinned arena goes back to the pool on every early return until a result owns it */
+  {
+    uint8_t*& p;
+    ~ArenaGuard() { if(p) pool_put(p); }
+  } arena_guard{hb};
   if(streamed)
   {
     hb = pool_get(J->bytes_cap);
@@ -1583,6 +1593,7 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
     if(overflow)
     { /* estimate too small: grow, compact everything again from the scratch slots, plain copy */
       pool_put(hb);
+      hb = nullptr;
       CUDA_TRY(cudaStreamSynchronize(st));
       cudaFree(J->d_bytes);
       J->bytes_cap = total + total / 8 + 4096;
@@ -1594,7 +1605,9 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
     else
     {
       CUDA_TRY(cudaEventRecord(J->ev[3], st));
-      if(int frc = fetch_result(J, st, &R, hb, shell, true)) return frc;
+      uint8_t* owned = hb;
+      hb = nullptr; /* fetch_result hands it to the result, or frees it with the result on failure */
+      if(int frc = fetch_result(J, st, &R, owned, shell, true)) return frc;
     }
   }
   if(!streamed)

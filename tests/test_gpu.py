@@ -536,3 +536,39 @@ def test_corrupt_streams_are_rejected_or_decoded_never_fatal(engine):
     engine.decode(cp, blocks, data, out)               # still healthy
     for a, s in zip(out, planes):
         assert np.array_equal(a, s)
+
+
+@pytest.mark.parametrize("sgnd", [False, True])
+def test_host_packing_matches_direct_copies(engine, sgnd):
+    """int32 entry points with host packing forced on (16-bit PCIe containers through the pinned ring, host
+    thread pool) against the same calls with packing off: same coded bytes, same pixels, lossless -- on a
+    geometry with ragged tiles, an odd canvas origin and (second case) signed samples, large enough
+    (>= 4 Msamples, several pipeline chunks) for the packed path to be taken, with unpinned caller planes."""
+    w, h, prec = 2501, 1803, (16 if sgnd else 12)
+    cp = G.make_coding(w, h, 3, prec, sgnd=sgnd, numres=5, tile=(700, 500), origin=(3, 5), numgbits=2 if sgnd else 1)
+    planes = P.synthetic_image(w, h, 3, prec, seed=11, origin=(3, 5))
+    if sgnd:
+        planes = [p - (1 << (prec - 1)) for p in planes]
+    strided = [np.zeros((h, w + 13), np.int32) for _ in planes]     # row stride != width
+    for s, p in zip(strided, planes):
+        s[:, :w] = p
+    views = [s[:, :w] for s in strided]
+    results = {}
+    try:
+        for mode, threads in (("direct", 0), ("packed", 3)):
+            G.set_host_threads(threads)
+            res = engine.encode(cp, views)
+            assert G.host_pack_last()[0] == (1 if threads else 0)
+            blocks, data = res.blocks.copy(), res.bytes.copy()
+            res.free()
+            out = [np.full((h, w + 5), -7, np.int32) for _ in planes]
+            engine.decode(cp, blocks, data, [o[:, :w] for o in out])
+            assert G.host_pack_last()[1] == (1 if threads else 0)
+            for o, p in zip(out, planes):
+                assert np.array_equal(o[:, :w], p)               # lossless
+                assert np.all(o[:, w:] == -7)                    # nothing written past the rows
+            results[mode] = (blocks, data)
+    finally:
+        G.set_host_threads(-1)
+    assert np.array_equal(results["direct"][1], results["packed"][1])
+    assert np.array_equal(results["direct"][0]["length"], results["packed"][0]["length"])
