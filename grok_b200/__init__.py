@@ -62,7 +62,8 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_result_to_gpup_tile", "b2k_job_create", "b2k_job_destroy", "b2k_job_upload", "b2k_job_forward",
            "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
-           "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last"]
+           "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last",
+           "b2k_codestream_write", "b2k_codestream_parse"]
 
 _lib = None
 
@@ -111,6 +112,10 @@ def lib():
     L.b2k_launch_count.restype = u64
     L.b2k_set_host_threads.argtypes = [C.c_int32]
     L.b2k_set_host_threads.restype = C.c_int32
+    L.b2k_codestream_write.argtypes = [C.POINTER(Coding), C.POINTER(Result), C.c_uint32, vp, u64]
+    L.b2k_codestream_write.restype = C.c_int64
+    L.b2k_codestream_parse.argtypes = [vp, u64, C.POINTER(Coding), vp, u64]
+    L.b2k_codestream_parse.restype = C.c_int64
     L.b2k_host_pack_last.argtypes = [C.c_int32]
     L.b2k_host_pack_last.restype = C.c_int32
     L.b2k_job_last_kernel_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(u64)]
@@ -167,6 +172,47 @@ def set_host_threads(n):
 def host_pack_last():
     """(encode, decode): 1 if the last int32 call went through 16-bit host packing, 0 direct, -1 none yet."""
     return int(lib().b2k_host_pack_last(0)), int(lib().b2k_host_pack_last(1))
+
+
+CS_TLM, CS_PLT = 1, 2
+
+
+def codestream_write(cp, blocks, data, flags=CS_TLM | CS_PLT, num_tiles=None):
+    """HTJ2K codestream (bytes, numpy uint8) from a coding, a full block table (BLOCK_DTYPE) and its byte arena
+    -- an EncodeResult's .blocks / .bytes, or tables built elsewhere (tests build them with the oracle)."""
+    blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    r = Result()
+    r.num_blocks = len(blocks)
+    r.blocks = C.cast(blocks.ctypes.data, C.POINTER(Block))
+    r.bytes = C.cast(data.ctypes.data, C.POINTER(C.c_uint8))
+    r.num_bytes = len(data)
+    r.num_tiles = int(blocks["tile"].max()) + 1 if num_tiles is None else num_tiles
+    n = lib().b2k_codestream_write(C.byref(cp), C.byref(r), flags, None, 0)
+    if n < 0:
+        raise EngineError("b2k_codestream_write: " + (lib().b2k_last_error() or b"").decode())
+    out = np.zeros(n, np.uint8)
+    n2 = lib().b2k_codestream_write(C.byref(cp), C.byref(r), flags, out.ctypes.data, n)
+    assert n2 == n
+    return out
+
+
+def codestream_parse(cs):
+    """-> (Coding, block table with offsets into cs).  Raises NotHandled for codestreams outside the path's scope."""
+    cs = np.ascontiguousarray(cs, dtype=np.uint8)
+    cp = Coding()
+    n = lib().b2k_codestream_parse(cs.ctypes.data, len(cs), C.byref(cp), None, 0)
+    if n < 0 or n == 1:
+        raise (NotHandled if n == 1 else EngineError)("b2k_codestream_parse: " + (lib().b2k_last_error() or b"").decode())
+    blocks = np.zeros(n, BLOCK_DTYPE)
+    m = lib().b2k_codestream_parse(cs.ctypes.data, len(cs), C.byref(cp), blocks.ctypes.data, n)
+    if m != n:
+        raise (NotHandled if m == 1 else EngineError)("b2k_codestream_parse: " + (lib().b2k_last_error() or b"").decode())
+    return cp, blocks
+
+
+class NotHandled(EngineError):
+    pass
 
 
 def pinned_empty(shape, dtype):

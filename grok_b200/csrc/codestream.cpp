@@ -1,0 +1,974 @@
+/*
+ * grok_b200/csrc/codestream.cpp -- HTJ2K codestream assembly and parsing on the host:
+ * the T2 step between the block coder's output (b2k_result) and a file a JPEG 2000 decoder reads.
+ *
+ * Replaces (reference, CPU):
+ *   main header   codestream/compress/CodeStreamCompress.cpp L1064-1098 (SOC, SIZ, CAP, COD, QCD, TLM order),
+ *                 codestream/markers/SIZMarker.cpp, t2/quantizer/part15/QuantizerOJPH.cpp L259-330 (CAP, MAGB)
+ *   tile parts    CodeStreamCompress::writeTilePart L1099-, codestream/markers/SOTMarker.cpp,
+ *                 PLMarker.cpp (PLT), TLMMarker.cpp (TLM)
+ *   packets       t2/T2Compress.cpp L261-489 (header: inclusion / zero-bit-plane tag trees, pass count, Lblock,
+ *                 lengths; body), t2/TagTree.h, t1_t2 BitIO (bit stuffing after 0xFF)
+ *   parsing       codestream/decompress/CodeStreamDecompress_ReadMarkers.cpp, t2/PacketParser.cpp,
+ *                 t1/codeblock/CodeblockDecompressImpl.h L205-420 (HT segments: cleanup | refinement, T.814 B.10.7)
+ * Scope: what this engine's path produces and consumes -- one quality layer, LRCP, one tile-part per tile, no
+ * SOP/EPH, no COC/QCC/POC/RGN/PPM/PPT, HT code blocks with 1..3 passes.  Anything else parses as "not handled".
+ * Written from the standard's rules (ITU-T T.800 Annex A/B, T.814 Annex A/B), not transcribed from the reference;
+ * tests decode the output with an independent decoder (OpenJPEG via Pillow / OpenCV) -- tests/test_codestream.py.
+ */
+#include "geometry.h"
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace b2k;
+
+extern "C" const char* b2k_last_error(void);
+void b2k_set_error(const char* msg); /* engine.cu */
+
+namespace
+{
+
+/* ---- packet-header bit I/O: MSB first, the byte after 0xFF carries 7 bits (T.800 B.10.1) ---------------- */
+struct BitWriter
+{
+  std::vector<uint8_t>& out;
+  uint32_t acc = 0;
+  int cap = 8, room = 8; /* bits the current byte holds / still free */
+  explicit BitWriter(std::vector<uint8_t>& o) : out(o) {}
+  void put(uint32_t bit)
+  {
+    --room;
+    acc |= (bit & 1u) << room;
+    if(room == 0)
+      emit();
+  }
+  void put_bits(uint32_t v, int n)
+  {
+    for(int i = n - 1; i >= 0; --i)
+      put((v >> i) & 1u);
+  }
+  void emit()
+  {
+    out.push_back((uint8_t)acc);
+    cap = room = (acc == 0xFF) ? 7 : 8;
+    acc = 0;
+  }
+  void flush()
+  {
+    if(room != cap)
+      emit();
+    if(!out.empty() && out.back() == 0xFF)
+      emit(); /* a header must not end on 0xFF: the stuffed byte follows */
+  }
+};
+struct BitReader
+{
+  const uint8_t* p;
+  const uint8_t* end;
+  uint32_t cur = 0;
+  int left = 0;
+  bool prev_ff = false, overrun = false;
+  BitReader(const uint8_t* b, const uint8_t* e) : p(b), end(e) {}
+  uint32_t get()
+  {
+    if(left == 0)
+    {
+      if(p >= end)
+      {
+        overrun = true;
+        return 0;
+      }
+      cur = *p++;
+      left = prev_ff ? 7 : 8;
+      prev_ff = (cur == 0xFF);
+    }
+    --left;
+    return (cur >> left) & 1u;
+  }
+  uint32_t get_bits(int n)
+  {
+    uint32_t v = 0;
+    for(int i = 0; i < n; ++i)
+      v = (v << 1) | get();
+    return v;
+  }
+  /* header ends byte aligned; a final 0xFF is followed by one stuffed byte */
+  const uint8_t* finish()
+  {
+    left = 0;
+    if(prev_ff && p < end)
+      ++p;
+    prev_ff = false;
+    return p;
+  }
+};
+
+/* ---- tag tree (T.800 B.10.2) ---------------------------------------------------------------------------- */
+struct TagTree
+{
+  struct Node
+  {
+    int parent;
+    uint32_t value, low;
+    bool known;
+  };
+  std::vector<Node> nodes;
+  uint32_t w = 0, h = 0;
+  static constexpr uint32_t INF = 0x7FFFFFFFu;
+  void init(uint32_t w_, uint32_t h_)
+  {
+    w = w_;
+    h = h_;
+    nodes.clear();
+    std::vector<std::pair<uint32_t, uint32_t>> dims;
+    uint32_t lw = w, lh = h;
+    for(;;)
+    {
+      dims.push_back({lw, lh});
+      if(lw <= 1 && lh <= 1)
+        break;
+      lw = (lw + 1) / 2;
+      lh = (lh + 1) / 2;
+    }
+    size_t total = 0;
+    std::vector<size_t> base;
+    for(auto& d : dims)
+    {
+      base.push_back(total);
+      total += (size_t)d.first * d.second;
+    }
+    nodes.assign(total, Node{-1, INF, 0, false});
+    for(size_t l = 0; l + 1 < dims.size(); ++l)
+      for(uint32_t y = 0; y < dims[l].second; ++y)
+        for(uint32_t x = 0; x < dims[l].first; ++x)
+          nodes[base[l] + (size_t)y * dims[l].first + x].parent = (int)(base[l + 1] + (size_t)(y / 2) * dims[l + 1].first + x / 2);
+  }
+  void set_value(uint32_t leaf, uint32_t v)
+  { /* encoder: a node holds the minimum of its leaves */
+    int n = (int)leaf;
+    while(n >= 0 && nodes[n].value > v)
+    {
+      nodes[n].value = v;
+      n = nodes[n].parent;
+    }
+  }
+  void encode(BitWriter& bw, uint32_t leaf, uint32_t threshold)
+  {
+    int path[32], np = 0;
+    for(int n = (int)leaf; n >= 0; n = nodes[n].parent)
+      path[np++] = n;
+    uint32_t low = 0;
+    for(int i = np - 1; i >= 0; --i)
+    {
+      Node& nd = nodes[path[i]];
+      if(low > nd.low)
+        nd.low = low;
+      else
+        low = nd.low;
+      while(low < threshold)
+      {
+        if(low >= nd.value)
+        {
+          if(!nd.known)
+          {
+            bw.put(1);
+            nd.known = true;
+          }
+          break;
+        }
+        bw.put(0);
+        ++low;
+      }
+      nd.low = low;
+    }
+  }
+  /* true if the leaf's value is < threshold (then nodes[leaf].value holds it) */
+  bool decode(BitReader& br, uint32_t leaf, uint32_t threshold)
+  {
+    int path[32], np = 0;
+    for(int n = (int)leaf; n >= 0; n = nodes[n].parent)
+      path[np++] = n;
+    uint32_t low = 0;
+    for(int i = np - 1; i >= 0; --i)
+    {
+      Node& nd = nodes[path[i]];
+      if(low > nd.low)
+        nd.low = low;
+      else
+        low = nd.low;
+      while(low < threshold && low < nd.value)
+      {
+        if(br.get())
+          nd.value = low;
+        else
+          ++low;
+      }
+      nd.low = low;
+    }
+    return nodes[leaf].value < threshold;
+  }
+};
+
+inline int floorlog2(uint32_t v)
+{
+  int l = 0;
+  while(v > 1)
+  {
+    v >>= 1;
+    ++l;
+  }
+  return l;
+}
+
+/* ---- packets of a tile in LRCP order, with where their blocks sit in the tile's enumeration ---------------- */
+struct PacketBand
+{
+  uint32_t first = 0, gw = 0, gh = 0; /* first block (index into the tile's blocks), code-block grid of the precinct */
+};
+struct Packet
+{
+  uint16_t comp;
+  uint8_t resno, nbands;
+  uint32_t precno;
+  PacketBand band[3];
+};
+/* mirrors enumerate_tile_blocks() (geometry.cpp): same loops, counts instead of blocks */
+void tile_packets(const b2k_coding& cp, const Rect& tile, std::vector<Packet>& lrcp, uint32_t& nblocks)
+{
+  const int numres = cp.numres;
+  std::vector<std::vector<Packet>> per_res_comp((size_t)numres * cp.numcomps);
+  uint32_t running = 0;
+  for(uint16_t comp = 0; comp < cp.numcomps; ++comp)
+    for(int resno = 0; resno < numres; ++resno)
+    {
+      const Rect res = resolution_rect(tile, numres, resno);
+      const uint32_t pw = cp.prcw_exp[resno] ? cp.prcw_exp[resno] : 15, ph = cp.prch_exp[resno] ? cp.prch_exp[resno] : 15;
+      const uint32_t px0 = (res.x0 >> pw) << pw, py0 = (res.y0 >> ph) << ph;
+      const uint64_t px1 = (uint64_t)ceil_div_pow2(res.x1, pw) << pw, py1 = (uint64_t)ceil_div_pow2(res.y1, ph) << ph;
+      uint32_t gridw = (uint32_t)((px1 >> pw) - (px0 >> pw)), gridh = (uint32_t)((py1 >> ph) - (py0 >> ph));
+      if(res.empty())
+        gridw = gridh = 0; /* an empty resolution has no precincts, hence no packets (T.800 B.6) */
+      const uint32_t bpw = resno ? pw - 1 : pw, bph = resno ? ph - 1 : ph;
+      const uint32_t bpx0 = resno ? px0 >> 1 : px0, bpy0 = resno ? py0 >> 1 : py0;
+      const uint32_t cbw = std::min<uint32_t>(cp.cblkw_exp, bpw), cbh = std::min<uint32_t>(cp.cblkh_exp, bph);
+      const int nbands = resno == 0 ? 1 : 3;
+      std::vector<Packet>& pk = per_res_comp[(size_t)resno * cp.numcomps + comp];
+      pk.resize((size_t)gridw * gridh);
+      for(size_t p = 0; p < pk.size(); ++p)
+      {
+        pk[p].comp = comp;
+        pk[p].resno = (uint8_t)resno;
+        pk[p].nbands = (uint8_t)nbands;
+        pk[p].precno = (uint32_t)p;
+      }
+      for(int b = 0; b < nbands; ++b)
+      {
+        const int orient = resno == 0 ? 0 : b + 1;
+        const Rect band = band_rect(tile, numres, resno, orient);
+        /* enumerate_tile_blocks walks the precinct grid computed from the (possibly empty) resolution too */
+        const uint32_t egw = (uint32_t)((px1 >> pw) - (px0 >> pw)), egh = (uint32_t)((py1 >> ph) - (py0 >> ph));
+        for(uint64_t p = 0; p < (uint64_t)egw * egh; ++p)
+        {
+          Rect prc;
+          prc.x0 = bpx0 + (uint32_t)((p % egw) << bpw);
+          prc.y0 = bpy0 + (uint32_t)((p / egw) << bph);
+          prc.x1 = (uint32_t)std::min<uint64_t>((uint64_t)prc.x0 + (1ull << bpw), band.x1);
+          prc.y1 = (uint32_t)std::min<uint64_t>((uint64_t)prc.y0 + (1ull << bph), band.y1);
+          prc.x0 = std::max(prc.x0, band.x0);
+          prc.y0 = std::max(prc.y0, band.y0);
+          if(prc.empty())
+            continue;
+          const uint32_t gx = prc.x0 >> cbw, gy = prc.y0 >> cbh;
+          const uint32_t gw = ceil_div_pow2(prc.x1, cbw) - gx, gh = ceil_div_pow2(prc.y1, cbh) - gy;
+          if(p < pk.size())
+          {
+            pk[p].band[b].first = running;
+            pk[p].band[b].gw = gw;
+            pk[p].band[b].gh = gh;
+          }
+          running += gw * gh;
+        }
+      }
+    }
+  nblocks = running;
+  lrcp.clear();
+  for(int resno = 0; resno < numres; ++resno)
+    for(uint16_t comp = 0; comp < cp.numcomps; ++comp)
+      for(const Packet& p : per_res_comp[(size_t)resno * cp.numcomps + comp])
+        lrcp.push_back(p);
+}
+
+void put16(std::vector<uint8_t>& o, uint32_t v)
+{
+  o.push_back((uint8_t)(v >> 8));
+  o.push_back((uint8_t)v);
+}
+void put32(std::vector<uint8_t>& o, uint32_t v)
+{
+  put16(o, v >> 16);
+  put16(o, v & 0xFFFF);
+}
+
+/* Ccap15's magnitude bound from the quantiser (QuantizerOJPH::get_MAGBp L259-280, ::write L281-330) */
+uint32_t magb_code(const b2k_coding& cp, const std::vector<BandQuant>& q)
+{
+  uint32_t B = 0;
+  const int ndecomp = cp.numres - 1;
+  for(size_t i = 0; i < q.size(); ++i)
+  {
+    if(!cp.irreversible)
+      B = std::max<uint32_t>(B, (uint32_t)q[i].expn + cp.numgbits - 1u);
+    else
+    {
+      const int nb = ndecomp - (i ? (int)((i - 1) / 3) : 0);
+      B = std::max<uint32_t>(B, (uint32_t)std::max(0, (int)q[i].expn + (int)cp.numgbits - nb));
+    }
+  }
+  if(B <= 8)
+    return 0;
+  if(B < 28)
+    return B - 8;
+  if(B < 48)
+    return 13 + (B >> 2);
+  return 31;
+}
+
+void write_main_header(const b2k_coding& cp, const TileGrid& g, const std::vector<BandQuant>& q, std::vector<uint8_t>& o)
+{
+  put16(o, 0xFF4F); /* SOC */
+  put16(o, 0xFF51); /* SIZ (T.800 A.5.1) */
+  put16(o, 38 + 3 * cp.numcomps);
+  put16(o, 0x4000); /* Rsiz: bit 14 = Part 15 capabilities, detailed in CAP */
+  put32(o, cp.x1);
+  put32(o, cp.y1);
+  put32(o, cp.x0);
+  put32(o, cp.y0);
+  put32(o, g.tw);
+  put32(o, g.th);
+  put32(o, g.tx0);
+  put32(o, g.ty0);
+  put16(o, cp.numcomps);
+  for(int c = 0; c < cp.numcomps; ++c)
+  {
+    o.push_back((uint8_t)((cp.prec - 1) | (cp.sgnd ? 0x80 : 0)));
+    o.push_back(1);
+    o.push_back(1);
+  }
+  put16(o, 0xFF50); /* CAP (T.814 A.3) */
+  put16(o, 8);
+  put32(o, 0x00020000u);                                        /* Pcap: bit 15 -> Ccap15 follows */
+  put16(o, (cp.irreversible ? 0x0020u : 0u) | magb_code(cp, q)); /* HTONLY, single HT set, RGN free, homogeneous */
+  bool user_prec = false;
+  for(int r = 0; r < cp.numres; ++r)
+    user_prec |= (cp.prcw_exp[r] && cp.prcw_exp[r] != 15) || (cp.prch_exp[r] && cp.prch_exp[r] != 15);
+  put16(o, 0xFF52); /* COD (A.6.1) */
+  put16(o, 12 + (user_prec ? cp.numres : 0));
+  o.push_back(user_prec ? 1 : 0);
+  o.push_back(0); /* LRCP */
+  put16(o, 1);    /* layers */
+  o.push_back(cp.mct ? 1 : 0);
+  o.push_back((uint8_t)(cp.numres - 1));
+  o.push_back((uint8_t)(cp.cblkw_exp - 2));
+  o.push_back((uint8_t)(cp.cblkh_exp - 2));
+  o.push_back((uint8_t)(0x40 | (cp.cblk_sty & 0x08))); /* HT code blocks (+ stripe causal) */
+  o.push_back(cp.irreversible ? 0 : 1);
+  if(user_prec)
+    for(int r = 0; r < cp.numres; ++r)
+      o.push_back((uint8_t)(((cp.prch_exp[r] ? cp.prch_exp[r] : 15) << 4) | (cp.prcw_exp[r] ? cp.prcw_exp[r] : 15)));
+  put16(o, 0xFF5C); /* QCD (A.6.4) */
+  const uint32_t nb = (uint32_t)q.size();
+  put16(o, 3 + (cp.irreversible ? 2 * nb : nb));
+  o.push_back((uint8_t)((cp.numgbits << 5) | (cp.irreversible ? 2 : 0)));
+  for(const BandQuant& b : q)
+  {
+    if(cp.irreversible)
+      put16(o, ((uint32_t)b.expn << 11) | b.mant);
+    else
+      o.push_back((uint8_t)(b.expn << 3));
+  }
+}
+
+/* ---- one tile's packets ----------------------------------------------------------------------------------- */
+int write_tile_packets(const b2k_coding& cp, const Rect& tile, const b2k_block* blk, uint32_t nblk, const uint8_t* arena,
+                       uint64_t arena_len, std::vector<uint8_t>& body, std::vector<uint32_t>& packet_len, std::string& err)
+{
+  std::vector<Packet> pkts;
+  uint32_t expect = 0;
+  tile_packets(cp, tile, pkts, expect);
+  if(expect != nblk)
+  {
+    err = "block table does not match the tile's enumeration";
+    return -1;
+  }
+  TagTree incl, imsb;
+  std::vector<uint8_t> hdr;
+  for(const Packet& pk : pkts)
+  {
+    const size_t start = body.size();
+    hdr.clear();
+    BitWriter bw(hdr);
+    bw.put(1); /* non-empty packet; like the reference also when it carries no block (T2Compress.cpp L304-307) */
+    for(int b = 0; b < pk.nbands; ++b)
+    {
+      const PacketBand& pb = pk.band[b];
+      const uint32_t n = pb.gw * pb.gh;
+      if(!n)
+        continue;
+      incl.init(pb.gw, pb.gh);
+      imsb.init(pb.gw, pb.gh);
+      for(uint32_t k = 0; k < n; ++k)
+      {
+        const b2k_block& B = blk[pb.first + k];
+        if(B.numpasses && B.length)
+        {
+          if(B.numbps > B.kmax || B.numpasses > 3)
+          {
+            err = "code block outside the writer's range (bit planes / passes)";
+            return -1;
+          }
+          incl.set_value(k, 0);
+          imsb.set_value(k, (uint32_t)B.kmax - B.numbps);
+        }
+        else
+          incl.set_value(k, 1); /* never included in the only layer */
+      }
+      for(uint32_t k = 0; k < n; ++k)
+      {
+        const b2k_block& B = blk[pb.first + k];
+        const bool in = B.numpasses && B.length;
+        incl.encode(bw, k, 1);
+        if(!in)
+          continue;
+        imsb.encode(bw, k, TagTree::INF);
+        /* number of passes (B.10.6): 1 -> 0, 2 -> 10, 3 -> 1100 */
+        if(B.numpasses == 1)
+          bw.put(0);
+        else if(B.numpasses == 2)
+          bw.put_bits(2, 2);
+        else
+          bw.put_bits(12, 4);
+        /* HT: cleanup segment, then one segment for the refinement passes (T.814 B.10.7) */
+        const uint32_t len1 = B.length, len2 = B.numpasses > 1 ? B.length2 : 0;
+        const int extra2 = B.numpasses > 1 ? floorlog2((uint32_t)B.numpasses - 1) : 0;
+        int lblock = 3, inc = 0;
+        inc = std::max(inc, floorlog2(len1) + 1 - lblock);
+        if(B.numpasses > 1)
+          inc = std::max(inc, floorlog2(std::max<uint32_t>(len2, 1)) + 1 - (lblock + extra2));
+        for(int i = 0; i < inc; ++i)
+          bw.put(1);
+        bw.put(0);
+        lblock += inc;
+        bw.put_bits(len1, lblock);
+        if(B.numpasses > 1)
+          bw.put_bits(len2, lblock + extra2);
+      }
+    }
+    bw.flush();
+    body.insert(body.end(), hdr.begin(), hdr.end());
+    for(int b = 0; b < pk.nbands; ++b)
+    {
+      const PacketBand& pb = pk.band[b];
+      for(uint32_t k = 0; k < pb.gw * pb.gh; ++k)
+      {
+        const b2k_block& B = blk[pb.first + k];
+        if(!(B.numpasses && B.length))
+          continue;
+        const uint64_t n = (uint64_t)B.length + (B.numpasses > 1 ? B.length2 : 0);
+        if(B.offset + n > arena_len)
+        {
+          err = "block offsets exceed the byte arena";
+          return -1;
+        }
+        body.insert(body.end(), arena + B.offset, arena + B.offset + n);
+      }
+    }
+    packet_len.push_back((uint32_t)(body.size() - start));
+  }
+  return 0;
+}
+
+thread_local std::string t_err;
+
+} // namespace
+
+/* ============================================================================================================ */
+extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(const b2k_coding* cp, const b2k_result* r,
+                                                                                uint32_t flags, uint8_t* out, uint64_t cap)
+{
+  if(!cp || !r)
+    return -1;
+  if(const char* why = unsupported_reason(*cp))
+  {
+    b2k_set_error(why);
+    return -1;
+  }
+  const TileGrid g = tile_grid(*cp);
+  const uint32_t ntiles = g.nx * g.ny;
+  if(r->num_tiles != ntiles)
+  {
+    b2k_set_error("the result does not hold every tile of the image (gather the shards first)");
+    return -1;
+  }
+  if(ntiles > 65535)
+  {
+    b2k_set_error("more than 65535 tiles");
+    return -1;
+  }
+  const std::vector<BandQuant> q = band_quant(*cp);
+  std::vector<uint8_t> o;
+  o.reserve((size_t)r->num_bytes + (size_t)r->num_blocks * 2 + 4096);
+  write_main_header(*cp, g, q, o);
+
+  /* tile parts first (their lengths feed TLM), then stitch */
+  std::vector<std::vector<uint8_t>> parts(ntiles);
+  uint64_t first = 0;
+  for(uint32_t t = 0; t < ntiles; ++t)
+  {
+    uint64_t n = 0;
+    while(first + n < r->num_blocks && r->blocks[first + n].tile == t)
+      ++n;
+    std::vector<uint8_t> body;
+    std::vector<uint32_t> plen;
+    std::string err;
+    if(write_tile_packets(*cp, tile_rect(*cp, g, t), r->blocks + first, (uint32_t)n, r->bytes, r->num_bytes, body, plen, err))
+    {
+      b2k_set_error(err.c_str());
+      return -1;
+    }
+    first += n;
+    std::vector<uint8_t>& tp = parts[t];
+    put16(tp, 0xFF90); /* SOT (A.4.2) */
+    put16(tp, 10);
+    put16(tp, t);
+    put32(tp, 0); /* Psot, patched below */
+    tp.push_back(0);
+    tp.push_back(1);
+    if(flags & B2K_CS_PLT)
+    { /* PLT (A.7.3): packet lengths, 7 bits per byte, continuation bit in the MSB */
+      std::vector<uint8_t> seg;
+      uint8_t z = 0;
+      auto flush_seg = [&] {
+        put16(tp, 0xFF58);
+        put16(tp, (uint32_t)seg.size() + 3);
+        tp.push_back(z++);
+        tp.insert(tp.end(), seg.begin(), seg.end());
+        seg.clear();
+      };
+      for(uint32_t L : plen)
+      {
+        uint8_t tmp[5];
+        int nb = 0;
+        do
+        {
+          tmp[nb++] = (uint8_t)(L & 0x7F);
+          L >>= 7;
+        } while(L);
+        if(seg.size() + nb > 65535 - 3)
+          flush_seg();
+        for(int i = nb - 1; i >= 0; --i)
+          seg.push_back((uint8_t)(tmp[i] | (i ? 0x80 : 0)));
+      }
+      if(!seg.empty() || plen.empty())
+        flush_seg();
+    }
+    put16(tp, 0xFF93); /* SOD */
+    tp.insert(tp.end(), body.begin(), body.end());
+    if(tp.size() > 0xFFFFFFFFull)
+    {
+      b2k_set_error("tile part longer than 4 GiB");
+      return -1;
+    }
+    const uint32_t psot = (uint32_t)tp.size();
+    tp[6] = (uint8_t)(psot >> 24);
+    tp[7] = (uint8_t)(psot >> 16);
+    tp[8] = (uint8_t)(psot >> 8);
+    tp[9] = (uint8_t)psot;
+  }
+  if(first != r->num_blocks)
+  {
+    b2k_set_error("block table is not in tile order");
+    return -1;
+  }
+  if(flags & B2K_CS_TLM)
+  { /* TLM (A.7.1): 16-bit tile index + 32-bit length per tile part; 10921 entries fit one marker segment */
+    uint8_t z = 0;
+    for(uint32_t t0 = 0; t0 < ntiles; t0 += 10000)
+    {
+      const uint32_t n = std::min(10000u, ntiles - t0);
+      put16(o, 0xFF55);
+      put16(o, 4 + 6 * n);
+      o.push_back(z++);
+      o.push_back(0x60); /* ST = 2 (16-bit Ttlm), SP = 1 (32-bit Ptlm) */
+      for(uint32_t t = t0; t < t0 + n; ++t)
+      {
+        put16(o, t);
+        put32(o, (uint32_t)parts[t].size());
+      }
+    }
+  }
+  for(auto& tp : parts)
+    o.insert(o.end(), tp.begin(), tp.end());
+  put16(o, 0xFFD9); /* EOC */
+  if(out && cap >= o.size())
+    memcpy(out, o.data(), o.size());
+  return (int64_t)o.size();
+}
+
+/* ============================================================================================================ */
+namespace
+{
+struct Cursor
+{
+  const uint8_t* p;
+  const uint8_t* end;
+  bool ok = true;
+  uint32_t u8()
+  {
+    if(p + 1 > end) { ok = false; return 0; }
+    return *p++;
+  }
+  uint32_t u16()
+  {
+    if(p + 2 > end) { ok = false; return 0; }
+    const uint32_t v = ((uint32_t)p[0] << 8) | p[1];
+    p += 2;
+    return v;
+  }
+  uint32_t u32()
+  {
+    const uint32_t a = u16();
+    return (a << 16) | u16();
+  }
+};
+} // namespace
+
+extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(const uint8_t* cs, uint64_t len, b2k_coding* cp_out,
+                                                                                b2k_block* blocks, uint64_t cap_blocks)
+{
+  if(!cs || !cp_out)
+    return -1;
+  auto fail = [&](const char* m, int rc) {
+    b2k_set_error(m);
+    return (int64_t)rc;
+  };
+  Cursor c{cs, cs + len};
+  if(c.u16() != 0xFF4F)
+    return fail("no SOC marker", -1);
+  b2k_coding cp;
+  memset(&cp, 0, sizeof(cp));
+  bool have_siz = false, have_cod = false, have_qcd = false, have_cap = false;
+  std::vector<uint32_t> qcd_vals;
+  uint32_t sqcd = 0;
+  /* ---- main header ---- */
+  for(;;)
+  {
+    const uint32_t m = c.u16();
+    if(!c.ok)
+      return fail("truncated main header", -1);
+    if(m == 0xFF90)
+    {
+      c.p -= 2;
+      break;
+    }
+    const uint32_t L = c.u16();
+    if(!c.ok || L < 2 || c.p + (L - 2) > c.end)
+      return fail("bad marker segment length", -1);
+    Cursor s{c.p, c.p + (L - 2)};
+    c.p += L - 2;
+    switch(m)
+    {
+      case 0xFF51: {
+        const uint32_t rsiz = s.u16();
+        (void)rsiz;
+        cp.x1 = s.u32(); cp.y1 = s.u32(); cp.x0 = s.u32(); cp.y0 = s.u32();
+        cp.tw = s.u32(); cp.th = s.u32(); cp.tx0 = s.u32(); cp.ty0 = s.u32();
+        const uint32_t nc = s.u16();
+        if(nc < 1 || nc > 4)
+          return fail("1..4 components handled", 1);
+        cp.numcomps = (uint16_t)nc;
+        for(uint32_t i = 0; i < nc; ++i)
+        {
+          const uint32_t ssiz = s.u8(), dx = s.u8(), dy = s.u8();
+          if(dx != 1 || dy != 1)
+            return fail("sub-sampled components are not handled", 1);
+          const uint8_t prec = (uint8_t)((ssiz & 0x7F) + 1), sg = (uint8_t)(ssiz >> 7);
+          if(i && (prec != cp.prec || sg != cp.sgnd))
+            return fail("components of different precision are not handled", 1);
+          cp.prec = prec;
+          cp.sgnd = sg;
+        }
+        have_siz = s.ok;
+        break;
+      }
+      case 0xFF50: {
+        const uint32_t pcap = s.u32();
+        have_cap = (pcap & 0x00020000u) != 0;
+        if(have_cap)
+        {
+          /* Ccap15 is the entry of the 15th capability bit among those set */
+          uint32_t idx = 0;
+          for(int b = 31; b > 17; --b)
+            idx += (pcap >> b) & 1u;
+          uint32_t ccap15 = 0;
+          for(uint32_t i = 0; i <= idx; ++i)
+            ccap15 = s.u16();
+          if((ccap15 >> 14) != 0)
+            return fail("only HTONLY codestreams are handled (no Part-1 or mixed code blocks)", 1);
+          if(ccap15 & 0x2000)
+            return fail("multiple HT sets per code block are not handled", 1);
+        }
+        break;
+      }
+      case 0xFF52: {
+        const uint32_t scod = s.u8();
+        if(scod & 0x06)
+          return fail("SOP / EPH markers are not handled", 1);
+        const uint32_t prog = s.u8(), layers = s.u16(), mct = s.u8();
+        cp.mct = (uint8_t)mct;
+        const uint32_t nd = s.u8();
+        cp.numres = (uint8_t)(nd + 1);
+        cp.cblkw_exp = (uint8_t)(s.u8() + 2);
+        cp.cblkh_exp = (uint8_t)(s.u8() + 2);
+        const uint32_t sty = s.u8(), xf = s.u8();
+        if(layers != 1)
+          return fail("one quality layer handled", 1);
+        if(prog != 0)
+          return fail("LRCP progression handled", 1);
+        if(!(sty & 0x40) || (sty & ~0x48u))
+          return fail("only HT code blocks (optionally stripe-causal) are handled", 1);
+        cp.cblk_sty = (uint8_t)(sty & 0x08);
+        if(xf > 1)
+          return fail("unknown wavelet", 1);
+        cp.irreversible = xf == 0;
+        for(int r = 0; r < 33; ++r)
+          cp.prcw_exp[r] = cp.prch_exp[r] = 15;
+        if(scod & 1)
+          for(uint32_t r = 0; r <= nd && r < 33; ++r)
+          {
+            const uint32_t v = s.u8();
+            cp.prcw_exp[r] = (uint8_t)(v & 0xF);
+            cp.prch_exp[r] = (uint8_t)(v >> 4);
+          }
+        have_cod = s.ok;
+        break;
+      }
+      case 0xFF5C: {
+        sqcd = s.u8();
+        cp.numgbits = (uint8_t)(sqcd >> 5);
+        const uint32_t style = sqcd & 0x1F;
+        if(style == 1)
+          return fail("derived quantisation is not handled", 1);
+        while(s.p < s.end)
+          qcd_vals.push_back(style == 0 ? s.u8() : s.u16());
+        have_qcd = s.ok;
+        break;
+      }
+      case 0xFF64: /* COM */
+      case 0xFF55: /* TLM: lengths are read from SOT */
+      case 0xFF63: /* CRG */
+        break;
+      case 0xFF53: case 0xFF5D: case 0xFF5E: case 0xFF5F: case 0xFF60: case 0xFF57:
+        return fail("COC / QCC / RGN / POC / PPM / PLM marker segments are not handled", 1);
+      default:
+        if(m < 0xFF00)
+          return fail("garbage in the main header", -1);
+        break; /* unknown informative segment: skip */
+    }
+  }
+  if(!have_siz || !have_cod || !have_qcd)
+    return fail("SIZ, COD and QCD are required", -1);
+  if(!have_cap)
+    return fail("not an HTJ2K codestream (no Part-15 capability)", 1);
+  if(cp.mct && cp.numcomps < 3)
+    return fail("MCT with fewer than three components", -1);
+  if(const char* why = unsupported_reason(cp))
+    return fail(why, 1);
+  /* the decoder works with the HT quantiser's step sizes: QCD must say the same (geometry.cpp band_quant) */
+  const std::vector<BandQuant> q = band_quant(cp);
+  if(qcd_vals.size() < q.size())
+    return fail("QCD has fewer entries than bands", -1);
+  if(((sqcd & 0x1F) == 2) != (cp.irreversible != 0))
+    return fail("quantisation style does not match the wavelet", 1);
+  for(size_t i = 0; i < q.size(); ++i)
+  {
+    const uint32_t want = cp.irreversible ? (((uint32_t)q[i].expn << 11) | q[i].mant) : ((uint32_t)q[i].expn << 3);
+    if(qcd_vals[i] != want)
+      return fail("QCD step sizes differ from the HT quantiser's tables: foreign quantiser, not handled", 1);
+  }
+  /* SIZ sanity (A.5.1) and a bound on what a damaged header can make us enumerate */
+  if(cp.tw == 0 || cp.th == 0 || cp.tx0 > cp.x0 || cp.ty0 > cp.y0 || (uint64_t)cp.tx0 + cp.tw <= cp.x0 ||
+     (uint64_t)cp.ty0 + cp.th <= cp.y0)
+    return fail("tile grid does not cover the image origin", -1);
+  if((uint64_t)(cp.x1 - cp.x0) * (cp.y1 - cp.y0) > (1ull << 32))
+    return fail("image larger than 2^32 samples per component", 1);
+  {
+    const uint64_t nx = ceil_div(cp.x1 - cp.tx0, cp.tw), ny = ceil_div(cp.y1 - cp.ty0, cp.th);
+    if(nx * ny > 65535)
+      return fail("more than 65535 tiles", -1);
+    uint64_t precincts = 0;
+    for(int r = 0; r < cp.numres; ++r)
+    { /* upper bound: precincts of resolution r over the whole image, plus one row / column per tile */
+      const int nd = cp.numres - 1 - r;
+      const uint64_t rw = (((uint64_t)(cp.x1 - cp.x0)) >> nd) + 2 * nx, rh = (((uint64_t)(cp.y1 - cp.y0)) >> nd) + 2 * ny;
+      const uint32_t pw = cp.prcw_exp[r] ? cp.prcw_exp[r] : 15, ph = cp.prch_exp[r] ? cp.prch_exp[r] : 15;
+      precincts += ((rw >> pw) + 2 * nx) * ((rh >> ph) + 2 * ny);
+    }
+    if(precincts * cp.numcomps > (1ull << 24))
+      return fail("more than 2^24 precincts", 1);
+    if((((uint64_t)(cp.x1 - cp.x0) * (cp.y1 - cp.y0) * cp.numcomps) >> (cp.cblkw_exp + cp.cblkh_exp)) > (1ull << 26))
+      return fail("more than 2^26 code blocks", 1);
+  }
+  const TileGrid g = tile_grid(cp);
+  const uint32_t ntiles = g.nx * g.ny;
+  /* block table in enumeration order */
+  std::vector<b2k_block> all;
+  std::vector<uint64_t> tile_first(ntiles + 1, 0);
+  for(uint32_t t = 0; t < ntiles; ++t)
+  {
+    tile_first[t] = all.size();
+    enumerate_tile_blocks(cp, t, tile_rect(cp, g, t), q, all);
+  }
+  tile_first[ntiles] = all.size();
+  *cp_out = cp;
+  if(!blocks)
+    return (int64_t)all.size();
+  if(cap_blocks < all.size())
+    return fail("block table too small", -1);
+
+  /* ---- tile parts ---- */
+  std::vector<uint8_t> seen(ntiles, 0);
+  for(;;)
+  {
+    const uint8_t* sot = c.p;
+    const uint32_t m = c.u16();
+    if(!c.ok)
+      break; /* a missing EOC is tolerated */
+    if(m == 0xFFD9)
+      break;
+    if(m != 0xFF90)
+      return fail("expected SOT or EOC", -1);
+    const uint32_t lsot = c.u16(), isot = c.u16();
+    const uint32_t psot = c.u32();
+    const uint32_t tpsot = c.u8(), tnsot = c.u8();
+    (void)tnsot;
+    if(!c.ok || lsot != 10 || isot >= ntiles)
+      return fail("bad SOT", -1);
+    if(tpsot != 0 || seen[isot])
+      return fail("several tile parts per tile are not handled", 1);
+    seen[isot] = 1;
+    const uint8_t* tp_end = psot ? sot + psot : c.end - ((len >= 2 && cs[len - 2] == 0xFF && cs[len - 1] == 0xD9) ? 2 : 0);
+    if(tp_end > c.end || tp_end < c.p)
+      return fail("Psot exceeds the codestream", -1);
+    for(;;)
+    { /* tile-part header */
+      const uint32_t tm = c.u16();
+      if(!c.ok)
+        return fail("truncated tile-part header", -1);
+      if(tm == 0xFF93)
+        break;
+      const uint32_t L = c.u16();
+      if(!c.ok || L < 2 || c.p + (L - 2) > tp_end)
+        return fail("bad tile-part marker segment", -1);
+      if(tm == 0xFF52 || tm == 0xFF53 || tm == 0xFF5C || tm == 0xFF5D || tm == 0xFF5E || tm == 0xFF5F || tm == 0xFF61)
+        return fail("tile-part COD / COC / QCD / QCC / RGN / POC / PPT are not handled", 1);
+      c.p += L - 2; /* PLT, COM: skipped */
+    }
+    /* packets */
+    std::vector<Packet> pkts;
+    uint32_t nblk = 0;
+    tile_packets(cp, tile_rect(cp, g, isot), pkts, nblk);
+    if(nblk != tile_first[isot + 1] - tile_first[isot])
+      return fail("internal: packet geometry and block enumeration disagree", -1);
+    b2k_block* tb = all.data() + tile_first[isot];
+    TagTree incl, imsb;
+    const uint8_t* p = c.p;
+    for(const Packet& pk : pkts)
+    {
+      BitReader br(p, tp_end);
+      struct Seg
+      {
+        uint32_t blk, n;
+      };
+      std::vector<Seg> order;
+      if(br.get())
+      {
+        for(int b = 0; b < pk.nbands; ++b)
+        {
+          const PacketBand& pb = pk.band[b];
+          const uint32_t n = pb.gw * pb.gh;
+          if(!n)
+            continue;
+          incl.init(pb.gw, pb.gh);
+          imsb.init(pb.gw, pb.gh);
+          for(uint32_t k = 0; k < n; ++k)
+          {
+            b2k_block& B = tb[pb.first + k];
+            if(!incl.decode(br, k, 1))
+              continue;
+            uint32_t zbp = 0;
+            for(uint32_t th = 1;; ++th)
+            {
+              if(imsb.decode(br, k, th))
+              {
+                zbp = imsb.nodes[k].value;
+                break;
+              }
+              if(th > 64 || br.overrun)
+                return fail("corrupt packet header (zero bit planes)", -1);
+            }
+            uint32_t np;
+            if(!br.get())
+              np = 1;
+            else if(!br.get())
+              np = 2;
+            else
+            {
+              const uint32_t v = br.get_bits(2);
+              if(v < 3)
+                np = 3 + v;
+              else
+              {
+                const uint32_t v5 = br.get_bits(5);
+                np = v5 < 31 ? 6 + v5 : 37 + br.get_bits(7);
+              }
+            }
+            if(np > 3)
+              return fail("HT code blocks with placeholder passes or several HT sets are not handled", 1);
+            int lblock = 3;
+            while(br.get())
+              ++lblock;
+            if(lblock > 32)
+              return fail("corrupt packet header (Lblock)", -1);
+            const uint32_t len1 = br.get_bits(lblock);
+            const uint32_t len2 = np > 1 ? br.get_bits(lblock + floorlog2(np - 1)) : 0;
+            if(zbp > B.kmax)
+              return fail("more zero bit planes than the band has bit planes", -1);
+            if(len1 < 2)
+              return fail("HT cleanup segment shorter than 2 bytes", -1);
+            B.numbps = (uint8_t)(B.kmax - zbp);
+            B.numpasses = (uint8_t)np;
+            B.length = len1;
+            B.length2 = len2;
+            order.push_back({pb.first + k, len1 + len2});
+          }
+        }
+      }
+      if(br.overrun)
+        return fail("packet header runs past the tile part", -1);
+      p = br.finish();
+      for(const Seg& sg : order)
+      {
+        if(p + sg.n > tp_end)
+          return fail("packet body runs past the tile part", -1);
+        tb[sg.blk].offset = (uint64_t)(p - cs);
+        p += sg.n;
+      }
+    }
+    c.p = tp_end;
+  }
+  memcpy(blocks, all.data(), all.size() * sizeof(b2k_block));
+  return (int64_t)all.size();
+}

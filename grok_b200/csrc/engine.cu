@@ -207,6 +207,7 @@ struct b2k_device_job
 
 /* -------------------------------------------------------------------------------------------- */
 extern "C" const char* b2k_last_error(void) { return g_err.c_str(); }
+void b2k_set_error(const char* msg) { g_err = msg ? msg : ""; } /* for the other translation units */
 extern "C" uint64_t b2k_launch_count(void) { return g_launches.load(); }
 
 extern "C" int32_t b2k_engine_create(int32_t device, b2k_engine** out)

@@ -409,6 +409,21 @@ B2K_API int32_t b2k_job_t1_decode_blocks(b2k_device_job* j, const b2k_block* blo
 /* fetch coded blocks of the last b2k_job_t1_encode as a host result */
 B2K_API int32_t b2k_job_fetch_result(b2k_device_job* j, b2k_result** out);
 B2K_API uint64_t b2k_job_num_blocks(const b2k_device_job* j);
+/* ---- codestream assembly / parsing on the host (the T2 step) -------------------------
+ * b2k_codestream_write: a complete HTJ2K codestream (SOC, SIZ, CAP, COD, QCD, [TLM], per tile SOT [PLT] SOD
+ * + packets, EOC; one layer, LRCP, one tile part per tile) from an encode result that holds every tile
+ * (cf. CodeStreamCompress::compress / T2Compress::compressPacket).  Returns the size; copies it to `out` if
+ * cap suffices (call with out = NULL to size the buffer).  < 0 on error.
+ * b2k_codestream_parse: main header -> *cp, packet headers -> block table in enumeration order with
+ * numbps / numpasses / length / length2 and offsets INTO `cs`, so that b2k_decode(engine, cp, blocks, n, cs,
+ * len, ...) decodes the file in place.  Returns the number of blocks (call with blocks = NULL to size the
+ * table), 1 if the codestream uses something this path does not cover (b2k_last_error says what), < 0 if it
+ * is damaged. */
+#define B2K_CS_TLM 1u
+#define B2K_CS_PLT 2u
+B2K_API int64_t b2k_codestream_write(const b2k_coding* cp, const b2k_result* r, uint32_t flags, uint8_t* out, uint64_t cap);
+B2K_API int64_t b2k_codestream_parse(const uint8_t* cs, uint64_t len, b2k_coding* cp, b2k_block* blocks, uint64_t cap_blocks);
+
 /* launches issued by this library since engine creation (bench.py "gpu_launches") */
 B2K_API uint64_t b2k_launch_count(void);
 /* per-kernel timing of the last forward()/inverse(): ms of the level-1 kernel and algorithmic
