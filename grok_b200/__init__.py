@@ -235,6 +235,7 @@ class EncodeResult:
         r = ptr.contents
         self.num_blocks = int(r.num_blocks)
         self.num_bytes = int(r.num_bytes)
+        self.num_tiles = int(r.num_tiles)
         self.timings = dict(h2d=r.ms_h2d, dwt=r.ms_dwt, t1=r.ms_t1, d2h=r.ms_d2h, total=r.ms_total)
         self.blocks = np.frombuffer((C.c_uint8 * (self.num_blocks * C.sizeof(Block))).from_address(
             C.addressof(r.blocks.contents)), dtype=BLOCK_DTYPE) if self.num_blocks else np.zeros(0, BLOCK_DTYPE)
@@ -275,6 +276,22 @@ class Engine:
         fn = "b2k_encode16" if planes[0].itemsize == 2 else "b2k_encode"
         _check(getattr(lib(), fn)(self._h, C.byref(cp), ptrs, strides, tile_mod, tile_rem, C.byref(out)), fn)
         return EncodeResult(out)
+
+    def encode_codestream(self, cp, planes, flags=CS_TLM | CS_PLT):
+        """planes -> a complete HTJ2K codestream (numpy uint8): b2k_encode + b2k_codestream_write."""
+        res = self.encode(cp, planes)
+        try:
+            return codestream_write(cp, res.blocks, res.bytes, flags, num_tiles=res.num_tiles)
+        finally:
+            res.free()
+
+    def decode_codestream(self, cs, dtype=np.int32):
+        """HTJ2K codestream -> (Coding, list of planes): b2k_codestream_parse + b2k_decode, block bytes read in place."""
+        cs = np.ascontiguousarray(cs, dtype=np.uint8)
+        cp, blocks = codestream_parse(cs)
+        out = [np.zeros((cp.y1 - cp.y0, cp.x1 - cp.x0), dtype) for _ in range(cp.numcomps)]
+        self.decode(cp, blocks, cs, out)
+        return cp, out
 
     def decode(self, cp, blocks, data, out_planes, tile_mod=1, tile_rem=0):
         ptrs, strides = _plane_ptrs(out_planes)

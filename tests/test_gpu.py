@@ -572,3 +572,30 @@ def test_host_packing_matches_direct_copies(engine, sgnd):
         G.set_host_threads(-1)
     assert np.array_equal(results["direct"][1], results["packed"][1])
     assert np.array_equal(results["direct"][0]["length"], results["packed"][0]["length"])
+
+
+@pytest.mark.parametrize("irreversible", [False, True])
+def test_codestream_files_round_trip_and_openjpeg_reads_them(engine, irreversible):
+    """b2k_encode + b2k_codestream_write gives a file an independent decoder (OpenJPEG, through OpenCV) reads:
+    exactly the source for the reversible path, within the reference's lossy tolerance for 9/7; and
+    b2k_codestream_parse + b2k_decode read it back on the device, block bytes taken in place from the file."""
+    cv2 = pytest.importorskip("cv2")
+    w, h = 1100, 700
+    cp = G.make_coding(w, h, 3, 12, numres=6, tile=(512, 512), irreversible=irreversible)
+    planes = P.synthetic_image(w, h, 3, 12, seed=31)
+    cs = engine.encode_codestream(cp, planes)
+    ext = cv2.imdecode(np.frombuffer(cs.tobytes(), np.uint8), cv2.IMREAD_UNCHANGED)
+    assert ext is not None and ext.shape == (h, w, 3)
+    ext = ext[:, :, ::-1].astype(np.int64)
+    src = np.stack(planes, axis=-1).astype(np.int64)
+    cp2, ours = engine.decode_codestream(cs)
+    ours = np.stack(ours, axis=-1).astype(np.int64)
+    if irreversible:
+        assert np.abs(ext - ours).max() <= 1
+        for rec in (ext, ours):
+            err = (rec - src).astype(np.float64)
+            assert np.abs(err).max() <= 16 and 10 * np.log10(4095.0 ** 2 / (err ** 2).mean()) > 50.0
+    else:
+        assert np.array_equal(ext, src)
+        assert np.array_equal(ours, src)
+    assert cp2.numres == cp.numres and cp2.tw == 512 and cp2.irreversible == cp.irreversible

@@ -3,7 +3,9 @@
 rank block-codes its own tiles with no data-path collective, then the coded segments are gathered
 to rank 0 (the codestream writer) with NCCL -- an all_gather of segment sizes followed by a
 gather of the variable-length byte arenas over NVLink -- and rank 0 decodes ALL tiles from the
-gathered segments and checks the image is bit-exact.
+gathered segments and checks the image is bit-exact, then assembles ONE tiled HTJ2K codestream from them
+(b2k_codestream_write: main header + TLM, per tile SOT + PLT + packets in tile-index order) and decodes
+that file again through b2k_codestream_parse + b2k_decode.
 
   torchrun --nproc-per-node N tools/sharded_multi_gpu.py [--size 16384] [--comps 4] [--prec 16]
 """
@@ -97,10 +99,16 @@ def main():
         eng2 = eng
         eng2.decode(cp, full, data, out)
         ok = all(np.array_equal(x, y) for x, y in zip(out, planes))
+        tw = time.perf_counter()
+        cs = G.codestream_write(cp, full, data)                     # the T2 / writer step, on the host
+        t_write = time.perf_counter() - tw
+        cp2, out2 = eng.decode_codestream(cs)
+        ok = ok and all(np.array_equal(x, y) for x, y in zip(out2, planes))
         pix = W * H
         print({"config": "%dx%dx%d %d-bit lossless, %d tiles sharded over %d GPU(s)" % (W, H, a.comps, a.prec, reps * reps, world),
                "encode_ms_max_over_ranks": float(tmax[0]) * 1e3, "nccl_gather_ms": float(tmax[1]) * 1e3,
-               "encode_Mpix_s": pix / float(tmax[0]) / 1e6, "coded_bytes_total": int(len(data)),
+               "encode_Mpix_s": pix / float(tmax[0]) / 1e6, "coded_bytes_total": int(len(data)), "codestream_bytes": int(len(cs)),
+               "codestream_write_ms": t_write * 1e3,
                "round_trip_bit_exact": bool(ok)})
     if world > 1:
         dist.barrier()
