@@ -393,6 +393,24 @@ def main():
     assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "e2e (no host packing) round trip is not lossless"
     G.set_host_threads(-1)
 
+    # ---------------- files: the same calls plus the host T2 step (codestream write / parse) ----------------
+    cs_buf = G.pinned_empty((int(nb) + int(nb) // 8 + (1 << 20),), np.uint8)
+
+    def file_step():
+        cs = eng.encode_codestream(cp, planes, out=cs_buf)
+        eng.decode_codestream(cs, out=out)
+        return len(cs)
+
+    for _ in range(3):
+        file_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(3, args.steps // 2)):
+        cs_len = file_step()
+    barrier()
+    dt_file = (time.perf_counter() - t0) / max(3, args.steps // 2)
+    assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "codestream round trip is not lossless"
+
     # ---------------- same, 16-bit sample containers (b2k_encode16 / b2k_decode16) ----------------
     p16 = [G.pinned_empty((H, W), np.uint16) for _ in range(NCOMP)]
     o16 = [G.pinned_empty((H, W), np.uint16) for _ in range(NCOMP)]
@@ -415,12 +433,12 @@ def main():
     assert all(np.array_equal(a, b) for a, b in zip(o16, p16)), "16-bit e2e round trip is not lossless"
 
     # max over ranks
-    times = torch.tensor([dt_dev, dt_e2e, dt_e2e16, dt_e2e32], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dt_dev, dt_e2e, dt_e2e16, dt_e2e32, dt_file], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
         dist.all_gather(sizes, torch.tensor([nb], dtype=torch.int64, device="cuda"))  # codestream segment sizes
-    dt_dev, dt_e2e, dt_e2e16, dt_e2e32 = float(times[0]), float(times[1]), float(times[2]), float(times[3])
+    dt_dev, dt_e2e, dt_e2e16, dt_e2e32, dt_file = (float(times[i]) for i in range(5))
 
     if rank == 0:
         pix = W * H * world
@@ -450,6 +468,10 @@ def main():
             "e2e_i32_direct": {"value": pix / dt_e2e32 / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_e2e32 * 1e3,
                                "h2d_bytes_per_step": int(img_bytes + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes + nb + nbk * 24),
                                "api": "same calls with b2k_set_host_threads(0): pinned int32 planes copied as they are"},
+            "e2e_codestream": {"value": pix / dt_file / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_file * 1e3,
+                               "codestream_bytes": int(cs_len),
+                               "api": "e2e plus the host T2 step: b2k_encode + b2k_codestream_write (TLM + PLT) into a pinned buffer, then "
+                                      "b2k_codestream_parse + b2k_decode reading the block bytes in place from the file"},
             "e2e_u16": {"value": pix / (dt_e2e16 / args.steps) / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_e2e16 / args.steps * 1e3,
                         "h2d_bytes_per_step": int(img_bytes // 2 + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes // 2 + nb + nbk * 24),
                         "api": "b2k_encode16 + b2k_decode16: same path, 16-bit sample containers (cf. gpup_batch_memory_submit_planes)"},

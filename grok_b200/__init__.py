@@ -177,9 +177,10 @@ def host_pack_last():
 CS_TLM, CS_PLT = 1, 2
 
 
-def codestream_write(cp, blocks, data, flags=CS_TLM | CS_PLT, num_tiles=None):
+def codestream_write(cp, blocks, data, flags=CS_TLM | CS_PLT, num_tiles=None, out=None):
     """HTJ2K codestream (bytes, numpy uint8) from a coding, a full block table (BLOCK_DTYPE) and its byte arena
-    -- an EncodeResult's .blocks / .bytes, or tables built elsewhere (tests build them with the oracle)."""
+    -- an EncodeResult's .blocks / .bytes, or tables built elsewhere (tests build them with the oracle).
+    out: optional uint8 buffer to write into (e.g. pinned); a view of the written part is returned."""
     blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
     data = np.ascontiguousarray(data, dtype=np.uint8)
     r = Result()
@@ -188,7 +189,12 @@ def codestream_write(cp, blocks, data, flags=CS_TLM | CS_PLT, num_tiles=None):
     r.bytes = C.cast(data.ctypes.data, C.POINTER(C.c_uint8))
     r.num_bytes = len(data)
     r.num_tiles = int(blocks["tile"].max()) + 1 if num_tiles is None else num_tiles
-    n = lib().b2k_codestream_write(C.byref(cp), C.byref(r), flags, None, 0)
+    if out is not None:
+        n = lib().b2k_codestream_write(C.byref(cp), C.byref(r), flags, out.ctypes.data, out.size)
+        if 0 <= n <= out.size:
+            return out[:n]
+    else:
+        n = lib().b2k_codestream_write(C.byref(cp), C.byref(r), flags, None, 0)
     if n < 0:
         raise EngineError("b2k_codestream_write: " + (lib().b2k_last_error() or b"").decode())
     out = np.zeros(n, np.uint8)
@@ -277,19 +283,20 @@ class Engine:
         _check(getattr(lib(), fn)(self._h, C.byref(cp), ptrs, strides, tile_mod, tile_rem, C.byref(out)), fn)
         return EncodeResult(out)
 
-    def encode_codestream(self, cp, planes, flags=CS_TLM | CS_PLT):
+    def encode_codestream(self, cp, planes, flags=CS_TLM | CS_PLT, out=None):
         """planes -> a complete HTJ2K codestream (numpy uint8): b2k_encode + b2k_codestream_write."""
         res = self.encode(cp, planes)
         try:
-            return codestream_write(cp, res.blocks, res.bytes, flags, num_tiles=res.num_tiles)
+            return codestream_write(cp, res.blocks, res.bytes, flags, num_tiles=res.num_tiles, out=out)
         finally:
             res.free()
 
-    def decode_codestream(self, cs, dtype=np.int32):
+    def decode_codestream(self, cs, dtype=np.int32, out=None):
         """HTJ2K codestream -> (Coding, list of planes): b2k_codestream_parse + b2k_decode, block bytes read in place."""
         cs = np.ascontiguousarray(cs, dtype=np.uint8)
         cp, blocks = codestream_parse(cs)
-        out = [np.zeros((cp.y1 - cp.y0, cp.x1 - cp.x0), dtype) for _ in range(cp.numcomps)]
+        if out is None:
+            out = [np.zeros((cp.y1 - cp.y0, cp.x1 - cp.x0), dtype) for _ in range(cp.numcomps)]
         self.decode(cp, blocks, cs, out)
         return cp, out
 

@@ -5,6 +5,7 @@
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
+#include <functional>
 #include <cuda_runtime.h>
 #include "../../include/grok_b200.h"
 
@@ -96,3 +97,5 @@ void b2k_host_session(bool begin); /* between begin and end the pool's idle work
 void b2k_host_set_threads(int n); /* 0 disables host packing, <0 restores the default */
 int b2k_host_threads(void);
 int b2k_host_local_peers(void);
+/* fn(i) for i in [0, n) on the host pool (plus the caller) */
+void b2k_host_parallel(size_t n, const std::function<void(size_t)>& fn);

@@ -17,6 +17,7 @@
  * tests decode the output with an independent decoder (OpenJPEG via Pillow / OpenCV) -- tests/test_codestream.py.
  */
 #include "geometry.h"
+#include "b2k_internal.h"
 
 #include <algorithm>
 #include <cstring>
@@ -392,8 +393,24 @@ void write_main_header(const b2k_coding& cp, const TileGrid& g, const std::vecto
 }
 
 /* ---- one tile's packets ----------------------------------------------------------------------------------- */
-int write_tile_packets(const b2k_coding& cp, const Rect& tile, const b2k_block* blk, uint32_t nblk, const uint8_t* arena,
-                       uint64_t arena_len, std::vector<uint8_t>& body, std::vector<uint32_t>& packet_len, std::string& err)
+/* A tile part is planned first (packet headers, which byte ranges of the arena follow each of them, lengths) and
+   written straight into the caller's buffer afterwards: the ~150 MB of block bytes of a config-2 image are copied
+   exactly once. */
+struct TilePlan
+{
+  std::vector<uint8_t> hdrs;          /* all packet headers, back to back */
+  std::vector<uint32_t> hdr_len;      /* per packet */
+  std::vector<uint32_t> nseg;         /* per packet: block byte ranges that follow its header */
+  std::vector<uint64_t> seg_off;      /* arena offsets */
+  std::vector<uint32_t> seg_len;
+  std::vector<uint32_t> packet_len;   /* header + body */
+  std::vector<uint8_t> plt;           /* complete PLT marker segments */
+  uint64_t body_bytes = 0;
+  uint64_t size() const { return 12 + plt.size() + 2 + body_bytes; } /* SOT + PLT + SOD + packets */
+};
+
+int plan_tile_packets(const b2k_coding& cp, const Rect& tile, const b2k_block* blk, uint32_t nblk, uint64_t arena_len,
+                      TilePlan& plan, std::string& err)
 {
   std::vector<Packet> pkts;
   uint32_t expect = 0;
@@ -407,7 +424,6 @@ int write_tile_packets(const b2k_coding& cp, const Rect& tile, const b2k_block* 
   std::vector<uint8_t> hdr;
   for(const Packet& pk : pkts)
   {
-    const size_t start = body.size();
     hdr.clear();
     BitWriter bw(hdr);
     bw.put(1); /* non-empty packet; like the reference also when it carries no block (T2Compress.cpp L304-307) */
@@ -467,7 +483,10 @@ int write_tile_packets(const b2k_coding& cp, const Rect& tile, const b2k_block* 
       }
     }
     bw.flush();
-    body.insert(body.end(), hdr.begin(), hdr.end());
+    plan.hdrs.insert(plan.hdrs.end(), hdr.begin(), hdr.end());
+    plan.hdr_len.push_back((uint32_t)hdr.size());
+    uint64_t plen = hdr.size();
+    uint32_t ns = 0;
     for(int b = 0; b < pk.nbands; ++b)
     {
       const PacketBand& pb = pk.band[b];
@@ -482,15 +501,28 @@ int write_tile_packets(const b2k_coding& cp, const Rect& tile, const b2k_block* 
           err = "block offsets exceed the byte arena";
           return -1;
         }
-        body.insert(body.end(), arena + B.offset, arena + B.offset + n);
+        if(ns && plan.seg_off.back() + plan.seg_len.back() == B.offset && (uint64_t)plan.seg_len.back() + n < 0xFFFFFFFFull)
+          plan.seg_len.back() += (uint32_t)n; /* neighbours in the arena: one copy */
+        else
+        {
+          plan.seg_off.push_back(B.offset);
+          plan.seg_len.push_back((uint32_t)n);
+          ++ns;
+        }
+        plen += n;
       }
     }
-    packet_len.push_back((uint32_t)(body.size() - start));
+    plan.nseg.push_back(ns);
+    if(plen > 0xFFFFFFFFull)
+    {
+      err = "packet longer than 4 GiB";
+      return -1;
+    }
+    plan.packet_len.push_back((uint32_t)plen);
+    plan.body_bytes += plen;
   }
   return 0;
 }
-
-thread_local std::string t_err;
 
 } // namespace
 
@@ -518,46 +550,49 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(c
     return -1;
   }
   const std::vector<BandQuant> q = band_quant(*cp);
-  std::vector<uint8_t> o;
-  o.reserve((size_t)r->num_bytes + (size_t)r->num_blocks * 2 + 4096);
-  write_main_header(*cp, g, q, o);
+  std::vector<uint8_t> head;
+  write_main_header(*cp, g, q, head);
 
-  /* tile parts first (their lengths feed TLM), then stitch */
-  std::vector<std::vector<uint8_t>> parts(ntiles);
-  uint64_t first = 0;
-  for(uint32_t t = 0; t < ntiles; ++t)
+  /* plan every tile part (their lengths feed TLM), then lay the codestream out */
+  std::vector<TilePlan> plans(ntiles);
+  std::vector<uint64_t> tile_first(ntiles + 1, 0);
   {
-    uint64_t n = 0;
-    while(first + n < r->num_blocks && r->blocks[first + n].tile == t)
-      ++n;
-    std::vector<uint8_t> body;
-    std::vector<uint32_t> plen;
-    std::string err;
-    if(write_tile_packets(*cp, tile_rect(*cp, g, t), r->blocks + first, (uint32_t)n, r->bytes, r->num_bytes, body, plen, err))
+    uint64_t i = 0;
+    for(uint32_t t = 0; t < ntiles; ++t)
     {
-      b2k_set_error(err.c_str());
+      tile_first[t] = i;
+      while(i < r->num_blocks && r->blocks[i].tile == t)
+        ++i;
+    }
+    tile_first[ntiles] = i;
+    if(i != r->num_blocks)
+    {
+      b2k_set_error("block table is not in tile order");
       return -1;
     }
-    first += n;
-    std::vector<uint8_t>& tp = parts[t];
-    put16(tp, 0xFF90); /* SOT (A.4.2) */
-    put16(tp, 10);
-    put16(tp, t);
-    put32(tp, 0); /* Psot, patched below */
-    tp.push_back(0);
-    tp.push_back(1);
+  }
+  std::vector<std::string> errs(ntiles);
+  b2k_host_parallel(ntiles, [&](size_t t) { /* tiles are independent: plan them on the host pool */
+    TilePlan& P = plans[t];
+    if(plan_tile_packets(*cp, tile_rect(*cp, g, (uint32_t)t), r->blocks + tile_first[t], (uint32_t)(tile_first[t + 1] - tile_first[t]),
+                         r->num_bytes, P, errs[t]))
+    {
+      if(errs[t].empty())
+        errs[t] = "tile planning failed";
+      return;
+    }
     if(flags & B2K_CS_PLT)
     { /* PLT (A.7.3): packet lengths, 7 bits per byte, continuation bit in the MSB */
       std::vector<uint8_t> seg;
       uint8_t z = 0;
       auto flush_seg = [&] {
-        put16(tp, 0xFF58);
-        put16(tp, (uint32_t)seg.size() + 3);
-        tp.push_back(z++);
-        tp.insert(tp.end(), seg.begin(), seg.end());
+        put16(P.plt, 0xFF58);
+        put16(P.plt, (uint32_t)seg.size() + 3);
+        P.plt.push_back(z++);
+        P.plt.insert(P.plt.end(), seg.begin(), seg.end());
         seg.clear();
       };
-      for(uint32_t L : plen)
+      for(uint32_t L : P.packet_len)
       {
         uint8_t tmp[5];
         int nb = 0;
@@ -571,26 +606,24 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(c
         for(int i = nb - 1; i >= 0; --i)
           seg.push_back((uint8_t)(tmp[i] | (i ? 0x80 : 0)));
       }
-      if(!seg.empty() || plen.empty())
+      if(!seg.empty() || P.packet_len.empty())
         flush_seg();
     }
-    put16(tp, 0xFF93); /* SOD */
-    tp.insert(tp.end(), body.begin(), body.end());
-    if(tp.size() > 0xFFFFFFFFull)
+  });
+  uint64_t total = 0;
+  for(uint32_t t = 0; t < ntiles; ++t)
+  {
+    if(!errs[t].empty())
+    {
+      b2k_set_error(errs[t].c_str());
+      return -1;
+    }
+    if(plans[t].size() > 0xFFFFFFFFull)
     {
       b2k_set_error("tile part longer than 4 GiB");
       return -1;
     }
-    const uint32_t psot = (uint32_t)tp.size();
-    tp[6] = (uint8_t)(psot >> 24);
-    tp[7] = (uint8_t)(psot >> 16);
-    tp[8] = (uint8_t)(psot >> 8);
-    tp[9] = (uint8_t)psot;
-  }
-  if(first != r->num_blocks)
-  {
-    b2k_set_error("block table is not in tile order");
-    return -1;
+    total += plans[t].size();
   }
   if(flags & B2K_CS_TLM)
   { /* TLM (A.7.1): 16-bit tile index + 32-bit length per tile part; 10921 entries fit one marker segment */
@@ -598,24 +631,163 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(c
     for(uint32_t t0 = 0; t0 < ntiles; t0 += 10000)
     {
       const uint32_t n = std::min(10000u, ntiles - t0);
-      put16(o, 0xFF55);
-      put16(o, 4 + 6 * n);
-      o.push_back(z++);
-      o.push_back(0x60); /* ST = 2 (16-bit Ttlm), SP = 1 (32-bit Ptlm) */
+      put16(head, 0xFF55);
+      put16(head, 4 + 6 * n);
+      head.push_back(z++);
+      head.push_back(0x60); /* ST = 2 (16-bit Ttlm), SP = 1 (32-bit Ptlm) */
       for(uint32_t t = t0; t < t0 + n; ++t)
       {
-        put16(o, t);
-        put32(o, (uint32_t)parts[t].size());
+        put16(head, t);
+        put32(head, (uint32_t)plans[t].size());
       }
     }
   }
-  for(auto& tp : parts)
-    o.insert(o.end(), tp.begin(), tp.end());
-  put16(o, 0xFFD9); /* EOC */
-  if(out && cap >= o.size())
-    memcpy(out, o.data(), o.size());
-  return (int64_t)o.size();
+  total += head.size() + 2; /* + EOC */
+  if(!out || cap < total)
+    return (int64_t)total;
+
+  memcpy(out, head.data(), head.size());
+  std::vector<uint64_t> tile_at(ntiles + 1, head.size());
+  for(uint32_t t = 0; t < ntiles; ++t)
+    tile_at[t + 1] = tile_at[t] + plans[t].size();
+  /* tile parts are independent byte ranges: copy them on the host pool */
+  b2k_host_parallel(ntiles, [&](size_t t) {
+    const TilePlan& P = plans[t];
+    uint8_t* w = out + tile_at[t];
+    const uint32_t psot = (uint32_t)P.size();
+    const uint8_t sot[12] = {0xFF, 0x90, 0, 10, (uint8_t)(t >> 8), (uint8_t)t, (uint8_t)(psot >> 24), (uint8_t)(psot >> 16),
+                             (uint8_t)(psot >> 8), (uint8_t)psot, 0, 1}; /* SOT (A.4.2): Isot, Psot, TPsot = 0, TNsot = 1 */
+    memcpy(w, sot, 12);
+    w += 12;
+    if(!P.plt.empty())
+    {
+      memcpy(w, P.plt.data(), P.plt.size());
+      w += P.plt.size();
+    }
+    *w++ = 0xFF; /* SOD */
+    *w++ = 0x93;
+    const uint8_t* h = P.hdrs.data();
+    size_t sg = 0;
+    for(size_t k = 0; k < P.hdr_len.size(); ++k)
+    {
+      memcpy(w, h, P.hdr_len[k]);
+      w += P.hdr_len[k];
+      h += P.hdr_len[k];
+      for(uint32_t i = 0; i < P.nseg[k]; ++i, ++sg)
+      {
+        memcpy(w, r->bytes + P.seg_off[sg], P.seg_len[sg]);
+        w += P.seg_len[sg];
+      }
+    }
+  });
+  uint8_t* w = out + tile_at[ntiles];
+  *w++ = 0xFF; /* EOC */
+  *w++ = 0xD9;
+  return (int64_t)(w - out);
 }
+
+namespace
+{
+/* packets of one tile part -> the tile's slice of the block table (offsets relative to `base`).
+   0 ok, 1 outside this path's scope, -1 damaged; err says why. */
+int parse_tile_packets(const b2k_coding& cp, const Rect& tile, b2k_block* tb, const uint8_t* p, const uint8_t* tp_end,
+                       const uint8_t* base, std::string& err)
+{
+  std::vector<Packet> pkts;
+  uint32_t nblk = 0;
+  tile_packets(cp, tile, pkts, nblk);
+  TagTree incl, imsb;
+  struct Seg
+  {
+    uint32_t blk, n;
+  };
+  std::vector<Seg> order;
+  auto fail = [&](const char* m, int rc) {
+    err = m;
+    return rc;
+  };
+  for(const Packet& pk : pkts)
+  {
+    BitReader br(p, tp_end);
+    order.clear();
+    if(br.get())
+    {
+      for(int b = 0; b < pk.nbands; ++b)
+      {
+        const PacketBand& pb = pk.band[b];
+        const uint32_t n = pb.gw * pb.gh;
+        if(!n)
+          continue;
+        incl.init(pb.gw, pb.gh);
+        imsb.init(pb.gw, pb.gh);
+        for(uint32_t k = 0; k < n; ++k)
+        {
+          b2k_block& B = tb[pb.first + k];
+          if(!incl.decode(br, k, 1))
+            continue;
+          uint32_t zbp = 0;
+          for(uint32_t th = 1;; ++th)
+          {
+            if(imsb.decode(br, k, th))
+            {
+              zbp = imsb.nodes[k].value;
+              break;
+            }
+            if(th > 64 || br.overrun)
+              return fail("corrupt packet header (zero bit planes)", -1);
+          }
+          uint32_t np; /* number of passes, B.10.6 */
+          if(!br.get())
+            np = 1;
+          else if(!br.get())
+            np = 2;
+          else
+          {
+            const uint32_t v = br.get_bits(2);
+            if(v < 3)
+              np = 3 + v;
+            else
+            {
+              const uint32_t v5 = br.get_bits(5);
+              np = v5 < 31 ? 6 + v5 : 37 + br.get_bits(7);
+            }
+          }
+          if(np > 3)
+            return fail("HT code blocks with placeholder passes or several HT sets are not handled", 1);
+          int lblock = 3;
+          while(br.get())
+            if(++lblock > 32)
+              return fail("corrupt packet header (Lblock)", -1);
+          /* HT: the cleanup pass is one segment, the refinement passes another (T.814 B.10.7) */
+          const uint32_t len1 = br.get_bits(lblock);
+          const uint32_t len2 = np > 1 ? br.get_bits(std::min(32, lblock + floorlog2(np - 1))) : 0;
+          if(zbp > B.kmax)
+            return fail("more zero bit planes than the band has bit planes", -1);
+          if(len1 < 2)
+            return fail("HT cleanup segment shorter than 2 bytes", -1);
+          B.numbps = (uint8_t)(B.kmax - zbp);
+          B.numpasses = (uint8_t)np;
+          B.length = len1;
+          B.length2 = len2;
+          order.push_back({pb.first + k, len1 + len2});
+        }
+      }
+    }
+    if(br.overrun)
+      return fail("packet header runs past the tile part", -1);
+    p = br.finish();
+    for(const Seg& sg : order)
+    {
+      if((uint64_t)(tp_end - p) < sg.n)
+        return fail("packet body runs past the tile part", -1);
+      tb[sg.blk].offset = (uint64_t)(p - base);
+      p += sg.n;
+    }
+  }
+  return 0;
+}
+
+} // namespace
 
 /* ============================================================================================================ */
 namespace
@@ -823,22 +995,29 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
   }
   const TileGrid g = tile_grid(cp);
   const uint32_t ntiles = g.nx * g.ny;
-  /* block table in enumeration order */
-  std::vector<b2k_block> all;
+  /* block table in enumeration order: sizes first, then every tile fills its own slice */
   std::vector<uint64_t> tile_first(ntiles + 1, 0);
   for(uint32_t t = 0; t < ntiles; ++t)
   {
-    tile_first[t] = all.size();
-    enumerate_tile_blocks(cp, t, tile_rect(cp, g, t), q, all);
+    std::vector<Packet> pk;
+    uint32_t nb = 0;
+    tile_packets(cp, tile_rect(cp, g, t), pk, nb);
+    tile_first[t + 1] = tile_first[t] + nb;
   }
-  tile_first[ntiles] = all.size();
+  const uint64_t nblocks = tile_first[ntiles];
   *cp_out = cp;
   if(!blocks)
-    return (int64_t)all.size();
-  if(cap_blocks < all.size())
+    return (int64_t)nblocks;
+  if(cap_blocks < nblocks)
     return fail("block table too small", -1);
 
-  /* ---- tile parts ---- */
+  /* ---- tile parts: locate them (SOT / Psot), then parse their packets tile by tile on the host pool ---- */
+  struct Part
+  {
+    uint32_t tile;
+    const uint8_t *data, *end;
+  };
+  std::vector<Part> parts;
   std::vector<uint8_t> seen(ntiles, 0);
   for(;;)
   {
@@ -876,99 +1055,30 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
         return fail("tile-part COD / COC / QCD / QCC / RGN / POC / PPT are not handled", 1);
       c.p += L - 2; /* PLT, COM: skipped */
     }
-    /* packets */
-    std::vector<Packet> pkts;
-    uint32_t nblk = 0;
-    tile_packets(cp, tile_rect(cp, g, isot), pkts, nblk);
-    if(nblk != tile_first[isot + 1] - tile_first[isot])
-      return fail("internal: packet geometry and block enumeration disagree", -1);
-    b2k_block* tb = all.data() + tile_first[isot];
-    TagTree incl, imsb;
-    const uint8_t* p = c.p;
-    for(const Packet& pk : pkts)
-    {
-      BitReader br(p, tp_end);
-      struct Seg
-      {
-        uint32_t blk, n;
-      };
-      std::vector<Seg> order;
-      if(br.get())
-      {
-        for(int b = 0; b < pk.nbands; ++b)
-        {
-          const PacketBand& pb = pk.band[b];
-          const uint32_t n = pb.gw * pb.gh;
-          if(!n)
-            continue;
-          incl.init(pb.gw, pb.gh);
-          imsb.init(pb.gw, pb.gh);
-          for(uint32_t k = 0; k < n; ++k)
-          {
-            b2k_block& B = tb[pb.first + k];
-            if(!incl.decode(br, k, 1))
-              continue;
-            uint32_t zbp = 0;
-            for(uint32_t th = 1;; ++th)
-            {
-              if(imsb.decode(br, k, th))
-              {
-                zbp = imsb.nodes[k].value;
-                break;
-              }
-              if(th > 64 || br.overrun)
-                return fail("corrupt packet header (zero bit planes)", -1);
-            }
-            uint32_t np;
-            if(!br.get())
-              np = 1;
-            else if(!br.get())
-              np = 2;
-            else
-            {
-              const uint32_t v = br.get_bits(2);
-              if(v < 3)
-                np = 3 + v;
-              else
-              {
-                const uint32_t v5 = br.get_bits(5);
-                np = v5 < 31 ? 6 + v5 : 37 + br.get_bits(7);
-              }
-            }
-            if(np > 3)
-              return fail("HT code blocks with placeholder passes or several HT sets are not handled", 1);
-            int lblock = 3;
-            while(br.get())
-              ++lblock;
-            if(lblock > 32)
-              return fail("corrupt packet header (Lblock)", -1);
-            const uint32_t len1 = br.get_bits(lblock);
-            const uint32_t len2 = np > 1 ? br.get_bits(lblock + floorlog2(np - 1)) : 0;
-            if(zbp > B.kmax)
-              return fail("more zero bit planes than the band has bit planes", -1);
-            if(len1 < 2)
-              return fail("HT cleanup segment shorter than 2 bytes", -1);
-            B.numbps = (uint8_t)(B.kmax - zbp);
-            B.numpasses = (uint8_t)np;
-            B.length = len1;
-            B.length2 = len2;
-            order.push_back({pb.first + k, len1 + len2});
-          }
-        }
-      }
-      if(br.overrun)
-        return fail("packet header runs past the tile part", -1);
-      p = br.finish();
-      for(const Seg& sg : order)
-      {
-        if(p + sg.n > tp_end)
-          return fail("packet body runs past the tile part", -1);
-        tb[sg.blk].offset = (uint64_t)(p - cs);
-        p += sg.n;
-      }
-    }
+    parts.push_back({isot, c.p, tp_end});
     c.p = tp_end;
   }
-  memcpy(blocks, all.data(), all.size() * sizeof(b2k_block));
-  return (int64_t)all.size();
+  std::vector<int> rcs(ntiles, 0);
+  std::vector<std::string> errs(ntiles);
+  std::vector<const Part*> part_of(ntiles, nullptr);
+  for(const Part& pt : parts)
+    part_of[pt.tile] = &pt;
+  b2k_host_parallel(ntiles, [&](size_t t) {
+    std::vector<b2k_block> tb;
+    tb.reserve(tile_first[t + 1] - tile_first[t]);
+    enumerate_tile_blocks(cp, (uint32_t)t, tile_rect(cp, g, (uint32_t)t), q, tb);
+    if(tb.size() != tile_first[t + 1] - tile_first[t])
+    {
+      rcs[t] = -1;
+      errs[t] = "internal: packet geometry and block enumeration disagree";
+      return;
+    }
+    if(part_of[t]) /* a tile without a tile part decodes as all zero (blocks stay uncoded) */
+      rcs[t] = parse_tile_packets(cp, tile_rect(cp, g, (uint32_t)t), tb.data(), part_of[t]->data, part_of[t]->end, cs, errs[t]);
+    memcpy(blocks + tile_first[t], tb.data(), tb.size() * sizeof(b2k_block));
+  });
+  for(uint32_t t = 0; t < ntiles; ++t)
+    if(rcs[t])
+      return fail(errs[t].c_str(), rcs[t]);
+  return (int64_t)nblocks;
 }

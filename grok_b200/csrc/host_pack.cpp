@@ -380,6 +380,15 @@ int b2k_host_threads(void)
   return g_threads;
 }
 
+void b2k_host_parallel(size_t n, const std::function<void(size_t)>& fn)
+{
+  if(HostPool* P = pool())
+    P->parallel_for(n, fn);
+  else
+    for(size_t i = 0; i < n; ++i)
+      fn(i);
+}
+
 void b2k_host_session(bool begin)
 {
   HostPool* P = pool();
