@@ -207,3 +207,80 @@ def test_host_pack_container_conversion(tmp_path):
                     os.path.join(ROOT, "grok_b200", "csrc", "host_pack.cpp"), "-o", exe, "-lpthread"], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+_WRITER_WORKER = r'''
+import io, os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import grok_b200 as G
+import oracle_pipeline as P
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% sys.argv[1], rank=int(sys.argv[2]), world_size=2)
+rank, world = dist.get_rank(), 2
+w, h = 200, 136
+cp = G.make_coding(w, h, 3, 8, numres=4, tile=(64, 64))
+planes = P.synthetic_image(w, h, 3, 8, seed=77)
+# this rank's tiles only: transform + block-code them with the oracle (the GPU engine's stand-in on a CPU box)
+rects = P.tile_rects(cp)
+my_tiles = [t for t in range(len(rects)) if t %% world == rank]
+coefs = P.forward(cp, planes, tiles=my_tiles)
+table = G.enumerate_blocks(cp, world, rank)
+blks = P.enumerate_all(cp, tiles=my_tiles)
+assert len(blks) == len(table)
+chunks, off = [], 0
+for i, (t, c, b) in enumerate(blks):
+    data = P.encode_block(cp, coefs, rects[t], c, b)
+    table[i]["length"], table[i]["offset"], table[i]["numbps"], table[i]["numpasses"] = len(data), off, 1, 1
+    chunks.append(data)
+    off += len(data)
+arena = np.concatenate(chunks)
+# gather block tables + byte arenas on the writer rank (sizes first: the segments are variable length)
+sizes = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(sizes, torch.tensor([len(arena), len(table)], dtype=torch.int64))
+sizes = [(int(s[0]), int(s[1])) for s in sizes]
+def padded(a, n):                                    # gloo's gather wants equal sizes (NCCL's does not)
+    t = torch.zeros(n, dtype=torch.uint8)
+    t[:len(a)] = torch.from_numpy(a.copy())
+    return t
+nseg, ntab = max(n for n, _ in sizes), max(k for _, k in sizes) * G.BLOCK_DTYPE.itemsize
+seg = padded(arena, nseg)
+tab = padded(table.view(np.uint8).reshape(-1), ntab)
+if rank == 0:
+    segs = [torch.zeros(nseg, dtype=torch.uint8) for _ in sizes]
+    tabs = [torch.zeros(ntab, dtype=torch.uint8) for _ in sizes]
+    dist.gather(seg, segs, dst=0)
+    dist.gather(tab, tabs, dst=0)
+    segs = [s[:n] for s, (n, _) in zip(segs, sizes)]
+    tabs = [t[:k * G.BLOCK_DTYPE.itemsize] for t, (_, k) in zip(tabs, sizes)]
+    full = G.enumerate_blocks(cp)
+    base = 0
+    for r in range(world):
+        tb = np.frombuffer(tabs[r].numpy().tobytes(), dtype=G.BLOCK_DTYPE).copy()
+        tb["offset"] += base
+        full[np.nonzero(full["tile"] %% world == r)[0]] = tb
+        base += sizes[r][0]
+    data = np.concatenate([s.numpy() for s in segs])
+    cs = G.codestream_write(cp, full, data)          # ONE tiled codestream, tile parts in index order
+    from PIL import Image
+    im = Image.open(io.BytesIO(cs.tobytes())); im.load()
+    assert np.array_equal(np.asarray(im).astype(np.int64), np.stack(planes, axis=-1)), "OpenJPEG does not give the source back"
+else:
+    dist.gather(seg, None, dst=0)
+    dist.gather(tab, None, dst=0)
+dist.barrier()
+print("rank", rank, "ok")
+'''
+
+
+def test_sharded_ranks_gather_into_one_codestream_gloo(tmp_path):
+    """world size 2, gloo: each rank codes the tiles t %% 2 == rank (oracle on the CPU), the variable-length segments
+    and block tables are gathered on rank 0, which writes one tiled codestream that OpenJPEG decodes to the source."""
+    pytest.importorskip("PIL.Image")
+    script = tmp_path / "writer_worker.py"
+    script.write_text(_WRITER_WORKER % (ROOT, ROOT))
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
