@@ -60,7 +60,7 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_engine_create", "b2k_engine_destroy", "b2k_last_error", "b2k_host_alloc", "b2k_host_free",
            "b2k_encode", "b2k_encode16", "b2k_result_free", "b2k_decode", "b2k_decode16", "b2k_enumerate",
            "b2k_result_to_gpup_tile", "b2k_job_create", "b2k_job_destroy", "b2k_job_upload", "b2k_job_forward",
-           "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_download",
+           "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_roundtrip_n", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
            "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last",
            "b2k_codestream_write", "b2k_codestream_parse"]
@@ -106,6 +106,7 @@ def lib():
     L.b2k_job_t1_decode.argtypes = [vp, C.POINTER(C.c_float)]
     L.b2k_job_t1_decode_blocks.argtypes = [vp, vp, u64, vp, u64, C.POINTER(C.c_float)]
     L.b2k_job_roundtrip.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
+    L.b2k_job_roundtrip_n.argtypes = [vp, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
     L.b2k_job_fetch_result.argtypes = [vp, C.POINTER(C.POINTER(Result))]
     L.b2k_job_num_blocks.argtypes = [vp]
     L.b2k_job_num_blocks.restype = u64
@@ -371,6 +372,16 @@ class Job:
         _check(lib().b2k_job_t1_decode_blocks(self._h, blocks.ctypes.data, len(blocks), data.ctypes.data, len(data), C.byref(ms)),
                "b2k_job_t1_decode_blocks")
         return ms.value
+
+    def roundtrip_n(self, steps):
+        """`steps` round trips queued back to back, one synchronisation.  Returns (total ms, [fwd, enc, dec, inv] ms
+        summed over the steps, level-1 DWT kernel ms summed, coded bytes)."""
+        ms, st, l1, nb = C.c_float(), (C.c_float * 4)(), C.c_float(), C.c_uint64()
+        rc = lib().b2k_job_roundtrip_n(self._h, steps, C.byref(ms), st, C.byref(l1), C.byref(nb))
+        if rc == 2:
+            rc = lib().b2k_job_roundtrip_n(self._h, steps, C.byref(ms), st, C.byref(l1), C.byref(nb))
+        _check(rc, "b2k_job_roundtrip_n")
+        return ms.value, [float(v) for v in st], l1.value, int(nb.value)
 
     def roundtrip(self):
         """forward -> block encode -> block decode -> inverse, device-resident, one synchronisation.

@@ -202,6 +202,7 @@ struct b2k_device_job
   uint64_t ring_slot_elems = 0, ring_elems = 0;
   cudaEvent_t ring_ev[16]{};
   PackTuner tune_enc, tune_dec;
+  std::vector<cudaEvent_t> q_ev;   /* per-step events of b2k_job_roundtrip_n */
   bool dec_has_refinement = false; /* the block table of the current decode carries SigProp / MagRef passes */
 };
 
@@ -586,6 +587,8 @@ extern "C" void b2k_job_destroy(b2k_device_job* J)
   cudaFreeHost(J->h_offsets);
   cudaFreeHost(J->h_stage16);
   cudaFreeHost(J->h_ring);
+  for(cudaEvent_t ev : J->q_ev)
+    cudaEventDestroy(ev);
   for(cudaEvent_t& ev : J->ring_ev)
     if(ev)
       cudaEventDestroy(ev);
@@ -959,8 +962,10 @@ static int ring_download_all(b2k_device_job* J, void* const* user, const uint32_
 
 /* ---- stages ----------------------------------------------------------------------------------- */
 static int enqueue_forward(b2k_device_job* J, cudaStream_t st, bool time_level1, size_t t0 = 0, size_t t1 = (size_t)-1,
-                           bool use16 = false)
+                           bool use16 = false, cudaEvent_t l1_begin = nullptr, cudaEvent_t l1_end = nullptr)
 {
+  if(!l1_begin) l1_begin = J->ev[4];
+  if(!l1_end) l1_end = J->ev[5];
   t1 = std::min(t1, J->tiles.size());
   bool first = true;
   for(size_t li = 0; li < J->fwd.size(); ++li)
@@ -970,12 +975,12 @@ static int enqueue_forward(b2k_device_job* J, cudaStream_t st, bool time_level1,
     LevelLaunch& L = J->fwd[li];
     const uint32_t d0 = L.tile_first[t0], d1 = L.tile_first[t1];
     if(first && time_level1)
-      CUDA_TRY(cudaEventRecord(J->ev[4], st));
+      CUDA_TRY(cudaEventRecord(l1_begin, st));
     if(d1 > d0)
       b2k_launch_dwt_fwd(L.d_descs + d0, (int)(d1 - d0), L.max_jobs, L.nc, J->cp.irreversible, l16, st);
     if(first && time_level1)
     {
-      CUDA_TRY(cudaEventRecord(J->ev[5], st));
+      CUDA_TRY(cudaEventRecord(l1_end, st));
       J->level1_alg_bytes = L.alg_bytes;
     }
     first = false;
@@ -1255,6 +1260,88 @@ extern "C" int32_t b2k_job_roundtrip(b2k_device_job* J, float* ms_total, float* 
   if(stage_ms)
     for(int i = 0; i < 4; ++i)
       stage_ms[i] = t[i];
+  if(total_bytes) *total_bytes = J->bytes_used;
+  int herr = 0;
+  CUDA_TRY(cudaMemcpy(&herr, J->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if(herr)
+  {
+    g_err = "HT decoder rejected " + std::to_string(herr) + " block(s)";
+    return -2;
+  }
+  return 0;
+}
+
+/* n device-resident round trips queued back to back on the stream, ONE synchronisation after the last: what a
+   benchmark step loop should cost when the host is not in the way (several ranks on one box).  Times come from
+   events recorded per step: ms_total = first step's start to last step's end; stage_ms[4] and level1_ms are sums
+   over the steps.  Returns 2 once if the coded size outgrew the arena (it has been resized: call again). */
+extern "C" int32_t b2k_job_roundtrip_n(b2k_device_job* J, uint32_t steps, float* ms_total, float* stage_ms, float* level1_ms,
+                                       uint64_t* total_bytes)
+{
+  if(!J || !steps) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  cudaStream_t st = J->eng->stream;
+  const uint32_t n = (uint32_t)J->h_enc_desc.size();
+  if(J->bytes_cap == 0)
+  { /* first use: size the arena (one synchronising pass) */
+    float t;
+    uint64_t b;
+    if(int rc = b2k_job_forward(J, &t)) return rc;
+    if(int rc = b2k_job_t1_encode(J, &t, &b)) return rc;
+  }
+  const size_t per = 7; /* start, l1 begin, l1 end, after forward, after encode, after decode, end */
+  while(J->q_ev.size() < per * steps)
+  {
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreate(&ev));
+    J->q_ev.push_back(ev);
+  }
+  CUDA_TRY(cudaMemsetAsync(J->d_err, 0, sizeof(int), st));
+  for(uint32_t s = 0; s < steps; ++s)
+  {
+    cudaEvent_t* e = J->q_ev.data() + per * s;
+    CUDA_TRY(cudaEventRecord(e[0], st));
+    if(enqueue_forward(J, st, true, 0, (size_t)-1, false, e[1], e[2])) return -1;
+    CUDA_TRY(cudaEventRecord(e[3], st));
+    if(enqueue_t1_encode(J, st)) return -1;
+    b2k_launch_ht_gather(J->d_enc_desc, J->d_out, J->d_offsets, J->d_scratch, J->d_bytes, n, J->bytes_cap, st);
+    if(s + 1 == steps)
+      CUDA_TRY(cudaMemcpyAsync(&J->h_offsets[n], J->d_offsets + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(e[4], st));
+    if(enqueue_t1_decode_own(J, st)) return -1;
+    CUDA_TRY(cudaEventRecord(e[5], st));
+    if(enqueue_inverse(J, st)) return -1;
+    CUDA_TRY(cudaEventRecord(e[6], st));
+  }
+  CUDA_TRY(cudaEventSynchronize(J->q_ev[per * (steps - 1) + 6]));
+  CUDA_TRY(cudaGetLastError());
+  if(J->h_offsets[n] > J->bytes_cap)
+  {
+    cudaFree(J->d_bytes);
+    J->bytes_cap = J->h_offsets[n] + J->h_offsets[n] / 8 + 4096;
+    CUDA_TRY(cudaMalloc(&J->d_bytes, J->bytes_cap));
+    g_err = "coded size grew past the arena: arena resized, call again";
+    return 2;
+  }
+  J->bytes_used = J->h_offsets[n];
+  float sums[4] = {0, 0, 0, 0}, l1 = 0, tot = 0;
+  for(uint32_t s = 0; s < steps; ++s)
+  {
+    cudaEvent_t* e = J->q_ev.data() + per * s;
+    float t = 0;
+    cudaEventElapsedTime(&t, e[0], e[3]); sums[0] += t;
+    cudaEventElapsedTime(&t, e[3], e[4]); sums[1] += t;
+    cudaEventElapsedTime(&t, e[4], e[5]); sums[2] += t;
+    cudaEventElapsedTime(&t, e[5], e[6]); sums[3] += t;
+    cudaEventElapsedTime(&t, e[1], e[2]); l1 += t;
+  }
+  cudaEventElapsedTime(&tot, J->q_ev[0], J->q_ev[per * (steps - 1) + 6]);
+  J->last_level1_ms = l1 / steps;
+  if(ms_total) *ms_total = tot;
+  if(stage_ms)
+    for(int i = 0; i < 4; ++i)
+      stage_ms[i] = sums[i];
+  if(level1_ms) *level1_ms = l1;
   if(total_bytes) *total_bytes = J->bytes_used;
   int herr = 0;
   CUDA_TRY(cudaMemcpy(&herr, J->d_err, sizeof(int), cudaMemcpyDeviceToHost));

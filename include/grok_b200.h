@@ -398,6 +398,10 @@ B2K_API int32_t b2k_job_inverse(b2k_device_job* j, float* ms);  /* inverse DWT+M
 /* all four stages enqueued back to back, one synchronisation; stage_ms[4] optional; returns 2 once if the
  * coded size outgrew the arena (arena resized: call again) */
 B2K_API int32_t b2k_job_roundtrip(b2k_device_job* j, float* ms_total, float* stage_ms, uint64_t* total_bytes);
+/* `steps` round trips queued back to back with one synchronisation after the last (a benchmark loop without the
+ * host in it); stage_ms[4] and level1_ms are sums over the steps, ms_total spans first start to last end. */
+B2K_API int32_t b2k_job_roundtrip_n(b2k_device_job* j, uint32_t steps, float* ms_total, float* stage_ms, float* level1_ms,
+                                    uint64_t* total_bytes);
 B2K_API int32_t b2k_job_download(b2k_device_job* j, int32_t* const* planes, const uint32_t* strides);
 /* copy the coefficient planes (Mallat layout per tile, image-shaped, int32 or float bits) */
 B2K_API int32_t b2k_job_download_coeffs(b2k_device_job* j, int32_t* const* planes, const uint32_t* strides);
