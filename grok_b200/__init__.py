@@ -63,7 +63,7 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_roundtrip_n", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
            "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last",
-           "b2k_codestream_write", "b2k_codestream_parse"]
+           "b2k_codestream_write", "b2k_codestream_parse", "b2k_jph_wrap", "b2k_jph_codestream"]
 
 _lib = None
 
@@ -117,6 +117,9 @@ def lib():
     L.b2k_codestream_write.restype = C.c_int64
     L.b2k_codestream_parse.argtypes = [vp, u64, C.POINTER(Coding), vp, u64]
     L.b2k_codestream_parse.restype = C.c_int64
+    L.b2k_jph_wrap.argtypes = [C.POINTER(Coding), vp, u64, vp, u64]
+    L.b2k_jph_wrap.restype = C.c_int64
+    L.b2k_jph_codestream.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.b2k_host_pack_last.argtypes = [C.c_int32]
     L.b2k_host_pack_last.restype = C.c_int32
     L.b2k_job_last_kernel_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(u64)]
@@ -216,6 +219,26 @@ def codestream_parse(cs):
     if m != n:
         raise (NotHandled if m == 1 else EngineError)("b2k_codestream_parse: " + (lib().b2k_last_error() or b"").decode())
     return cp, blocks
+
+
+def jph_wrap(cp, cs):
+    """codestream -> .jph file bytes (JP2 boxes, brand 'jph ')."""
+    cs = np.ascontiguousarray(cs, dtype=np.uint8)
+    n = lib().b2k_jph_wrap(C.byref(cp), cs.ctypes.data, len(cs), None, 0)
+    if n < 0:
+        raise EngineError("b2k_jph_wrap: " + (lib().b2k_last_error() or b"").decode())
+    out = np.zeros(n, np.uint8)
+    assert lib().b2k_jph_wrap(C.byref(cp), cs.ctypes.data, len(cs), out.ctypes.data, n) == n
+    return out
+
+
+def jph_codestream(data):
+    """.jph / .jp2 file bytes (or a raw codestream) -> view of the contiguous codestream."""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off, n = C.c_uint64(), C.c_uint64()
+    if lib().b2k_jph_codestream(data.ctypes.data, len(data), C.byref(off), C.byref(n)) != 0:
+        raise EngineError("b2k_jph_codestream: " + (lib().b2k_last_error() or b"").decode())
+    return data[off.value:off.value + n.value]
 
 
 class NotHandled(EngineError):

@@ -1082,3 +1082,101 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
       return fail(errs[t].c_str(), rcs[t]);
   return (int64_t)nblocks;
 }
+
+/* ============================================================================================================
+ * JPH file format (T.814 Annex D: the JP2 box structure with brand 'jph '), the container Grok writes by default for
+ * HT codestreams (fileformat/compress/FileFormatJP2Compress.cpp; brand selection in FileFormatJPHCompress).  Minimal
+ * form: signature, file type, header (image header + enumerated colour space), contiguous codestream.
+ * ============================================================================================================ */
+namespace
+{
+void box(std::vector<uint8_t>& o, const char* type, const std::vector<uint8_t>& payload)
+{
+  put32(o, (uint32_t)payload.size() + 8);
+  o.insert(o.end(), type, type + 4);
+  o.insert(o.end(), payload.begin(), payload.end());
+}
+} // namespace
+
+extern "C" __attribute__((visibility("default"))) int64_t b2k_jph_wrap(const b2k_coding* cp, const uint8_t* cs, uint64_t cs_len,
+                                                                        uint8_t* out, uint64_t cap)
+{
+  if(!cp || (!cs && cs_len))
+    return -1;
+  std::vector<uint8_t> o;
+  box(o, "jP  ", {0x0D, 0x0A, 0x87, 0x0A});
+  {
+    std::vector<uint8_t> p = {'j', 'p', 'h', ' ', 0, 0, 0, 0, 'j', 'p', 'h', ' '};
+    box(o, "ftyp", p);
+  }
+  {
+    std::vector<uint8_t> ihdr, colr, hdr;
+    put32(ihdr, cp->y1 - cp->y0);
+    put32(ihdr, cp->x1 - cp->x0);
+    put16(ihdr, cp->numcomps);
+    ihdr.push_back((uint8_t)((cp->prec - 1) | (cp->sgnd ? 0x80 : 0)));
+    ihdr.push_back(7); /* compression type */
+    ihdr.push_back(0); /* colour space known */
+    ihdr.push_back(0); /* no IPR */
+    colr = {1, 0, 0};  /* enumerated colour space */
+    put32(colr, cp->numcomps >= 3 ? 16u : 17u); /* sRGB / greyscale */
+    box(hdr, "ihdr", ihdr);
+    box(hdr, "colr", colr);
+    box(o, "jp2h", hdr);
+  }
+  const uint64_t total = o.size() + 8 + cs_len;
+  if(total > 0xFFFFFFFFull)
+  {
+    b2k_set_error("file larger than 4 GiB: extended box lengths are not written");
+    return -1;
+  }
+  if(!out || cap < total)
+    return (int64_t)total;
+  put32(o, (uint32_t)(cs_len + 8));
+  o.insert(o.end(), {'j', 'p', '2', 'c'});
+  memcpy(out, o.data(), o.size());
+  memcpy(out + o.size(), cs, cs_len);
+  return (int64_t)total;
+}
+
+/* locate the contiguous codestream inside a JP2 / JPH file (or accept a raw codestream): 0 + offset/length, <0 none */
+extern "C" __attribute__((visibility("default"))) int32_t b2k_jph_codestream(const uint8_t* file, uint64_t len, uint64_t* off,
+                                                                              uint64_t* n)
+{
+  if(!file || !off || !n)
+    return -1;
+  if(len >= 2 && file[0] == 0xFF && file[1] == 0x4F)
+  {
+    *off = 0;
+    *n = len;
+    return 0;
+  }
+  uint64_t p = 0;
+  while(p + 8 <= len)
+  {
+    uint64_t L = ((uint64_t)file[p] << 24) | ((uint64_t)file[p + 1] << 16) | ((uint64_t)file[p + 2] << 8) | file[p + 3];
+    uint64_t hdr = 8;
+    if(L == 1)
+    { /* extended length */
+      if(p + 16 > len)
+        break;
+      L = 0;
+      for(int i = 0; i < 8; ++i)
+        L = (L << 8) | file[p + 8 + i];
+      hdr = 16;
+    }
+    else if(L == 0)
+      L = len - p; /* box runs to the end of the file */
+    if(L < hdr || p + L > len)
+      break;
+    if(memcmp(file + p + 4, "jp2c", 4) == 0)
+    {
+      *off = p + hdr;
+      *n = L - hdr;
+      return 0;
+    }
+    p += L;
+  }
+  b2k_set_error("no contiguous codestream box");
+  return -1;
+}

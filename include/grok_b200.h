@@ -428,6 +428,11 @@ B2K_API uint64_t b2k_job_num_blocks(const b2k_device_job* j);
 B2K_API int64_t b2k_codestream_write(const b2k_coding* cp, const b2k_result* r, uint32_t flags, uint8_t* out, uint64_t cap);
 B2K_API int64_t b2k_codestream_parse(const uint8_t* cs, uint64_t len, b2k_coding* cp, b2k_block* blocks, uint64_t cap_blocks);
 
+/* JPH container (JP2 boxes, brand 'jph '): wrap a codestream / find the codestream inside a .jph / .jp2 file
+ * (a raw codestream is accepted as it is). */
+B2K_API int64_t b2k_jph_wrap(const b2k_coding* cp, const uint8_t* cs, uint64_t cs_len, uint8_t* out, uint64_t cap);
+B2K_API int32_t b2k_jph_codestream(const uint8_t* file, uint64_t len, uint64_t* offset, uint64_t* length);
+
 /* launches issued by this library since engine creation (bench.py "gpu_launches") */
 B2K_API uint64_t b2k_launch_count(void);
 /* per-kernel timing of the last forward()/inverse(): ms of the level-1 kernel and algorithmic

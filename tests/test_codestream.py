@@ -205,3 +205,19 @@ def test_parser_declines_or_rejects_what_it_does_not_cover():
             G.codestream_parse(d)
         except G.EngineError:
             pass
+
+
+def test_jph_container_round_trip_and_openjpeg():
+    """.jph (JP2 boxes, brand 'jph '): OpenJPEG opens the wrapped file, and the codestream comes back out of it."""
+    cp = G.make_coding(160, 96, 3, 8, numres=4, tile=(64, 64))
+    planes = P.synthetic_image(160, 96, 3, 8, seed=41)
+    table, data, _ = oracle_encode(cp, planes)
+    cs = G.codestream_write(cp, table, data)
+    jph = G.jph_wrap(cp, cs)
+    assert bytes(jph[4:8]) == b"jP  " and bytes(jph[16:24]) == b"ftypjph "
+    assert np.array_equal(G.jph_codestream(jph), cs)
+    assert np.array_equal(G.jph_codestream(cs), cs)          # a raw codestream is accepted as it is
+    got = openjpeg_pillow(jph)
+    assert np.array_equal(got.astype(np.int64), np.stack(planes, axis=-1))
+    with pytest.raises(G.EngineError):
+        G.jph_codestream(jph[:40])
