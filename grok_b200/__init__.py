@@ -178,7 +178,12 @@ def host_pack_last():
     return int(lib().b2k_host_pack_last(0)), int(lib().b2k_host_pack_last(1))
 
 
-CS_TLM, CS_PLT = 1, 2
+CS_TLM, CS_PLT, CS_TPARTS_R = 1, 2, 4
+LRCP, RLCP, RPCL, PCRL, CPRL = range(5)
+
+
+def CS_PROG(n):
+    return (n & 7) << 8
 
 
 def codestream_write(cp, blocks, data, flags=CS_TLM | CS_PLT, num_tiles=None, out=None):

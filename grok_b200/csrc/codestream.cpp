@@ -234,10 +234,12 @@ struct Packet
   uint16_t comp;
   uint8_t resno, nbands;
   uint32_t precno;
+  uint32_t xpos, ypos; /* where the position-driven progressions meet this precinct on the reference grid (B.12.1.3-5) */
   PacketBand band[3];
 };
 /* mirrors enumerate_tile_blocks() (geometry.cpp): same loops, counts instead of blocks */
-void tile_packets(const b2k_coding& cp, const Rect& tile, std::vector<Packet>& lrcp, uint32_t& nblocks)
+/* prog: 0 LRCP, 1 RLCP, 2 RPCL, 3 PCRL, 4 CPRL (one layer, so the first two coincide) */
+void tile_packets(const b2k_coding& cp, const Rect& tile, std::vector<Packet>& lrcp, uint32_t& nblocks, int prog = 0)
 {
   const int numres = cp.numres;
   std::vector<std::vector<Packet>> per_res_comp((size_t)numres * cp.numcomps);
@@ -258,12 +260,19 @@ void tile_packets(const b2k_coding& cp, const Rect& tile, std::vector<Packet>& l
       const int nbands = resno == 0 ? 1 : 3;
       std::vector<Packet>& pk = per_res_comp[(size_t)resno * cp.numcomps + comp];
       pk.resize((size_t)gridw * gridh);
+      const int nd = numres - 1 - resno;
       for(size_t p = 0; p < pk.size(); ++p)
       {
         pk[p].comp = comp;
         pk[p].resno = (uint8_t)resno;
         pk[p].nbands = (uint8_t)nbands;
         pk[p].precno = (uint32_t)p;
+        /* a precinct is met where its corner lies on the reference grid; the first column / row of a resolution
+           whose origin is not precinct aligned is met at the tile's edge instead */
+        const uint32_t ix = (uint32_t)(p % gridw), iy = (uint32_t)(p / gridw);
+        const uint64_t cx = ((uint64_t)(px0 >> pw) + ix) << (pw + nd), cy = ((uint64_t)(py0 >> ph) + iy) << (ph + nd);
+        pk[p].xpos = (ix == 0 && px0 != res.x0) ? tile.x0 : (uint32_t)std::min<uint64_t>(cx, 0xFFFFFFFFull);
+        pk[p].ypos = (iy == 0 && py0 != res.y0) ? tile.y0 : (uint32_t)std::min<uint64_t>(cy, 0xFFFFFFFFull);
       }
       for(int b = 0; b < nbands; ++b)
       {
@@ -300,6 +309,29 @@ void tile_packets(const b2k_coding& cp, const Rect& tile, std::vector<Packet>& l
     for(uint16_t comp = 0; comp < cp.numcomps; ++comp)
       for(const Packet& p : per_res_comp[(size_t)resno * cp.numcomps + comp])
         lrcp.push_back(p);
+  if(prog >= 2)
+  { /* the position-driven orders are the nested loops of B.12.1.3-5 read as sort keys (stable: ties keep LRCP order) */
+    auto key = [prog](const Packet& a) {
+      struct K
+      {
+        uint64_t k[4];
+      } k;
+      if(prog == 2)
+        k = {{a.resno, a.ypos, a.xpos, a.comp}};
+      else if(prog == 3)
+        k = {{a.ypos, a.xpos, a.comp, a.resno}};
+      else
+        k = {{a.comp, a.ypos, a.xpos, a.resno}};
+      return k;
+    };
+    std::stable_sort(lrcp.begin(), lrcp.end(), [&](const Packet& a, const Packet& b) {
+      const auto ka = key(a), kb = key(b);
+      for(int i = 0; i < 4; ++i)
+        if(ka.k[i] != kb.k[i])
+          return ka.k[i] < kb.k[i];
+      return false;
+    });
+  }
 }
 
 void put16(std::vector<uint8_t>& o, uint32_t v)
@@ -337,7 +369,7 @@ uint32_t magb_code(const b2k_coding& cp, const std::vector<BandQuant>& q)
   return 31;
 }
 
-void write_main_header(const b2k_coding& cp, const TileGrid& g, const std::vector<BandQuant>& q, std::vector<uint8_t>& o)
+void write_main_header(const b2k_coding& cp, const TileGrid& g, const std::vector<BandQuant>& q, std::vector<uint8_t>& o, int prog)
 {
   put16(o, 0xFF4F); /* SOC */
   put16(o, 0xFF51); /* SIZ (T.800 A.5.1) */
@@ -368,7 +400,7 @@ void write_main_header(const b2k_coding& cp, const TileGrid& g, const std::vecto
   put16(o, 0xFF52); /* COD (A.6.1) */
   put16(o, 12 + (user_prec ? cp.numres : 0));
   o.push_back(user_prec ? 1 : 0);
-  o.push_back(0); /* LRCP */
+  o.push_back((uint8_t)prog); /* progression order */
   put16(o, 1);    /* layers */
   o.push_back(cp.mct ? 1 : 0);
   o.push_back((uint8_t)(cp.numres - 1));
@@ -404,17 +436,30 @@ struct TilePlan
   std::vector<uint64_t> seg_off;      /* arena offsets */
   std::vector<uint32_t> seg_len;
   std::vector<uint32_t> packet_len;   /* header + body */
-  std::vector<uint8_t> plt;           /* complete PLT marker segments */
-  uint64_t body_bytes = 0;
-  uint64_t size() const { return 12 + plt.size() + 2 + body_bytes; } /* SOT + PLT + SOD + packets */
+  std::vector<uint8_t> res_of;        /* per packet: its resolution (tile parts may be split there) */
+  /* tile parts: [first packet, end packet), their PLT marker segments and sizes (SOT + PLT + SOD + packets) */
+  struct Part
+  {
+    size_t p0, p1, h0, s0; /* packets, offset into hdrs, first segment */
+    std::vector<uint8_t> plt;
+    uint64_t bytes;
+  };
+  std::vector<Part> parts;
+  uint64_t size() const
+  {
+    uint64_t n = 0;
+    for(const Part& pt : parts)
+      n += pt.bytes;
+    return n;
+  }
 };
 
 int plan_tile_packets(const b2k_coding& cp, const Rect& tile, const b2k_block* blk, uint32_t nblk, uint64_t arena_len,
-                      TilePlan& plan, std::string& err)
+                      TilePlan& plan, std::string& err, int prog)
 {
   std::vector<Packet> pkts;
   uint32_t expect = 0;
-  tile_packets(cp, tile, pkts, expect);
+  tile_packets(cp, tile, pkts, expect, prog);
   if(expect != nblk)
   {
     err = "block table does not match the tile's enumeration";
@@ -485,6 +530,7 @@ int plan_tile_packets(const b2k_coding& cp, const Rect& tile, const b2k_block* b
     bw.flush();
     plan.hdrs.insert(plan.hdrs.end(), hdr.begin(), hdr.end());
     plan.hdr_len.push_back((uint32_t)hdr.size());
+    plan.res_of.push_back(pk.resno);
     uint64_t plen = hdr.size();
     uint32_t ns = 0;
     for(int b = 0; b < pk.nbands; ++b)
@@ -519,9 +565,63 @@ int plan_tile_packets(const b2k_coding& cp, const Rect& tile, const b2k_block* b
       return -1;
     }
     plan.packet_len.push_back((uint32_t)plen);
-    plan.body_bytes += plen;
   }
   return 0;
+}
+
+/* cut the planned packets into tile parts and build each part's PLT (A.7.3: 7 bits per byte, MSB = continuation) */
+void plan_tile_parts(TilePlan& P, bool split_res, bool want_plt)
+{
+  const size_t np = P.packet_len.size();
+  size_t p = 0, h = 0, sg = 0;
+  do
+  {
+    TilePlan::Part part;
+    part.p0 = p;
+    part.h0 = h;
+    part.s0 = sg;
+    uint64_t body = 0;
+    const uint8_t r0 = np ? P.res_of[p] : 0;
+    while(p < np && (!split_res || P.res_of[p] == r0))
+    {
+      body += P.packet_len[p];
+      h += P.hdr_len[p];
+      sg += P.nseg[p];
+      ++p;
+    }
+    part.p1 = p;
+    if(want_plt)
+    {
+      std::vector<uint8_t> seg;
+      uint8_t z = 0;
+      auto flush_seg = [&] {
+        put16(part.plt, 0xFF58);
+        put16(part.plt, (uint32_t)seg.size() + 3);
+        part.plt.push_back(z++);
+        part.plt.insert(part.plt.end(), seg.begin(), seg.end());
+        seg.clear();
+      };
+      for(size_t k = part.p0; k < part.p1; ++k)
+      {
+        uint32_t L = P.packet_len[k];
+        uint8_t tmp[5];
+        int nb = 0;
+        do
+        {
+          tmp[nb++] = (uint8_t)(L & 0x7F);
+          L >>= 7;
+        } while(L);
+        if(seg.size() + nb > 65535 - 3)
+          flush_seg();
+        for(int i = nb - 1; i >= 0; --i)
+          seg.push_back((uint8_t)(tmp[i] | (i ? 0x80 : 0)));
+      }
+      if(!seg.empty() || part.p0 == part.p1)
+        flush_seg();
+    }
+    part.bytes = 12 + part.plt.size() + 2 + body;
+    P.parts.push_back(std::move(part));
+  } while(p < np);
 }
 
 } // namespace
@@ -551,7 +651,14 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(c
   }
   const std::vector<BandQuant> q = band_quant(*cp);
   std::vector<uint8_t> head;
-  write_main_header(*cp, g, q, head);
+  const int prog = (int)((flags >> 8) & 7);
+  if(prog > 4)
+  {
+    b2k_set_error("unknown progression order");
+    return -1;
+  }
+  const bool split_res = (flags & B2K_CS_TPARTS_R) != 0 && prog <= 2; /* a tile part per resolution needs a resolution-major order */
+  write_main_header(*cp, g, q, head, prog);
 
   /* plan every tile part (their lengths feed TLM), then lay the codestream out */
   std::vector<TilePlan> plans(ntiles);
@@ -575,40 +682,15 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(c
   b2k_host_parallel(ntiles, [&](size_t t) { /* tiles are independent: plan them on the host pool */
     TilePlan& P = plans[t];
     if(plan_tile_packets(*cp, tile_rect(*cp, g, (uint32_t)t), r->blocks + tile_first[t], (uint32_t)(tile_first[t + 1] - tile_first[t]),
-                         r->num_bytes, P, errs[t]))
+                         r->num_bytes, P, errs[t], prog))
     {
       if(errs[t].empty())
         errs[t] = "tile planning failed";
       return;
     }
-    if(flags & B2K_CS_PLT)
-    { /* PLT (A.7.3): packet lengths, 7 bits per byte, continuation bit in the MSB */
-      std::vector<uint8_t> seg;
-      uint8_t z = 0;
-      auto flush_seg = [&] {
-        put16(P.plt, 0xFF58);
-        put16(P.plt, (uint32_t)seg.size() + 3);
-        P.plt.push_back(z++);
-        P.plt.insert(P.plt.end(), seg.begin(), seg.end());
-        seg.clear();
-      };
-      for(uint32_t L : P.packet_len)
-      {
-        uint8_t tmp[5];
-        int nb = 0;
-        do
-        {
-          tmp[nb++] = (uint8_t)(L & 0x7F);
-          L >>= 7;
-        } while(L);
-        if(seg.size() + nb > 65535 - 3)
-          flush_seg();
-        for(int i = nb - 1; i >= 0; --i)
-          seg.push_back((uint8_t)(tmp[i] | (i ? 0x80 : 0)));
-      }
-      if(!seg.empty() || P.packet_len.empty())
-        flush_seg();
-    }
+    plan_tile_parts(P, split_res, (flags & B2K_CS_PLT) != 0);
+    if(P.parts.size() > 255)
+      errs[t] = "more than 255 tile parts";
   });
   uint64_t total = 0;
   for(uint32_t t = 0; t < ntiles; ++t)
@@ -618,27 +700,32 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(c
       b2k_set_error(errs[t].c_str());
       return -1;
     }
-    if(plans[t].size() > 0xFFFFFFFFull)
-    {
-      b2k_set_error("tile part longer than 4 GiB");
-      return -1;
-    }
+    for(const TilePlan::Part& pt : plans[t].parts)
+      if(pt.bytes > 0xFFFFFFFFull)
+      {
+        b2k_set_error("tile part longer than 4 GiB");
+        return -1;
+      }
     total += plans[t].size();
   }
   if(flags & B2K_CS_TLM)
-  { /* TLM (A.7.1): 16-bit tile index + 32-bit length per tile part; 10921 entries fit one marker segment */
+  { /* TLM (A.7.1): 16-bit tile index + 32-bit length per tile part, in codestream order; 10921 entries fit a segment */
+    std::vector<std::pair<uint32_t, uint32_t>> ent;
+    for(uint32_t t = 0; t < ntiles; ++t)
+      for(const TilePlan::Part& pt : plans[t].parts)
+        ent.push_back({t, (uint32_t)pt.bytes});
     uint8_t z = 0;
-    for(uint32_t t0 = 0; t0 < ntiles; t0 += 10000)
+    for(size_t e0 = 0; e0 < ent.size(); e0 += 10000)
     {
-      const uint32_t n = std::min(10000u, ntiles - t0);
+      const size_t n = std::min<size_t>(10000, ent.size() - e0);
       put16(head, 0xFF55);
-      put16(head, 4 + 6 * n);
+      put16(head, (uint32_t)(4 + 6 * n));
       head.push_back(z++);
       head.push_back(0x60); /* ST = 2 (16-bit Ttlm), SP = 1 (32-bit Ptlm) */
-      for(uint32_t t = t0; t < t0 + n; ++t)
+      for(size_t e = e0; e < e0 + n; ++e)
       {
-        put16(head, t);
-        put32(head, (uint32_t)plans[t].size());
+        put16(head, ent[e].first);
+        put32(head, ent[e].second);
       }
     }
   }
@@ -654,29 +741,33 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(c
   b2k_host_parallel(ntiles, [&](size_t t) {
     const TilePlan& P = plans[t];
     uint8_t* w = out + tile_at[t];
-    const uint32_t psot = (uint32_t)P.size();
-    const uint8_t sot[12] = {0xFF, 0x90, 0, 10, (uint8_t)(t >> 8), (uint8_t)t, (uint8_t)(psot >> 24), (uint8_t)(psot >> 16),
-                             (uint8_t)(psot >> 8), (uint8_t)psot, 0, 1}; /* SOT (A.4.2): Isot, Psot, TPsot = 0, TNsot = 1 */
-    memcpy(w, sot, 12);
-    w += 12;
-    if(!P.plt.empty())
+    for(size_t pi = 0; pi < P.parts.size(); ++pi)
     {
-      memcpy(w, P.plt.data(), P.plt.size());
-      w += P.plt.size();
-    }
-    *w++ = 0xFF; /* SOD */
-    *w++ = 0x93;
-    const uint8_t* h = P.hdrs.data();
-    size_t sg = 0;
-    for(size_t k = 0; k < P.hdr_len.size(); ++k)
-    {
-      memcpy(w, h, P.hdr_len[k]);
-      w += P.hdr_len[k];
-      h += P.hdr_len[k];
-      for(uint32_t i = 0; i < P.nseg[k]; ++i, ++sg)
+      const TilePlan::Part& pt = P.parts[pi];
+      const uint32_t psot = (uint32_t)pt.bytes;
+      const uint8_t sot[12] = {0xFF, 0x90, 0, 10, (uint8_t)(t >> 8), (uint8_t)t, (uint8_t)(psot >> 24), (uint8_t)(psot >> 16),
+                               (uint8_t)(psot >> 8), (uint8_t)psot, (uint8_t)pi, (uint8_t)P.parts.size()}; /* SOT (A.4.2) */
+      memcpy(w, sot, 12);
+      w += 12;
+      if(!pt.plt.empty())
       {
-        memcpy(w, r->bytes + P.seg_off[sg], P.seg_len[sg]);
-        w += P.seg_len[sg];
+        memcpy(w, pt.plt.data(), pt.plt.size());
+        w += pt.plt.size();
+      }
+      *w++ = 0xFF; /* SOD */
+      *w++ = 0x93;
+      const uint8_t* h = P.hdrs.data() + pt.h0;
+      size_t sg = pt.s0;
+      for(size_t k = pt.p0; k < pt.p1; ++k)
+      {
+        memcpy(w, h, P.hdr_len[k]);
+        w += P.hdr_len[k];
+        h += P.hdr_len[k];
+        for(uint32_t i = 0; i < P.nseg[k]; ++i, ++sg)
+        {
+          memcpy(w, r->bytes + P.seg_off[sg], P.seg_len[sg]);
+          w += P.seg_len[sg];
+        }
       }
     }
   });
@@ -690,12 +781,19 @@ namespace
 {
 /* packets of one tile part -> the tile's slice of the block table (offsets relative to `base`).
    0 ok, 1 outside this path's scope, -1 damaged; err says why. */
-int parse_tile_packets(const b2k_coding& cp, const Rect& tile, b2k_block* tb, const uint8_t* p, const uint8_t* tp_end,
-                       const uint8_t* base, std::string& err)
+struct ByteRange
+{
+  const uint8_t *begin, *end;
+};
+int parse_tile_packets(const b2k_coding& cp, const Rect& tile, b2k_block* tb, const std::vector<ByteRange>& parts,
+                       const uint8_t* base, int prog, std::string& err)
 {
   std::vector<Packet> pkts;
   uint32_t nblk = 0;
-  tile_packets(cp, tile, pkts, nblk);
+  tile_packets(cp, tile, pkts, nblk, prog);
+  size_t part = 0;
+  const uint8_t* p = parts.empty() ? nullptr : parts[0].begin;
+  const uint8_t* tp_end = parts.empty() ? nullptr : parts[0].end;
   TagTree incl, imsb;
   struct Seg
   {
@@ -708,6 +806,14 @@ int parse_tile_packets(const b2k_coding& cp, const Rect& tile, b2k_block* tb, co
   };
   for(const Packet& pk : pkts)
   {
+    while(p == tp_end && part + 1 < parts.size())
+    { /* a packet never straddles tile parts: continue in the next one */
+      ++part;
+      p = parts[part].begin;
+      tp_end = parts[part].end;
+    }
+    if(p == tp_end)
+      break; /* the tile's data ends here (truncated or resolution-progressive file): what follows stays uncoded */
     BitReader br(p, tp_end);
     order.clear();
     if(br.get())
@@ -832,6 +938,7 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
   b2k_coding cp;
   memset(&cp, 0, sizeof(cp));
   bool have_siz = false, have_cod = false, have_qcd = false, have_cap = false;
+  int progression = 0;
   std::vector<uint32_t> qcd_vals;
   uint32_t sqcd = 0;
   /* ---- main header ---- */
@@ -907,8 +1014,9 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
         const uint32_t sty = s.u8(), xf = s.u8();
         if(layers != 1)
           return fail("one quality layer handled", 1);
-        if(prog != 0)
-          return fail("LRCP progression handled", 1);
+        if(prog > 4)
+          return fail("unknown progression order", -1);
+        progression = (int)prog;
         if(!(sty & 0x40) || (sty & ~0x48u))
           return fail("only HT code blocks (optionally stripe-causal) are handled", 1);
         cp.cblk_sty = (uint8_t)(sty & 0x08);
@@ -1012,13 +1120,8 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
     return fail("block table too small", -1);
 
   /* ---- tile parts: locate them (SOT / Psot), then parse their packets tile by tile on the host pool ---- */
-  struct Part
-  {
-    uint32_t tile;
-    const uint8_t *data, *end;
-  };
-  std::vector<Part> parts;
-  std::vector<uint8_t> seen(ntiles, 0);
+  std::vector<std::vector<ByteRange>> tile_parts(ntiles);
+  std::vector<uint32_t> next_tp(ntiles, 0);
   for(;;)
   {
     const uint8_t* sot = c.p;
@@ -1035,9 +1138,9 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
     (void)tnsot;
     if(!c.ok || lsot != 10 || isot >= ntiles)
       return fail("bad SOT", -1);
-    if(tpsot != 0 || seen[isot])
-      return fail("several tile parts per tile are not handled", 1);
-    seen[isot] = 1;
+    if(tpsot != next_tp[isot])
+      return fail("tile parts out of order", 1);
+    ++next_tp[isot];
     const uint8_t* tp_end = psot ? sot + psot : c.end - ((len >= 2 && cs[len - 2] == 0xFF && cs[len - 1] == 0xD9) ? 2 : 0);
     if(tp_end > c.end || tp_end < c.p)
       return fail("Psot exceeds the codestream", -1);
@@ -1055,14 +1158,11 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
         return fail("tile-part COD / COC / QCD / QCC / RGN / POC / PPT are not handled", 1);
       c.p += L - 2; /* PLT, COM: skipped */
     }
-    parts.push_back({isot, c.p, tp_end});
+    tile_parts[isot].push_back({c.p, tp_end});
     c.p = tp_end;
   }
   std::vector<int> rcs(ntiles, 0);
   std::vector<std::string> errs(ntiles);
-  std::vector<const Part*> part_of(ntiles, nullptr);
-  for(const Part& pt : parts)
-    part_of[pt.tile] = &pt;
   b2k_host_parallel(ntiles, [&](size_t t) {
     std::vector<b2k_block> tb;
     tb.reserve(tile_first[t + 1] - tile_first[t]);
@@ -1073,8 +1173,8 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
       errs[t] = "internal: packet geometry and block enumeration disagree";
       return;
     }
-    if(part_of[t]) /* a tile without a tile part decodes as all zero (blocks stay uncoded) */
-      rcs[t] = parse_tile_packets(cp, tile_rect(cp, g, (uint32_t)t), tb.data(), part_of[t]->data, part_of[t]->end, cs, errs[t]);
+    if(!tile_parts[t].empty()) /* a tile without a tile part decodes as all zero (blocks stay uncoded) */
+      rcs[t] = parse_tile_packets(cp, tile_rect(cp, g, (uint32_t)t), tb.data(), tile_parts[t], cs, progression, errs[t]);
     memcpy(blocks + tile_first[t], tb.data(), tb.size() * sizeof(b2k_block));
   });
   for(uint32_t t = 0; t < ntiles; ++t)

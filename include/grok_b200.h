@@ -415,7 +415,8 @@ B2K_API int32_t b2k_job_fetch_result(b2k_device_job* j, b2k_result** out);
 B2K_API uint64_t b2k_job_num_blocks(const b2k_device_job* j);
 /* ---- codestream assembly / parsing on the host (the T2 step) -------------------------
  * b2k_codestream_write: a complete HTJ2K codestream (SOC, SIZ, CAP, COD, QCD, [TLM], per tile SOT [PLT] SOD
- * + packets, EOC; one layer, LRCP, one tile part per tile) from an encode result that holds every tile
+ * + packets, EOC; one layer, any of the five progression orders, optionally a tile part per resolution) from an
+ * encode result that holds every tile
  * (cf. CodeStreamCompress::compress / T2Compress::compressPacket).  Returns the size; copies it to `out` if
  * cap suffices (call with out = NULL to size the buffer).  < 0 on error.
  * b2k_codestream_parse: main header -> *cp, packet headers -> block table in enumeration order with
@@ -425,6 +426,8 @@ B2K_API uint64_t b2k_job_num_blocks(const b2k_device_job* j);
  * is damaged. */
 #define B2K_CS_TLM 1u
 #define B2K_CS_PLT 2u
+#define B2K_CS_TPARTS_R 4u                 /* one tile part per resolution (LRCP / RLCP / RPCL only), cf. grk_compress -u R */
+#define B2K_CS_PROG(n) (((n) & 7u) << 8)   /* progression order: 0 LRCP (default), 1 RLCP, 2 RPCL, 3 PCRL, 4 CPRL */
 B2K_API int64_t b2k_codestream_write(const b2k_coding* cp, const b2k_result* r, uint32_t flags, uint8_t* out, uint64_t cap);
 B2K_API int64_t b2k_codestream_parse(const uint8_t* cs, uint64_t len, b2k_coding* cp, b2k_block* blocks, uint64_t cap_blocks);
 

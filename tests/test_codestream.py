@@ -221,3 +221,31 @@ def test_jph_container_round_trip_and_openjpeg():
     assert np.array_equal(got.astype(np.int64), np.stack(planes, axis=-1))
     with pytest.raises(G.EngineError):
         G.jph_codestream(jph[:40])
+
+
+@pytest.mark.parametrize("prog", [G.LRCP, G.RLCP, G.RPCL, G.PCRL, G.CPRL])
+@pytest.mark.parametrize("tparts", [0, G.CS_TPARTS_R])
+def test_progression_orders_and_tile_parts(prog, tparts):
+    """The five progression orders (position-driven ones with precincts of different sizes per resolution, a tile
+    grid that does not start at the image origin, ragged tiles) and a tile part per resolution: OpenJPEG decodes
+    every variant exactly, and the parser reads every variant back to the same block table and bytes."""
+    args = dict(width=290, height=203, numcomps=3, prec=8, numres=4, tile=(128, 96), origin=(5, 3), tile_origin=(2, 1),
+                precincts=[(16, 16), (32, 16), (32, 64), (64, 64)], cblk=(16, 16))
+    cp = G.make_coding(**args)
+    planes = P.synthetic_image(args["width"], args["height"], 3, 8, seed=51, origin=args["origin"])
+    table, data, _ = oracle_encode(cp, planes)
+    flags = G.CS_TLM | G.CS_PLT | tparts | G.CS_PROG(prog)
+    cs = G.codestream_write(cp, table, data, flags)
+    i = bytes(cs).find(b"\xff\x52")
+    assert cs[i + 5] == prog
+    nparts = bytes(cs).count(b"\xff\x90\x00\x0a")
+    ntiles = len(P.tile_rects(cp))
+    assert nparts == (ntiles * cp.numres if (tparts and prog <= G.RPCL) else ntiles)
+    got = openjpeg_pillow(cs)
+    assert np.array_equal(got.astype(np.int64), np.stack(planes, axis=-1))
+    cp2, blocks = G.codestream_parse(cs)
+    for f in ("numbps", "numpasses", "length"):
+        assert np.array_equal(blocks[f], table[f]), f
+    for k in range(0, len(table), 5):
+        o, n = int(blocks[k]["offset"]), int(blocks[k]["length"])
+        assert np.array_equal(cs[o:o + n], data[int(table[k]["offset"]):int(table[k]["offset"]) + n])
