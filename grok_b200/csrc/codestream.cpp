@@ -11,8 +11,9 @@
  *                 lengths; body), t2/TagTree.h, t1_t2 BitIO (bit stuffing after 0xFF)
  *   parsing       codestream/decompress/CodeStreamDecompress_ReadMarkers.cpp, t2/PacketParser.cpp,
  *                 t1/codeblock/CodeblockDecompressImpl.h L205-420 (HT segments: cleanup | refinement, T.814 B.10.7)
- * Scope: what this engine's path produces and consumes -- one quality layer, LRCP, one tile-part per tile, no
- * SOP/EPH, no COC/QCC/POC/RGN/PPM/PPT, HT code blocks with 1..3 passes.  Anything else parses as "not handled".
+ * Scope: what this engine's path produces and consumes -- one quality layer, any of the five progression orders,
+ * any number of tile parts per tile (in order), no SOP/EPH, no COC/QCC/POC/RGN/PPM/PPT, HT code blocks with 1..3
+ * passes, the HT quantiser's QCD.  Anything else parses as "not handled".
  * Written from the standard's rules (ITU-T T.800 Annex A/B, T.814 Annex A/B), not transcribed from the reference;
  * tests decode the output with an independent decoder (OpenJPEG via Pillow / OpenCV) -- tests/test_codestream.py.
  */
