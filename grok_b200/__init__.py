@@ -27,7 +27,8 @@ class Coding(C.Structure):
                 ("numcomps", C.c_uint16), ("prec", C.c_uint8), ("sgnd", C.c_uint8),
                 ("numres", C.c_uint8), ("cblkw_exp", C.c_uint8), ("cblkh_exp", C.c_uint8),
                 ("irreversible", C.c_uint8), ("mct", C.c_uint8), ("numgbits", C.c_uint8),
-                ("prcw_exp", C.c_uint8 * 33), ("prch_exp", C.c_uint8 * 33), ("cblk_sty", C.c_uint8)]
+                ("prcw_exp", C.c_uint8 * 33), ("prch_exp", C.c_uint8 * 33), ("cblk_sty", C.c_uint8),
+                ("qcd_explicit", C.c_uint8), ("qcd_expn", C.c_uint8 * 97), ("qcd_mant", C.c_uint16 * 97)]
 
 
 class Block(C.Structure):

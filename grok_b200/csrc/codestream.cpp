@@ -1040,8 +1040,8 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
         sqcd = s.u8();
         cp.numgbits = (uint8_t)(sqcd >> 5);
         const uint32_t style = sqcd & 0x1F;
-        if(style == 1)
-          return fail("derived quantisation is not handled", 1);
+        if(style > 2)
+          return fail("unknown quantisation style", -1);
         while(s.p < s.end)
           qcd_vals.push_back(style == 0 ? s.u8() : s.u16());
         have_qcd = s.ok;
@@ -1067,18 +1067,48 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
     return fail("MCT with fewer than three components", -1);
   if(const char* why = unsupported_reason(cp))
     return fail(why, 1);
-  /* the decoder works with the HT quantiser's step sizes: QCD must say the same (geometry.cpp band_quant) */
-  const std::vector<BandQuant> q = band_quant(cp);
-  if(qcd_vals.size() < q.size())
-    return fail("QCD has fewer entries than bands", -1);
-  if(((sqcd & 0x1F) == 2) != (cp.irreversible != 0))
-    return fail("quantisation style does not match the wavelet", 1);
-  for(size_t i = 0; i < q.size(); ++i)
+  /* band exponents / mantissas: Grok's HT quantiser tables when QCD agrees with them, else QCD's own values */
   {
-    const uint32_t want = cp.irreversible ? (((uint32_t)q[i].expn << 11) | q[i].mant) : ((uint32_t)q[i].expn << 3);
-    if(qcd_vals[i] != want)
-      return fail("QCD step sizes differ from the HT quantiser's tables: foreign quantiser, not handled", 1);
+    const uint32_t style = sqcd & 0x1F;
+    if((style != 0) != (cp.irreversible != 0))
+      return fail("quantisation style does not match the wavelet", 1);
+    const size_t nbands = 3 * (size_t)(cp.numres - 1) + 1;
+    std::vector<uint32_t> vals(nbands);
+    if(style == 1)
+    { /* scalar derived (A.6.4, E.1.1.1): (e_b, m_b) = (e_0 - N_L + n_b, m_0), n_b = decomposition level of the band */
+      if(qcd_vals.empty())
+        return fail("QCD has no entry", -1);
+      const int e0 = (int)(qcd_vals[0] >> 11), m0 = (int)(qcd_vals[0] & 0x7FF), NL = cp.numres - 1;
+      for(size_t i = 0; i < nbands; ++i)
+      {
+        const int nb = i == 0 ? NL : NL - (int)((i - 1) / 3);
+        vals[i] = (uint32_t)(std::max(0, e0 - NL + nb) << 11) | (uint32_t)m0;
+      }
+    }
+    else
+    {
+      if(qcd_vals.size() < nbands)
+        return fail("QCD has fewer entries than bands", -1);
+      for(size_t i = 0; i < nbands; ++i)
+        vals[i] = style == 0 ? (qcd_vals[i] >> 3) << 11 : qcd_vals[i];
+    }
+    const std::vector<BandQuant> dflt = band_quant(cp);
+    bool same = true;
+    for(size_t i = 0; i < nbands; ++i)
+      same &= (vals[i] >> 11) == dflt[i].expn && (cp.irreversible ? (vals[i] & 0x7FF) == dflt[i].mant : true);
+    if(!same)
+    {
+      cp.qcd_explicit = 1;
+      for(size_t i = 0; i < nbands && i < 97; ++i)
+      {
+        cp.qcd_expn[i] = (uint8_t)(vals[i] >> 11);
+        cp.qcd_mant[i] = (uint16_t)(vals[i] & 0x7FF);
+      }
+    }
   }
+  if(const char* why = unsupported_reason(cp))
+    return fail(why, 1);
+  const std::vector<BandQuant> q = band_quant(cp);
   /* SIZ sanity (A.5.1) and a bound on what a damaged header can make us enumerate */
   if(cp.tw == 0 || cp.th == 0 || cp.tx0 > cp.x0 || cp.ty0 > cp.y0 || (uint64_t)cp.tx0 + cp.tw <= cp.x0 ||
      (uint64_t)cp.ty0 + cp.th <= cp.y0)

@@ -141,6 +141,12 @@ std::vector<BandQuant> band_quant(const b2k_coding& cp)
       s++;
     }
   }
+  if(cp.qcd_explicit)
+    for(int i = 0; i < 3 * D + 1 && i < 97; ++i)
+    { /* a foreign stream's QCD (or a caller's own choice) instead of the HT quantiser's tables */
+      expn[i] = cp.qcd_expn[i];
+      mant[i] = cp.irreversible ? (uint16_t)(cp.qcd_mant[i] & 0x7FF) : 0;
+    }
   for(int i = 0; i < 3 * D + 1; ++i)
   {
     const int orient = i == 0 ? 0 : ((i - 1) % 3) + 1;

@@ -296,6 +296,12 @@ typedef struct b2k_coding
   uint8_t prcw_exp[33], prch_exp[33]; /* precinct exponents per resolution (15 = maximal) */
   uint8_t cblk_sty;                /* code-block style bits (COD); only 0x08 = vertically stripe-causal matters,
                                       and only to the decoder's SigProp pass (CoderOJPH.cpp L248) */
+  uint8_t qcd_explicit;            /* 0: band exponents / mantissas are the HT quantiser's (QuantizerOJPH.cpp L193-259),
+                                      as Grok's encoder signals them.  1: take them from qcd_expn / qcd_mant below --
+                                      what b2k_codestream_parse fills in for a foreign stream's QCD (band order of QCD:
+                                      LL, then HL, LH, HH per resolution) */
+  uint8_t qcd_expn[97];
+  uint16_t qcd_mant[97];
 } b2k_coding;
 
 /* One coded block as the host's T2 needs it (cf. compress_synch_with_plugin,

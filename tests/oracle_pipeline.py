@@ -115,6 +115,9 @@ def quant_tables(cp):
     mant = np.zeros(n, np.uint16)
     got = O.lib().orc_ht_stepsizes(cp.numres - 1, cp.prec, cp.mct, cp.sgnd, 0 if cp.irreversible else 1, expn, mant)
     assert got == n
+    if getattr(cp, "qcd_explicit", 0):        # a foreign stream's QCD / the caller's own exponents (b2k_coding)
+        expn = np.array(list(cp.qcd_expn)[:n], np.uint8)
+        mant = np.array(list(cp.qcd_mant)[:n], np.uint16) if cp.irreversible else np.zeros(n, np.uint16)
     return expn, mant
 
 

@@ -94,7 +94,7 @@ def test_reversible_codestream_is_decoded_exactly_by_openjpeg(args, flags):
     # and our own parser reads back exactly what went in: coding, block table, byte ranges
     cp2, blocks = G.codestream_parse(cs)
     for f, _ in G.Coding._fields_:
-        if f not in ("tx0", "ty0", "tw", "th", "prcw_exp", "prch_exp"):
+        if f not in ("tx0", "ty0", "tw", "th", "prcw_exp", "prch_exp", "qcd_expn", "qcd_mant"):
             assert getattr(cp2, f) == getattr(cp, f), f
     assert P.tile_rects(cp2) == P.tile_rects(cp)         # an untiled coding comes back as one explicit tile
     assert list(cp2.prcw_exp)[:cp.numres] == list(cp.prcw_exp)[:cp.numres]
@@ -249,3 +249,39 @@ def test_progression_orders_and_tile_parts(prog, tparts):
     for k in range(0, len(table), 5):
         o, n = int(blocks[k]["offset"]), int(blocks[k]["length"])
         assert np.array_equal(cs[o:o + n], data[int(table[k]["offset"]):int(table[k]["offset"]) + n])
+
+
+@pytest.mark.parametrize("irreversible", [False, True])
+def test_explicit_qcd_exponents(irreversible):
+    """b2k_coding.qcd_explicit: band exponents / mantissas other than the HT quantiser's (what a foreign encoder
+    signals).  The product's geometry follows them (Kmax, step sizes), the writer puts them into QCD, OpenJPEG
+    dequantises with them, and the parser hands them back."""
+    w, h = 192, 160
+    cp = G.make_coding(w, h, 3, 8, numres=4, irreversible=irreversible)
+    base_e, base_m = P.quant_tables(cp)
+    cp.qcd_explicit = 1
+    for i in range(len(base_e)):
+        cp.qcd_expn[i] = int(base_e[i]) + (1 if not irreversible else -1 + (i % 2))   # more head room / other step sizes
+        cp.qcd_mant[i] = (int(base_m[i]) + 37 * i) % 2048 if irreversible else 0
+    for gb in G.enumerate_blocks(cp):
+        kmax, step_enc, _ = P.band_params(cp, int(gb["resno"]), int(gb["orient"]))
+        assert gb["kmax"] == kmax and gb["stepsize"] == np.float32(step_enc)
+    planes = P.synthetic_image(w, h, 3, 8, seed=61)
+    table, data, _ = oracle_encode(cp, planes)
+    cs = G.codestream_write(cp, table, data)
+    cp2, blocks = G.codestream_parse(cs)
+    n = len(base_e)
+    assert cp2.qcd_explicit == 1 and list(cp2.qcd_expn)[:n] == list(cp.qcd_expn)[:n]
+    if irreversible:
+        assert list(cp2.qcd_mant)[:n] == list(cp.qcd_mant)[:n]
+    got = openjpeg_cv2(cs).astype(np.int64)
+    ours = np.stack(oracle_decode(cp2, blocks, cs), axis=-1).astype(np.int64)
+    src = np.stack(planes, axis=-1).astype(np.int64)
+    if irreversible:
+        assert np.abs(got - ours).max() <= 1 and np.abs(ours - src).max() <= 6
+    else:
+        assert np.array_equal(got, src) and np.array_equal(ours, src)
+    # the default tables come back as "not explicit"
+    cp3 = G.make_coding(w, h, 3, 8, numres=4, irreversible=irreversible)
+    t3, d3, _ = oracle_encode(cp3, planes)
+    assert G.codestream_parse(G.codestream_write(cp3, t3, d3))[0].qcd_explicit == 0

@@ -599,3 +599,23 @@ def test_codestream_files_round_trip_and_openjpeg_reads_them(engine, irreversibl
         assert np.array_equal(ext, src)
         assert np.array_equal(ours, src)
     assert cp2.numres == cp.numres and cp2.tw == 512 and cp2.irreversible == cp.irreversible
+
+
+def test_explicit_qcd_on_the_device(engine):
+    """b2k_coding.qcd_explicit (band exponents other than the HT quantiser's, as a foreign stream's QCD gives them):
+    the device encodes and decodes with them -- OpenJPEG reads the file exactly, and so does the engine."""
+    cv2 = pytest.importorskip("cv2")
+    w, h = 640, 400
+    cp = G.make_coding(w, h, 3, 8, numres=5, tile=(256, 256))
+    e, _ = P.quant_tables(cp)
+    cp.qcd_explicit = 1
+    for i in range(len(e)):
+        cp.qcd_expn[i] = int(e[i]) + 1 + (i % 2)
+    planes = P.synthetic_image(w, h, 3, 8, seed=71)
+    cs = engine.encode_codestream(cp, planes)
+    ext = cv2.imdecode(np.frombuffer(cs.tobytes(), np.uint8), cv2.IMREAD_UNCHANGED)[:, :, ::-1].astype(np.int64)
+    assert np.array_equal(ext, np.stack(planes, axis=-1))
+    cp2, ours = engine.decode_codestream(cs)
+    assert cp2.qcd_explicit == 1
+    for a, b in zip(ours, planes):
+        assert np.array_equal(a, b)
