@@ -619,3 +619,80 @@ def test_explicit_qcd_on_the_device(engine):
     assert cp2.qcd_explicit == 1
     for a, b in zip(ours, planes):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("args", [
+    dict(width=61, height=9, numcomps=1, prec=8, numres=6),                                          # levels run out of samples
+    dict(width=64, height=64, numcomps=3, prec=10, numres=3, tile=(1, 64)),                          # 1-pixel-wide tiles
+    dict(width=40, height=33, numcomps=1, prec=12, numres=2, tile=(7, 1), cblk=(4, 4)),              # 1-pixel-high tiles
+    dict(width=333, height=217, numcomps=3, prec=12, numres=4, origin=(3, 5), tile=(100, 90)),       # odd origin, ragged tiles
+])
+def test_irreversible_degenerate_geometry(engine, args):
+    """GrkDegenerate97Test / GrkShortTileRoundTripTest shapes on the 9/7 + ICT path: width / height 1 special cases
+    (WaveletFwd.cpp L444-455, L639-654), odd parities, ragged tiles -- coefficients and coded bytes bit-exact against
+    the oracle's fp32 restatement, decode within the reference's lossy tolerance of the source."""
+    cp = G.make_coding(irreversible=True, **args)
+    planes = P.synthetic_image(args["width"], args["height"], args["numcomps"], args["prec"], seed=81,
+                               origin=args.get("origin", (0, 0)))
+    ref = P.forward(cp, planes)
+    job = engine.job(cp)
+    job.upload(planes)
+    job.forward()
+    got = [np.zeros_like(p) for p in planes]
+    job.download_coeffs(got)
+    for c, (g, r) in enumerate(zip(got, ref)):
+        assert np.array_equal(g, r), "component %d: %d coefficients differ" % (c, int((g != r).sum()))
+    job.t1_encode()
+    res = job.fetch_result()
+    _compare_blocks(cp, res, ref)
+    job.t1_decode()
+    job.inverse()
+    rec = [np.zeros_like(p) for p in planes]
+    job.download(rec)
+    peak = (1 << args["prec"]) - 1
+    for g, s in zip(rec, planes):
+        assert np.abs(g - s).max() <= max(2, peak // 256)
+    res.free()
+    job.close()
+
+
+def test_repeated_and_concurrent_calls_are_deterministic(engine):
+    """GrkPluginBatchMemoryTest's determinism check (L970) and GrkConcurrencyTest's shape: the same image encoded
+    repeatedly, packed and direct, and from four threads at once (the engine serialises them) gives the same bytes
+    every time, and every decode gives the source back."""
+    import threading
+    w, h = 2048, 1536
+    cp = G.make_coding(w, h, 3, 12, numres=6, tile=(512, 512))
+    planes = P.synthetic_image(w, h, 3, 12, seed=91)
+    res = engine.encode(cp, planes)
+    want_blocks, want = res.blocks.copy(), res.bytes.copy()
+    res.free()
+    try:
+        for threads in (0, 2, 0, 2):
+            G.set_host_threads(threads)
+            r = engine.encode(cp, planes)
+            assert np.array_equal(r.bytes, want) and np.array_equal(r.blocks["length"], want_blocks["length"])
+            r.free()
+    finally:
+        G.set_host_threads(-1)
+    errors = []
+
+    def worker(i):
+        try:
+            for _ in range(3):
+                r = engine.encode(cp, planes)
+                ok = np.array_equal(r.bytes, want)
+                out = [np.zeros_like(p) for p in planes]
+                engine.decode(cp, r.blocks, r.bytes, out)
+                r.free()
+                if not ok or not all(np.array_equal(a, b) for a, b in zip(out, planes)):
+                    errors.append("thread %d: mismatch" % i)
+        except Exception as e:      # noqa: BLE001
+            errors.append("thread %d: %r" % (i, e))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
