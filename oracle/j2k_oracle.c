@@ -8,13 +8,20 @@
  *
  * Every function cites the reference file:line it restates.  Pinning status:
  *   - HT cleanup encoder / decoder : byte-for-byte vs the reference's own OpenJPH sources
- *     compiled into oracle/_ref (tests/test_oracle_vs_ref.py), fixtures in tests/golden/.
+ *     compiled into oracle/_ref (tests/test_oracle.py), fixtures in tests/golden/.
+ *   - HT SigProp / MagRef          : word-for-word vs the same decoders with 2 / 3 passes
+ *     (tests/golden/ht_refine.npz), and decoded identically by OpenJPEG (tests/test_codestream.py).
  *   - forward 5/3 and 9/7 lifting  : vs grk::dwt53 / grk::dwt97 compiled from
  *     wavelet/WaveletFwd.cpp into oracle/_ref, fixtures in tests/golden/.
  *   - inverse 5/3                  : exact inverse of the pinned forward (perfect reconstruction).
- *   - RCT / ICT, inverse 9/7, quantiser tables, geometry: restatement of the cited lines
- *     (the reference classes need the whole Tile object graph; "parity unpinned" beyond the
- *     reference's own round-trip properties, which tests/ reproduces).
+ *   - RCT / ICT, inverse 9/7, quantiser tables, geometry: restatement of the cited lines (the
+ *     reference classes need the whole Tile object graph, so there is no per-function pin against
+ *     Grok).  They are pinned END TO END against an independent JPEG 2000 implementation instead:
+ *     codestreams assembled from this oracle's blocks are decoded by OpenJPEG 2.5 (Pillow's and
+ *     OpenCV's builds) exactly to the source on the reversible path -- which fixes RCT, DC shift,
+ *     5/3, geometry, precinct / code-block partition, exponents and Kmax -- and to within one code of
+ *     this oracle's own decode on the 9/7 + ICT path with default and with explicit step sizes --
+ *     which fixes ICT, inverse 9/7 and the step-size formula (tests/test_codestream.py).
  */
 #include <stdint.h>
 #include <stddef.h>
