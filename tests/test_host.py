@@ -284,3 +284,83 @@ def test_sharded_ranks_gather_into_one_codestream_gloo(tmp_path):
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_ht_bit_plane_limits_are_declined_with_a_reason():
+    """GrkHTBandBitPlanesTest: the 32-bit HT block coder carries at most 30 magnitude bits.  Codings whose bands would
+    need more (deep samples + guard bits + sub-band gain) are 'not handled' with a reason -- the host keeps them --
+    rather than coded wrongly; the deepest supported one still enumerates."""
+    lib = G.lib()
+    ok = G.make_coding(256, 256, 3, 16, numres=6, numgbits=2)
+    assert lib.b2k_enumerate(C.byref(ok), 1, 0, None, 0) > 0
+    kmax = G.enumerate_blocks(ok)["kmax"]
+    assert kmax.max() <= 29 and kmax.min() >= 1
+    deep = G.make_coding(256, 256, 3, 16, numres=6, numgbits=7)       # 16 bits + RCT + gains + 7 guard bits: Kmax 27, fine
+    assert lib.b2k_enumerate(C.byref(deep), 1, 0, None, 0) > 0 and G.enumerate_blocks(deep)["kmax"].max() == 27
+    deep.qcd_explicit = 1                                                # a foreign QCD asking for 31 + 6 bit planes
+    for i in range(16):
+        deep.qcd_expn[i] = 31
+    assert lib.b2k_enumerate(C.byref(deep), 1, 0, None, 0) < 0
+    assert b"bit planes" in lib.b2k_last_error()
+    for bad in (dict(prec=17), dict(numcomps=5), dict(cblk=(1024, 8)), dict(numres=9)):
+        args = dict(width=64, height=64, numcomps=1, prec=8, numres=3)
+        args.update(bad)
+        assert lib.b2k_enumerate(C.byref(G.make_coding(**args)), 1, 0, None, 0) < 0, bad
+
+
+def test_gpup_tile_tree_from_a_result_multi_tile_with_precincts():
+    """b2k_result_to_gpup_tile (the per-tile seam of INTEGRATION.md section 2) without a GPU: a result built from
+    oracle-coded blocks of a multi-tile image with user precincts is turned into the gpup_tile tree of each tile;
+    walking it in Grok's order (plugin_bridge.cpp L62-111: comp -> res -> band -> precinct -> block) meets exactly the
+    enumeration's blocks, with their rectangles, bytes, pass bookkeeping (rate = length - 1) and band step sizes."""
+    from gpup_ctypes import GpupTile
+    lib = G.lib()
+    cp = G.make_coding(200, 150, 3, 8, numres=4, tile=(128, 96), precincts=[(32, 32), (64, 64)], cblk=(16, 16))
+    planes = P.synthetic_image(200, 150, 3, 8, seed=5)
+    coefs = P.forward(cp, planes)
+    table = G.enumerate_blocks(cp)
+    blks = P.enumerate_all(cp)
+    rects = P.tile_rects(cp)
+    chunks, off = [], 0
+    for i, (t, c, b) in enumerate(blks):
+        data = P.encode_block(cp, coefs, rects[t], c, b)
+        table[i]["length"], table[i]["offset"], table[i]["numbps"], table[i]["numpasses"] = len(data), off, 1, 1
+        chunks.append(data)
+        off += len(data)
+    arena = np.concatenate(chunks)
+    r = G.Result()
+    r.num_blocks, r.blocks = len(table), C.cast(table.ctypes.data, C.POINTER(G.Block))
+    r.bytes, r.num_bytes, r.num_tiles = C.cast(arena.ctypes.data, C.POINTER(C.c_uint8)), len(arena), len(rects)
+    lib.b2k_result_to_gpup_tile.restype = C.POINTER(GpupTile)
+    lib.b2k_result_to_gpup_tile.argtypes = [C.POINTER(G.Coding), C.POINTER(G.Result), C.c_uint32]
+    lib.gpup_tile_free.argtypes = [C.POINTER(GpupTile)]
+    k = 0
+    for t in range(len(rects)):
+        tile = lib.b2k_result_to_gpup_tile(C.byref(cp), C.byref(r), t)
+        assert tile, lib.b2k_last_error()
+        T = tile.contents
+        assert T.numComponents == 3
+        for c in range(3):
+            tc = T.tileComponents[c].contents
+            assert tc.numResolutions == cp.numres
+            for rr in range(cp.numres):
+                res = tc.resolutions[rr].contents
+                assert res.numBands == (1 if rr == 0 else 3)
+                for b in range(res.numBands):
+                    band = res.band[b].contents
+                    assert band.orientation == (0 if rr == 0 else b + 1)
+                    for p in range(band.numPrecincts):
+                        prc = band.precincts[p].contents
+                        for j in range(prc.numBlocks):
+                            cb = prc.blocks[j].contents
+                            row = table[k]
+                            assert (row["tile"], row["comp"], row["resno"], row["band_index"], row["precno"], row["cblkno"]) == (t, c, rr, b, p, j)
+                            assert (cb.x0, cb.y0, cb.x1, cb.y1) == (row["x0"], row["y0"], row["x1"], row["y1"])
+                            assert cb.numPasses == 1 and cb.numBitPlanes == 1 and cb.compressedDataLength == row["length"]
+                            assert cb.passes[0].rate == row["length"] - 1
+                            have = np.ctypeslib.as_array(cb.compressedData, shape=(cb.compressedDataLength,))
+                            assert np.array_equal(have, arena[int(row["offset"]):int(row["offset"]) + int(row["length"])])
+                            assert band.stepsize == row["stepsize"]
+                            k += 1
+        lib.gpup_tile_free(tile)
+    assert k == len(table)
