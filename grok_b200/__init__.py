@@ -179,7 +179,7 @@ def host_pack_last():
     return int(lib().b2k_host_pack_last(0)), int(lib().b2k_host_pack_last(1))
 
 
-CS_TLM, CS_PLT, CS_TPARTS_R = 1, 2, 4
+CS_TLM, CS_PLT, CS_TPARTS_R, CS_SOP, CS_EPH = 1, 2, 4, 16, 32
 LRCP, RLCP, RPCL, PCRL, CPRL = range(5)
 
 

@@ -12,7 +12,7 @@
  *   parsing       codestream/decompress/CodeStreamDecompress_ReadMarkers.cpp, t2/PacketParser.cpp,
  *                 t1/codeblock/CodeblockDecompressImpl.h L205-420 (HT segments: cleanup | refinement, T.814 B.10.7)
  * Scope: what this engine's path produces and consumes -- one quality layer, any of the five progression orders,
- * any number of tile parts per tile (in order), no SOP/EPH, no COC/QCC/POC/RGN/PPM/PPT, HT code blocks with 1..3
+ * any number of tile parts per tile (in order), SOP / EPH markers, no COC/QCC/POC/RGN/PPM/PPT, HT code blocks with 1..3
  * passes, the HT quantiser's QCD.  Anything else parses as "not handled".
  * Written from the standard's rules (ITU-T T.800 Annex A/B, T.814 Annex A/B), not transcribed from the reference;
  * tests decode the output with an independent decoder (OpenJPEG via Pillow / OpenCV) -- tests/test_codestream.py.
@@ -370,7 +370,8 @@ uint32_t magb_code(const b2k_coding& cp, const std::vector<BandQuant>& q)
   return 31;
 }
 
-void write_main_header(const b2k_coding& cp, const TileGrid& g, const std::vector<BandQuant>& q, std::vector<uint8_t>& o, int prog)
+void write_main_header(const b2k_coding& cp, const TileGrid& g, const std::vector<BandQuant>& q, std::vector<uint8_t>& o, int prog,
+                       bool sop, bool eph)
 {
   put16(o, 0xFF4F); /* SOC */
   put16(o, 0xFF51); /* SIZ (T.800 A.5.1) */
@@ -400,7 +401,7 @@ void write_main_header(const b2k_coding& cp, const TileGrid& g, const std::vecto
     user_prec |= (cp.prcw_exp[r] && cp.prcw_exp[r] != 15) || (cp.prch_exp[r] && cp.prch_exp[r] != 15);
   put16(o, 0xFF52); /* COD (A.6.1) */
   put16(o, 12 + (user_prec ? cp.numres : 0));
-  o.push_back(user_prec ? 1 : 0);
+  o.push_back((uint8_t)((user_prec ? 1 : 0) | (sop ? 2 : 0) | (eph ? 4 : 0)));
   o.push_back((uint8_t)prog); /* progression order */
   put16(o, 1);    /* layers */
   o.push_back(cp.mct ? 1 : 0);
@@ -456,8 +457,9 @@ struct TilePlan
 };
 
 int plan_tile_packets(const b2k_coding& cp, const Rect& tile, const b2k_block* blk, uint32_t nblk, uint64_t arena_len,
-                      TilePlan& plan, std::string& err, int prog)
+                      TilePlan& plan, std::string& err, int prog, bool sop, bool eph)
 {
+  uint32_t nsop = 0;
   std::vector<Packet> pkts;
   uint32_t expect = 0;
   tile_packets(cp, tile, pkts, expect, prog);
@@ -471,6 +473,13 @@ int plan_tile_packets(const b2k_coding& cp, const Rect& tile, const b2k_block* b
   for(const Packet& pk : pkts)
   {
     hdr.clear();
+    if(sop)
+    { /* SOP (A.8.1): marker, Lsop = 4, packet counter modulo 65536 (T2Compress.cpp L420-438) */
+      const uint8_t m[6] = {0xFF, 0x91, 0, 4, (uint8_t)(nsop >> 8), (uint8_t)nsop};
+      hdr.insert(hdr.end(), m, m + 6);
+      nsop = (nsop + 1) & 0xFFFF;
+    }
+    const size_t bits_at = hdr.size();
     BitWriter bw(hdr);
     bw.put(1); /* non-empty packet; like the reference also when it carries no block (T2Compress.cpp L304-307) */
     for(int b = 0; b < pk.nbands; ++b)
@@ -529,6 +538,12 @@ int plan_tile_packets(const b2k_coding& cp, const Rect& tile, const b2k_block* b
       }
     }
     bw.flush();
+    (void)bits_at;
+    if(eph)
+    { /* EPH (A.8.2) */
+      hdr.push_back(0xFF);
+      hdr.push_back(0x92);
+    }
     plan.hdrs.insert(plan.hdrs.end(), hdr.begin(), hdr.end());
     plan.hdr_len.push_back((uint32_t)hdr.size());
     plan.res_of.push_back(pk.resno);
@@ -659,7 +674,8 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(c
     return -1;
   }
   const bool split_res = (flags & B2K_CS_TPARTS_R) != 0 && prog <= 2; /* a tile part per resolution needs a resolution-major order */
-  write_main_header(*cp, g, q, head, prog);
+  const bool sop = (flags & B2K_CS_SOP) != 0, eph = (flags & B2K_CS_EPH) != 0;
+  write_main_header(*cp, g, q, head, prog, sop, eph);
 
   /* plan every tile part (their lengths feed TLM), then lay the codestream out */
   std::vector<TilePlan> plans(ntiles);
@@ -683,7 +699,7 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(c
   b2k_host_parallel(ntiles, [&](size_t t) { /* tiles are independent: plan them on the host pool */
     TilePlan& P = plans[t];
     if(plan_tile_packets(*cp, tile_rect(*cp, g, (uint32_t)t), r->blocks + tile_first[t], (uint32_t)(tile_first[t + 1] - tile_first[t]),
-                         r->num_bytes, P, errs[t], prog))
+                         r->num_bytes, P, errs[t], prog, sop, eph))
     {
       if(errs[t].empty())
         errs[t] = "tile planning failed";
@@ -787,7 +803,7 @@ struct ByteRange
   const uint8_t *begin, *end;
 };
 int parse_tile_packets(const b2k_coding& cp, const Rect& tile, b2k_block* tb, const std::vector<ByteRange>& parts,
-                       const uint8_t* base, int prog, std::string& err)
+                       const uint8_t* base, int prog, bool sop, bool eph, std::string& err)
 {
   std::vector<Packet> pkts;
   uint32_t nblk = 0;
@@ -815,6 +831,8 @@ int parse_tile_packets(const b2k_coding& cp, const Rect& tile, b2k_block* tb, co
     }
     if(p == tp_end)
       break; /* the tile's data ends here (truncated or resolution-progressive file): what follows stays uncoded */
+    if(sop && tp_end - p >= 6 && p[0] == 0xFF && p[1] == 0x91)
+      p += 6; /* SOP may be there when COD allows it (A.8.1) */
     BitReader br(p, tp_end);
     order.clear();
     if(br.get())
@@ -883,6 +901,12 @@ int parse_tile_packets(const b2k_coding& cp, const Rect& tile, b2k_block* tb, co
     if(br.overrun)
       return fail("packet header runs past the tile part", -1);
     p = br.finish();
+    if(eph)
+    { /* EPH shall follow every packet header when COD says so (A.8.2) */
+      if(tp_end - p < 2 || p[0] != 0xFF || p[1] != 0x92)
+        return fail("EPH marker missing after a packet header", -1);
+      p += 2;
+    }
     for(const Seg& sg : order)
     {
       if((uint64_t)(tp_end - p) < sg.n)
@@ -940,6 +964,7 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
   memset(&cp, 0, sizeof(cp));
   bool have_siz = false, have_cod = false, have_qcd = false, have_cap = false;
   int progression = 0;
+  bool use_sop = false, use_eph = false;
   std::vector<uint32_t> qcd_vals;
   uint32_t sqcd = 0;
   /* ---- main header ---- */
@@ -1004,8 +1029,8 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
       }
       case 0xFF52: {
         const uint32_t scod = s.u8();
-        if(scod & 0x06)
-          return fail("SOP / EPH markers are not handled", 1);
+        use_sop = (scod & 0x02) != 0;
+        use_eph = (scod & 0x04) != 0;
         const uint32_t prog = s.u8(), layers = s.u16(), mct = s.u8();
         cp.mct = (uint8_t)mct;
         const uint32_t nd = s.u8();
@@ -1205,7 +1230,7 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
       return;
     }
     if(!tile_parts[t].empty()) /* a tile without a tile part decodes as all zero (blocks stay uncoded) */
-      rcs[t] = parse_tile_packets(cp, tile_rect(cp, g, (uint32_t)t), tb.data(), tile_parts[t], cs, progression, errs[t]);
+      rcs[t] = parse_tile_packets(cp, tile_rect(cp, g, (uint32_t)t), tb.data(), tile_parts[t], cs, progression, use_sop, use_eph, errs[t]);
     memcpy(blocks + tile_first[t], tb.data(), tb.size() * sizeof(b2k_block));
   });
   for(uint32_t t = 0; t < ntiles; ++t)

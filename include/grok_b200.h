@@ -432,6 +432,8 @@ B2K_API uint64_t b2k_job_num_blocks(const b2k_device_job* j);
  * is damaged. */
 #define B2K_CS_TLM 1u
 #define B2K_CS_PLT 2u
+#define B2K_CS_SOP 16u                     /* SOP marker segment before every packet */
+#define B2K_CS_EPH 32u                     /* EPH marker after every packet header */
 #define B2K_CS_TPARTS_R 4u                 /* one tile part per resolution (LRCP / RLCP / RPCL only), cf. grk_compress -u R */
 #define B2K_CS_PROG(n) (((n) & 7u) << 8)   /* progression order: 0 LRCP (default), 1 RLCP, 2 RPCL, 3 PCRL, 4 CPRL */
 B2K_API int64_t b2k_codestream_write(const b2k_coding* cp, const b2k_result* r, uint32_t flags, uint8_t* out, uint64_t cap);

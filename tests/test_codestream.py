@@ -285,3 +285,19 @@ def test_explicit_qcd_exponents(irreversible):
     cp3 = G.make_coding(w, h, 3, 8, numres=4, irreversible=irreversible)
     t3, d3, _ = oracle_encode(cp3, planes)
     assert G.codestream_parse(G.codestream_write(cp3, t3, d3))[0].qcd_explicit == 0
+
+
+@pytest.mark.parametrize("flags", [G.CS_SOP, G.CS_EPH, G.CS_SOP | G.CS_EPH | G.CS_PLT | G.CS_TPARTS_R])
+def test_sop_and_eph_markers(flags):
+    cp = G.make_coding(150, 100, 3, 8, numres=4, tile=(64, 64), precincts=[(32, 32)])
+    planes = P.synthetic_image(150, 100, 3, 8, seed=52)
+    table, data, _ = oracle_encode(cp, planes)
+    cs = G.codestream_write(cp, table, data, flags)
+    assert (bytes(cs).count(b"\xff\x91\x00\x04") > 0) == bool(flags & G.CS_SOP)
+    got = openjpeg_pillow(cs)
+    assert np.array_equal(got.astype(np.int64), np.stack(planes, axis=-1))
+    cp2, blocks = G.codestream_parse(cs)
+    assert np.array_equal(blocks["length"], table["length"]) and np.array_equal(blocks["numbps"], table["numbps"])
+    for k in range(0, len(table), 3):
+        o, n = int(blocks[k]["offset"]), int(blocks[k]["length"])
+        assert np.array_equal(cs[o:o + n], data[int(table[k]["offset"]):int(table[k]["offset"]) + n])
