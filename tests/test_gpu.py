@@ -25,6 +25,11 @@ GEOMS = [
          cblk=(16, 128)),
     dict(width=700, height=500, numcomps=3, prec=12, numres=5, tile=(512, 256), origin=(5, 11), precincts=[(128, 128)]),  # many precincts
     dict(width=260, height=140, numcomps=3, prec=16, sgnd=True, numres=4, numgbits=2),                                   # signed 16 bit, 2 guard bits
+    dict(width=2100, height=40, numcomps=1, prec=10, numres=2, cblk=(1024, 4)),                                           # widest code blocks
+    dict(width=40, height=2100, numcomps=1, prec=10, numres=2, cblk=(4, 1024)),                                           # tallest code blocks
+    dict(width=500, height=300, numcomps=3, prec=12, numres=3, cblk=(128, 32)),
+    dict(width=300, height=500, numcomps=1, prec=9, numres=3, cblk=(32, 128), tile=(150, 250)),
+    dict(width=700, height=90, numcomps=1, prec=8, numres=3, cblk=(256, 16)),
 ]
 
 
