@@ -301,3 +301,38 @@ def test_sop_and_eph_markers(flags):
     for k in range(0, len(table), 3):
         o, n = int(blocks[k]["offset"]), int(blocks[k]["length"])
         assert np.array_equal(cs[o:o + n], data[int(table[k]["offset"]):int(table[k]["offset"]) + n])
+
+
+def test_parser_tolerates_what_the_standard_allows():
+    """Things other writers do: a COM segment in the main and in a tile-part header, Psot = 0 on the last tile part
+    ("until EOC"), a missing EOC, no TLM / PLT, unknown informative marker segments."""
+    cp = G.make_coding(130, 90, 1, 8, numres=3, tile=(64, 64))
+    planes = P.synthetic_image(130, 90, 1, 8, seed=53)
+    table, data, _ = oracle_encode(cp, planes)
+    cs = bytes(G.codestream_write(cp, table, data, 0))
+
+    def check(buf):
+        buf = np.frombuffer(buf, np.uint8)
+        cp2, blocks = G.codestream_parse(buf)
+        assert np.array_equal(blocks["length"], table["length"])
+        rec = oracle_decode(cp2, blocks, buf)
+        assert np.array_equal(rec[0], planes[0])
+
+    check(cs)
+    com = b"\xff\x64" + (2 + 2 + 5).to_bytes(2, "big") + b"\x00\x01hello"
+    i = cs.find(b"\xff\x52")                                    # before COD
+    check(cs[:i] + com + cs[i:])
+    # COM inside the first tile-part header: Psot grows by its length
+    j = cs.find(b"\xff\x90")
+    psot = int.from_bytes(cs[j + 6:j + 10], "big")
+    tp = cs[j:j + 12][:6] + (psot + len(com)).to_bytes(4, "big") + cs[j + 10:j + 12]
+    check(cs[:j] + tp + com + cs[j + 12:])
+    # unknown informative segment (0xFF30-0xFF3F have no parameters and are not used here; take 0xFF70 with a length)
+    unk = b"\xff\x70" + (2 + 3).to_bytes(2, "big") + b"abc"
+    check(cs[:i] + unk + cs[i:])
+    # last tile part with Psot = 0, with and without EOC
+    k = cs.rfind(b"\xff\x90\x00\x0a")
+    last0 = cs[:k + 6] + b"\x00\x00\x00\x00" + cs[k + 10:]
+    check(last0)
+    check(last0[:-2])
+    check(cs[:-2])                                              # EOC missing, Psot intact
