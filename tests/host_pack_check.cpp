@@ -1,5 +1,6 @@
 // CPU check of grok_b200/csrc/host_pack.cpp (container conversion + fork-join pool); built and run by tests/test_host.py
 #include "../grok_b200/csrc/b2k_internal.h"
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -41,6 +42,24 @@ int main()
             if(back[y * ss + x] != -7) ++bad;
         }
       }
+  }
+  /* fork-join pool under churn: resized pools, spinning sessions on and off, empty and tiny loops -- every index
+     must be visited exactly once */
+  for(int round = 0; round < 24; ++round)
+  {
+    b2k_host_set_threads(1 + (int)(next() % 8));
+    const bool hot = next() & 1;
+    if(hot) b2k_host_session(true);
+    for(int it = 0; it < 1000; ++it)
+    {
+      const size_t n = next() % 40;
+      std::vector<std::atomic<int>> hits(n);
+      for(auto& h : hits) h.store(0);
+      b2k_host_parallel(n, [&](size_t i) { hits[i].fetch_add(1); });
+      for(size_t i = 0; i < n; ++i)
+        if(hits[i].load() != 1) ++bad;
+    }
+    if(hot) b2k_host_session(false);
   }
   b2k_host_set_threads(0);
   if(b2k_host_threads() != 0) ++bad;
