@@ -336,3 +336,24 @@ def test_parser_tolerates_what_the_standard_allows():
     check(last0)
     check(last0[:-2])
     check(cs[:-2])                                              # EOC missing, Psot intact
+
+
+@pytest.mark.parametrize("args", CASES[:5] + [dict(width=290, height=203, numcomps=3, prec=8, numres=4, tile=(128, 96), origin=(5, 3),
+                                                   tile_origin=(2, 1), precincts=[(16, 16), (32, 16), (32, 64), (64, 64)], cblk=(16, 16))])
+def test_writer_matches_the_python_t2_oracle_byte_for_byte(args):
+    """Two implementations of the T2 step, written independently (grok_b200/csrc/codestream.cpp in C++, tests/oracle_t2.py
+    as a plain restatement of T2Compress.cpp / the marker writers): identical codestreams, byte for byte, with and
+    without TLM + PLT -- and OpenJPEG decodes the oracle's stream as well."""
+    import oracle_t2 as T2
+    cp = G.make_coding(**args)
+    planes = P.synthetic_image(args["width"], args["height"], args["numcomps"], args["prec"], seed=21,
+                               origin=args.get("origin", (0, 0)))
+    table, data, _ = oracle_encode(cp, planes)
+    for tlm_plt in (False, True):
+        want = T2.write_codestream(cp, table, data, tlm=tlm_plt, plt=tlm_plt)
+        got = G.codestream_write(cp, table, data, (G.CS_TLM | G.CS_PLT) if tlm_plt else 0)
+        assert len(want) == len(got) and np.array_equal(want, got)
+    if args["prec"] == 8 or args["numcomps"] == 1:
+        dec = openjpeg_pillow(want)
+        src = planes[0] if len(planes) == 1 else np.stack(planes, axis=-1)
+        assert np.array_equal(dec.astype(np.int64), src)
