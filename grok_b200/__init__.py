@@ -64,7 +64,7 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_roundtrip_n", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
            "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last",
-           "b2k_codestream_write", "b2k_codestream_parse", "b2k_jph_wrap", "b2k_jph_codestream"]
+           "b2k_codestream_write", "b2k_codestream_parse", "b2k_jph_wrap", "b2k_jph_codestream", "b2k_result_merge"]
 
 _lib = None
 
@@ -118,6 +118,7 @@ def lib():
     L.b2k_codestream_write.restype = C.c_int64
     L.b2k_codestream_parse.argtypes = [vp, u64, C.POINTER(Coding), vp, u64]
     L.b2k_codestream_parse.restype = C.c_int64
+    L.b2k_result_merge.argtypes = [C.POINTER(Coding), C.POINTER(C.POINTER(Result)), u32, C.POINTER(C.POINTER(Result))]
     L.b2k_jph_wrap.argtypes = [C.POINTER(Coding), vp, u64, vp, u64]
     L.b2k_jph_wrap.restype = C.c_int64
     L.b2k_jph_codestream.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(u64)]
@@ -225,6 +226,28 @@ def codestream_parse(cs):
     if m != n:
         raise (NotHandled if m == 1 else EngineError)("b2k_codestream_parse: " + (lib().b2k_last_error() or b"").decode())
     return cp, blocks
+
+
+def result_from_tables(blocks, data, num_tiles):
+    """A ctypes Result viewing a numpy block table + byte arena (keep both alive while it is in use)."""
+    r = Result()
+    r.num_blocks = len(blocks)
+    r.blocks = C.cast(blocks.ctypes.data, C.POINTER(Block))
+    r.bytes = C.cast(data.ctypes.data, C.POINTER(C.c_uint8))
+    r.num_bytes = len(data)
+    r.num_tiles = num_tiles
+    return r
+
+
+def merge_shards(cp, shards):
+    """shards: [(block table, byte arena)] of ranks 0..n-1 (rank r coded the tiles t % n == r) -> EncodeResult holding
+    every tile in enumeration order (b2k_result_merge)."""
+    keep = [(np.ascontiguousarray(b, dtype=BLOCK_DTYPE), np.ascontiguousarray(d, dtype=np.uint8)) for b, d in shards]
+    rs = [result_from_tables(b, d, 0) for b, d in keep]
+    arr = (C.POINTER(Result) * len(rs))(*[C.pointer(r) for r in rs])
+    out = C.POINTER(Result)()
+    _check(lib().b2k_result_merge(C.byref(cp), arr, len(rs), C.byref(out)), "b2k_result_merge")
+    return EncodeResult(out)
 
 
 def jph_wrap(cp, cs):

@@ -1372,6 +1372,7 @@ struct PinnedPool
   std::mutex mu;
   std::vector<std::pair<uint8_t*, uint64_t>> free_list;
   std::vector<std::pair<uint8_t*, uint64_t>> live;
+  std::vector<uint8_t*> heap; /* arenas that had to come from malloc (no CUDA device: b2k_result_merge on a writer-only host) */
 };
 static PinnedPool g_pool;
 static uint8_t* pool_get(uint64_t bytes)
@@ -1395,6 +1396,13 @@ static uint8_t* pool_get(uint64_t bytes)
 static void pool_put(uint8_t* p)
 {
   std::lock_guard<std::mutex> lock(g_pool.mu);
+  for(size_t i = 0; i < g_pool.heap.size(); ++i)
+    if(g_pool.heap[i] == p)
+    {
+      g_pool.heap.erase(g_pool.heap.begin() + i);
+      free(p);
+      return;
+    }
   for(size_t i = 0; i < g_pool.live.size(); ++i)
     if(g_pool.live[i].first == p)
     {
@@ -1488,6 +1496,100 @@ extern "C" void b2k_result_free(b2k_result* r)
   free(r->blocks);
   if(r->bytes) pool_put(r->bytes);
   delete r;
+}
+
+/* Merge the results of ranks that each coded the tiles t with t % nshards == rank (tile_mod / tile_rem of b2k_encode)
+   into one result in full enumeration order -- what the writer rank needs for b2k_codestream_write after gathering the
+   shards' block tables and byte arenas.  The shards are not modified; free the merged result with
+   b2k_result_free. */
+extern "C" int32_t b2k_result_merge(const b2k_coding* cp, const b2k_result* const* shards, uint32_t nshards, b2k_result** out)
+{
+  if(!cp || !shards || !nshards || !out)
+    return -1;
+  if(const char* why = unsupported_reason(*cp))
+  {
+    g_err = why;
+    return -1;
+  }
+  const TileGrid g = tile_grid(*cp);
+  const uint32_t ntiles = g.nx * g.ny;
+  const std::vector<BandQuant> q = band_quant(*cp);
+  std::vector<b2k_block> all;
+  for(uint32_t t = 0; t < ntiles; ++t)
+    enumerate_tile_blocks(*cp, t, tile_rect(*cp, g, t), q, all);
+  uint64_t total_bytes = 0;
+  std::vector<uint64_t> base(nshards, 0);
+  for(uint32_t s = 0; s < nshards; ++s)
+  {
+    if(!shards[s])
+    {
+      g_err = "missing shard";
+      return -1;
+    }
+    base[s] = total_bytes;
+    total_bytes += shards[s]->num_bytes;
+  }
+  b2k_result* R = new b2k_result();
+  memset(R, 0, sizeof(*R));
+  R->num_blocks = all.size();
+  R->num_tiles = ntiles;
+  R->num_bytes = total_bytes;
+  R->blocks = (b2k_block*)malloc(sizeof(b2k_block) * std::max<size_t>(1, all.size()));
+  uint8_t* arena = nullptr;
+  if(cudaHostAlloc(&arena, std::max<uint64_t>(64, total_bytes), cudaHostAllocDefault) == cudaSuccess)
+  {
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    g_pool.live.push_back({arena, std::max<uint64_t>(64, total_bytes)});
+  }
+  else
+  {
+    (void)cudaGetLastError();
+    arena = (uint8_t*)malloc(std::max<uint64_t>(64, total_bytes));
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    g_pool.heap.push_back(arena);
+  }
+  R->bytes = arena;
+  if(!R->blocks || !arena)
+  {
+    b2k_result_free(R);
+    g_err = "out of memory";
+    return -1;
+  }
+  std::vector<uint64_t> next(nshards, 0);
+  for(size_t i = 0; i < all.size(); ++i)
+  {
+    const uint32_t s = all[i].tile % nshards;
+    const b2k_result* S = shards[s];
+    if(next[s] >= S->num_blocks)
+    {
+      b2k_result_free(R);
+      g_err = "a shard holds fewer blocks than its tiles have";
+      return -1;
+    }
+    const b2k_block& b = S->blocks[next[s]++];
+    if(b.tile != all[i].tile || b.comp != all[i].comp || b.resno != all[i].resno || b.band_index != all[i].band_index ||
+       b.precno != all[i].precno || b.cblkno != all[i].cblkno)
+    {
+      b2k_result_free(R);
+      g_err = "a shard's block table is not the enumeration of the tiles t % nshards == shard";
+      return -1;
+    }
+    R->blocks[i] = b;
+    R->blocks[i].offset = b.offset + base[s];
+  }
+  for(uint32_t s = 0; s < nshards; ++s)
+  {
+    if(next[s] != shards[s]->num_blocks)
+    {
+      b2k_result_free(R);
+      g_err = "a shard holds more blocks than its tiles have";
+      return -1;
+    }
+    if(shards[s]->num_bytes)
+      memcpy(arena + base[s], shards[s]->bytes, shards[s]->num_bytes);
+  }
+  *out = R;
+  return 0;
 }
 
 /* ---- one-call host paths ---------------------------------------------------------------------- */

@@ -419,6 +419,10 @@ B2K_API int32_t b2k_job_t1_decode_blocks(b2k_device_job* j, const b2k_block* blo
 /* fetch coded blocks of the last b2k_job_t1_encode as a host result */
 B2K_API int32_t b2k_job_fetch_result(b2k_device_job* j, b2k_result** out);
 B2K_API uint64_t b2k_job_num_blocks(const b2k_device_job* j);
+/* Merge per-rank results (rank r coded the tiles t with t % nshards == r) into one result in full enumeration order,
+ * for the writer rank after it has gathered the shards (block tables + byte arenas).  Free with b2k_result_free. */
+B2K_API int32_t b2k_result_merge(const b2k_coding* cp, const b2k_result* const* shards, uint32_t nshards, b2k_result** out);
+
 /* ---- codestream assembly / parsing on the host (the T2 step) -------------------------
  * b2k_codestream_write: a complete HTJ2K codestream (SOC, SIZ, CAP, COD, QCD, [TLM], per tile SOT [PLT] SOD
  * + packets, EOC; one layer, any of the five progression orders, optionally a tile part per resolution) from an

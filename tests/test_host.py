@@ -252,15 +252,11 @@ if rank == 0:
     dist.gather(tab, tabs, dst=0)
     segs = [s[:n] for s, (n, _) in zip(segs, sizes)]
     tabs = [t[:k * G.BLOCK_DTYPE.itemsize] for t, (_, k) in zip(tabs, sizes)]
-    full = G.enumerate_blocks(cp)
-    base = 0
-    for r in range(world):
-        tb = np.frombuffer(tabs[r].numpy().tobytes(), dtype=G.BLOCK_DTYPE).copy()
-        tb["offset"] += base
-        full[np.nonzero(full["tile"] %% world == r)[0]] = tb
-        base += sizes[r][0]
-    data = np.concatenate([s.numpy() for s in segs])
-    cs = G.codestream_write(cp, full, data)          # ONE tiled codestream, tile parts in index order
+    shards = [(np.frombuffer(tabs[r].numpy().tobytes(), dtype=G.BLOCK_DTYPE), segs[r].numpy()) for r in range(world)]
+    merged = G.merge_shards(cp, shards)              # b2k_result_merge: full enumeration order, offsets rebased
+    assert merged.num_tiles == len(rects) and merged.num_blocks == len(G.enumerate_blocks(cp))
+    cs = G.codestream_write(cp, merged.blocks, merged.bytes, num_tiles=merged.num_tiles)   # ONE tiled codestream
+    merged.free()
     from PIL import Image
     im = Image.open(io.BytesIO(cs.tobytes())); im.load()
     assert np.array_equal(np.asarray(im).astype(np.int64), np.stack(planes, axis=-1)), "OpenJPEG does not give the source back"

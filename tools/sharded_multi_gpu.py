@@ -80,19 +80,11 @@ def main():
     ok = True
     if rank == 0:
         # writer side: merge the per-rank tables into the full enumeration order and decode everything
-        full = G.enumerate_blocks(cp)
-        arena = []
-        base_off = 0
         if world > 1:
-            for r in range(world):
-                tb = np.frombuffer(tabs[r].cpu().numpy().tobytes(), dtype=G.BLOCK_DTYPE).copy()
-                sel = np.nonzero(full["tile"] % world == r)[0]
-                assert len(sel) == len(tb)
-                tb["offset"] += base_off
-                full[sel] = tb
-                arena.append(segs[r].cpu().numpy())
-                base_off += sizes[r][0]
-            data = np.concatenate(arena)
+            merged = G.merge_shards(cp, [(np.frombuffer(tabs[r].cpu().numpy().tobytes(), dtype=G.BLOCK_DTYPE), segs[r].cpu().numpy())
+                                         for r in range(world)])          # b2k_result_merge
+            full, data = merged.blocks.copy(), merged.bytes.copy()
+            merged.free()
         else:
             full, data = res.blocks.copy(), res.bytes.copy()
         out = [np.zeros((H, W), np.int32) for _ in range(a.comps)]
