@@ -355,10 +355,22 @@ uint32_t magb_code(const b2k_coding& cp, const std::vector<BandQuant>& q)
   {
     if(!cp.irreversible)
       B = std::max<uint32_t>(B, (uint32_t)q[i].expn + cp.numgbits - 1u);
-    else
-    {
+    else if(cp.qcd_explicit)
+    { /* foreign step sizes: the bound T.814 asks for (the "scalar expounded" branch of get_MAGBp) */
       const int nb = ndecomp - (i ? (int)((i - 1) / 3) : 0);
       B = std::max<uint32_t>(B, (uint32_t)std::max(0, (int)q[i].expn + (int)cp.numgbits - nb));
+    }
+    else
+    { /* What the reference actually writes: its Sqcd never carries the quantisation style (Quantizer.cpp L24), so
+         get_MAGBp takes the reversible branch and scans the first 3*ndecomp+1 BYTES of the 16-bit (exponent << 11 |
+         mantissa) array through the u8/u16 union (Quantizer.h L52-57, little endian).  A looser bound than the
+         standard's, still a valid one; mirrored so that main headers stay byte-identical to grk_compress's. */
+      if(i >= (size_t)(3 * ndecomp + 1))
+        break;
+      const BandQuant& w = q[i / 2];
+      const uint32_t word = ((uint32_t)w.expn << 11) | (uint32_t)w.mant;
+      const uint32_t byte = (i & 1) ? (word >> 8) & 0xFF : word & 0xFF;
+      B = std::max<uint32_t>(B, (byte >> 3) + cp.numgbits - 1u);
     }
   }
   if(B <= 8)
@@ -1057,6 +1069,10 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
             const uint32_t v = s.u8();
             cp.prcw_exp[r] = (uint8_t)(v & 0xF);
             cp.prch_exp[r] = (uint8_t)(v >> 4);
+            /* PPx / PPy = 0 (1-sample precincts, legal at resolution 0 only): b2k_coding reads exponent 0 as
+               "default 15", so such a stream is declined rather than enumerated wrongly */
+            if(s.ok && ((v & 0xF) == 0 || (v >> 4) == 0))
+              return fail("precinct exponent 0 is not handled", 1);
           }
         have_cod = s.ok;
         break;

@@ -240,7 +240,8 @@ __device__ __forceinline__ void fetch97(const DwtLevelDesc& D, const Job& J, int
       {
         const float r = (float)(raw[0][i] + D.shift[0]), g = (float)(raw[1][i] + D.shift[1]),
                     b = (float)(raw[2][i] + D.shift[2]);
-        const float y = __fadd_rn(__fadd_rn(__fmul_rn(a_r, r), __fmul_rn(a_g, g)), __fmul_rn(a_b, b));
+        /* the reference build contracts a_r*r + a_g*g + a_b*b into two FMAs (pinned against libgrokj2k, tests/test_interop.py) */
+        const float y = __fmaf_rn(a_b, b, __fmaf_rn(a_g, g, __fmul_rn(a_r, r)));
         out[0][i] = y;
         out[1][i] = __fmul_rn(cb, __fsub_rn(b, y));
         out[2][i] = __fmul_rn(cr, __fsub_rn(r, y));
@@ -823,7 +824,8 @@ __device__ __forceinline__ void ict_fwd_convert(const DwtLevelDesc& D, const int
       {
         const float r = (float)(raw[0][i] + D.shift[0]), g = (float)(raw[NC > 1 ? 1 : 0][i] + D.shift[1]),
                     b = (float)(raw[NC > 2 ? 2 : 0][i] + D.shift[2]);
-        const float y = __fadd_rn(__fadd_rn(__fmul_rn(a_r, r), __fmul_rn(a_g, g)), __fmul_rn(a_b, b));
+        /* the reference build contracts a_r*r + a_g*g + a_b*b into two FMAs (pinned against libgrokj2k, tests/test_interop.py) */
+        const float y = __fmaf_rn(a_b, b, __fmaf_rn(a_g, g, __fmul_rn(a_r, r)));
         out[0][i] = y;
         out[NC > 1 ? 1 : 0][i] = __fmul_rn(cb, __fsub_rn(b, y));
         out[NC > 2 ? 2 : 0][i] = __fmul_rn(cr, __fsub_rn(r, y));
@@ -1110,11 +1112,11 @@ __device__ __forceinline__ void store_rows97(const DwtLevelDesc& D, const Job& J
       if(NC == 3)
       { /* mct.cpp L318-391 */
         const float y = x[0][i], u = x[1][i], w = x[2][i];
-        f[0] = __fadd_rn(y, __fmul_rn(w, 1.402f));
+        f[0] = __fmaf_rn(w, 1.402f, y); /* FMA / FNMA as the reference build contracts them (tests/test_interop.py) */
         if(NC > 1)
-          f[NC > 1 ? 1 : 0] = __fsub_rn(__fsub_rn(y, __fmul_rn(u, 0.34413f)), __fmul_rn(w, 0.71414f));
+          f[NC > 1 ? 1 : 0] = __fmaf_rn(-w, 0.71414f, __fmaf_rn(-u, 0.34413f, y));
         if(NC > 2)
-          f[NC > 2 ? 2 : 0] = __fadd_rn(y, __fmul_rn(u, 1.772f));
+          f[NC > 2 ? 2 : 0] = __fmaf_rn(u, 1.772f, y);
       }
       else
         f[0] = x[0][i];
@@ -1525,9 +1527,9 @@ __device__ __forceinline__ void store_rows97_fast(const DwtLevelDesc& D, const O
       if(NC == 3)
       { /* mct.cpp L318-391 */
         const float y = x[0][i], u = x[NC > 1 ? 1 : 0][i], w = x[NC > 2 ? 2 : 0][i];
-        f[0] = __fadd_rn(y, __fmul_rn(w, 1.402f));
-        f[NC > 1 ? 1 : 0] = __fsub_rn(__fsub_rn(y, __fmul_rn(u, 0.34413f)), __fmul_rn(w, 0.71414f));
-        f[NC > 2 ? 2 : 0] = __fadd_rn(y, __fmul_rn(u, 1.772f));
+        f[0] = __fmaf_rn(w, 1.402f, y); /* FMA / FNMA as the reference build contracts them (tests/test_interop.py) */
+        f[NC > 1 ? 1 : 0] = __fmaf_rn(-w, 0.71414f, __fmaf_rn(-u, 0.34413f, y));
+        f[NC > 2 ? 2 : 0] = __fmaf_rn(u, 1.772f, y);
       }
       else
         f[0] = x[0][i];

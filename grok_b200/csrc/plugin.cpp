@@ -107,17 +107,35 @@ static bool coding_from_gpup(const gpup_compress_params* p, const gpup_image* im
     cp->prcw_exp[r] = 15;
     cp->prch_exp[r] = 15;
   }
-  if(p->csty & 1)
-    for(uint32_t r = 0; r < p->res_spec && r < 33; ++r)
-    { /* CodeStreamCompress.cpp L805-837: specified coarsest-last */
-      const uint32_t pw = p->prcw_init[r], ph = p->prch_init[r];
-      const int rr = (int)p->numresolution - 1 - (int)r;
-      if(rr >= 0 && pw && ph)
+  if((p->csty & 1) && p->res_spec)
+  { /* CodeStreamCompress.cpp L793-825: sizes are given finest resolution first; once the list runs out every
+       coarser resolution takes the last given size halved again per level; a size below 1 means exponent 1 */
+    const uint32_t spec = p->res_spec < 33 ? p->res_spec : 33;
+    uint32_t k = 0;
+    for(int rr = (int)p->numresolution - 1; rr >= 0; --rr, ++k)
+    {
+      uint32_t pw, ph;
+      if(k < spec)
       {
-        cp->prcw_exp[rr] = (uint8_t)floor_log2_u32(pw);
-        cp->prch_exp[rr] = (uint8_t)floor_log2_u32(ph);
+        pw = p->prcw_init[k];
+        ph = p->prch_init[k];
+      }
+      else
+      {
+        const uint32_t sh = k - (spec - 1);
+        pw = sh < 32 ? p->prcw_init[spec - 1] >> sh : 0;
+        ph = sh < 32 ? p->prch_init[spec - 1] >> sh : 0;
+      }
+      const int ew = pw < 1 ? 1 : floor_log2_u32(pw), eh = ph < 1 ? 1 : floor_log2_u32(ph);
+      if(ew < 1 || eh < 1 || ew > 15 || eh > 15)
+        return false; /* 1-sample precincts: b2k_coding reads exponent 0 as "default"; left to the host */
+      if(rr < 33)
+      {
+        cp->prcw_exp[rr] = (uint8_t)ew;
+        cp->prch_exp[rr] = (uint8_t)eh;
       }
     }
+  }
   return unsupported_reason(*cp) == nullptr;
 }
 

@@ -90,6 +90,9 @@ int init_decompressors(gpup_header_info* h, gpup_image* image)
   {
     cp.prcw_exp[r] = r < h->numresolutions && h->prcw_init[r] ? (uint8_t)floor_log2_u32(h->prcw_init[r]) : 15;
     cp.prch_exp[r] = r < h->numresolutions && h->prch_init[r] ? (uint8_t)floor_log2_u32(h->prch_init[r]) : 15;
+    /* the host hands 1 << PPx; PPx = 0 would read as "default" in b2k_coding -> leave such streams to the host */
+    if(r < h->numresolutions && (h->prcw_init[r] == 1 || h->prch_init[r] == 1))
+      return 0;
   }
   if(unsupported_reason(cp))
     return 0;

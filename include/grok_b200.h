@@ -293,7 +293,8 @@ typedef struct b2k_coding
   uint8_t irreversible;            /* 0: 5/3 + RCT, 1: 9/7 + ICT */
   uint8_t mct;                     /* 1: colour transform on components 0..2 */
   uint8_t numgbits;                /* guard bits; Grok's HT CLI forces 1 (GrkCompress.cpp L849) */
-  uint8_t prcw_exp[33], prch_exp[33]; /* precinct exponents per resolution (15 = maximal) */
+  uint8_t prcw_exp[33], prch_exp[33]; /* precinct exponents per resolution, 1..15 (15 = maximal); 0 reads as 15.
+                                         A true exponent 0 (1-sample precincts) is declined by every entry point */
   uint8_t cblk_sty;                /* code-block style bits (COD); only 0x08 = vertically stripe-causal matters,
                                       and only to the decoder's SigProp pass (CoderOJPH.cpp L248) */
   uint8_t qcd_explicit;            /* 0: band exponents / mantissas are the HT quantiser's (QuantizerOJPH.cpp L193-259),

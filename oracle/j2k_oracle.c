@@ -100,7 +100,9 @@ ORC_API void orc_ict_fwd(const int32_t* r_in, const int32_t* g_in, const int32_t
   {
     float r = (float)(r_in[i] + shift[0]), g = (float)(g_in[i] + shift[1]),
           b = (float)(b_in[i] + shift[2]);
-    float y = a_r * r + a_g * g + a_b * b;
+    /* libgrokj2k (gcc, Highway AVX2/AVX-512 targets) contracts this into fma(a_b,b, fma(a_g,g, a_r*r)); pinned against
+       the real library's code-block bytes by tests/test_interop.py */
+    float y = fmaf(a_b, b, fmaf(a_g, g, a_r * r));
     y_out[i] = y;
     cb_out[i] = cb * (b - y);
     cr_out[i] = cr * (r - y);
@@ -115,9 +117,11 @@ ORC_API void orc_ict_inv(const float* y_in, const float* cb_in, const float* cr_
   for(size_t i = 0; i < n; ++i)
   {
     float y = y_in[i], u = cb_in[i], v = cr_in[i];
-    float fr = y + v * 1.402f;
-    float fg = y - u * 0.34413f - v * 0.71414f;
-    float fb = y + u * 1.772f;
+    /* as libgrokj2k's build contracts them (FMA / FNMA); pinned against the real library's decoded pixels by
+       tests/test_interop.py */
+    float fr = fmaf(v, 1.402f, y);
+    float fg = fmaf(-v, 0.71414f, fmaf(-u, 0.34413f, y));
+    float fb = fmaf(u, 1.772f, y);
     int32_t r = (int32_t)lrintf(fr) + shift[0];
     int32_t g = (int32_t)lrintf(fg) + shift[1];
     int32_t b = (int32_t)lrintf(fb) + shift[2];

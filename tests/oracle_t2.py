@@ -7,8 +7,8 @@ so that the two can be compared byte for byte.  It follows the reference's write
                         putnumpasses, comma-coded Lblock increment, lengths, flush; bodies in band / block order)
   tag tree              t2/TagTree.h (encode with threshold, value known once written)
   bit stuffing          t1_t2 BitIO: after a 0xFF byte the next one carries 7 bits; flush appends a byte after 0xFF
-Pinning: the reference's T2 cannot be compiled from a few files (Tile object graph), so this oracle is pinned by an
-independent decoder -- OpenJPEG decodes what it writes (tests/test_codestream.py) -- not by Grok's own output.
+Pinning: whole codestreams written this way are byte-identical to grk_compress's (the real libgrokj2k built by
+baseline/build_ref.sh; tests/test_interop.py, COM marker aside), and OpenJPEG decodes them (tests/test_codestream.py).
 Pure Python loops: small cases only."""
 import numpy as np
 
@@ -146,9 +146,15 @@ def write_codestream(cp, table, data, tlm=False, plt=False):
     for i in range(len(expn)):
         if not cp.irreversible:
             B = max(B, int(expn[i]) + cp.numgbits - 1)
-        else:
+        elif cp.qcd_explicit:
             nb = (cp.numres - 1) - ((i - 1) // 3 if i else 0)
             B = max(B, max(0, int(expn[i]) + cp.numgbits - nb))
+        elif i < 3 * (cp.numres - 1) + 1:
+            # QuantizerOJPH::get_MAGBp as it actually runs (Sqcd's style bits are never set, Quantizer.cpp L24): the
+            # reversible branch over the first 3*ndecomp+1 BYTES of the little-endian 16-bit SPqcd array
+            word = (int(expn[i // 2]) << 11) | int(mant[i // 2])
+            byte = (word >> 8) & 0xFF if i & 1 else word & 0xFF
+            B = max(B, (byte >> 3) + cp.numgbits - 1)
     Bp = 0 if B <= 8 else (B - 8 if B < 28 else (13 + (B >> 2) if B < 48 else 31))
     o += b"\xff\x50" + _u16(8) + _u32(0x00020000) + _u16((0x20 if cp.irreversible else 0) | Bp)
     user = any((cp.prcw_exp[r] or 15) != 15 or (cp.prch_exp[r] or 15) != 15 for r in range(cp.numres))
