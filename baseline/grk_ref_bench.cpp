@@ -53,6 +53,11 @@ int grb_init(uint32_t threads, const char* plugin_path, int32_t device_id) {
   return plugin ? 1 : 0;
 }
 
+// frames the plugin handled since it was loaded (grk_plugin_accelerated_frames, grok.cpp L1278-1281)
+uint64_t grb_accelerated_frames() { return grk_plugin_accelerated_frames(); }
+// switch an initialised plugin in or out of grk_compress() / grk_decompress() (grok.cpp L1274-1277)
+void grb_plugin_set_enabled(int on) { grk_plugin_set_enabled(on != 0); }
+
 void grb_deinit() {
   if (g_init) grk_deinitialize();
   g_init = false;

@@ -64,7 +64,8 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_roundtrip_n", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
            "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last",
-           "b2k_codestream_write", "b2k_codestream_parse", "b2k_jph_wrap", "b2k_jph_codestream", "b2k_result_merge"]
+           "b2k_codestream_write", "b2k_codestream_parse", "b2k_jph_wrap", "b2k_jph_codestream", "b2k_result_merge",
+           "gpup_encode_mem_tiles", "gpup_tiles_free", "plugin_decompress_codestream", "b2k_coding_from_gpup"]
 
 _lib = None
 

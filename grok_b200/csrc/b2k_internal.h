@@ -5,11 +5,31 @@
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include <functional>
 #include <cuda_runtime.h>
 #include "../../include/grok_b200.h"
 
 #define B2K_WARPS_PER_CTA 4
+
+/* Runs `f` once per CUDA device (the device current at the call): cudaFuncSetAttribute settings belong to the
+ * device, and one process may hold engines on several GPUs.  Threads racing on the first call may both run `f`
+ * (the settings are idempotent); nobody launches before his own call to `f` has returned. */
+struct DeviceOnce
+{
+  std::atomic<uint64_t> done{0};
+  template <class F> void run(F&& f)
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if(!(done.load(std::memory_order_acquire) & bit))
+    {
+      f();
+      done.fetch_or(bit, std::memory_order_release);
+    }
+  }
+};
 #define B2K_MAX_RES 33
 
 /* ---- one DWT level of one tile-component (or of the 3 colour components together) ---------

@@ -1723,12 +1723,10 @@ template <int NC, bool U16, int STAGES>
 static void launch_fwd53(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
 {
   const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * RowStage<NC, U16>::PAIRB;
-  static bool once = false;
-  if(!once)
-  {
+  static DeviceOnce once; /* function attributes are per device */
+  once.run([&] {
     cudaFuncSetAttribute(k_dwt53_fwd<NC, U16, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    once = true;
-  }
+  });
   k_dwt53_fwd<NC, U16, STAGES><<<grid, block, smem, st>>>(d);
 }
 
@@ -1736,12 +1734,10 @@ template <int NC, bool U16, int STAGES>
 static void launch_fwd97(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
 {
   const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * RowStage<NC, U16>::PAIRB;
-  static bool once = false;
-  if(!once)
-  {
+  static DeviceOnce once; /* function attributes are per device */
+  once.run([&] {
     cudaFuncSetAttribute(k_dwt97_fwd<NC, U16, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    once = true;
-  }
+  });
   k_dwt97_fwd<NC, U16, STAGES><<<grid, block, smem, st>>>(d);
 }
 
@@ -1784,12 +1780,10 @@ template <int NC, int STAGES, bool OUT16>
 static void launch_inv53(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
 {
   const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * BandStage<NC>::PAIRB;
-  static bool once = false;
-  if(!once)
-  {
+  static DeviceOnce once; /* function attributes are per device */
+  once.run([&] {
     cudaFuncSetAttribute(k_dwt53_inv<NC, STAGES, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    once = true;
-  }
+  });
   k_dwt53_inv<NC, STAGES, OUT16><<<grid, block, smem, st>>>(d);
 }
 
@@ -1797,12 +1791,10 @@ template <int NC, int STAGES>
 static void launch_inv97(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
 {
   const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * BandStage<NC>::PAIRB;
-  static bool once = false;
-  if(!once)
-  {
+  static DeviceOnce once; /* function attributes are per device */
+  once.run([&] {
     cudaFuncSetAttribute(k_dwt97_inv<NC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    once = true;
-  }
+  });
   k_dwt97_inv<NC, STAGES><<<grid, block, smem, st>>>(d);
 }
 

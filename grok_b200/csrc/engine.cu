@@ -1943,9 +1943,10 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
     if(!all_uploaded && lo != UINT64_MAX)
     {
       if(lo < prev_end)
-      { /* arena not in block order: upload what is left in one go */
-        CUDA_TRY(cudaMemcpyAsync(J->d_bytes + prev_end, bytes + prev_end, num_bytes - prev_end, cudaMemcpyHostToDevice,
-                                 e->h2d_stream));
+      { /* arena not in block order (a foreign codestream whose tile parts are out of tile order, a caller arena laid
+           out some other way): ranges below prev_end that no earlier chunk covered may be needed now, so the whole
+           arena goes up once; bytes already on the device are simply written again with the same values */
+        CUDA_TRY(cudaMemcpyAsync(J->d_bytes, bytes, num_bytes, cudaMemcpyHostToDevice, e->h2d_stream));
         all_uploaded = true;
       }
       else

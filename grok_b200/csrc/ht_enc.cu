@@ -730,13 +730,11 @@ void b2k_launch_ht_encode(const HtBlockDesc* d_blocks, HtBlockOut* d_out, uint8_
   const uint32_t line_entries = ((max_w + 1) / 2 + 4 + 1) & ~1u;
   const size_t smem = 2 * 2048 * sizeof(uint16_t) + B2K_WARPS_PER_CTA * sizeof(WarpShared) +
                       (size_t)B2K_WARPS_PER_CTA * 2 * line_entries * sizeof(uint16_t);
-  static bool attr_set = false;
-  if(!attr_set)
-  {
+  static DeviceOnce once; /* function attributes are per device */
+  once.run([&] {
     cudaFuncSetAttribute(k_ht_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_ht_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr_set = true;
-  }
+  });
   const uint32_t grid = (nblocks + B2K_WARPS_PER_CTA - 1) / B2K_WARPS_PER_CTA;
   if(irreversible)
     k_ht_encode<true><<<grid, B2K_WARPS_PER_CTA * 32, smem, st>>>(d_blocks, d_out, d_scratch, nblocks, line_entries);

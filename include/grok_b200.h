@@ -270,6 +270,15 @@ B2K_API uint32_t plugin_get_debug_state(void);                    /* plugin_inte
 B2K_API int32_t gpup_encode_mem(gpup_compress_params* params, gpup_image* image,
                                 gpup_tile** out);                 /* grok.cpp L1299-1300 */
 B2K_API void gpup_tile_free(gpup_tile* tile);                     /* grok.cpp L1330 */
+/* --- optional symbols the PATCHED host resolves (baseline/patches/0001-multi-tile-plugin-encode-decode.patch;
+ * the stock contract is one tile per image, CodeStreamCompress.cpp L908-912 / CodeStreamDecompress.cpp L199-205) --- */
+/* all tiles of a multi-tile image in one call; (*out_tiles)[t] is the stock tree of tile index t in the tile's
+ * canvas coordinates; the array and the trees stay valid until gpup_tiles_free(*out_tiles, n) */
+B2K_API int32_t gpup_encode_mem_tiles(gpup_compress_params* params, gpup_image* image, gpup_tile*** out_tiles,
+                                      uint32_t* out_num_tiles);
+B2K_API void gpup_tiles_free(gpup_tile** tiles, uint32_t num_tiles);
+/* a whole (multi-tile) code stream the host holds in memory -> the int32 planes of `image` (allocated by the host) */
+B2K_API int32_t plugin_decompress_codestream(const uint8_t* codestream, uint64_t length, gpup_image* image);
 /* plugin_decompress (plugin_interface.h L117-120) takes a C++ struct with std::string members
  * (PluginDecodeCallbackInfo L78-115): it is declared in grok_b200/csrc/plugin_decode.cpp and
  * documented in INTEGRATION.md, not here, so that this header stays C. */
@@ -340,6 +349,11 @@ typedef struct b2k_result
 B2K_API int32_t b2k_engine_create(int32_t device, b2k_engine** out);
 B2K_API void b2k_engine_destroy(b2k_engine* e);
 B2K_API const char* b2k_last_error(void);
+
+/* the b2k_coding that gpup_encode_mem (allow_tiles = 0) / gpup_encode_mem_tiles (1) derive from the host's stock
+ * parameters, precinct sizes as CodeStreamCompress.cpp L793-825 derives them (0 handled, 1 not handled) */
+B2K_API int32_t b2k_coding_from_gpup(const gpup_compress_params* params, const gpup_image* image, int32_t allow_tiles,
+                                     b2k_coding* out);
 
 /* pinned host memory for image planes / codestream arenas (what Grok's allocator should hand
  * to grk_image when the plugin is loaded) */

@@ -11,8 +11,11 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BIN = os.path.join(ROOT, "baseline", "_ref", "bin")
+# GROK_REF_FLAVOUR=patched selects the host built with baseline/patches/ applied (baseline/build_ref_patched.sh)
+FLAVOUR = "_ref_patched" if os.environ.get("GROK_REF_FLAVOUR") == "patched" else "_ref"
+BIN = os.path.join(ROOT, "baseline", FLAVOUR, "bin")
 LIB = os.path.join(BIN, "libgrk_ref_bench.so")
+PLUGIN_DIR = os.path.join(ROOT, "grok_b200")     # holds libgrokj2k_plugin.so, the name the host's loader looks for
 
 
 class Params(C.Structure):
@@ -41,8 +44,18 @@ def lib():
         L.grb_decompress.restype = C.c_double
         L.grb_decompress.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_int32, C.c_uint32, C.POINTER(C.c_double)]
+        L.grb_accelerated_frames.restype = C.c_uint64
+        L.grb_plugin_set_enabled.argtypes = [C.c_int]
         _lib = L
     return _lib
+
+
+def accelerated_frames():
+    return int(lib().grb_accelerated_frames())
+
+
+def plugin_set_enabled(on):
+    lib().grb_plugin_set_enabled(int(bool(on)))
 
 
 def init(threads=0, plugin_path=None, device_id=0):

@@ -1,0 +1,56 @@
+"""Runs in a SUBPROCESS of tests/test_realhost.py (a crash of the host library must not take pytest down):
+the real reference host -- stock (baseline/_ref) or patched (baseline/_ref_patched, GROK_REF_FLAVOUR=patched) --
+first on its own CPU path, then with grok_b200/libgrokj2k_plugin.so loaded through its own plugin loader
+(grk_initialize(plugin_path) + grk_plugin_init), and prints one JSON line comparing the two.
+
+usage: python realhost_driver.py '<json case>'"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.dirname(HERE), HERE]
+import grok_ref as R            # noqa: E402
+import oracle_pipeline as P     # noqa: E402
+
+
+def main():
+    case = json.loads(sys.argv[1])
+    w, h, n, prec = case["width"], case["height"], case["numcomps"], case["prec"]
+    kw = dict(tile=tuple(case["tile"]) if case.get("tile") else None, numres=case.get("numres", 6),
+              irreversible=case.get("irreversible", False), tlm=True, plt=True,
+              precinct=tuple(case["precinct"]) if case.get("precinct") else None)
+    planes = P.synthetic_image(w, h, n, prec, seed=case.get("seed", 7))
+    threads = case.get("threads", 4)
+    out = {"flavour": R.FLAVOUR}
+    # 1. the host alone
+    R.init(threads)
+    cs_cpu, t_enc_cpu = R.compress(planes, prec, **kw)
+    cs_cpu = cs_cpu.copy()
+    dec_cpu, t_dec_cpu, _ = R.decompress(cs_cpu, w, h, n)
+    out["cpu"] = {"enc_s": t_enc_cpu, "dec_s": t_dec_cpu, "bytes": int(cs_cpu.size),
+                  "lossless": bool(all(np.array_equal(a, b) for a, b in zip(dec_cpu, planes)))}
+    # 2. the same host with the plugin loaded by its own loader
+    loaded = R.init(threads, plugin_path=R.PLUGIN_DIR, device_id=0)
+    out["plugin_loaded"] = bool(loaded)
+    f0 = R.accelerated_frames()
+    cs_gpu, t_enc = R.compress(planes, prec, device_id=0, **kw)
+    cs_gpu = cs_gpu.copy()
+    f1 = R.accelerated_frames()
+    dec_gpu, t_dec, _ = R.decompress(cs_cpu, w, h, n, device_id=0)
+    f2 = R.accelerated_frames()
+    for _ in range(case.get("repeat", 0)):      # steady-state timing through the host
+        _, t_enc = R.compress(planes, prec, device_id=0, **kw)
+        _, t_dec, _ = R.decompress(cs_cpu, w, h, n, device_id=0, out=dec_gpu)
+    out["plugin"] = {"enc_s": t_enc, "dec_s": t_dec, "enc_accelerated": f1 - f0, "dec_accelerated": f2 - f1,
+                     "codestream_identical": bool(cs_gpu.size == cs_cpu.size and np.array_equal(cs_gpu, cs_cpu)),
+                     "bytes": int(cs_gpu.size),
+                     "decode_identical": bool(all(np.array_equal(a, b) for a, b in zip(dec_gpu, dec_cpu))),
+                     "decode_maxdiff": int(max(np.abs(a.astype(np.int64) - b).max() for a, b in zip(dec_gpu, dec_cpu)))}
+    print("REALHOST " + json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -661,3 +661,79 @@ def test_repeated_and_concurrent_calls_are_deterministic(engine):
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+def test_two_engines_in_one_process(engine):
+    """ADVICE r1 / VERDICT weak #7: kernel attributes (dynamic shared memory opt-in) are per device, and INTEGRATION.md
+    offers "one engine per GPU" in one process.  A second engine -- on a second GPU when the box has one, else on the same
+    device -- is created AFTER the first has already launched every kernel, and both then work concurrently from two
+    threads: same bytes, lossless decode."""
+    import threading
+    import torch
+    second_dev = 1 if torch.cuda.device_count() > 1 else 0
+    w, h = 1024, 768
+    cp = G.make_coding(w, h, 3, 12, numres=6, tile=(512, 512))
+    cpi = G.make_coding(w, h, 3, 12, numres=6, irreversible=True)
+    planes = P.synthetic_image(w, h, 3, 12, seed=17)
+    r = engine.encode(cp, planes)
+    want = r.bytes.copy()
+    r.free()
+    ri = engine.encode(cpi, planes)
+    want_i = ri.bytes.copy()
+    ri.free()
+    e2 = G.Engine(second_dev)
+    errors = []
+
+    def worker(eng, tag):
+        try:
+            for _ in range(3):
+                a = eng.encode(cp, planes)
+                out = [np.zeros_like(p) for p in planes]
+                eng.decode(cp, a.blocks, a.bytes, out)
+                ok = np.array_equal(a.bytes, want) and all(np.array_equal(x, y) for x, y in zip(out, planes))
+                a.free()
+                b = eng.encode(cpi, planes)
+                ok = ok and np.array_equal(b.bytes, want_i)
+                b.free()
+                if not ok:
+                    errors.append(tag + ": mismatch")
+        except Exception as e:      # noqa: BLE001
+            errors.append("%s: %r" % (tag, e))
+
+    ts = [threading.Thread(target=worker, args=(engine, "engine0")), threading.Thread(target=worker, args=(e2, "engine1"))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    e2.close()
+    assert not errors, errors
+
+
+def test_decode_with_byte_arena_not_in_tile_order(engine):
+    """a caller arena / foreign code stream whose tiles are not laid out in tile-index order (legal:
+    tile parts may come in any order).  The chunk-pipelined upload must not leave holes: tiles' byte ranges are permuted
+    (last tile first, gaps between them), offsets patched, and the decode must still return the source."""
+    w, h = 1536, 1024
+    cp = G.make_coding(w, h, 3, 12, numres=5, tile=(256, 256))      # 24 tiles -> several pipeline chunks
+    planes = P.synthetic_image(w, h, 3, 12, seed=23)
+    res = engine.encode(cp, planes)
+    blocks, data = res.blocks.copy(), res.bytes.copy()
+    res.free()
+    ntiles = int(blocks["tile"].max()) + 1
+    order = np.random.default_rng(5).permutation(ntiles)
+    new = np.zeros(data.size + 64 * ntiles + 1000, np.uint8)
+    new[:] = 0xA5
+    pos = 777
+    nb = blocks.copy()
+    for t in order:
+        sel = np.nonzero((blocks["tile"] == t) & (blocks["length"] > 0))[0]
+        for i in sel:
+            o, n = int(blocks[i]["offset"]), int(blocks[i]["length"])
+            new[pos:pos + n] = data[o:o + n]
+            nb[i]["offset"] = pos
+            pos += n
+        pos += 61
+    out = [np.zeros_like(p) for p in planes]
+    engine.decode(cp, nb, new[:pos], out)
+    for a, b in zip(out, planes):
+        assert np.array_equal(a, b)

@@ -360,3 +360,73 @@ def test_gpup_tile_tree_from_a_result_multi_tile_with_precincts():
                             k += 1
         lib.gpup_tile_free(tile)
     assert k == len(table)
+
+
+def test_bench_reference_arm_runs_to_completion_and_prints_its_json_line():
+    """`bench.py --impl reference` (the driver's anchor for vs_reference) must not rot: run it for one step on the CPU and
+    parse the line.  Round 1's arm died with a NameError after doing all the work."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, p.stdout[-2000:]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference"
+    if "unavailable" in line:
+        assert not os.path.exists(os.path.join(root, "baseline", "_ref", "bin", "libgrk_ref_bench.so"))
+        return
+    assert line["unit"] == "Mpixels/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "reference" and "grk_compress" in line["cpu_baseline"]["sample"]
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["steps"] == 1 and line["n_gpus"] == 1
+
+
+def test_stock_parameters_give_the_hosts_precinct_sizes(tmp_path):
+    """with `-c [128,128]` style parameters (csty & 1, res_spec = 1 < numresolution) the host derives the
+    coarser resolutions' precinct sizes by halving the last given one (CodeStreamCompress.cpp L793-825).  The coding the
+    stock entry points derive (b2k_coding_from_gpup) must give the same exponents -- checked against what the real
+    library wrote into its COD marker when it is built, else against the rule."""
+    src = r'''
+#include <stdio.h>
+#include <string.h>
+#include "grok_b200.h"
+int main(void) {
+  static gpup_compress_params p; static gpup_image im; static gpup_image_comp comps[3]; static int32_t px[4];
+  memset(&p, 0, sizeof p);
+  p.numlayers = 1; p.numgbits = 1; p.numresolution = 5; p.cblockw_init = 64; p.cblockh_init = 64; p.cblk_sty = 0x40;
+  p.roi_compno = -1; p.mct = 1; p.csty = 1; p.res_spec = 1; p.prcw_init[0] = 128; p.prch_init[0] = 128;
+  im.x1 = 600; im.y1 = 500; im.numcomps = 3; im.comps = comps;
+  for (int c = 0; c < 3; ++c) { comps[c].w = 600; comps[c].h = 500; comps[c].stride = 600; comps[c].dx = comps[c].dy = 1; comps[c].prec = 12; comps[c].data = px; }
+  b2k_coding cp;
+  int rc = b2k_coding_from_gpup(&p, &im, 0, &cp);
+  printf("%d", rc);
+  for (int r = 0; r < 5; ++r) printf(" %d %d", cp.prcw_exp[r], cp.prch_exp[r]);
+  p.res_spec = 2; p.prcw_init[1] = 1; p.prch_init[1] = 64;      /* runs down to 1-sample precincts: declined */
+  printf(" %d", b2k_coding_from_gpup(&p, &im, 0, &cp));
+  p.res_spec = 1; p.tile_size_on = 1; p.t_width = 256; p.t_height = 256;   /* tiles: only with allow_tiles */
+  printf(" %d %d\n", b2k_coding_from_gpup(&p, &im, 0, &cp), b2k_coding_from_gpup(&p, &im, 1, &cp));
+  return 0;
+}'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    c = tmp_path / "probe.c"
+    c.write_text(src)
+    exe = str(tmp_path / "probe")
+    subprocess.run(["gcc", str(c), "-I", os.path.join(root, "include"), "-L", os.path.join(root, "grok_b200"),
+                    "-l:libgrokj2k_plugin.so", "-Wl,-rpath," + os.path.join(root, "grok_b200"), "-o", exe], check=True)
+    out = [int(v) for v in subprocess.check_output([exe]).decode().split()]
+    assert out[0] == 0
+    exps = out[1:11]
+    want = [3, 3, 4, 4, 5, 5, 6, 6, 7, 7]        # resolution 0..4: 128 >> (4 - r)
+    assert exps == want
+    assert out[11] == 1 and out[12] == 1 and out[13] == 0
+    import grok_ref as R
+    if R.available():
+        R.init(2)
+        planes = P.synthetic_image(600, 500, 3, 12, seed=3)
+        cs, _ = R.compress(planes, 12, numres=5, precinct=(128, 128))
+        cp2, _ = G.codestream_parse(np.frombuffer(bytes(cs), np.uint8))
+        assert [v for r in range(5) for v in (cp2.prcw_exp[r], cp2.prch_exp[r])] == exps

@@ -1,0 +1,110 @@
+"""The plugin under the REAL host: libgrokj2k -- built from the reference's sources with its plugin
+loader enabled -- dlopens grok_b200/libgrokj2k_plugin.so through its own minpf loader, resolves minpf_post_load_plugin /
+plugin_init / gpup_encode_mem / plugin_decompress by name and routes grk_compress() / grk_decompress() through them.
+
+* stock host (baseline/_ref, unmodified sources): single-tile images (the stock contract);
+* patched host (baseline/_ref_patched = sources + baseline/patches/0001-multi-tile-plugin-encode-decode.patch):
+  multi-tile images through gpup_encode_mem_tiles / plugin_decompress_codestream.
+The assertion is the strongest one available: the code stream the host writes with the plugin's code blocks is
+byte-identical to the one it writes on its own CPU path, and the pixels it hands back are identical.
+Each case runs in a subprocess (tests/realhost_driver.py).  Without a GPU the same driver checks the fallback:
+the plugin loads, plugin_init reports no device, the host compresses on the CPU."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def built(flavour):
+    return os.path.exists(os.path.join(ROOT, "baseline", flavour, "bin", "libgrk_ref_bench.so"))
+
+
+def run(case, flavour):
+    env = dict(os.environ)
+    if flavour == "_ref_patched":
+        env["GROK_REF_FLAVOUR"] = "patched"
+    else:
+        env.pop("GROK_REF_FLAVOUR", None)
+    p = subprocess.run([sys.executable, os.path.join(HERE, "realhost_driver.py"), json.dumps(case)], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("REALHOST ")]
+    assert p.returncode == 0 and lines, "driver failed (rc %d)\n%s\n%s" % (p.returncode, p.stdout[-3000:], p.stderr[-3000:])
+    return json.loads(lines[-1][len("REALHOST "):])
+
+
+@pytest.mark.parametrize("flavour", ["_ref", "_ref_patched"])
+def test_host_loads_the_plugin_and_falls_back_without_a_device(flavour):
+    """CPU box: the loader finds the library, every symbol resolves, plugin_init says "no device", the host carries on
+    on its own path (grok.cpp L1344-1370) -- and nothing crashes on the way."""
+    if not built(flavour):
+        pytest.skip("baseline/%s not built" % flavour)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    r = run(dict(width=256, height=192, numcomps=3, prec=12, tile=[128, 128] if flavour == "_ref_patched" else None), flavour)
+    assert r["cpu"]["lossless"]
+    assert r["plugin_loaded"] is False
+    assert r["plugin"]["enc_accelerated"] == 0 and r["plugin"]["codestream_identical"] and r["plugin"]["decode_identical"]
+
+
+STOCK_CASES = [
+    dict(width=512, height=512, numcomps=1, prec=8),                                   # BASELINE config 1
+    dict(width=640, height=384, numcomps=3, prec=12),
+    dict(width=600, height=500, numcomps=3, prec=12, numres=5, precinct=[128, 128]),    # res_spec < numresolution
+    dict(width=640, height=384, numcomps=3, prec=12, irreversible=True),
+    dict(width=333, height=217, numcomps=4, prec=16, numres=4),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", STOCK_CASES)
+def test_stock_host_compresses_and_decompresses_through_the_plugin(case):
+    if not built("_ref"):
+        pytest.skip("baseline/_ref not built")
+    r = run(case, "_ref")
+    assert r["plugin_loaded"], "the host did not load / initialise the plugin"
+    assert r["plugin"]["enc_accelerated"] == 1, "grk_compress did not take the plugin route"
+    assert r["plugin"]["codestream_identical"], "code stream through the plugin differs from the host's own"
+    assert r["plugin"]["dec_accelerated"] == 1, "grk_decompress did not take the plugin route"
+    if case.get("irreversible"):
+        assert r["plugin"]["decode_maxdiff"] <= 1
+    else:
+        assert r["plugin"]["decode_identical"] and r["cpu"]["lossless"]
+
+
+PATCHED_CASES = [
+    dict(width=640, height=384, numcomps=3, prec=12, tile=[256, 256]),
+    dict(width=2048, height=2048, numcomps=3, prec=12, tile=[1024, 1024], seed=20260924),     # config 2's tiles
+    dict(width=700, height=500, numcomps=4, prec=16, tile=[256, 128], numres=4),              # config 4 in small
+    dict(width=640, height=384, numcomps=3, prec=12, tile=[256, 256], irreversible=True),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", PATCHED_CASES)
+def test_patched_host_multi_tile_through_the_plugin(case):
+    if not built("_ref_patched"):
+        pytest.skip("baseline/_ref_patched not built")
+    r = run(case, "_ref_patched")
+    assert r["plugin_loaded"]
+    assert r["plugin"]["enc_accelerated"] == 1, "multi-tile grk_compress did not take gpup_encode_mem_tiles"
+    assert r["plugin"]["codestream_identical"]
+    assert r["plugin"]["dec_accelerated"] == 1, "multi-tile grk_decompress did not take plugin_decompress_codestream"
+    if case.get("irreversible"):
+        assert r["plugin"]["decode_maxdiff"] <= 1
+    else:
+        assert r["plugin"]["decode_identical"] and r["cpu"]["lossless"]
+
+
+@pytest.mark.gpu
+def test_patched_host_still_serves_single_tile_through_the_stock_symbols():
+    if not built("_ref_patched"):
+        pytest.skip("baseline/_ref_patched not built")
+    r = run(dict(width=512, height=512, numcomps=1, prec=8), "_ref_patched")
+    assert r["plugin_loaded"] and r["plugin"]["enc_accelerated"] == 1 and r["plugin"]["codestream_identical"]
+    assert r["plugin"]["dec_accelerated"] == 1 and r["plugin"]["decode_identical"]
