@@ -55,6 +55,10 @@ struct b2k_engine
   cudaStream_t stream = nullptr, copy_stream = nullptr, h2d_stream = nullptr;
   cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr}; /* latency-bound side kernels run concurrently here */
   cudaDeviceProp prop{};
+  /* b2k_encode / b2k_decode keep the job (device buffers, plans) of the last coding they saw.  The cache and its lock
+     belong to the engine: calls on one engine are serialised, engines (one per GPU) run side by side */
+  std::mutex mu;
+  b2k_device_job* cached = nullptr;
 };
 
 /* ---- a plane set: `n` image-shaped 32-bit planes addressed by canvas coordinate ------------- */
@@ -247,6 +251,11 @@ extern "C" void b2k_engine_destroy(b2k_engine* e)
   if(!e)
     return;
   cudaSetDevice(e->device);
+  if(e->cached)
+  {
+    b2k_job_destroy(e->cached);
+    e->cached = nullptr;
+  }
   if(e->stream)
     cudaStreamDestroy(e->stream);
   if(e->copy_stream)
@@ -1606,17 +1615,11 @@ static bool dbg_timing()
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());       \
   } while(0)
 
-struct JobCache
-{
-  std::mutex mu;
-  b2k_device_job* job = nullptr;
-};
-static JobCache g_cache;
-
 static b2k_device_job* cached_job(b2k_engine* e, const b2k_coding* cp, uint32_t mod, uint32_t rem, int* rc)
 {
-  b2k_device_job*& J = g_cache.job;
-  if(J && (J->eng != e || memcmp(&J->cp, cp, sizeof(b2k_coding)) != 0 || J->tile_mod != mod || J->tile_rem != rem))
+  b2k_device_job*& J = e->cached;
+  cudaSetDevice(e->device);
+  if(J && (memcmp(&J->cp, cp, sizeof(b2k_coding)) != 0 || J->tile_mod != mod || J->tile_rem != rem))
   {
     b2k_job_destroy(J);
     J = nullptr;
@@ -1633,7 +1636,7 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
 {
   if(!e || !cp || !planes || !strides || !out)
     return -1;
-  std::lock_guard<std::mutex> lock(g_cache.mu);
+  std::lock_guard<std::mutex> lock(e->mu);
   int rc = 0;
   b2k_device_job* J = cached_job(e, cp, mod, rem, &rc);
   if(rc)
@@ -1861,7 +1864,7 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
 {
   if(!e || !cp || !blocks || !planes || !strides)
     return -1;
-  std::lock_guard<std::mutex> lock(g_cache.mu);
+  std::lock_guard<std::mutex> lock(e->mu);
   int rc = 0;
   b2k_device_job* J = cached_job(e, cp, tile_mod, tile_rem, &rc);
   if(rc)

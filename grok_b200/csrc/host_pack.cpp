@@ -77,6 +77,8 @@ public:
         fn(i);
       return;
     }
+    /* one fork-join at a time: engines on several GPUs (or a codestream writer) may call from different threads */
+    std::lock_guard<std::mutex> call(call_mu_);
     fn_ = &fn;
     n_ = n;
     next_.store(0, std::memory_order_relaxed);
@@ -202,6 +204,7 @@ private:
   }
   std::vector<std::thread> workers_;
   std::mutex mu_;
+  std::mutex call_mu_;
   std::condition_variable cv_;
   std::atomic<bool> stop_{false};
   std::atomic<int> hot_{0};
