@@ -82,8 +82,15 @@ void b2k_launch_dwt_fwd(const DwtLevelDesc* d_descs, int ndesc, int max_jobs, in
                         bool in_u16, cudaStream_t st);
 void b2k_launch_dwt_inv(const DwtLevelDesc* d_descs, int ndesc, int max_jobs, int nc, bool irreversible, bool out_u16,
                         cudaStream_t st);
+/* per-launch limits the encoder sizes its shared memory from (host: build_block_plan) */
+struct HtEncodeLimits
+{
+  uint32_t stage_words; /* max over the launch's blocks of b2k_ht_encode_stage_words(w) */
+  uint32_t max_kmax;    /* max Kmax over the launch's blocks */
+};
+uint32_t b2k_ht_encode_stage_words(uint32_t w);
 void b2k_launch_ht_encode(const HtBlockDesc* d_blocks, HtBlockOut* d_out, uint8_t* d_scratch, uint32_t nblocks,
-                          uint32_t max_w, bool irreversible, cudaStream_t st);
+                          const HtEncodeLimits& lim, bool irreversible, cudaStream_t st);
 void b2k_launch_ht_gather(const HtBlockDesc* d_blocks, const HtBlockOut* d_out, const uint64_t* d_offsets,
                           const uint8_t* d_scratch, uint8_t* d_bytes, uint32_t nblocks, uint64_t cap, cudaStream_t st);
 void b2k_launch_scan_lengths(const HtBlockOut* d_out, uint64_t* d_offsets, uint32_t nblocks, cudaStream_t st);

@@ -170,6 +170,7 @@ struct b2k_device_job
   std::vector<uint32_t> chunk_tile;    /* pipeline chunks: selected tiles [chunk_tile[k], chunk_tile[k+1]) */
   cudaEvent_t chunk_ev[5 * (B2K_MAX_CHUNKS + 1)]{}; /* [purpose][chunk], see CEV() */
   uint32_t max_cblk_w = 0;
+  HtEncodeLimits enc_limits{0, 0};     /* shared-memory sizing of the HT encoder launches */
 
   Planes img, coef, ll[2];
   Planes16 img16;                      /* 16-bit sample containers (b2k_encode16 / b2k_decode16), lazily */
@@ -471,6 +472,8 @@ static int build_block_plan(b2k_device_job* J)
     d.rec_off = (uint32_t)J->total_quads;
     J->total_quads += (uint64_t)((d.w + 1) / 2) * ((d.h + 1) / 2);
     J->max_cblk_w = std::max<uint32_t>(J->max_cblk_w, d.w);
+    J->enc_limits.stage_words = std::max(J->enc_limits.stage_words, b2k_ht_encode_stage_words(d.w));
+    J->enc_limits.max_kmax = std::max<uint32_t>(J->enc_limits.max_kmax, d.kmax);
     J->h_enc_desc.push_back(d);
     J->dec_quant.push_back(bq.step_dec / (float)(1u << (31 - bq.kmax)));
     J->coded_index.push_back(i);
@@ -1020,7 +1023,7 @@ static int enqueue_t1_blocks(b2k_device_job* J, cudaStream_t st, size_t t0, size
   t1 = std::min(t1, J->tiles.size());
   const uint32_t b0 = J->coded_first[t0], b1 = J->coded_first[t1];
   if(b1 > b0)
-    b2k_launch_ht_encode(J->d_enc_desc + b0, J->d_out + b0, J->d_scratch, b1 - b0, J->max_cblk_w, J->cp.irreversible, st);
+    b2k_launch_ht_encode(J->d_enc_desc + b0, J->d_out + b0, J->d_scratch, b1 - b0, J->enc_limits, J->cp.irreversible, st);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -1028,7 +1031,7 @@ static int enqueue_t1_blocks(b2k_device_job* J, cudaStream_t st, size_t t0, size
 static int enqueue_t1_encode(b2k_device_job* J, cudaStream_t st)
 {
   const uint32_t n = (uint32_t)J->h_enc_desc.size();
-  b2k_launch_ht_encode(J->d_enc_desc, J->d_out, J->d_scratch, n, J->max_cblk_w, J->cp.irreversible, st);
+  b2k_launch_ht_encode(J->d_enc_desc, J->d_out, J->d_scratch, n, J->enc_limits, J->cp.irreversible, st);
   b2k_launch_scan_lengths(J->d_out, J->d_offsets, n, st);
   CUDA_TRY(cudaGetLastError());
   return 0;
