@@ -496,13 +496,67 @@ def main():
     dt_e2e16 = time.perf_counter() - t0
     assert all(np.array_equal(a, b) for a, b in zip(o16, p16)), "16-bit e2e round trip is not lossless"
 
+    # ---------------- streamed: an encode stream feeding a decode stream, 3 frames in flight each ----------------
+    # 16-bit sample containers in and out (what the reference's batch interface carries, gpup_batch_memory_submit_planes):
+    # frame k+1's upload overlaps frame k's kernels and download, and the decode of frame k-1 runs beside both
+    depth = int(os.environ.get("B2K_BENCH_STREAM_DEPTH", "3"))
+    outs = [[G.pinned_empty((H, W), np.uint16) for _ in range(NCOMP)] for _ in range(2 * depth + 1)]
+    free_outs = list(range(len(outs)))
+    lock, done, live, bad, used = threading.Lock(), threading.Semaphore(0), {}, [], set()
+    room = threading.Semaphore(len(outs))
+
+    def on_decoded(tag, status):
+        res, slot = live.pop(tag)
+        res.free()
+        if status != 0:
+            bad.append(status)
+        with lock:
+            free_outs.append(slot)
+        room.release()
+        done.release()
+
+    dec_stream = G.DecodeStream(depth=depth, sample_bytes=2, on_decoded=on_decoded, device=local)
+
+    def on_encoded(tag, res, status):
+        if status != 0 or res is None:
+            bad.append(status)
+            done.release()
+            return
+        room.acquire()
+        with lock:
+            slot = free_outs.pop()
+            used.add(slot)
+        live[tag] = (res, slot)
+        dec_stream.submit(cp, res.blocks, res.bytes, outs[slot], tag)
+
+    enc_stream = G.EncodeStream(cp, depth=depth, sample_bytes=2, on_encoded=on_encoded, device=local)
+
+    def streamed(nframes):
+        t0 = time.perf_counter()
+        for i in range(nframes):
+            enc_stream.submit(p16, i)
+        for _ in range(nframes):
+            done.acquire()
+        return time.perf_counter() - t0
+
+    streamed(3 * depth + 3)           # warm-up: every worker's engine has built its job, the pinned result arenas exist
+    barrier()
+    n_stream = max(16, args.steps)
+    dt_stream = streamed(n_stream) / n_stream
+    barrier()
+    enc_stream.end()
+    dec_stream.end()
+    assert not bad, bad
+    for slot in used:
+        assert all(np.array_equal(a, b) for a, b in zip(outs[slot], p16)), "streamed round trip is not lossless"
+
     # max over ranks
-    times = torch.tensor([dt_dev, dt_e2e, dt_e2e16, dt_e2e32, dt_file, dt_enc, dt_dec], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dt_dev, dt_e2e, dt_e2e16, dt_e2e32, dt_file, dt_enc, dt_dec, dt_stream], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
         dist.all_gather(sizes, torch.tensor([nb], dtype=torch.int64, device="cuda"))  # codestream segment sizes
-    dt_dev, dt_e2e, dt_e2e16, dt_e2e32, dt_file, dt_enc, dt_dec = (float(times[i]) for i in range(7))
+    dt_dev, dt_e2e, dt_e2e16, dt_e2e32, dt_file, dt_enc, dt_dec, dt_stream = (float(times[i]) for i in range(8))
 
     if rank == 0:
         pix = W * H * world
@@ -545,6 +599,11 @@ def main():
             "e2e_u16": {"value": pix / (dt_e2e16 / args.steps) / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_e2e16 / args.steps * 1e3,
                         "h2d_bytes_per_step": int(img_bytes // 2 + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes // 2 + nb + nbk * 24),
                         "api": "b2k_encode16 + b2k_decode16: same path, 16-bit sample containers (cf. gpup_batch_memory_submit_planes)"},
+            "e2e_batch": {"value": pix / dt_stream / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_stream * 1e3, "frames": n_stream,
+                          "h2d_bytes_per_step": int(img_bytes // 2 + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes // 2 + nb + nbk * 24),
+                          "api": "b2k_stream_encode_* feeding b2k_stream_decode_* (SURVEY 8f N2, cf. gpup_batch_memory_*): 3 frames in flight "
+                                 "per direction on one GPU, 16-bit sample containers, host buffers pinned; wall clock from the first submit "
+                                 "to the last decoded frame / frames"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_dwt53_fwd<3> (DC shift + RCT + level-1 5/3, all 64 tiles x 3 comps)",

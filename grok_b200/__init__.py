@@ -65,7 +65,10 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
            "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last",
            "b2k_codestream_write", "b2k_codestream_parse", "b2k_jph_wrap", "b2k_jph_codestream", "b2k_result_merge",
-           "gpup_encode_mem_tiles", "gpup_tiles_free", "plugin_decompress_codestream", "b2k_coding_from_gpup"]
+           "gpup_encode_mem_tiles", "gpup_tiles_free", "plugin_decompress_codestream", "b2k_coding_from_gpup",
+           "b2k_stream_encode_begin", "b2k_stream_encode_submit", "b2k_stream_decode_begin", "b2k_stream_decode_submit",
+           "b2k_stream_decode_submit_codestream", "b2k_stream_end",
+           "gpup_batch_memory_begin", "gpup_batch_memory_submit", "gpup_batch_memory_submit_planes", "gpup_batch_memory_end"]
 
 _lib = None
 
@@ -467,3 +470,113 @@ def enumerate_blocks(cp, tile_mod=1, tile_rem=0):
     out = np.zeros(n, BLOCK_DTYPE)
     lib().b2k_enumerate(C.byref(cp), tile_mod, tile_rem, out.ctypes.data, n)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# streaming (include/grok_b200.h "streaming", csrc/stream.cpp): `depth` frames in flight on one GPU
+# ------------------------------------------------------------------------------------------------
+_ENCODED_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Result), C.c_int32)
+_DECODED_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int32)
+
+
+def _bind_stream():
+    L = lib()
+    if getattr(L, "_b2k_stream_bound", False):
+        return L
+    vp, u32, i32, u64 = C.c_void_p, C.c_uint32, C.c_int32, C.c_uint64
+    pp = C.POINTER(C.c_void_p)
+    L.b2k_stream_encode_begin.argtypes = [i32, C.POINTER(Coding), u32, u32, _ENCODED_FN, vp, pp]
+    L.b2k_stream_encode_submit.argtypes = [vp, pp, C.POINTER(u32), vp]
+    L.b2k_stream_decode_begin.argtypes = [i32, u32, u32, _DECODED_FN, vp, pp]
+    L.b2k_stream_decode_submit.argtypes = [vp, C.POINTER(Coding), vp, u64, vp, u64, pp, C.POINTER(u32), vp]
+    L.b2k_stream_decode_submit_codestream.argtypes = [vp, vp, u64, u32, pp, C.POINTER(u32), vp]
+    L.b2k_stream_end.argtypes = [vp]
+    L._b2k_stream_bound = True
+    return L
+
+
+class EncodeStream:
+    """b2k_stream_encode_*: submit(planes, tag) hands a frame to an idle worker (blocks while `depth` frames are in
+    flight); on_encoded(tag, EncodeResult or None, status) runs on a worker thread -- the EncodeResult is the caller's
+    (free it).  The planes must stay alive and unchanged until the callback for their frame has run."""
+
+    def __init__(self, cp, depth=3, sample_bytes=4, on_encoded=None, device=0):
+        L = _bind_stream()
+        self._cp = cp
+        self._tags = {}
+        self._next = 1
+        self._user_cb = on_encoded
+
+        def cb(_user, frame_user, result, status):
+            tag, keep = self._tags.pop(int(frame_user or 0), (None, None))
+            res = EncodeResult(result) if (status == 0 and result) else None
+            if self._user_cb:
+                self._user_cb(tag, res, status)
+            elif res is not None:
+                res.free()
+            return 1 if res is not None else 0      # the EncodeResult owns the b2k_result now
+
+        self._cb = _ENCODED_FN(cb)
+        self._h = C.c_void_p()
+        _check(L.b2k_stream_encode_begin(device, C.byref(cp), depth, sample_bytes, self._cb, None, C.byref(self._h)),
+               "b2k_stream_encode_begin")
+
+    def submit(self, planes, tag=None):
+        ptrs, strides = _plane_ptrs(planes)
+        key = self._next
+        self._next += 1
+        self._tags[key] = (tag, planes)              # keeps the planes alive until the callback
+        _check(lib().b2k_stream_encode_submit(self._h, ptrs, strides, C.c_void_p(key)), "b2k_stream_encode_submit")
+
+    def end(self):
+        if self._h:
+            rc = lib().b2k_stream_end(self._h)
+            self._h = C.c_void_p()
+            return rc
+        return 0
+
+
+class DecodeStream:
+    """b2k_stream_decode_*: submit(cp, blocks, data, out_planes, tag) / submit_codestream(cs, out_planes, tag);
+    on_decoded(tag, status) runs on a worker thread once out_planes hold the pixels."""
+
+    def __init__(self, depth=3, sample_bytes=4, on_decoded=None, device=0):
+        L = _bind_stream()
+        self._tags = {}
+        self._next = 1
+        self._user_cb = on_decoded
+
+        def cb(_user, frame_user, status):
+            tag = self._tags.pop(int(frame_user or 0), (None,))[0]
+            if self._user_cb:
+                self._user_cb(tag, status)
+
+        self._cb = _DECODED_FN(cb)
+        self._h = C.c_void_p()
+        _check(L.b2k_stream_decode_begin(device, depth, sample_bytes, self._cb, None, C.byref(self._h)), "b2k_stream_decode_begin")
+
+    def submit(self, cp, blocks, data, out_planes, tag=None):
+        ptrs, strides = _plane_ptrs(out_planes)
+        blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        key = self._next
+        self._next += 1
+        self._tags[key] = (tag, blocks, data, out_planes, cp)
+        _check(lib().b2k_stream_decode_submit(self._h, C.byref(cp), blocks.ctypes.data, len(blocks), data.ctypes.data, len(data),
+                                              ptrs, strides, C.c_void_p(key)), "b2k_stream_decode_submit")
+
+    def submit_codestream(self, cs, out_planes, tag=None):
+        ptrs, strides = _plane_ptrs(out_planes)
+        cs = np.ascontiguousarray(cs, dtype=np.uint8)
+        key = self._next
+        self._next += 1
+        self._tags[key] = (tag, cs, out_planes)
+        _check(lib().b2k_stream_decode_submit_codestream(self._h, cs.ctypes.data, len(cs), len(out_planes), ptrs, strides,
+                                                         C.c_void_p(key)), "b2k_stream_decode_submit_codestream")
+
+    def end(self):
+        if self._h:
+            rc = lib().b2k_stream_end(self._h)
+            self._h = C.c_void_p()
+            return rc
+        return 0

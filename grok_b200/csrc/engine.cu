@@ -1420,7 +1420,7 @@ static void pool_put(uint8_t* p)
     {
       g_pool.free_list.push_back(g_pool.live[i]);
       g_pool.live.erase(g_pool.live.begin() + i);
-      while(g_pool.free_list.size() > 4)
+      while(g_pool.free_list.size() > 16) /* streams keep depth-many results alive per direction; re-pinning 150 MB costs tens of ms */
       {
         cudaFreeHost(g_pool.free_list.front().first);
         g_pool.free_list.erase(g_pool.free_list.begin());

@@ -169,6 +169,122 @@ __device__ __forceinline__ void vlc_fill32(VlcR& v)
 }
 __device__ __forceinline__ uint32_t vlc_head(const VlcR& v) { return (uint32_t)v.tmp; }
 
+/* ---- phase A readers: the serial parse is latency-bound, so its byte streams must not put a global load into the
+ * dependency chain for every byte.  Both streams are read through an aligned 8-byte register window with the NEXT
+ * window already in flight (issued when the current one is entered, ~4 quad pairs of parsing ahead of its first use). */
+struct VlcFast
+{ /* backward reader of the VLC segment (rev_read / rev_init, ojph_block_decoder32.cpp L296-395) */
+  const uint8_t* d;
+  const uint64_t* ap; /* aligned window holding the byte at `pos` */
+  uint64_t cur, nxt, tmp;
+  int pos, lo, bits, unstuff;
+};
+__device__ __forceinline__ uint64_t vlcf_load(const VlcFast& v, const uint64_t* a)
+{ /* a window that lies wholly below the segment is never looked at */
+  return reinterpret_cast<const uint8_t*>(a) + 7 >= v.d + v.lo ? __ldg(a) : 0ull;
+}
+__device__ __forceinline__ void vlcf_init(VlcFast& v)
+{
+  const uint8_t* a = v.d + (v.pos > 0 ? v.pos : 0);
+  v.ap = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)7);
+  v.cur = vlcf_load(v, v.ap);
+  v.nxt = vlcf_load(v, v.ap - 1);
+}
+__device__ __forceinline__ void vlcf_fill32(VlcFast& v)
+{
+  while(v.bits < 32)
+  {
+    uint32_t b = 0;
+    if(v.pos >= v.lo)
+    {
+      const uint8_t* a = v.d + v.pos;
+      if(a < reinterpret_cast<const uint8_t*>(v.ap))
+      {
+        --v.ap;
+        v.cur = v.nxt;
+        v.nxt = vlcf_load(v, v.ap - 1);
+      }
+      b = (uint32_t)(v.cur >> (8 * (int)(a - reinterpret_cast<const uint8_t*>(v.ap)))) & 0xFFu;
+    }
+    v.pos--;
+    const int nb = 8 - ((v.unstuff && ((b & 0x7F) == 0x7F)) ? 1 : 0);
+    v.tmp |= (uint64_t)b << v.bits;
+    v.bits += nb;
+    v.unstuff = b > 0x8F;
+  }
+}
+struct MelFast
+{ /* forward reader of the MEL segment (mel_read / mel_decode, L92-206) */
+  const uint8_t* d;
+  const uint64_t* ap;
+  uint64_t cur, nxt;
+  int size, pos, bits, unstuff, k, run, have;
+  uint32_t tmp;
+};
+__device__ __forceinline__ void melf_init(MelFast& m)
+{
+  m.ap = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(m.d) & ~(uintptr_t)7);
+  m.cur = __ldg(m.ap);
+  m.nxt = reinterpret_cast<const uint8_t*>(m.ap + 1) < m.d + m.size ? __ldg(m.ap + 1) : 0ull;
+}
+__device__ __forceinline__ int melf_bit(MelFast& m)
+{
+  if(m.bits == 0)
+  {
+    uint32_t v = 0xFF;
+    if(m.pos < m.size)
+    {
+      const uint8_t* a = m.d + m.pos;
+      if(a >= reinterpret_cast<const uint8_t*>(m.ap + 1))
+      {
+        ++m.ap;
+        m.cur = m.nxt;
+        m.nxt = reinterpret_cast<const uint8_t*>(m.ap + 1) < m.d + m.size ? __ldg(m.ap + 1) : 0ull;
+      }
+      v = (uint32_t)(m.cur >> (8 * (int)(a - reinterpret_cast<const uint8_t*>(m.ap)))) & 0xFFu;
+      if(m.pos == m.size - 1)
+        v |= 0xF;
+      m.pos++;
+    }
+    m.bits = 8 - m.unstuff;
+    m.tmp = v;
+    m.unstuff = (v == 0xFF);
+  }
+  m.bits--;
+  return (int)((m.tmp >> m.bits) & 1u);
+}
+__device__ __forceinline__ int melf_symbol(MelFast& m)
+{
+  if(!m.have)
+  {
+    const int ev = mel_exp_d(m.k);
+    if(melf_bit(m))
+    {
+      m.run = 1 << ev;
+      m.have = 1;
+      m.k = min(12, m.k + 1);
+    }
+    else
+    {
+      int r = 0;
+      for(int i = 0; i < ev; ++i)
+        r = (r << 1) | melf_bit(m);
+      m.run = r;
+      m.have = 2;
+      m.k = max(0, m.k - 1);
+    }
+  }
+  if(m.run > 0)
+  {
+    m.run--;
+    if(m.run == 0 && m.have == 1)
+      m.have = 0;
+    return 0;
+  }
+  m.have = 0;
+  return 1;
+}
+
 /* significance of the previous / current quad row's bottom samples, one bit per quad.
    WIDE = false: blocks at most 64 samples wide (32 quads) -> plain registers. */
 template <bool WIDE>
@@ -200,6 +316,7 @@ struct SigRows
   }
 };
 
+#define VLCF_SKIP(v, n) do { (v).tmp >>= (n); (v).bits -= (n); } while(0)
 template <bool WIDE>
 __global__ void __launch_bounds__(128)
     k_ht_decode_vlc(const HtBlockDesc* __restrict__ blocks, const uint8_t* __restrict__ bytes, uint32_t* __restrict__ recs,
@@ -237,14 +354,23 @@ __global__ void __launch_bounds__(128)
   }
   st.ms_len = lcup - (uint32_t)scup;
 
-  MelR mel = {data + lcup - scup, scup - 1, 0, 0, 0, 0, 0, 0, 0};
-  VlcR vlc = {data, (int)lcup - 3, (int)lcup - scup, 0, 0, 0};
+  MelFast mel;
+  mel.d = data + lcup - scup;
+  mel.size = scup - 1;
+  mel.pos = mel.bits = mel.unstuff = mel.k = mel.run = mel.have = 0;
+  mel.tmp = 0;
+  melf_init(mel);
+  VlcFast vlc;
+  vlc.d = data;
+  vlc.pos = (int)lcup - 3;
+  vlc.lo = (int)lcup - scup;
   {
     const uint32_t d = __ldg(data + lcup - 2);
     vlc.tmp = d >> 4;
     vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1 : 0);
     vlc.unstuff = (d | 0xF) > 0x8F;
   }
+  vlcf_init(vlc);
   uint32_t* rec = recs + B.rec_off;
   SigRows<WIDE> sig;
   sig.clear();
@@ -255,7 +381,7 @@ __global__ void __launch_bounds__(128)
     int rho_left = 0;
     for(int q0 = 0; q0 < nq; q0 += 2)
     {
-      vlc_fill32(vlc);
+      vlcf_fill32(vlc);
       const bool has1 = q0 + 1 < nq;
       /* ---- CxtVLC of the two quads ---- */
       int cq0, cq1 = 0;
@@ -264,10 +390,10 @@ __global__ void __launch_bounds__(128)
       else
         cq0 = ((q0 > 0 ? sig.prev_br(q0 - 1) : 0) | sig.prev_bl(q0)) | ((rho_left & 0xC) ? 2 : 0) |
               ((sig.prev_br(q0) | (has1 ? sig.prev_bl(q0 + 1) : 0)) << 2);
-      uint32_t t0 = tbl[(cq0 << 7) | (vlc_head(vlc) & 0x7F)];
-      if(cq0 == 0 && !mel_symbol(mel))
+      uint32_t t0 = tbl[(cq0 << 7) | (((uint32_t)vlc.tmp) & 0x7F)];
+      if(cq0 == 0 && !melf_symbol(mel))
         t0 = 0;
-      vlc_skip(vlc, (int)(t0 >> 13));
+      VLCF_SKIP(vlc, (int)(t0 >> 13));
       const int rho0 = t0 & 0xF;
       sig.set(q0, rho0);
       uint32_t t1 = 0;
@@ -279,10 +405,10 @@ __global__ void __launch_bounds__(128)
         else
           cq1 = (sig.prev_br(q0) | sig.prev_bl(q0 + 1)) | ((rho0 & 0xC) ? 2 : 0) |
                 ((sig.prev_br(q0 + 1) | (q0 + 2 < nq ? sig.prev_bl(q0 + 2) : 0)) << 2);
-        t1 = tbl[(cq1 << 7) | (vlc_head(vlc) & 0x7F)];
-        if(cq1 == 0 && !mel_symbol(mel))
+        t1 = tbl[(cq1 << 7) | (((uint32_t)vlc.tmp) & 0x7F)];
+        if(cq1 == 0 && !melf_symbol(mel))
           t1 = 0;
-        vlc_skip(vlc, (int)(t1 >> 13));
+        VLCF_SKIP(vlc, (int)(t1 >> 13));
         rho1 = t1 & 0xF;
         sig.set(q0 + 1, rho1);
         rho_left = rho1;
@@ -297,38 +423,38 @@ __global__ void __launch_bounds__(128)
         int len;
         if(y == 0 && uoff0 && uoff1)
         {
-          if(mel_symbol(mel))
+          if(melf_symbol(mel))
           {
-            const int p0 = uvlc_prefix(vlc_head(vlc), len);
-            vlc_skip(vlc, len);
-            const int p1 = uvlc_prefix(vlc_head(vlc), len);
-            vlc_skip(vlc, len);
+            const int p0 = uvlc_prefix(((uint32_t)vlc.tmp), len);
+            VLCF_SKIP(vlc, len);
+            const int p1 = uvlc_prefix(((uint32_t)vlc.tmp), len);
+            VLCF_SKIP(vlc, len);
             const int l0 = uvlc_suflen(p0), l1 = uvlc_suflen(p1);
-            u0 = 2 + p0 + (int)(vlc_head(vlc) & ((1u << l0) - 1u));
-            vlc_skip(vlc, l0);
-            u1 = 2 + p1 + (int)(vlc_head(vlc) & ((1u << l1) - 1u));
-            vlc_skip(vlc, l1);
+            u0 = 2 + p0 + (int)(((uint32_t)vlc.tmp) & ((1u << l0) - 1u));
+            VLCF_SKIP(vlc, l0);
+            u1 = 2 + p1 + (int)(((uint32_t)vlc.tmp) & ((1u << l1) - 1u));
+            VLCF_SKIP(vlc, l1);
           }
           else
           {
-            const int p0 = uvlc_prefix(vlc_head(vlc), len);
-            vlc_skip(vlc, len);
+            const int p0 = uvlc_prefix(((uint32_t)vlc.tmp), len);
+            VLCF_SKIP(vlc, len);
             if(p0 > 2)
             {
-              u1 = 1 + (int)(vlc_head(vlc) & 1u);
-              vlc_skip(vlc, 1);
+              u1 = 1 + (int)(((uint32_t)vlc.tmp) & 1u);
+              VLCF_SKIP(vlc, 1);
               const int l0 = uvlc_suflen(p0);
-              u0 = p0 + (int)(vlc_head(vlc) & ((1u << l0) - 1u));
-              vlc_skip(vlc, l0);
+              u0 = p0 + (int)(((uint32_t)vlc.tmp) & ((1u << l0) - 1u));
+              VLCF_SKIP(vlc, l0);
             }
             else
             {
-              const int p1 = uvlc_prefix(vlc_head(vlc), len);
-              vlc_skip(vlc, len);
+              const int p1 = uvlc_prefix(((uint32_t)vlc.tmp), len);
+              VLCF_SKIP(vlc, len);
               const int l1 = uvlc_suflen(p1);
               u0 = p0;
-              u1 = p1 + (int)(vlc_head(vlc) & ((1u << l1) - 1u));
-              vlc_skip(vlc, l1);
+              u1 = p1 + (int)(((uint32_t)vlc.tmp) & ((1u << l1) - 1u));
+              VLCF_SKIP(vlc, l1);
             }
           }
         }
@@ -337,25 +463,25 @@ __global__ void __launch_bounds__(128)
           int pf0 = 0, pf1 = 0;
           if(uoff0)
           {
-            pf0 = uvlc_prefix(vlc_head(vlc), len);
-            vlc_skip(vlc, len);
+            pf0 = uvlc_prefix(((uint32_t)vlc.tmp), len);
+            VLCF_SKIP(vlc, len);
           }
           if(uoff1)
           {
-            pf1 = uvlc_prefix(vlc_head(vlc), len);
-            vlc_skip(vlc, len);
+            pf1 = uvlc_prefix(((uint32_t)vlc.tmp), len);
+            VLCF_SKIP(vlc, len);
           }
           if(uoff0)
           {
             const int l = uvlc_suflen(pf0);
-            u0 = pf0 + (int)(vlc_head(vlc) & ((1u << l) - 1u));
-            vlc_skip(vlc, l);
+            u0 = pf0 + (int)(((uint32_t)vlc.tmp) & ((1u << l) - 1u));
+            VLCF_SKIP(vlc, l);
           }
           if(uoff1)
           {
             const int l = uvlc_suflen(pf1);
-            u1 = pf1 + (int)(vlc_head(vlc) & ((1u << l) - 1u));
-            vlc_skip(vlc, l);
+            u1 = pf1 + (int)(((uint32_t)vlc.tmp) & ((1u << l) - 1u));
+            VLCF_SKIP(vlc, l);
           }
         }
       }

@@ -331,6 +331,13 @@ void b2k_plugin_free_tree(gpup_tile* T)
   free(T);
 }
 
+int32_t b2k_plugin_device(void) { return g_device; }
+void b2k_gpup_tile_free_tree(gpup_tile* tile)
+{
+  if(tile)
+    free_tree(tile);
+}
+
 /* the engine the stock entry points share (created by plugin_init, or lazily on first use) */
 b2k_engine* b2k_plugin_engine(void)
 {

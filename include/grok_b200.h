@@ -279,6 +279,46 @@ B2K_API int32_t gpup_encode_mem_tiles(gpup_compress_params* params, gpup_image* 
 B2K_API void gpup_tiles_free(gpup_tile** tiles, uint32_t num_tiles);
 /* a whole (multi-tile) code stream the host holds in memory -> the int32 planes of `image` (allocated by the host) */
 B2K_API int32_t plugin_decompress_codestream(const uint8_t* codestream, uint64_t length, gpup_image* image);
+
+/* --- in-memory batch compress (grok.cpp L1538-1545, L1655-1857): frames of one shape, several in flight --- */
+typedef struct _gpup_stream_params /* gpu_plugin_shared.h L415-421 */
+{
+  const char* file;
+  uint8_t* buf;
+  size_t buf_len;
+  size_t buf_compressed_len;
+} gpup_stream_params;
+typedef struct _gpup_compress_callback_info /* L428-440 */
+{
+  const char* input_file_name;
+  bool outputFileNameIsRelative;
+  const char* output_file_name;
+  gpup_compress_params* compressor_parameters;
+  gpup_image* image;
+  gpup_tile* tile;
+  gpup_stream_params stream_params;
+  unsigned int error_code;
+  void* host_data;
+} gpup_compress_callback_info;
+typedef uint64_t (*GPUP_COMPRESS_USER_CALLBACK)(gpup_compress_callback_info* info); /* L442 */
+typedef enum { GPUP_SOURCE_PLANAR_RGB = 0, GPUP_SOURCE_YUV420P = 1, GPUP_SOURCE_YUV422P = 2, GPUP_SOURCE_RGB48LE = 3 } gpup_source_format; /* L127-136 */
+typedef enum { GPUP_YUV_BT601 = 0, GPUP_YUV_BT709 = 1, GPUP_YUV_BT2020 = 2 } gpup_yuv_matrix;                                             /* L139-144 */
+typedef struct _gpup_batch_memory_info /* L454-473 */
+{
+  gpup_compress_params* compress_parameters;
+  uint32_t width, height, numcomps;
+  uint32_t source_prec; /* bits per sample the caller submits */
+  uint32_t prec;        /* bits per sample the code stream carries */
+  GPUP_COMPRESS_USER_CALLBACK callback;
+  bool xyz_on_device;   /* written by begin */
+  gpup_source_format source_format;
+  gpup_yuv_matrix yuv_matrix;
+  bool yuv_full_range;
+} gpup_batch_memory_info;
+B2K_API int32_t gpup_batch_memory_begin(gpup_batch_memory_info* info);
+B2K_API bool gpup_batch_memory_submit(const uint8_t* packed, void* host_data);
+B2K_API bool gpup_batch_memory_submit_planes(const uint8_t* const planes[3], const size_t stride_bytes[3], void* host_data);
+B2K_API bool gpup_batch_memory_end(void);
 /* plugin_decompress (plugin_interface.h L117-120) takes a C++ struct with std::string members
  * (PluginDecodeCallbackInfo L78-115): it is declared in grok_b200/csrc/plugin_decode.cpp and
  * documented in INTEGRATION.md, not here, so that this header stays C. */
@@ -462,6 +502,28 @@ B2K_API int64_t b2k_codestream_parse(const uint8_t* cs, uint64_t len, b2k_coding
  * (a raw codestream is accepted as it is). */
 B2K_API int64_t b2k_jph_wrap(const b2k_coding* cp, const uint8_t* cs, uint64_t cs_len, uint8_t* out, uint64_t cap);
 B2K_API int32_t b2k_jph_codestream(const uint8_t* file, uint64_t len, uint64_t* offset, uint64_t* length);
+
+/* ---- streaming: `depth` frames in flight on one GPU, so that frame k+1's host->device copies
+ * overlap frame k's kernels and device->host copies.  Each of the `depth` workers is a host thread with its own engine;
+ * a submit hands the frame to an idle worker (and blocks while all are busy); results come back through the callback on
+ * that worker's thread, possibly out of submission order.  The caller's planes / code-stream bytes are NOT copied: they
+ * must stay valid and unchanged until the frame's callback has run.
+ *   on_encoded: `result` is valid during the call; return non-zero to keep it (then free it with b2k_result_free).
+ * b2k_stream_end drains the stream, joins the workers, frees everything; returns the first device error (< 0) or 0. */
+typedef struct b2k_stream b2k_stream;
+typedef int32_t (*b2k_encoded_fn)(void* user, void* frame_user, b2k_result* result, int32_t status);
+typedef void (*b2k_decoded_fn)(void* user, void* frame_user, int32_t status);
+B2K_API int32_t b2k_stream_encode_begin(int32_t device, const b2k_coding* cp, uint32_t depth, uint32_t sample_bytes /* 2 or 4 */,
+                                        b2k_encoded_fn on_encoded, void* user, b2k_stream** out);
+B2K_API int32_t b2k_stream_encode_submit(b2k_stream* s, const void* const* planes, const uint32_t* strides, void* frame_user);
+B2K_API int32_t b2k_stream_decode_begin(int32_t device, uint32_t depth, uint32_t sample_bytes /* 2 or 4 */, b2k_decoded_fn on_decoded,
+                                        void* user, b2k_stream** out);
+B2K_API int32_t b2k_stream_decode_submit(b2k_stream* s, const b2k_coding* cp, const b2k_block* blocks, uint64_t num_blocks,
+                                         const uint8_t* bytes, uint64_t num_bytes, void* const* planes, const uint32_t* strides,
+                                         void* frame_user);
+B2K_API int32_t b2k_stream_decode_submit_codestream(b2k_stream* s, const uint8_t* codestream, uint64_t length, uint32_t numcomps,
+                                                    void* const* planes, const uint32_t* strides, void* frame_user);
+B2K_API int32_t b2k_stream_end(b2k_stream* s);
 
 /* launches issued by this library since engine creation (bench.py "gpu_launches") */
 B2K_API uint64_t b2k_launch_count(void);

@@ -737,3 +737,137 @@ def test_decode_with_byte_arena_not_in_tile_order(engine):
     engine.decode(cp, nb, new[:pos], out)
     for a, b in zip(out, planes):
         assert np.array_equal(a, b)
+
+
+def test_streaming_encode_decode_matches_the_synchronous_calls(engine):
+    """frames in flight on several engines of one GPU.  Six different frames go through an encode stream
+    (depth 3) whose callback feeds a decode stream (depth 3): every frame's coded bytes equal the synchronous
+    b2k_encode's, every decoded frame equals its source -- GrkPluginBatchMemoryTest's property (all frames come back,
+    each lossless) plus byte identity with the per-call path."""
+    import threading
+    w, h = 1536, 1024
+    cp = G.make_coding(w, h, 3, 12, numres=6, tile=(512, 512))
+    frames = [P.synthetic_image(w, h, 3, 12, seed=100 + i) for i in range(6)]
+    want = []
+    for f in frames:
+        r = engine.encode(cp, f)
+        want.append(r.bytes.copy())
+        r.free()
+    outs = [[np.zeros((h, w), np.int32) for _ in range(3)] for _ in frames]
+    results, errors, done = {}, [], threading.Semaphore(0)
+
+    def on_decoded(tag, status):
+        if status != 0:
+            errors.append("decode %r: status %d" % (tag, status))
+        done.release()
+
+    dec = G.DecodeStream(depth=3, on_decoded=on_decoded)
+
+    def on_encoded(tag, res, status):
+        if status != 0 or res is None:
+            errors.append("encode %r: status %d" % (tag, status))
+            done.release()
+            return
+        results[tag] = res
+        dec.submit(cp, res.blocks, res.bytes, outs[tag], tag)
+
+    enc = G.EncodeStream(cp, depth=3, on_encoded=on_encoded)
+    for i, f in enumerate(frames):
+        enc.submit(f, i)
+    for _ in frames:
+        assert done.acquire(timeout=120)
+    assert enc.end() == 0 and dec.end() == 0
+    assert not errors, errors
+    for i, f in enumerate(frames):
+        assert np.array_equal(results[i].bytes, want[i]), "frame %d: streamed bytes differ from b2k_encode's" % i
+        for a, b in zip(outs[i], f):
+            assert np.array_equal(a, b)
+        results[i].free()
+
+
+def test_stock_batch_memory_symbols(engine):
+    """gpup_batch_memory_begin / _submit / _end (grok.cpp L1655-1857) driven the way the host drives them: frames as
+    pixel-interleaved 16-bit samples, results through the compress callback as stock gpup_tile trees, concurrently."""
+    import os
+    import threading
+    from gpup_ctypes import GpupTile
+    lib = G.lib()
+    w, h, nc, prec = 640, 384, 3, 12
+    cp = G.make_coding(w, h, nc, prec, numres=6)
+    frames = [P.synthetic_image(w, h, nc, prec, seed=300 + i) for i in range(5)]
+    want = []
+    for f in frames:
+        r = engine.encode(cp, f)
+        want.append([r.block_bytes(i).copy() for i in range(r.num_blocks)])
+        r.free()
+
+    class StreamParams(C.Structure):
+        _fields_ = [("file", C.c_char_p), ("buf", C.c_void_p), ("buf_len", C.c_size_t), ("buf_compressed_len", C.c_size_t)]
+
+    class CbInfo(C.Structure):
+        _fields_ = [("input_file_name", C.c_char_p), ("outputFileNameIsRelative", C.c_bool), ("output_file_name", C.c_char_p),
+                    ("compressor_parameters", C.c_void_p), ("image", C.c_void_p), ("tile", C.POINTER(GpupTile)),
+                    ("stream_params", StreamParams), ("error_code", C.c_uint), ("host_data", C.c_void_p)]
+    assert C.sizeof(CbInfo) == 96
+
+    class BatchInfo(C.Structure):
+        _fields_ = [("compress_parameters", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("numcomps", C.c_uint32),
+                    ("source_prec", C.c_uint32), ("prec", C.c_uint32), ("callback", C.c_void_p), ("xyz_on_device", C.c_bool),
+                    ("source_format", C.c_int), ("yuv_matrix", C.c_int), ("yuv_full_range", C.c_bool)]
+    assert C.sizeof(BatchInfo) == 56
+    got, lock = {}, threading.Lock()
+    CB = C.CFUNCTYPE(C.c_uint64, C.POINTER(CbInfo))
+
+    def cb(pinfo):
+        info = pinfo.contents
+        blocks = []
+        if info.error_code == 0 and info.tile:
+            T = info.tile.contents
+            for c in range(T.numComponents):
+                tc = T.tileComponents[c].contents
+                for r in range(tc.numResolutions):
+                    res = tc.resolutions[r].contents
+                    for b in range(res.numBands):
+                        band = res.band[b].contents
+                        for p in range(band.numPrecincts):
+                            prc = band.precincts[p].contents
+                            for j in range(prc.numBlocks):
+                                cb_ = prc.blocks[j].contents
+                                blocks.append(bytes(np.ctypeslib.as_array(cb_.compressedData, shape=(cb_.compressedDataLength,)))
+                                              if cb_.compressedDataLength else b"")
+        with lock:
+            got[int(info.host_data)] = blocks
+        return 1
+
+    cb_keep = CB(cb)
+    params = (C.c_uint8 * 12696)()
+    probe = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "grok_b200.h"
+#define O(f) printf(#f " %zu\n", offsetof(gpup_compress_params, f));
+int main(void){ O(numlayers) O(csty) O(numgbits) O(numresolution) O(cblockw_init) O(cblockh_init) O(cblk_sty) O(irreversible) O(roi_compno) O(mct) return 0; }'''
+    import subprocess
+    exe = "/tmp/b2k_off2_%d" % os.getpid()
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(os.path.dirname(G._HERE), "include"), "-o", exe], input=probe.encode(), check=True)
+    off = dict((k, int(v)) for k, v in (l.split() for l in subprocess.check_output([exe]).decode().splitlines()))
+
+    def put(o, val, typ):
+        typ.from_buffer(params, o).value = val
+    put(off["numlayers"], 1, C.c_uint16); put(off["numgbits"], 1, C.c_uint8); put(off["numresolution"], 6, C.c_uint8)
+    put(off["cblockw_init"], 64, C.c_uint32); put(off["cblockh_init"], 64, C.c_uint32); put(off["cblk_sty"], 0x40, C.c_uint8)
+    put(off["roi_compno"], -1, C.c_int32); put(off["mct"], 1, C.c_uint8)
+    info = BatchInfo(C.addressof(params), w, h, nc, prec, prec, C.cast(cb_keep, C.c_void_p), False, 0, 0, False)
+    lib.gpup_batch_memory_begin.argtypes = [C.POINTER(BatchInfo)]
+    lib.gpup_batch_memory_submit.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gpup_batch_memory_submit.restype = C.c_bool
+    lib.gpup_batch_memory_end.restype = C.c_bool
+    assert lib.gpup_batch_memory_begin(C.byref(info)) == 0, lib.b2k_last_error()
+    for i, f in enumerate(frames):
+        packed = np.ascontiguousarray(np.stack(f, axis=-1).astype(np.uint16))       # pixel interleaved, little endian
+        assert lib.gpup_batch_memory_submit(packed.ctypes.data, C.c_void_p(i + 1))   # copied before the call returns
+        packed[:] = 0xFFFF
+    assert lib.gpup_batch_memory_end()
+    assert sorted(got) == [i + 1 for i in range(len(frames))]
+    for i in range(len(frames)):
+        assert got[i + 1] == [bytes(b) for b in want[i]]

@@ -32,13 +32,14 @@ _ABI_PROBE = r'''
 #include <stddef.h>
 %s
 int main(void){
-  printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\n", sizeof(gpup_code_block), sizeof(gpup_compress_params),
+  printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\n", sizeof(gpup_code_block), sizeof(gpup_compress_params),
    offsetof(gpup_compress_params, cblk_sty), sizeof(gpup_image_comp), sizeof(gpup_image), sizeof(gpup_tile), sizeof(gpup_band),
    sizeof(gpup_header_info), sizeof(gpup_decompress_params), sizeof(gpup_decompress_callback_info),
-   offsetof(gpup_compress_params, apply_xyz_transform));
+   offsetof(gpup_compress_params, apply_xyz_transform), sizeof(gpup_batch_memory_info), offsetof(gpup_batch_memory_info, source_format),
+   sizeof(gpup_compress_callback_info), offsetof(gpup_compress_callback_info, host_data));
   return 0; }'''
 # measured from the reference's own gpu_plugin_shared.h (g++ 13, x86-64); re-checked live below when the tree is here
-_ABI_REFERENCE = [1672, 12696, 4152, 40, 32, 24, 32, 312, 8272, 424, 12694]
+_ABI_REFERENCE = [1672, 12696, 4152, 40, 32, 24, 32, 312, 8272, 424, 12694, 56, 44, 96, 88]
 
 
 def _probe(include_line, flags, compiler):
