@@ -338,6 +338,110 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+def run_config4(args, rank, world, local):
+    """--workload config4 (BASELINE.json configs[3]): ONE 16384x16384x4 16-bit lossless image, 256 tiles of 1024x1024
+    sharded over the N ranks (tile t -> rank t % N, no data-path collective), STRONG scaling.  The timed step holds
+    everything north_star names: every rank encodes its tiles from pinned host planes (b2k_encode with tile_mod / tile_rem),
+    an NCCL all_gather of the segment sizes, the NCCL gather of the variable-length coded segments + block tables to the
+    writer rank, b2k_result_merge and b2k_codestream_write (TLM + PLT) there.  value = image pixels / step time."""
+    import torch
+    import grok_b200 as G
+    import oracle_pipeline as P
+    torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W4 = H4 = int(os.environ.get("B2K_CONFIG4_SIZE", "16384"))
+    NC4, PREC4 = 4, 16
+    cp = G.make_coding(W4, H4, NC4, PREC4, numres=NUMRES, tile=(TILE, TILE), mct=1)
+    base = P.synthetic_image(TILE, TILE, NC4, PREC4, seed=20260926)
+    reps = W4 // TILE
+    # every rank holds the planes of the tiles it codes (the others' stay untouched zeros): 16-bit containers, pinned
+    planes = [G.pinned_empty((H4, W4), np.uint16) for _ in range(NC4)]
+    for t in range(reps * reps):
+        if t % world == rank:
+            ty, tx = divmod(t, reps)
+            for c in range(NC4):
+                planes[c][ty * TILE:(ty + 1) * TILE, tx * TILE:(tx + 1) * TILE] = (base[c] + 257 * t) & 0xFFFF
+    eng = G.Engine(local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    info = {}
+
+    def step():
+        res = eng.encode(cp, planes, tile_mod=world, tile_rem=rank)
+        cs_len = 0
+        if world > 1:
+            sizes = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([res.num_bytes, res.num_blocks], dtype=torch.int64, device="cuda"))
+            sizes = [(int(x[0]), int(x[1])) for x in sizes]
+            seg = torch.from_numpy(res.bytes).cuda(non_blocking=True)
+            tab = torch.from_numpy(res.blocks.view(np.uint8).reshape(-1)).cuda(non_blocking=True)
+            if rank == 0:
+                segs = [torch.empty(n, dtype=torch.uint8, device="cuda") for n, _ in sizes]
+                tabs = [torch.empty(k * G.BLOCK_DTYPE.itemsize, dtype=torch.uint8, device="cuda") for _, k in sizes]
+                dist.gather(seg, segs, dst=0)
+                dist.gather(tab, tabs, dst=0)
+                merged = G.merge_shards(cp, [(np.frombuffer(tabs[r].cpu().numpy().tobytes(), dtype=G.BLOCK_DTYPE), segs[r].cpu().numpy())
+                                             for r in range(world)])
+                cs = G.codestream_write(cp, merged.blocks, merged.bytes, G.CS_TLM | G.CS_PLT, num_tiles=reps * reps)
+                cs_len = len(cs)
+                info["coded_bytes"] = int(merged.num_bytes)
+                merged.free()
+            else:
+                dist.gather(seg, None, dst=0)
+                dist.gather(tab, None, dst=0)
+        else:
+            cs = G.codestream_write(cp, res.blocks, res.bytes, G.CS_TLM | G.CS_PLT, num_tiles=reps * reps)
+            cs_len = len(cs)
+            info["coded_bytes"] = int(res.num_bytes)
+        res.free()
+        return cs_len
+
+    sampler = ClockSampler(range(int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))) if world > 1 else [local], enabled=(rank == 0))
+    sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler.wait_ready()
+    barrier()
+    sampler.begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cs_len = step()
+    barrier()
+    dt = (time.perf_counter() - t0) / args.steps
+    sampler.end()
+    clocks = sampler.stop()
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt[0])
+    if rank == 0:
+        pix = W4 * H4
+        line = {"metric": "Mpixels/s encode %dx%dx4 16-bit HTJ2K lossless, 1024x1024 tiles sharded over the GPUs (BASELINE config 4)" % (W4, H4),
+                "value": pix / dt / 1e6, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+                "config": {"workload": "config4: one %dx%dx4 16-bit lossless image (5/3 + RCT on components 0-2), %d tiles, tile t -> rank t %% N; "
+                                       "step = sharded b2k_encode16 from pinned host planes + NCCL all_gather of sizes + NCCL gather of coded "
+                                       "segments and block tables to rank 0 + b2k_result_merge + b2k_codestream_write (TLM + PLT)" % (W4, H4, reps * reps),
+                           "timing": "host wall clock around the K steps incl. barriers, max over ranks (the step ends on the host: the code stream is in host memory)",
+                           "codestream_bytes": int(cs_len), **info},
+                "e2e": {"value": pix / dt / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int(W4 * H4 * NC4 * 2), "d2h_bytes_per_step": int(info.get("coded_bytes", 0))},
+                "clocks": clocks}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -345,6 +449,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config4"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -354,6 +459,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "config4":
+        run_config4(args, rank, world, local)
         return
 
     import torch

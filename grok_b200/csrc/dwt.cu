@@ -407,6 +407,42 @@ __device__ __forceinline__ void cp_async_wait()
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+/* ---- bulk asynchronous copies (the TMA engine: SASS UBLKCP) completing on an mbarrier -------------------------
+ * A warp whose 32 lanes all sit inside the line stages a whole 1 KB warp-row with ONE instruction issued by one lane
+ * instead of 64 LDGSTS (two per lane): the copy engine generates the addresses, the LSU issue slots go back to the
+ * lifting code.  The row lands linearly (no XOR swizzle -- a bulk copy is contiguous); the lanes' two 128-bit reads
+ * are then 2-way bank conflicted, which costs nothing here: shared memory moves 16 B/clk/SM of the 128 it can. */
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "MBAR_WAIT_%=:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra MBAR_DONE_%=;\n"
+               "bra MBAR_WAIT_%=;\n"
+               "MBAR_DONE_%=:\n"
+               "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(parity)
+               : "memory");
+}
+
 template <int NC, bool U16>
 struct RowStage
 {
@@ -495,6 +531,27 @@ struct RowStage
         out[c][4] = b.x; out[c][5] = b.y; out[c][6] = b.z; out[c][7] = b.w;
       }
       /* lanes beyond the right halo hold stale shared memory: nothing they compute is stored */
+    }
+  }
+  /* bulk path (32-bit samples, every lane fast): one lane asks the copy engine for the NC whole warp-rows of canvas
+     row v; they land linearly in the slot and complete on `bar` (the caller has armed it with expect_tx) */
+  static __device__ __forceinline__ void fill_bulk(uint8_t* stage, int which, const DwtLevelDesc& D, const Job& J, int v, uint64_t* bar)
+  {
+    const int r = mirror_rel(v - D.v0, J.hn);
+    const int rel0 = J.ulane - D.u0 - 8 * J.lane; /* lane 0's first column */
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+      bulk_g2s(stage + (which * NC + c) * ROWB, reinterpret_cast<const int32_t*>(D.in[c]) + (size_t)r * D.in_pitch + rel0, ROWB, bar);
+  }
+  static __device__ __forceinline__ void read_linear(const uint8_t* stage, int which, const Job& J, int (&out)[NC][8])
+  {
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+      const uint8_t* src = stage + (which * NC + c) * ROWB + J.lane * 32;
+      const int4 a = *reinterpret_cast<const int4*>(src), b = *reinterpret_cast<const int4*>(src + 16);
+      out[c][0] = a.x; out[c][1] = a.y; out[c][2] = a.z; out[c][3] = a.w;
+      out[c][4] = b.x; out[c][5] = b.y; out[c][6] = b.z; out[c][7] = b.w;
     }
   }
   /* lane can use 16-byte async copies: its 8 columns are inside the line and 16-byte aligned */
@@ -670,8 +727,22 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_fwd(const DwtL
   const BandGeom g = band_geom(D);
   const StoreCtx SC = store_ctx(D, J, g);
   uint8_t* wsm = smem_dwt + (size_t)(threadIdx.x >> 5) * STAGES * RS::PAIRB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dwt + (size_t)B2K_WARPS_PER_CTA * STAGES * RS::PAIRB) + (threadIdx.x >> 5) * STAGES;
   const bool fast = RS::lane_fast(D, J);
   const unsigned fastmask = __ballot_sync(0xffffffffu, fast);
+  /* interior strip: rows arrive by bulk copy (TMA engine) on per-slot mbarriers; edge strips keep the LDGSTS path */
+  const bool bulk = !U16 && fastmask == 0xffffffffu;
+  if(bulk)
+  {
+    if(J.lane == 0)
+    {
+#pragma unroll
+      for(int s = 0; s < STAGES; ++s)
+        mbar_init(bars + s, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
   int mcol[8]; /* mirrored column of each of the lane's samples: only edge lanes use them */
 #pragma unroll
   for(int i = 0; i < 8; ++i)
@@ -680,15 +751,29 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_fwd(const DwtL
   /* pairs t = jbeg-1 .. jend-1 : rows (2t+1, 2t+2); the even row before them is fetched directly */
   const int tfirst = J.jbeg - 1, tlast = J.jend - 1;
   int tfill = tfirst;
+  auto fill_pair = [&](int tf) {
+    const int slot = (tf - tfirst) % STAGES;
+    uint8_t* st = wsm + (size_t)slot * RS::PAIRB;
+    if(bulk)
+    {
+      if(J.lane == 0)
+      {
+        mbar_expect_tx(bars + slot, RS::PAIRB);
+        RS::fill_bulk(st, 0, D, J, 2 * tf + 1, bars + slot);
+        RS::fill_bulk(st, 1, D, J, 2 * tf + 2, bars + slot);
+      }
+    }
+    else
+    {
+      RS::fill(st, 0, D, J, 2 * tf + 1, fast, fastmask, mcol);
+      RS::fill(st, 1, D, J, 2 * tf + 2, fast, fastmask, mcol);
+    }
+  };
 #pragma unroll
   for(int s = 0; s < STAGES - 1; ++s)
   {
     if(tfill <= tlast)
-    {
-      uint8_t* st = wsm + (size_t)((tfill - tfirst) % STAGES) * RS::PAIRB;
-      RS::fill(st, 0, D, J, 2 * tfill + 1, fast, fastmask, mcol);
-      RS::fill(st, 1, D, J, 2 * tfill + 2, fast, fastmask, mcol);
-    }
+      fill_pair(tfill);
     cp_async_commit();
     ++tfill;
   }
@@ -704,19 +789,24 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_fwd(const DwtL
   {
     __syncwarp(); /* every lane has read the stage that is refilled next */
     if(tfill <= tlast)
-    {
-      uint8_t* st = wsm + (size_t)((tfill - tfirst) % STAGES) * RS::PAIRB;
-      RS::fill(st, 0, D, J, 2 * tfill + 1, fast, fastmask, mcol);
-      RS::fill(st, 1, D, J, 2 * tfill + 2, fast, fastmask, mcol);
-    }
+      fill_pair(tfill);
     cp_async_commit();
     ++tfill;
-    cp_async_wait<STAGES - 1>();
-    __syncwarp(); /* rows were copied cooperatively */
     const uint8_t* st = wsm + (size_t)((t - tfirst) % STAGES) * RS::PAIRB;
     int O[NC][8], E2[NC][8];
-    RS::read(st, 0, D, J, O);
-    RS::read(st, 1, D, J, E2);
+    if(bulk)
+    {
+      mbar_wait(bars + (t - tfirst) % STAGES, (unsigned)(((t - tfirst) / STAGES) & 1));
+      RS::read_linear(st, 0, J, O);
+      RS::read_linear(st, 1, J, E2);
+    }
+    else
+    {
+      cp_async_wait<STAGES - 1>();
+      __syncwarp(); /* rows were copied cooperatively */
+      RS::read(st, 0, D, J, O);
+      RS::read(st, 1, D, J, E2);
+    }
     rct_fwd_inplace<NC>(D, O);
     rct_fwd_inplace<NC>(D, E2);
     const bool emit = t >= J.jbeg;
@@ -861,8 +951,21 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_fwd(const DwtL
   const BandGeom g = band_geom(D);
   const StoreCtx SC = store_ctx(D, J, g);
   uint8_t* wsm = smem_dwt + (size_t)(threadIdx.x >> 5) * STAGES * RS::PAIRB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dwt + (size_t)B2K_WARPS_PER_CTA * STAGES * RS::PAIRB) + (threadIdx.x >> 5) * STAGES;
   const bool fast = RS::lane_fast(D, J);
   const unsigned fastmask = __ballot_sync(0xffffffffu, fast);
+  const bool bulk = !U16 && fastmask == 0xffffffffu; /* interior strip: rows by bulk copy (TMA engine), see k_dwt53_fwd */
+  if(bulk)
+  {
+    if(J.lane == 0)
+    {
+#pragma unroll
+      for(int s = 0; s < STAGES; ++s)
+        mbar_init(bars + s, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
   int mcol[8];
 #pragma unroll
   for(int i = 0; i < 8; ++i)
@@ -873,15 +976,29 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_fwd(const DwtL
   /* pairs t = jbeg-2 .. jend : rows (2t+1, 2t+2); output pair t-1 from t = jbeg+1 on */
   const int tfirst = J.jbeg - 2, tlast = J.jend;
   int tfill = tfirst;
+  auto fill_pair = [&](int tf) {
+    const int slot = (tf - tfirst) % STAGES;
+    uint8_t* st = wsm + (size_t)slot * RS::PAIRB;
+    if(bulk)
+    {
+      if(J.lane == 0)
+      {
+        mbar_expect_tx(bars + slot, RS::PAIRB);
+        RS::fill_bulk(st, 0, D, J, 2 * tf + 1, bars + slot);
+        RS::fill_bulk(st, 1, D, J, 2 * tf + 2, bars + slot);
+      }
+    }
+    else
+    {
+      RS::fill(st, 0, D, J, 2 * tf + 1, fast, fastmask, mcol);
+      RS::fill(st, 1, D, J, 2 * tf + 2, fast, fastmask, mcol);
+    }
+  };
 #pragma unroll
   for(int s = 0; s < STAGES - 1; ++s)
   {
     if(tfill <= tlast)
-    {
-      uint8_t* st = wsm + (size_t)((tfill - tfirst) % STAGES) * RS::PAIRB;
-      RS::fill(st, 0, D, J, 2 * tfill + 1, fast, fastmask, mcol);
-      RS::fill(st, 1, D, J, 2 * tfill + 2, fast, fastmask, mcol);
-    }
+      fill_pair(tfill);
     cp_async_commit();
     ++tfill;
   }
@@ -897,22 +1014,29 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_fwd(const DwtL
   {
     __syncwarp();
     if(tfill <= tlast)
-    {
-      uint8_t* st = wsm + (size_t)((tfill - tfirst) % STAGES) * RS::PAIRB;
-      RS::fill(st, 0, D, J, 2 * tfill + 1, fast, fastmask, mcol);
-      RS::fill(st, 1, D, J, 2 * tfill + 2, fast, fastmask, mcol);
-    }
+      fill_pair(tfill);
     cp_async_commit();
     ++tfill;
-    cp_async_wait<STAGES - 1>();
-    __syncwarp();
+    if(bulk)
+      mbar_wait(bars + (t - tfirst) % STAGES, (unsigned)(((t - tfirst) / STAGES) & 1));
+    else
+    {
+      cp_async_wait<STAGES - 1>();
+      __syncwarp();
+    }
     const uint8_t* st = wsm + (size_t)((t - tfirst) % STAGES) * RS::PAIRB;
     float O[NC][8], E2[NC][8];
     {
       int raw[NC][8];
-      RS::read(st, 0, D, J, raw);
+      if(bulk)
+        RS::read_linear(st, 0, J, raw);
+      else
+        RS::read(st, 0, D, J, raw);
       ict_fwd_convert<NC>(D, raw, O);
-      RS::read(st, 1, D, J, raw);
+      if(bulk)
+        RS::read_linear(st, 1, J, raw);
+      else
+        RS::read(st, 1, D, J, raw);
       ict_fwd_convert<NC>(D, raw, E2);
     }
     const bool emit = (t - 1) >= J.jbeg;
@@ -1722,7 +1846,7 @@ constexpr int FWD_STAGES = 3;
 template <int NC, bool U16, int STAGES>
 static void launch_fwd53(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
 {
-  const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * RowStage<NC, U16>::PAIRB;
+  const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * RowStage<NC, U16>::PAIRB + (size_t)B2K_WARPS_PER_CTA * STAGES * sizeof(uint64_t);
   static DeviceOnce once; /* function attributes are per device */
   once.run([&] {
     cudaFuncSetAttribute(k_dwt53_fwd<NC, U16, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1733,7 +1857,7 @@ static void launch_fwd53(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelD
 template <int NC, bool U16, int STAGES>
 static void launch_fwd97(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
 {
-  const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * RowStage<NC, U16>::PAIRB;
+  const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * RowStage<NC, U16>::PAIRB + (size_t)B2K_WARPS_PER_CTA * STAGES * sizeof(uint64_t);
   static DeviceOnce once; /* function attributes are per device */
   once.run([&] {
     cudaFuncSetAttribute(k_dwt97_fwd<NC, U16, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -408,6 +408,26 @@ static int build_dwt_plan(b2k_device_job* J)
       }
       mctL.tile_first.push_back((uint32_t)mctL.descs.size());
       sglL.tile_first.push_back((uint32_t)sglL.descs.size());
+      /* Coarse levels have few rows: with 32 row pairs per warp-job the whole level is a handful of long serial
+         chains on an almost empty GPU (level 3 of config 2: 34.7 us for 64 MB).  Cut the segments until the level
+         offers about two warp-jobs per resident warp (or segments of 8 pairs, where the recomputed halo rows start
+         to dominate): the work is L2-resident there, parallelism is what it lacks. */
+      for(LevelLaunch* LL : {&mctL, &sglL})
+      {
+        int Pl = P;
+        auto jobs = [&] {
+          uint64_t n = 0;
+          for(const DwtLevelDesc& d : LL->descs)
+            n += (uint64_t)d.nstrips * d.nsegs;
+          return n;
+        };
+        while(!LL->descs.empty() && Pl > 8 && jobs() < 3552)
+        {
+          Pl >>= 1;
+          for(DwtLevelDesc& d : LL->descs)
+            fill_strips(d, Pl);
+        }
+      }
       if(dir == 0)
       {
         if(!mctL.descs.empty()) out.push_back(std::move(mctL));
