@@ -256,7 +256,9 @@ def grok_tune_threads(st):
     cands = [os.cpu_count() or 1]
     q = cpu_quota()
     if q and int(q) < cands[0]:
-        cands.append(max(1, int(q)))
+        # a container with a CPU-time quota: the quota's worth of threads, and twice that (never every logical CPU of a
+        # 128-way host against a 16-CPU quota: that only burns the quota and the box's memory)
+        cands = [max(1, int(q)), min(cands[0], 2 * max(1, int(q)))]
     if os.environ.get("B2K_REF_THREADS"):
         cands = [int(os.environ["B2K_REF_THREADS"])]
     best = None
@@ -552,111 +554,117 @@ def main():
     clocks = sampler.stop()   # clocks / throttle reasons over both timed regions
     assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "e2e round trip is not lossless"
 
-    # ---------------- same call with host packing off: the int32 planes cross PCIe as they are ----------------
-    G.set_host_threads(0)
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(max(3, args.steps // 2)):
-        e2e_step()
-    barrier()
-    dt_e2e32 = (time.perf_counter() - t0) / max(3, args.steps // 2)
-    assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "e2e (no host packing) round trip is not lossless"
-    G.set_host_threads(-1)
-
-    # ---------------- files: the same calls plus the host T2 step (codestream write / parse) ----------------
-    cs_buf = G.pinned_empty((int(nb) + int(nb) // 8 + (1 << 20),), np.uint8)
-
-    def file_step():
-        cs = eng.encode_codestream(cp, planes, out=cs_buf)
-        eng.decode_codestream(cs, out=out)
-        return len(cs)
-
-    for _ in range(3):
-        file_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(max(3, args.steps // 2)):
-        cs_len = file_step()
-    barrier()
-    dt_file = (time.perf_counter() - t0) / max(3, args.steps // 2)
-    assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "codestream round trip is not lossless"
-
-    # ---------------- same, 16-bit sample containers (b2k_encode16 / b2k_decode16) ----------------
-    p16 = [G.pinned_empty((H, W), np.uint16) for _ in range(NCOMP)]
-    o16 = [G.pinned_empty((H, W), np.uint16) for _ in range(NCOMP)]
-    for p, q in zip(p16, img):
-        p[:] = q
-
-    def e2e16_step():
-        res = eng.encode(cp, p16)
-        eng.decode(cp, res.blocks, res.bytes, o16)
-        res.free()
-
-    for _ in range(2):
-        e2e16_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e16_step()
-    barrier()
-    dt_e2e16 = time.perf_counter() - t0
-    assert all(np.array_equal(a, b) for a, b in zip(o16, p16)), "16-bit e2e round trip is not lossless"
-
-    # ---------------- streamed: an encode stream feeding a decode stream, 3 frames in flight each ----------------
-    # 16-bit sample containers in and out (what the reference's batch interface carries, gpup_batch_memory_submit_planes):
-    # frame k+1's upload overlaps frame k's kernels and download, and the decode of frame k-1 runs beside both
-    depth = int(os.environ.get("B2K_BENCH_STREAM_DEPTH", "3"))
-    outs = [[G.pinned_empty((H, W), np.uint16) for _ in range(NCOMP)] for _ in range(2 * depth + 1)]
-    free_outs = list(range(len(outs)))
-    lock, done, live, bad, used = threading.Lock(), threading.Semaphore(0), {}, [], set()
-    room = threading.Semaphore(len(outs))
-
-    def on_decoded(tag, status):
-        res, slot = live.pop(tag)
-        res.free()
-        if status != 0:
-            bad.append(status)
-        with lock:
-            free_outs.append(slot)
-        room.release()
-        done.release()
-
-    dec_stream = G.DecodeStream(depth=depth, sample_bytes=2, on_decoded=on_decoded, device=local)
-
-    def on_encoded(tag, res, status):
-        if status != 0 or res is None:
-            bad.append(status)
-            done.release()
-            return
-        room.acquire()
-        with lock:
-            slot = free_outs.pop()
-            used.add(slot)
-        live[tag] = (res, slot)
-        dec_stream.submit(cp, res.blocks, res.bytes, outs[slot], tag)
-
-    enc_stream = G.EncodeStream(cp, depth=depth, sample_bytes=2, on_encoded=on_encoded, device=local)
-
-    def streamed(nframes):
+    # the legs below are extras (other containers, files, streams): with several ranks on one host they only add pinned
+    # memory and time to a run whose purpose is the scaling of `value` and `e2e`, so they run at N = 1 only
+    extras = world == 1 or bool(os.environ.get("B2K_BENCH_ALL_LEGS"))
+    dt_e2e32 = dt_file = dt_e2e16 = dt_stream = 0.0
+    cs_len, n_stream = 0, 0
+    if extras:
+        # ---------------- same call with host packing off: the int32 planes cross PCIe as they are ----------------
+        G.set_host_threads(0)
+        for _ in range(2):
+            e2e_step()
+        barrier()
         t0 = time.perf_counter()
-        for i in range(nframes):
-            enc_stream.submit(p16, i)
-        for _ in range(nframes):
-            done.acquire()
-        return time.perf_counter() - t0
+        for _ in range(max(3, args.steps // 2)):
+            e2e_step()
+        barrier()
+        dt_e2e32 = (time.perf_counter() - t0) / max(3, args.steps // 2)
+        assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "e2e (no host packing) round trip is not lossless"
+        G.set_host_threads(-1)
 
-    streamed(3 * depth + 3)           # warm-up: every worker's engine has built its job, the pinned result arenas exist
-    barrier()
-    n_stream = max(16, args.steps)
-    dt_stream = streamed(n_stream) / n_stream
-    barrier()
-    enc_stream.end()
-    dec_stream.end()
-    assert not bad, bad
-    for slot in used:
-        assert all(np.array_equal(a, b) for a, b in zip(outs[slot], p16)), "streamed round trip is not lossless"
+        # ---------------- files: the same calls plus the host T2 step (codestream write / parse) ----------------
+        cs_buf = G.pinned_empty((int(nb) + int(nb) // 8 + (1 << 20),), np.uint8)
+
+        def file_step():
+            cs = eng.encode_codestream(cp, planes, out=cs_buf)
+            eng.decode_codestream(cs, out=out)
+            return len(cs)
+
+        for _ in range(3):
+            file_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(3, args.steps // 2)):
+            cs_len = file_step()
+        barrier()
+        dt_file = (time.perf_counter() - t0) / max(3, args.steps // 2)
+        assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "codestream round trip is not lossless"
+
+        # ---------------- same, 16-bit sample containers (b2k_encode16 / b2k_decode16) ----------------
+        p16 = [G.pinned_empty((H, W), np.uint16) for _ in range(NCOMP)]
+        o16 = [G.pinned_empty((H, W), np.uint16) for _ in range(NCOMP)]
+        for p, q in zip(p16, img):
+            p[:] = q
+
+        def e2e16_step():
+            res = eng.encode(cp, p16)
+            eng.decode(cp, res.blocks, res.bytes, o16)
+            res.free()
+
+        for _ in range(2):
+            e2e16_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e16_step()
+        barrier()
+        dt_e2e16 = time.perf_counter() - t0
+        assert all(np.array_equal(a, b) for a, b in zip(o16, p16)), "16-bit e2e round trip is not lossless"
+
+        # ---------------- streamed: an encode stream feeding a decode stream, 3 frames in flight each ----------------
+        # 16-bit sample containers in and out (what the reference's batch interface carries, gpup_batch_memory_submit_planes):
+        # frame k+1's upload overlaps frame k's kernels and download, and the decode of frame k-1 runs beside both
+        depth = int(os.environ.get("B2K_BENCH_STREAM_DEPTH", "3"))
+        outs = [[G.pinned_empty((H, W), np.uint16) for _ in range(NCOMP)] for _ in range(2 * depth + 1)]
+        free_outs = list(range(len(outs)))
+        lock, done, live, bad, used = threading.Lock(), threading.Semaphore(0), {}, [], set()
+        room = threading.Semaphore(len(outs))
+
+        def on_decoded(tag, status):
+            res, slot = live.pop(tag)
+            res.free()
+            if status != 0:
+                bad.append(status)
+            with lock:
+                free_outs.append(slot)
+            room.release()
+            done.release()
+
+        dec_stream = G.DecodeStream(depth=depth, sample_bytes=2, on_decoded=on_decoded, device=local)
+
+        def on_encoded(tag, res, status):
+            if status != 0 or res is None:
+                bad.append(status)
+                done.release()
+                return
+            room.acquire()
+            with lock:
+                slot = free_outs.pop()
+                used.add(slot)
+            live[tag] = (res, slot)
+            dec_stream.submit(cp, res.blocks, res.bytes, outs[slot], tag)
+
+        enc_stream = G.EncodeStream(cp, depth=depth, sample_bytes=2, on_encoded=on_encoded, device=local)
+
+        def streamed(nframes):
+            t0 = time.perf_counter()
+            for i in range(nframes):
+                enc_stream.submit(p16, i)
+            for _ in range(nframes):
+                done.acquire()
+            return time.perf_counter() - t0
+
+        streamed(3 * depth + 3)           # warm-up: every worker's engine has built its job, the pinned result arenas exist
+        barrier()
+        n_stream = max(16, args.steps)
+        dt_stream = streamed(n_stream) / n_stream
+        barrier()
+        enc_stream.end()
+        dec_stream.end()
+        assert not bad, bad
+        for slot in used:
+            assert all(np.array_equal(a, b) for a, b in zip(outs[slot], p16)), "streamed round trip is not lossless"
 
     # max over ranks
     times = torch.tensor([dt_dev, dt_e2e, dt_e2e16, dt_e2e32, dt_file, dt_enc, dt_dec, dt_stream], dtype=torch.float64, device="cuda")
@@ -697,21 +705,6 @@ def main():
                     "host_threads": host_threads, "host_pack": {"encode": pack_mode[0], "decode": pack_mode[1]},
                     "api": "b2k_encode + b2k_decode (include/grok_b200.h), host int32 planes (the gpup_image layout); samples "
                            "<= 16 bit cross PCIe in 16-bit containers, narrowed/widened per chunk by host_threads host threads"},
-            "e2e_i32_direct": {"value": pix / dt_e2e32 / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_e2e32 * 1e3,
-                               "h2d_bytes_per_step": int(img_bytes + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes + nb + nbk * 24),
-                               "api": "same calls with b2k_set_host_threads(0): pinned int32 planes copied as they are"},
-            "e2e_codestream": {"value": pix / dt_file / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_file * 1e3,
-                               "codestream_bytes": int(cs_len),
-                               "api": "e2e plus the host T2 step: b2k_encode + b2k_codestream_write (TLM + PLT) into a pinned buffer, then "
-                                      "b2k_codestream_parse + b2k_decode reading the block bytes in place from the file"},
-            "e2e_u16": {"value": pix / (dt_e2e16 / args.steps) / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_e2e16 / args.steps * 1e3,
-                        "h2d_bytes_per_step": int(img_bytes // 2 + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes // 2 + nb + nbk * 24),
-                        "api": "b2k_encode16 + b2k_decode16: same path, 16-bit sample containers (cf. gpup_batch_memory_submit_planes)"},
-            "e2e_batch": {"value": pix / dt_stream / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_stream * 1e3, "frames": n_stream,
-                          "h2d_bytes_per_step": int(img_bytes // 2 + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes // 2 + nb + nbk * 24),
-                          "api": "b2k_stream_encode_* feeding b2k_stream_decode_* (SURVEY 8f N2, cf. gpup_batch_memory_*): 3 frames in flight "
-                                 "per direction on one GPU, 16-bit sample containers, host buffers pinned; wall clock from the first submit "
-                                 "to the last decoded frame / frames"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_dwt53_fwd<3> (DC shift + RCT + level-1 5/3, all 64 tiles x 3 comps)",
@@ -720,6 +713,24 @@ def main():
                          "algorithmic_bytes_per_launch": int(l1_bytes),
                          "ms_per_launch": l1_ms, "traffic": TRAFFIC_NCU},
         }
+        if extras:
+            line.update({
+                "e2e_i32_direct": {"value": pix / dt_e2e32 / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_e2e32 * 1e3,
+                                   "h2d_bytes_per_step": int(img_bytes + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes + nb + nbk * 24),
+                                   "api": "same calls with b2k_set_host_threads(0): pinned int32 planes copied as they are"},
+                "e2e_codestream": {"value": pix / dt_file / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_file * 1e3,
+                                   "codestream_bytes": int(cs_len),
+                                   "api": "e2e plus the host T2 step: b2k_encode + b2k_codestream_write (TLM + PLT) into a pinned buffer, then "
+                                          "b2k_codestream_parse + b2k_decode reading the block bytes in place from the file"},
+                "e2e_u16": {"value": pix / (dt_e2e16 / args.steps) / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_e2e16 / args.steps * 1e3,
+                            "h2d_bytes_per_step": int(img_bytes // 2 + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes // 2 + nb + nbk * 24),
+                            "api": "b2k_encode16 + b2k_decode16: same path, 16-bit sample containers (cf. gpup_batch_memory_submit_planes)"},
+                "e2e_batch": {"value": pix / dt_stream / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_stream * 1e3, "frames": n_stream,
+                              "h2d_bytes_per_step": int(img_bytes // 2 + nb + nbk * 64), "d2h_bytes_per_step": int(img_bytes // 2 + nb + nbk * 24),
+                              "api": "b2k_stream_encode_* feeding b2k_stream_decode_* (SURVEY 8f N2, cf. gpup_batch_memory_*): 3 frames in flight "
+                                     "per direction on one GPU, 16-bit sample containers, host buffers pinned; wall clock from the first submit "
+                                     "to the last decoded frame / frames"}
+            })
         if world == 1 and not args.no_cpu_baseline:
             try:
                 os.sched_setaffinity(0, range(os.cpu_count()))   # the CPU arm gets every core back
