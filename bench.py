@@ -383,22 +383,25 @@ def run_config4(args, rank, world, local):
             sizes = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
             dist.all_gather(sizes, torch.tensor([res.num_bytes, res.num_blocks], dtype=torch.int64, device="cuda"))
             sizes = [(int(x[0]), int(x[1])) for x in sizes]
-            seg = torch.from_numpy(res.bytes).cuda(non_blocking=True)
-            tab = torch.from_numpy(res.blocks.view(np.uint8).reshape(-1)).cuda(non_blocking=True)
+            # variable-length segments: grouped NCCL send / recv (ncclGroupStart ... ncclSend/ncclRecv ... ncclGroupEnd)
             if rank == 0:
-                segs = [torch.empty(n, dtype=torch.uint8, device="cuda") for n, _ in sizes]
-                tabs = [torch.empty(k * G.BLOCK_DTYPE.itemsize, dtype=torch.uint8, device="cuda") for _, k in sizes]
-                dist.gather(seg, segs, dst=0)
-                dist.gather(tab, tabs, dst=0)
-                merged = G.merge_shards(cp, [(np.frombuffer(tabs[r].cpu().numpy().tobytes(), dtype=G.BLOCK_DTYPE), segs[r].cpu().numpy())
-                                             for r in range(world)])
+                segs = [None] + [torch.empty(n, dtype=torch.uint8, device="cuda") for n, _ in sizes[1:]]
+                tabs = [None] + [torch.empty(k * G.BLOCK_DTYPE.itemsize, dtype=torch.uint8, device="cuda") for _, k in sizes[1:]]
+                ops = [dist.P2POp(dist.irecv, segs[r], r) for r in range(1, world)] + [dist.P2POp(dist.irecv, tabs[r], r) for r in range(1, world)]
+                for w_ in dist.batch_isend_irecv(ops):
+                    w_.wait()
+                shards = [(res.blocks, res.bytes)] + [(np.frombuffer(tabs[r].cpu().numpy().tobytes(), dtype=G.BLOCK_DTYPE), segs[r].cpu().numpy())
+                                                       for r in range(1, world)]
+                merged = G.merge_shards(cp, shards)
                 cs = G.codestream_write(cp, merged.blocks, merged.bytes, G.CS_TLM | G.CS_PLT, num_tiles=reps * reps)
                 cs_len = len(cs)
                 info["coded_bytes"] = int(merged.num_bytes)
                 merged.free()
             else:
-                dist.gather(seg, None, dst=0)
-                dist.gather(tab, None, dst=0)
+                seg = torch.from_numpy(res.bytes).cuda(non_blocking=True)
+                tab = torch.from_numpy(res.blocks.view(np.uint8).reshape(-1)).cuda(non_blocking=True)
+                for w_ in dist.batch_isend_irecv([dist.P2POp(dist.isend, seg, 0), dist.P2POp(dist.isend, tab, 0)]):
+                    w_.wait()
         else:
             cs = G.codestream_write(cp, res.blocks, res.bytes, G.CS_TLM | G.CS_PLT, num_tiles=reps * reps)
             cs_len = len(cs)
