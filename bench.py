@@ -376,8 +376,20 @@ def run_config4(args, rank, world, local):
 
     info = {}
 
+    pinned_cache = {}
+
+    def pinned_like(key, n):
+        """pinned host landing buffers of the writer rank, kept between steps (re-pinning costs more than the copy)"""
+        t = pinned_cache.get(key)
+        if t is None or t.numel() < n:
+            t = torch.empty(int(n * 1.1) + 4096, dtype=torch.uint8, pin_memory=True)
+            pinned_cache[key] = t
+        return t[:n]
+
     def step():
+        tp = [time.perf_counter()]
         res = eng.encode(cp, planes, tile_mod=world, tile_rem=rank)
+        tp.append(time.perf_counter())
         cs_len = 0
         if world > 1:
             sizes = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
@@ -390,12 +402,25 @@ def run_config4(args, rank, world, local):
                 ops = [dist.P2POp(dist.irecv, segs[r], r) for r in range(1, world)] + [dist.P2POp(dist.irecv, tabs[r], r) for r in range(1, world)]
                 for w_ in dist.batch_isend_irecv(ops):
                     w_.wait()
-                shards = [(res.blocks, res.bytes)] + [(np.frombuffer(tabs[r].cpu().numpy().tobytes(), dtype=G.BLOCK_DTYPE), segs[r].cpu().numpy())
-                                                       for r in range(1, world)]
+                torch.cuda.synchronize()
+                tp.append(time.perf_counter())
+                host = []
+                for r in range(1, world):      # device -> pinned host, all copies in flight together
+                    hs, ht = pinned_like(("seg", r), segs[r].numel()), pinned_like(("tab", r), tabs[r].numel())
+                    hs.copy_(segs[r], non_blocking=True)
+                    ht.copy_(tabs[r], non_blocking=True)
+                    host.append((ht, hs))
+                torch.cuda.synchronize()
+                tp.append(time.perf_counter())
+                shards = [(res.blocks, res.bytes)] + [(ht.numpy().view(G.BLOCK_DTYPE), hs.numpy()) for ht, hs in host]
                 merged = G.merge_shards(cp, shards)
+                tp.append(time.perf_counter())
                 cs = G.codestream_write(cp, merged.blocks, merged.bytes, G.CS_TLM | G.CS_PLT, num_tiles=reps * reps)
                 cs_len = len(cs)
+                tp.append(time.perf_counter())
                 info["coded_bytes"] = int(merged.num_bytes)
+                info["phase_ms_rank0"] = dict(zip(["encode_own_tiles", "nccl_sizes_and_recv", "d2h_to_pinned", "merge", "codestream_write"],
+                                                  [round((b - a) * 1e3, 2) for a, b in zip(tp, tp[1:])]))
                 merged.free()
             else:
                 seg = torch.from_numpy(res.bytes).cuda(non_blocking=True)
@@ -405,7 +430,10 @@ def run_config4(args, rank, world, local):
         else:
             cs = G.codestream_write(cp, res.blocks, res.bytes, G.CS_TLM | G.CS_PLT, num_tiles=reps * reps)
             cs_len = len(cs)
+            tp.append(time.perf_counter())
             info["coded_bytes"] = int(res.num_bytes)
+            info["phase_ms_rank0"] = dict(zip(["encode_own_tiles", "codestream_write"], [round((b - a) * 1e3, 2) for a, b in zip(tp, tp[1:])]))
+            info["encode_timings_ms"] = {k: round(v, 2) for k, v in res.timings.items()}
         res.free()
         return cs_len
 

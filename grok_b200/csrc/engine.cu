@@ -1567,13 +1567,9 @@ extern "C" int32_t b2k_result_merge(const b2k_coding* cp, const b2k_result* cons
   R->num_tiles = ntiles;
   R->num_bytes = total_bytes;
   R->blocks = (b2k_block*)malloc(sizeof(b2k_block) * std::max<size_t>(1, all.size()));
-  uint8_t* arena = nullptr;
-  if(cudaHostAlloc(&arena, std::max<uint64_t>(64, total_bytes), cudaHostAllocDefault) == cudaSuccess)
-  {
-    std::lock_guard<std::mutex> lock(g_pool.mu);
-    g_pool.live.push_back({arena, std::max<uint64_t>(64, total_bytes)});
-  }
-  else
+  /* recycled pinned arena (pinning a gigabyte costs hundreds of milliseconds); plain memory on a writer-only host */
+  uint8_t* arena = pool_get(std::max<uint64_t>(64, total_bytes));
+  if(!arena)
   {
     (void)cudaGetLastError();
     arena = (uint8_t*)malloc(std::max<uint64_t>(64, total_bytes));
@@ -1617,8 +1613,15 @@ extern "C" int32_t b2k_result_merge(const b2k_coding* cp, const b2k_result* cons
       g_err = "a shard holds more blocks than its tiles have";
       return -1;
     }
-    if(shards[s]->num_bytes)
-      memcpy(arena + base[s], shards[s]->bytes, shards[s]->num_bytes);
+  }
+  { /* the arenas, 8 MB pieces on the host pool */
+    struct Piece { uint8_t* dst; const uint8_t* src; size_t n; };
+    std::vector<Piece> pieces;
+    const size_t step = (size_t)8 << 20;
+    for(uint32_t s = 0; s < nshards; ++s)
+      for(size_t o = 0; o < shards[s]->num_bytes; o += step)
+        pieces.push_back({arena + base[s] + o, shards[s]->bytes + o, std::min<size_t>(step, shards[s]->num_bytes - o)});
+    b2k_host_parallel(pieces.size(), [&](size_t i) { memcpy(pieces[i].dst, pieces[i].src, pieces[i].n); });
   }
   *out = R;
   return 0;
