@@ -64,7 +64,7 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_roundtrip_n", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
            "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last",
-           "b2k_codestream_write", "b2k_codestream_parse", "b2k_jph_wrap", "b2k_jph_codestream", "b2k_result_merge",
+           "b2k_codestream_write", "b2k_codestream_parse", "b2k_codestream_parse_window", "b2k_jph_wrap", "b2k_jph_codestream", "b2k_result_merge",
            "gpup_encode_mem_tiles", "gpup_tiles_free", "plugin_decompress_codestream", "b2k_coding_from_gpup",
            "b2k_stream_encode_begin", "b2k_stream_encode_submit", "b2k_stream_decode_begin", "b2k_stream_decode_submit",
            "b2k_stream_decode_submit_codestream", "b2k_stream_end",
@@ -356,6 +356,32 @@ class Engine:
             out = [np.zeros((cp.y1 - cp.y0, cp.x1 - cp.x0), dtype) for _ in range(cp.numcomps)]
         self.decode(cp, blocks, cs, out)
         return cp, out
+
+    def decode_window(self, cs, window=None, reduce=0, dtype=np.int32):
+        """Tile-granular windowed / reduced-resolution decode of an HTJ2K codestream (b2k_codestream_parse_window +
+        b2k_decode + crop).  window = (x0, y0, x1, y1) on the full-resolution canvas or None; returns (virtual Coding,
+        planes of the window at 1 / 2**reduce resolution)."""
+        cs = np.ascontiguousarray(cs, dtype=np.uint8)
+        L = lib()
+        L.b2k_codestream_parse_window.restype = C.c_int64
+        L.b2k_codestream_parse_window.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(Coding), C.c_void_p, C.c_uint64]
+        win = (C.c_uint32 * 4)(*window) if window is not None else None
+        cp = Coding()
+        n = L.b2k_codestream_parse_window(cs.ctypes.data, len(cs), win, reduce, C.byref(cp), None, 0)
+        if n <= 1:
+            raise EngineError("b2k_codestream_parse_window: %d %s" % (n, (L.b2k_last_error() or b"").decode()))
+        blocks = np.zeros(n, BLOCK_DTYPE)
+        m = L.b2k_codestream_parse_window(cs.ctypes.data, len(cs), win, reduce, C.byref(cp), blocks.ctypes.data, n)
+        if m != n:
+            raise EngineError("b2k_codestream_parse_window: %d %s" % (m, (L.b2k_last_error() or b"").decode()))
+        full = [np.zeros((cp.y1 - cp.y0, cp.x1 - cp.x0), dtype) for _ in range(cp.numcomps)]
+        self.decode(cp, blocks, cs, full)
+        if window is None:
+            return cp, full
+        sh = (1 << reduce) - 1
+        x0, y0, x1, y1 = [(v + sh) >> reduce for v in window]
+        x0, y0, x1, y1 = max(x0, cp.x0), max(y0, cp.y0), min(x1, cp.x1), min(y1, cp.y1)
+        return cp, [p[y0 - cp.y0:y1 - cp.y0, x0 - cp.x0:x1 - cp.x0] for p in full]
 
     def decode(self, cp, blocks, data, out_planes, tile_mod=1, tile_rem=0):
         ptrs, strides = _plane_ptrs(out_planes)

@@ -960,8 +960,11 @@ struct Cursor
 };
 } // namespace
 
-extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(const uint8_t* cs, uint64_t len, b2k_coding* cp_out,
-                                                                                b2k_block* blocks, uint64_t cap_blocks)
+/* window: x0,y0,x1,y1 on the full-resolution canvas, or NULL for the whole image; reduce: highest resolutions to drop.
+   *cp_out is the coding to DECODE WITH: for a window / reduced decode a virtual image that holds exactly the tiles the
+   window touches, at the reduced resolution (see b2k_codestream_parse_window below). */
+static int64_t parse_impl(const uint8_t* cs, uint64_t len, const uint32_t* window, uint32_t reduce, b2k_coding* cp_out,
+                          b2k_block* blocks, uint64_t cap_blocks)
 {
   if(!cs || !cp_out)
     return -1;
@@ -1175,23 +1178,89 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
   }
   const TileGrid g = tile_grid(cp);
   const uint32_t ntiles = g.nx * g.ny;
-  /* block table in enumeration order: sizes first, then every tile fills its own slice */
-  std::vector<uint64_t> tile_first(ntiles + 1, 0);
-  for(uint32_t t = 0; t < ntiles; ++t)
+
+  /* ---- the tiles to deliver and the coding to decode them with ---------------------------------------------------
+   * Whole image at full resolution: the stream's own coding.  Otherwise a VIRTUAL image: its area is the bounding box
+   * of the tiles the window touches (clipped to the image), its tile grid is the stream's grid re-anchored at the first
+   * of those tiles, and for reduce > 0 everything is divided by 2^reduce and the highest `reduce` resolutions are
+   * dropped -- by the standard's own definitions (B.5: resolution r of a tile component is the tile rectangle
+   * ceil-divided by 2^(N_L - r)) the remaining resolutions, precinct grids and code blocks of every tile are exactly
+   * those of the original, so the parsed blocks carry over one to one
+   * (cf. CodeStreamDecompress.cpp L670-870: tiles from the window, resolutions from `reduce`). */
+  uint32_t ta_x = 0, ta_y = 0, tb_x = g.nx, tb_y = g.ny;
+  if(window)
+  {
+    const uint32_t wx0 = std::max(window[0], cp.x0), wy0 = std::max(window[1], cp.y0), wx1 = std::min(window[2], cp.x1),
+                   wy1 = std::min(window[3], cp.y1);
+    if(wx0 >= wx1 || wy0 >= wy1)
+      return fail("the window does not intersect the image", -1);
+    ta_x = (wx0 - g.tx0) / g.tw;
+    ta_y = (wy0 - g.ty0) / g.th;
+    tb_x = (uint32_t)ceil_div(wx1 - g.tx0, g.tw);
+    tb_y = (uint32_t)ceil_div(wy1 - g.ty0, g.th);
+  }
+  if((int)reduce >= cp.numres)
+    return fail("reduce exceeds the number of decomposition levels", -1);
+  const bool whole = ta_x == 0 && ta_y == 0 && tb_x == g.nx && tb_y == g.ny && reduce == 0;
+  b2k_coding vcp = cp;
+  if(!whole)
+  {
+    vcp.tx0 = g.tx0 + ta_x * g.tw;
+    vcp.ty0 = g.ty0 + ta_y * g.th;
+    vcp.tw = g.tw;
+    vcp.th = g.th;
+    vcp.x0 = std::max(cp.x0, vcp.tx0);
+    vcp.y0 = std::max(cp.y0, vcp.ty0);
+    vcp.x1 = (uint32_t)std::min<uint64_t>(cp.x1, (uint64_t)g.tx0 + (uint64_t)tb_x * g.tw);
+    vcp.y1 = (uint32_t)std::min<uint64_t>(cp.y1, (uint64_t)g.ty0 + (uint64_t)tb_y * g.th);
+    /* the band exponents are the stream's: spelled out, since the default tables depend on the level count */
+    vcp.qcd_explicit = 1;
+    for(size_t i = 0; i < q.size() && i < 97; ++i)
+    {
+      vcp.qcd_expn[i] = q[i].expn;
+      vcp.qcd_mant[i] = q[i].mant;
+    }
+    const bool one_tile = tb_x - ta_x == 1 && tb_y - ta_y == 1;
+    if(one_tile)
+      vcp.tx0 = vcp.ty0 = vcp.tw = vcp.th = 0; /* the tile is the (virtual) image: no grid to keep aligned */
+    if(reduce)
+    {
+      const uint32_t m = (1u << reduce) - 1u;
+      if(!one_tile && ((vcp.tx0 & m) || (vcp.ty0 & m) || (vcp.tw & m) || (vcp.th & m)))
+        return fail("reduced decode of several tiles needs a tile grid aligned to 2^reduce", 1);
+      vcp.tx0 >>= reduce; vcp.ty0 >>= reduce; vcp.tw >>= reduce; vcp.th >>= reduce;
+      vcp.x0 = (vcp.x0 + m) >> reduce; vcp.y0 = (vcp.y0 + m) >> reduce;
+      vcp.x1 = (vcp.x1 + m) >> reduce; vcp.y1 = (vcp.y1 + m) >> reduce;
+      vcp.numres = (uint8_t)(cp.numres - reduce);
+      if(vcp.x1 <= vcp.x0 || vcp.y1 <= vcp.y0)
+        return fail("nothing left at this resolution", -1);
+    }
+    if(const char* why = unsupported_reason(vcp))
+      return fail(why, 1);
+  }
+  const TileGrid vg = tile_grid(vcp);
+  const uint32_t vnt = vg.nx * vg.ny;
+  if(!whole && (vg.nx != tb_x - ta_x || vg.ny != tb_y - ta_y))
+    return fail("internal: virtual tile grid", -1);
+  const std::vector<BandQuant> vq = whole ? q : band_quant(vcp);
+  /* block table of the virtual coding in enumeration order: sizes first, then every tile fills its own slice */
+  std::vector<uint64_t> tile_first(vnt + 1, 0);
+  for(uint32_t t = 0; t < vnt; ++t)
   {
     std::vector<Packet> pk;
     uint32_t nb = 0;
-    tile_packets(cp, tile_rect(cp, g, t), pk, nb);
+    tile_packets(vcp, tile_rect(vcp, vg, t), pk, nb);
     tile_first[t + 1] = tile_first[t] + nb;
   }
-  const uint64_t nblocks = tile_first[ntiles];
-  *cp_out = cp;
+  const uint64_t nblocks = tile_first[vnt];
+  *cp_out = vcp;
   if(!blocks)
     return (int64_t)nblocks;
   if(cap_blocks < nblocks)
     return fail("block table too small", -1);
 
-  /* ---- tile parts: locate them (SOT / Psot), then parse their packets tile by tile on the host pool ---- */
+  /* ---- tile parts: locate them (SOT / Psot: one hop per tile part), then parse the packets of the wanted tiles on the
+     host pool -- the other tiles' packets are never looked at ---- */
   std::vector<std::vector<ByteRange>> tile_parts(ntiles);
   std::vector<uint32_t> next_tp(ntiles, 0);
   for(;;)
@@ -1216,6 +1285,12 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
     const uint8_t* tp_end = psot ? sot + psot : c.end - ((len >= 2 && cs[len - 2] == 0xFF && cs[len - 1] == 0xD9) ? 2 : 0);
     if(tp_end > c.end || tp_end < c.p)
       return fail("Psot exceeds the codestream", -1);
+    const uint32_t ix = isot % g.nx, iy = isot / g.nx;
+    if(ix < ta_x || ix >= tb_x || iy < ta_y || iy >= tb_y)
+    { /* not wanted: hop over it */
+      c.p = tp_end;
+      continue;
+    }
     for(;;)
     { /* tile-part header */
       const uint32_t tm = c.u16();
@@ -1233,26 +1308,78 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(c
     tile_parts[isot].push_back({c.p, tp_end});
     c.p = tp_end;
   }
-  std::vector<int> rcs(ntiles, 0);
-  std::vector<std::string> errs(ntiles);
-  b2k_host_parallel(ntiles, [&](size_t t) {
+  std::vector<int> rcs(vnt, 0);
+  std::vector<std::string> errs(vnt);
+  b2k_host_parallel(vnt, [&](size_t vt) {
+    const uint32_t t = whole ? (uint32_t)vt : (ta_y + (uint32_t)vt / vg.nx) * g.nx + ta_x + (uint32_t)vt % vg.nx; /* the stream's tile */
     std::vector<b2k_block> tb;
-    tb.reserve(tile_first[t + 1] - tile_first[t]);
-    enumerate_tile_blocks(cp, (uint32_t)t, tile_rect(cp, g, (uint32_t)t), q, tb);
-    if(tb.size() != tile_first[t + 1] - tile_first[t])
+    enumerate_tile_blocks(cp, t, tile_rect(cp, g, t), q, tb);
+    if(!tile_parts[t].empty()) /* a tile without a tile part decodes as all zero (blocks stay uncoded) */
+      rcs[vt] = parse_tile_packets(cp, tile_rect(cp, g, t), tb.data(), tile_parts[t], cs, progression, use_sop, use_eph, errs[vt]);
+    if(whole)
     {
-      rcs[t] = -1;
-      errs[t] = "internal: packet geometry and block enumeration disagree";
+      if(tb.size() != tile_first[vt + 1] - tile_first[vt])
+      {
+        rcs[vt] = -1;
+        errs[vt] = "internal: packet geometry and block enumeration disagree";
+        return;
+      }
+      memcpy(blocks + tile_first[vt], tb.data(), tb.size() * sizeof(b2k_block));
       return;
     }
-    if(!tile_parts[t].empty()) /* a tile without a tile part decodes as all zero (blocks stay uncoded) */
-      rcs[t] = parse_tile_packets(cp, tile_rect(cp, g, (uint32_t)t), tb.data(), tile_parts[t], cs, progression, use_sop, use_eph, errs[t]);
-    memcpy(blocks + tile_first[t], tb.data(), tb.size() * sizeof(b2k_block));
+    /* the virtual tile's own enumeration; the stream's blocks of the kept resolutions follow in the same order */
+    std::vector<b2k_block> vb;
+    enumerate_tile_blocks(vcp, (uint32_t)vt, tile_rect(vcp, vg, (uint32_t)vt), vq, vb);
+    size_t k = 0;
+    for(const b2k_block& b : tb)
+    {
+      if(b.resno >= vcp.numres)
+        continue;
+      if(k >= vb.size() || vb[k].comp != b.comp || vb[k].resno != b.resno || vb[k].band_index != b.band_index ||
+         vb[k].precno != b.precno || vb[k].cblkno != b.cblkno || vb[k].x1 - vb[k].x0 != b.x1 - b.x0 || vb[k].y1 - vb[k].y0 != b.y1 - b.y0)
+      {
+        rcs[vt] = -1;
+        errs[vt] = "internal: virtual and original block enumerations disagree";
+        return;
+      }
+      vb[k].length = b.length;
+      vb[k].length2 = b.length2;
+      vb[k].offset = b.offset;
+      vb[k].numbps = b.numbps;
+      vb[k].numpasses = b.numpasses;
+      ++k;
+    }
+    if(k != vb.size() || vb.size() != tile_first[vt + 1] - tile_first[vt])
+    {
+      rcs[vt] = -1;
+      errs[vt] = "internal: virtual tile holds a different number of blocks";
+      return;
+    }
+    memcpy(blocks + tile_first[vt], vb.data(), vb.size() * sizeof(b2k_block));
   });
-  for(uint32_t t = 0; t < ntiles; ++t)
+  for(uint32_t t = 0; t < vnt; ++t)
     if(rcs[t])
       return fail(errs[t].c_str(), rcs[t]);
   return (int64_t)nblocks;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse(const uint8_t* cs, uint64_t len, b2k_coding* cp_out,
+                                                                                b2k_block* blocks, uint64_t cap_blocks)
+{
+  return parse_impl(cs, len, nullptr, 0, cp_out, blocks, cap_blocks);
+}
+
+/* Windowed / reduced-resolution parse (reference: CodeStreamDecompress.cpp L670-870 window -> tiles,
+ * t2/SelectiveFetchRanges.cpp, grk_decompress_parameters.core.reduce).  Tile-granular: *cp_out describes a virtual image
+ * made of exactly the tiles the window touches, at 1 / 2^reduce of the resolution; decoding it with b2k_decode gives the
+ * samples of that area, of which the window is a crop: window sample (x, y) at the reduced resolution -- x in
+ * [ceil(wx0 / 2^reduce), ceil(wx1 / 2^reduce)) -- sits at column x - cp_out->x0 of the decoded planes.  Only the wanted
+ * tiles' packet headers are parsed (tile parts are hopped over through Psot), only their code blocks are decoded. */
+extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_parse_window(const uint8_t* cs, uint64_t len, const uint32_t* window,
+                                                                                       uint32_t reduce, b2k_coding* cp_out, b2k_block* blocks,
+                                                                                       uint64_t cap_blocks)
+{
+  return parse_impl(cs, len, window, reduce, cp_out, blocks, cap_blocks);
 }
 
 /* ============================================================================================================

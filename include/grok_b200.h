@@ -497,6 +497,14 @@ B2K_API int32_t b2k_result_merge(const b2k_coding* cp, const b2k_result* const* 
 #define B2K_CS_PROG(n) (((n) & 7u) << 8)   /* progression order: 0 LRCP (default), 1 RLCP, 2 RPCL, 3 PCRL, 4 CPRL */
 B2K_API int64_t b2k_codestream_write(const b2k_coding* cp, const b2k_result* r, uint32_t flags, uint8_t* out, uint64_t cap);
 B2K_API int64_t b2k_codestream_parse(const uint8_t* cs, uint64_t len, b2k_coding* cp, b2k_block* blocks, uint64_t cap_blocks);
+/* Windowed / reduced-resolution decode, tile-granular: `window` = x0,y0,x1,y1 on the full-resolution
+ * canvas (NULL: whole image), `reduce` = highest resolutions to drop.  *cp becomes a VIRTUAL coding: the image made of the
+ * tiles the window touches, at 1 / 2^reduce of the resolution -- decode it with b2k_decode(cp, blocks, ..., cs, ...) into
+ * planes of (cp->x1 - cp->x0) x (cp->y1 - cp->y0) samples and crop: window column x (reduced resolution, x >=
+ * ceil(wx0 / 2^reduce)) is plane column x - cp->x0.  Only the wanted tiles' packets are parsed and decoded.  Return as
+ * b2k_codestream_parse (reduce > 0 needs a tile grid aligned to 2^reduce: 1 = not handled otherwise). */
+B2K_API int64_t b2k_codestream_parse_window(const uint8_t* cs, uint64_t len, const uint32_t* window, uint32_t reduce, b2k_coding* cp,
+                                            b2k_block* blocks, uint64_t cap_blocks);
 
 /* JPH container (JP2 boxes, brand 'jph '): wrap a codestream / find the codestream inside a .jph / .jp2 file
  * (a raw codestream is accepted as it is). */

@@ -245,3 +245,91 @@ def test_config4_full_size_sharded_tiles_match_grok(engine):
     _, rec = engine.decode_codestream(theirs)
     for a, b in zip(rec, planes):
         assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------------
+# windowed / reduced-resolution decode: the virtual coding b2k_codestream_parse_window derives
+# ------------------------------------------------------------------------------------------------------
+def _parse_window(cs, window, reduce):
+    import ctypes as C
+    L = G.lib()
+    L.b2k_codestream_parse_window.restype = C.c_int64
+    L.b2k_codestream_parse_window.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(G.Coding), C.c_void_p, C.c_uint64]
+    win = (C.c_uint32 * 4)(*window) if window is not None else None
+    cp = G.Coding()
+    n = L.b2k_codestream_parse_window(cs.ctypes.data, len(cs), win, reduce, C.byref(cp), None, 0)
+    assert n > 1, (n, L.b2k_last_error())
+    blocks = np.zeros(n, G.BLOCK_DTYPE)
+    assert L.b2k_codestream_parse_window(cs.ctypes.data, len(cs), win, reduce, C.byref(cp), blocks.ctypes.data, n) == n, L.b2k_last_error()
+    return cp, blocks
+
+
+WINDOW_CASES = [
+    (dict(width=700, height=500, numcomps=3, prec=12, tile=(256, 128), numres=5), (300, 150, 520, 300), 0),
+    (dict(width=700, height=500, numcomps=3, prec=12, tile=(256, 128), numres=5), None, 1),
+    (dict(width=700, height=500, numcomps=3, prec=12, tile=(256, 128), numres=5), (10, 300, 400, 500), 2),
+    (dict(width=640, height=384, numcomps=1, prec=8, tile=(128, 128), numres=4), (129, 1, 255, 127), 1),
+    (dict(width=333, height=217, numcomps=3, prec=12, numres=5), None, 2),                      # single tile, reduce only
+]
+
+
+@pytest.mark.parametrize("args,window,reduce", WINDOW_CASES)
+def test_window_and_reduce_parse_matches_grok(args, window, reduce):
+    """The virtual coding decodes (on the oracle) to exactly what Grok delivers for the same window / reduce factor:
+    grk_decompress at `reduce` gives the reference for the resolution, the window is a crop of it."""
+    cp = mk(args)
+    planes = synth(args, seed=12)
+    theirs = grok_compress(args, planes)
+    w, h, n = args["width"], args["height"], args["numcomps"]
+    rw, rh = -(-w >> reduce), -(-h >> reduce)
+    ref, _, _ = R.decompress(theirs, rw, rh, n, reduce=reduce)                # Grok's own reduced decode of the whole image
+    if reduce == 0:
+        for a, b in zip(ref, planes):
+            assert np.array_equal(a, b)
+    vcp, blocks = _parse_window(theirs, window, reduce)
+    rec = oracle_decode(vcp, blocks, theirs)
+    sh = (1 << reduce) - 1
+    full_win = (0, 0, w, h) if window is None else window
+    x0, y0, x1, y1 = [(v + sh) >> reduce for v in full_win]
+    assert vcp.x0 <= x0 and vcp.y0 <= y0 and vcp.x1 >= x1 and vcp.y1 >= y1
+    if window is not None:       # tile-granular: at most the touched tiles are decoded
+        tw, th = args["tile"]
+        assert (vcp.x1 - vcp.x0) <= ((-(-window[2] // tw) - window[0] // tw) * tw + sh) >> reduce
+    for a, b in zip(rec, ref):
+        assert np.array_equal(a[y0 - vcp.y0:y1 - vcp.y0, x0 - vcp.x0:x1 - vcp.x0], b[y0:y1, x0:x1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args,window,reduce", WINDOW_CASES)
+def test_gpu_window_and_reduce_decode_matches_grok(engine, args, window, reduce):
+    planes = synth(args, seed=12)
+    theirs = grok_compress(args, planes)
+    w, h, n = args["width"], args["height"], args["numcomps"]
+    ref, _, _ = R.decompress(theirs, -(-w >> reduce), -(-h >> reduce), n, reduce=reduce)
+    _, got = engine.decode_window(theirs, window, reduce)
+    sh = (1 << reduce) - 1
+    x0, y0, x1, y1 = [(v + sh) >> reduce for v in ((0, 0, w, h) if window is None else window)]
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b[y0:y1, x0:x1])
+
+
+@pytest.mark.gpu
+def test_config5_random_rois_of_a_large_tiled_stream(engine):
+    """configs[4] in shape: a TLM / PLT indexed code stream of 1024x1024 tiles, 8 seeded 2048x2048 windows at random
+    positions; every window equals the crop of the source (lossless) -- here on an 8192x8192 canvas (64 tiles) so that the
+    test stays in seconds; tools/config5_roi_bench.py runs the 32768x32768 version."""
+    w = h = 8192
+    cp = G.make_coding(w, h, 3, 12, numres=6, tile=(1024, 1024))
+    base = P.synthetic_image(1024, 1024, 3, 12, seed=20260927)
+    planes = [np.empty((h, w), np.int32) for _ in range(3)]
+    for t in range(64):
+        ty, tx = divmod(t, 8)
+        for c in range(3):
+            planes[c][ty * 1024:(ty + 1) * 1024, tx * 1024:(tx + 1) * 1024] = (base[c] + 37 * t) & 0xFFF
+    cs = engine.encode_codestream(cp, planes, flags=G.CS_TLM | G.CS_PLT)
+    rng = np.random.default_rng(20260927)
+    for _ in range(8):
+        x0, y0 = int(rng.integers(0, w - 2048)), int(rng.integers(0, h - 2048))
+        _, got = engine.decode_window(cs, (x0, y0, x0 + 2048, y0 + 2048))
+        for a, b in zip(got, planes):
+            assert np.array_equal(a, b[y0:y0 + 2048, x0:x0 + 2048])
