@@ -360,7 +360,8 @@ class Engine:
     def decode_window(self, cs, window=None, reduce=0, dtype=np.int32):
         """Tile-granular windowed / reduced-resolution decode of an HTJ2K codestream (b2k_codestream_parse_window +
         b2k_decode + crop).  window = (x0, y0, x1, y1) on the full-resolution canvas or None; returns (virtual Coding,
-        planes of the window at 1 / 2**reduce resolution)."""
+        planes of the window at 1 / 2**reduce resolution).  The planes are views of pinned buffers the engine keeps and
+        reuses for later windows of the same tile-box shape: copy them to keep them."""
         cs = np.ascontiguousarray(cs, dtype=np.uint8)
         L = lib()
         L.b2k_codestream_parse_window.restype = C.c_int64
@@ -374,7 +375,14 @@ class Engine:
         m = L.b2k_codestream_parse_window(cs.ctypes.data, len(cs), win, reduce, C.byref(cp), blocks.ctypes.data, n)
         if m != n:
             raise EngineError("b2k_codestream_parse_window: %d %s" % (m, (L.b2k_last_error() or b"").decode()))
-        full = [np.zeros((cp.y1 - cp.y0, cp.x1 - cp.x0), dtype) for _ in range(cp.numcomps)]
+        # pinned landing planes, kept per shape (windows of one size keep hitting the same few tile-box shapes)
+        cache = self.__dict__.setdefault("_win_planes", {})
+        key = (cp.y1 - cp.y0, cp.x1 - cp.x0, cp.numcomps, np.dtype(dtype).str)
+        full = cache.get(key)
+        if full is None:
+            if len(cache) >= 8:
+                cache.pop(next(iter(cache)))
+            full = cache[key] = [pinned_empty((cp.y1 - cp.y0, cp.x1 - cp.x0), dtype) for _ in range(cp.numcomps)]
         self.decode(cp, blocks, cs, full)
         if window is None:
             return cp, full

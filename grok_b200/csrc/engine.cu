@@ -23,7 +23,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <mutex>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -60,6 +62,108 @@ struct b2k_engine
   std::mutex mu;
   b2k_device_job* cached = nullptr;
 };
+
+/* ---- device memory cache --------------------------------------------------------------------------------------
+ * Jobs come and go with the coding (every windowed decode is a new virtual image) and cudaMalloc /
+ * cudaFree synchronise the device and cost milliseconds per gigabyte.  Freed job buffers are kept per device and
+ * handed out again to requests of about the same size (best fit, at most 25 % slack); the cache is trimmed, largest
+ * first, above B2K_DEV_CACHE_GB (default 32). */
+namespace {
+struct DevCache
+{
+  std::mutex mu;
+  std::multimap<size_t, void*> free_;
+  std::unordered_map<void*, size_t> live;
+  size_t cached = 0;
+};
+DevCache g_devcache[32];
+size_t dev_cache_limit()
+{
+  static const size_t v = [] {
+    const char* e = getenv("B2K_DEV_CACHE_GB");
+    return (size_t)(e ? atof(e) : 32.0) << 30;
+  }();
+  return v;
+}
+cudaError_t dev_alloc(void** p, size_t n)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevCache& C = g_devcache[dev & 31];
+  const size_t gran = std::max<size_t>(256u << 10, n >> 4);
+  const size_t want = (n + gran - 1) / gran * gran;
+  {
+    std::lock_guard<std::mutex> lk(C.mu);
+    auto it = C.free_.lower_bound(want);
+    if(it != C.free_.end() && it->first <= want + want / 4)
+    {
+      *p = it->second;
+      C.live[*p] = it->first;
+      C.cached -= it->first;
+      C.free_.erase(it);
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMalloc(p, want);
+  if(e != cudaSuccess)
+  { /* give the cache back and try once more */
+    (void)cudaGetLastError();
+    std::vector<void*> drop;
+    {
+      std::lock_guard<std::mutex> lk(C.mu);
+      for(auto& kv : C.free_)
+        drop.push_back(kv.second);
+      C.free_.clear();
+      C.cached = 0;
+    }
+    for(void* q : drop)
+      cudaFree(q);
+    e = cudaMalloc(p, want);
+  }
+  if(e == cudaSuccess)
+  {
+    std::lock_guard<std::mutex> lk(C.mu);
+    C.live[*p] = want;
+  }
+  return e;
+}
+cudaError_t dev_free(void* p)
+{
+  if(!p)
+    return cudaSuccess;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevCache& C = g_devcache[dev & 31];
+  std::vector<void*> drop;
+  {
+    std::lock_guard<std::mutex> lk(C.mu);
+    auto it = C.live.find(p);
+    if(it == C.live.end())
+      drop.push_back(p); /* not ours (or another device's): plain free */
+    else
+    {
+      C.free_.insert({it->second, p});
+      C.cached += it->second;
+      C.live.erase(it);
+      while(C.cached > dev_cache_limit() && !C.free_.empty())
+      {
+        auto big = std::prev(C.free_.end());
+        drop.push_back(big->second);
+        C.cached -= big->first;
+        C.free_.erase(big);
+      }
+    }
+  }
+  for(void* q : drop)
+    cudaFree(q);
+  return cudaSuccess;
+}
+} // namespace
+template <class T>
+static inline cudaError_t dev_alloc_t(T** p, size_t n) { return dev_alloc(reinterpret_cast<void**>(p), n); }
+/* from here on the engine's device buffers come from the cache */
+#define cudaMalloc(p, n) dev_alloc_t((p), (n))
+#define cudaFree(p) dev_free((void*)(p))
 
 /* ---- a plane set: `n` image-shaped 32-bit planes addressed by canvas coordinate ------------- */
 struct Planes
