@@ -161,9 +161,76 @@ cudaError_t dev_free(void* p)
 } // namespace
 template <class T>
 static inline cudaError_t dev_alloc_t(T** p, size_t n) { return dev_alloc(reinterpret_cast<void**>(p), n); }
-/* from here on the engine's device buffers come from the cache */
+
+/* the same for pinned host memory (descriptor tables, staging rings): cudaHostAlloc / cudaFreeHost are slower still */
+namespace {
+struct HostCache
+{
+  std::mutex mu;
+  std::multimap<size_t, void*> free_;
+  std::unordered_map<void*, size_t> live;
+  size_t cached = 0;
+} g_hostcache;
+cudaError_t host_alloc(void** p, size_t n)
+{
+  const size_t gran = std::max<size_t>(64u << 10, n >> 4);
+  const size_t want = (n + gran - 1) / gran * gran;
+  {
+    std::lock_guard<std::mutex> lk(g_hostcache.mu);
+    auto it = g_hostcache.free_.lower_bound(want);
+    if(it != g_hostcache.free_.end() && it->first <= want + want / 4)
+    {
+      *p = it->second;
+      g_hostcache.live[*p] = it->first;
+      g_hostcache.cached -= it->first;
+      g_hostcache.free_.erase(it);
+      return cudaSuccess;
+    }
+  }
+  const cudaError_t e = cudaHostAlloc(p, want, cudaHostAllocDefault);
+  if(e == cudaSuccess)
+  {
+    std::lock_guard<std::mutex> lk(g_hostcache.mu);
+    g_hostcache.live[*p] = want;
+  }
+  return e;
+}
+cudaError_t host_free(void* p)
+{
+  if(!p)
+    return cudaSuccess;
+  std::vector<void*> drop;
+  {
+    std::lock_guard<std::mutex> lk(g_hostcache.mu);
+    auto it = g_hostcache.live.find(p);
+    if(it == g_hostcache.live.end())
+      drop.push_back(p);
+    else
+    {
+      g_hostcache.free_.insert({it->second, p});
+      g_hostcache.cached += it->second;
+      g_hostcache.live.erase(it);
+      while(g_hostcache.cached > ((size_t)8 << 30) && !g_hostcache.free_.empty())
+      {
+        auto big = std::prev(g_hostcache.free_.end());
+        drop.push_back(big->second);
+        g_hostcache.cached -= big->first;
+        g_hostcache.free_.erase(big);
+      }
+    }
+  }
+  for(void* q : drop)
+    cudaFreeHost(q);
+  return cudaSuccess;
+}
+} // namespace
+template <class T>
+static inline cudaError_t host_alloc_t(T** p, size_t n) { return host_alloc(reinterpret_cast<void**>(p), n); }
+/* from here on the engine's device and pinned buffers come from the caches */
 #define cudaMalloc(p, n) dev_alloc_t((p), (n))
 #define cudaFree(p) dev_free((void*)(p))
+#define cudaHostAlloc(p, n, flags) host_alloc_t((p), (n))
+#define cudaFreeHost(p) host_free((void*)(p))
 
 /* ---- a plane set: `n` image-shaped 32-bit planes addressed by canvas coordinate ------------- */
 struct Planes
