@@ -356,7 +356,7 @@ struct b2k_device_job
   uint32_t* d_recs = nullptr;     /* decode: per-quad records between the two decode phases */
   float* d_dec_quant = nullptr;
   HtBlockOut* d_dec_status = nullptr;
-  uint64_t total_quads = 0;
+  uint64_t total_quads = 0, group_quads = 0; /* record scratch: closed groups / largest block of the open group */
   uint8_t* d_scratch = nullptr;
   uint64_t scratch_bytes = 0;
   uint8_t* d_bytes = nullptr;
@@ -660,8 +660,18 @@ static int build_block_plan(b2k_device_job* J)
     d.slot_cap = slot_capacity(d.w, d.h, bq.kmax);
     d.slot_off = off;
     off += d.slot_cap;
-    d.rec_off = (uint32_t)J->total_quads;
-    J->total_quads += (uint64_t)((d.w + 1) / 2) * ((d.h + 1) / 2);
+    { /* per-quad records of 32 consecutive coded blocks are interleaved word by word (ht_dec.cu phase A): a group of 32
+         takes 32 x its largest block's quads; entry k of block j of the group sits at group_base + 32 k + j */
+      const size_t j = J->h_enc_desc.size() & 31u;
+      const uint64_t quads = (uint64_t)((d.w + 1) / 2) * ((d.h + 1) / 2);
+      if(j == 0)
+      {
+        J->total_quads += 32 * J->group_quads; /* close the previous group */
+        J->group_quads = 0;
+      }
+      J->group_quads = std::max(J->group_quads, quads);
+      d.rec_off = (uint32_t)(J->total_quads + j);
+    }
     J->max_cblk_w = std::max<uint32_t>(J->max_cblk_w, d.w);
     J->enc_limits.stage_words = std::max(J->enc_limits.stage_words, b2k_ht_encode_stage_words(d.w));
     J->enc_limits.max_kmax = std::max<uint32_t>(J->enc_limits.max_kmax, d.kmax);
@@ -692,7 +702,7 @@ static int build_block_plan(b2k_device_job* J)
     CUDA_TRY(cudaMalloc(&J->d_offsets, (n + 1) * sizeof(uint64_t)));
     CUDA_TRY(cudaMemset(J->d_offsets, 0, (n + 1) * sizeof(uint64_t))); /* offsets[0] stays 0: the scan's base */
     CUDA_TRY(cudaMalloc(&J->d_scratch, J->scratch_bytes + 64));
-    CUDA_TRY(cudaMalloc(&J->d_recs, (J->total_quads + 64) * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&J->d_recs, (J->total_quads + 32 * J->group_quads + 64) * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&J->d_dec_status, n * sizeof(HtBlockOut)));
     CUDA_TRY(cudaMalloc(&J->d_dec_quant, n * sizeof(float)));
     CUDA_TRY(cudaMemcpy(J->d_dec_quant, J->dec_quant.data(), n * sizeof(float), cudaMemcpyHostToDevice));

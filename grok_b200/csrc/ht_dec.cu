@@ -18,6 +18,7 @@
  * 32 bytes at a time (one byte per lane, stuffing resolved with one ballot since on the decode
  * side a byte's width only depends on its predecessor's VALUE).
  */
+#include <cstdlib>
 #include "b2k_internal.h"
 #define HT_TABLE_QUAL static __device__ const
 #include "ht_tables.h"
@@ -149,7 +150,9 @@ __device__ __forceinline__ T warp_excl_scan_d(T v, int lane, T& total)
  * are independent: 32 blocks per warp keep every lane busy (a warp-per-block version of this
  * loop runs the same instruction stream with 1/32 of the lanes doing useful work).
  * Output: one record per quad in global scratch, rho[3:0] | e_k[7:4] | e_1[11:8] | u[17:12],
- * consumed by phase B (k_ht_decode_magsgn, warp per block).
+ * consumed by phase B (k_ht_decode_magsgn, warp per block).  The records of 32 consecutive blocks are
+ * interleaved word by word (entry k of a block sits at rec_off + 32 k): the 32 lanes of this kernel
+ * -- 32 different blocks at the same quad -- store 128 contiguous bytes instead of 32 scattered words.
  * =========================================================================================== */
 /* refill so that at least 32 un-stuffed bits are buffered: one quad pair consumes at most
    7+7 (CxtVLC) + 3+3+5+5 (UVLC) + 1 = 31 bits, so the parse of a pair needs no further checks */
@@ -485,12 +488,195 @@ __global__ void __launch_bounds__(128)
           }
         }
       }
-      rec[q0] = (t0 & 0xFFFu) | ((uint32_t)u0 << 12); /* rho | e_k<<4 | e_1<<8 | u<<12 */
+      rec[(size_t)q0 * 32] = (t0 & 0xFFFu) | ((uint32_t)u0 << 12); /* rho | e_k<<4 | e_1<<8 | u<<12 */
       if(has1)
-        rec[q0 + 1] = (t1 & 0xFFFu) | ((uint32_t)u1 << 12);
+        rec[(size_t)(q0 + 1) * 32] = (t1 & 0xFFFu) | ((uint32_t)u1 << 12);
     }
-    rec += nq;
+    rec += (size_t)nq * 32; /* records of 32 consecutive blocks are interleaved word by word */
     sig.next_row();
+  }
+  status[bidx] = st;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Phase A, fast path (blocks at most 64 samples wide): the same parse, arranged so that a quad pair
+ * costs one refill check, two CxtVLC look-ups and ONE U-VLC look-up instead of a tree of branches:
+ *  - uvlc[mode * 64 + next 6 bits] holds, for the pair's two u-offset flags (mode 0..3) and for the
+ *    first row's "both flags set, MEL said 0" rule (mode 4, T.814 7.3.6 / ojph_block_decoder32.cpp
+ *    L966-1010), the bits the two prefixes take, the two suffix lengths and the two base values;
+ *    the table is built in shared memory at kernel start from the prefix code itself;
+ *  - the neighbourhood bit of a quad's context is one shift of a per-row mask (A = bl | br << 1).
+ * The serial chain per quad is what bounds this phase; this halves it.
+ * ------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t uvlc_entry(int mode, uint32_t bits)
+{ /* plen[2:0] | l0[5:3] | l1[8:6] | p0[11:9] | p1[14:12] */
+  int plen = 0, l0 = 0, l1 = 0, p0 = 0, p1 = 0, len;
+  if(mode < 4)
+  {
+    if(mode & 1)
+    {
+      p0 = uvlc_prefix(bits, len);
+      bits >>= len;
+      plen += len;
+      l0 = uvlc_suflen(p0);
+    }
+    if(mode & 2)
+    {
+      p1 = uvlc_prefix(bits, len);
+      plen += len;
+      l1 = uvlc_suflen(p1);
+    }
+  }
+  else
+  { /* first quad row, both u-offsets set, MEL symbol 0 */
+    p0 = uvlc_prefix(bits, len);
+    bits >>= len;
+    plen += len;
+    if(p0 > 2)
+    {
+      p1 = 1 + (int)(bits & 1u); /* u1 is 1 or 2: one bit, sitting where the second prefix would */
+      plen += 1;
+      l0 = uvlc_suflen(p0);
+    }
+    else
+    {
+      p1 = uvlc_prefix(bits, len);
+      plen += len;
+      l1 = uvlc_suflen(p1);
+    }
+  }
+  return (uint32_t)plen | ((uint32_t)l0 << 3) | ((uint32_t)l1 << 6) | ((uint32_t)p0 << 9) | ((uint32_t)p1 << 12);
+}
+
+__global__ void __launch_bounds__(32)
+    k_ht_decode_vlc_fast(const HtBlockDesc* __restrict__ blocks, const uint8_t* __restrict__ bytes, uint32_t* __restrict__ recs,
+                         HtBlockOut* __restrict__ status, uint32_t nblocks)
+{
+  __shared__ uint16_t tbl0[1024], tbl1[1024], uvlc[5 * 64];
+  for(int i = threadIdx.x; i < 1024; i += blockDim.x)
+  {
+    tbl0[i] = HT_DEC_VLC0[i];
+    tbl1[i] = HT_DEC_VLC1[i];
+  }
+  for(int i = threadIdx.x; i < 5 * 64; i += blockDim.x)
+    uvlc[i] = (uint16_t)uvlc_entry(i >> 6, (uint32_t)(i & 63));
+  __syncthreads();
+  const uint32_t bidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if(bidx >= nblocks)
+    return;
+  const HtBlockDesc B = blocks[bidx];
+  const int w = B.w, h = B.h, nq = (w + 1) >> 1;
+  const uint32_t lcup = B.length;
+  const uint8_t* data = bytes + B.slot_off;
+  HtBlockOut st;
+  st.ms_len = 0; st.mel_len = 0; st.vlc_len = 0; st.total = 0;
+  int scup = 0;
+  if(lcup >= 2)
+  {
+    scup = ((int)__ldg(data + lcup - 1) << 4) + (int)(__ldg(data + lcup - 2) & 0xF);
+    if(scup < 2 || scup > (int)lcup || scup > 4079 || B.mmsbs > 29)
+      st.total = 2; /* malformed */
+  }
+  else
+    st.total = lcup == 0 ? 1 : 2; /* 1: empty block (all zero), 2: malformed */
+  if(st.total)
+  {
+    status[bidx] = st;
+    return;
+  }
+  st.ms_len = lcup - (uint32_t)scup;
+
+  MelFast mel;
+  mel.d = data + lcup - scup;
+  mel.size = scup - 1;
+  mel.pos = mel.bits = mel.unstuff = mel.k = mel.run = mel.have = 0;
+  mel.tmp = 0;
+  melf_init(mel);
+  VlcFast vlc;
+  vlc.d = data;
+  vlc.pos = (int)lcup - 3;
+  vlc.lo = (int)lcup - scup;
+  {
+    const uint32_t d = __ldg(data + lcup - 2);
+    vlc.tmp = d >> 4;
+    vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1 : 0);
+    vlc.unstuff = (d | 0xF) > 0x8F;
+  }
+  vlcf_init(vlc);
+  uint32_t* rec = recs + B.rec_off;
+  uint32_t pbl = 0, pbr = 0; /* significance of the row above's bottom-left / bottom-right samples, one bit per quad */
+
+  for(int y = 0; y < h; y += 2)
+  {
+    const uint16_t* tbl = y ? tbl1 : tbl0;
+    const uint64_t A = (uint64_t)pbl | ((uint64_t)pbr << 1); /* bit q: something significant above-left or above quad q (q up to 32) */
+    uint32_t cbl = 0, cbr = 0;
+    int rho_left = 0;
+    for(int q0 = 0; q0 < nq; q0 += 2)
+    {
+      vlcf_fill32(vlc);
+      const bool has1 = q0 + 1 < nq;
+      uint64_t tmp = vlc.tmp;
+      /* ---- CxtVLC of the two quads ---- */
+      const int cq0 = y == 0 ? ((rho_left >> 1) | (rho_left & 1))
+                             : (int)(((A >> q0) & 1u) | ((rho_left & 0xC) ? 2u : 0u) | (((A >> (q0 + 1)) & 1u) << 2));
+      uint32_t t0 = tbl[(cq0 << 7) | ((uint32_t)tmp & 0x7F)];
+      if(cq0 == 0 && !melf_symbol(mel))
+        t0 = 0;
+      tmp >>= (t0 >> 13);
+      int used = (int)(t0 >> 13);
+      const int rho0 = t0 & 0xF;
+      uint32_t t1 = 0;
+      int rho1 = 0;
+      if(has1)
+      {
+        const int cq1 = y == 0 ? ((rho0 >> 1) | (rho0 & 1))
+                               : (int)(((A >> (q0 + 1)) & 1u) | ((rho0 & 0xC) ? 2u : 0u) | (((A >> (q0 + 2)) & 1u) << 2));
+        t1 = tbl[(cq1 << 7) | ((uint32_t)tmp & 0x7F)];
+        if(cq1 == 0 && !melf_symbol(mel))
+          t1 = 0;
+        tmp >>= (t1 >> 13);
+        used += (int)(t1 >> 13);
+        rho1 = t1 & 0xF;
+      }
+      rho_left = has1 ? rho1 : rho0;
+      cbl |= ((uint32_t)((rho0 >> 1) & 1) << q0) | ((uint32_t)((rho1 >> 1) & 1) << (q0 + 1));
+      cbr |= ((uint32_t)((rho0 >> 3) & 1) << q0) | ((uint32_t)((rho1 >> 3) & 1) << (q0 + 1));
+      /* ---- U-VLC of the pair: one look-up ---- */
+      int u0 = 0, u1 = 0;
+      const int uo = (int)((t0 >> 12) & 1u) | (int)(((t1 >> 12) & 1u) << 1);
+      if(uo)
+      {
+        int mode = uo, add = 0;
+        if(y == 0 && uo == 3)
+        {
+          if(melf_symbol(mel))
+            add = 2; /* both > 2: the plain codes, offset by 2 */
+          else
+            mode = 4;
+        }
+        const uint32_t e = uvlc[mode * 64 + ((uint32_t)tmp & 63u)];
+        const int plen = e & 7, l0 = (e >> 3) & 7, l1 = (e >> 6) & 7;
+        tmp >>= plen;
+        u0 = (int)((e >> 9) & 7u) + (int)((uint32_t)tmp & ((1u << l0) - 1u));
+        tmp >>= l0;
+        u1 = (int)((e >> 12) & 7u) + (int)((uint32_t)tmp & ((1u << l1) - 1u));
+        tmp >>= l1;
+        used += plen + l0 + l1;
+        if(uo & 1)
+          u0 += add;
+        if(uo & 2)
+          u1 += add;
+      }
+      vlc.tmp = tmp;
+      vlc.bits -= used;
+      rec[(size_t)q0 * 32] = (t0 & 0xFFFu) | ((uint32_t)u0 << 12); /* rho | e_k<<4 | e_1<<8 | u<<12 */
+      if(has1)
+        rec[(size_t)(q0 + 1) * 32] = (t1 & 0xFFFu) | ((uint32_t)u1 << 12);
+    }
+    rec += (size_t)nq * 32; /* records of 32 consecutive blocks are interleaved word by word */
+    pbl = cbl;
+    pbr = cbr;
   }
   status[bidx] = st;
 }
@@ -601,7 +787,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
 
       const int q = qb + lane, x = 2 * q;
       const bool qv = q < nq;
-      const uint32_t r = qv ? __ldg(rec + q) : 0u;
+      const uint32_t r = qv ? __ldg(rec + (size_t)q * 32) : 0u;
       const int rho = r & 0xF, ekq = (r >> 4) & 0xF, e1q = (r >> 8) & 0xF, uq = (int)(r >> 12);
       int kappa = 1;
       if(y > 0 && qv)
@@ -688,7 +874,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
       bad = __any_sync(0xffffffffu, bad);
       __syncwarp();
     }
-    rec += nq;
+    rec += (size_t)nq * 32; /* records of 32 consecutive blocks are interleaved word by word */
   }
   if(bad)
   {
@@ -973,8 +1159,10 @@ void b2k_launch_ht_decode_vlc(const HtBlockDesc* d_blocks, const uint8_t* d_byte
      SMs as possible instead of packing 4 warps onto one */
   if(max_w > 64)
     k_ht_decode_vlc<true><<<(nblocks + 31) / 32, 32, 0, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks);
-  else
+  else if(getenv("B2K_VLC_GENERIC")) /* the branchy reference formulation, kept for A/B runs */
     k_ht_decode_vlc<false><<<(nblocks + 31) / 32, 32, 0, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks);
+  else
+    k_ht_decode_vlc_fast<<<(nblocks + 31) / 32, 32, 0, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks);
   b2k_count_launch();
 }
 
