@@ -179,7 +179,7 @@ struct VlcFast
 { /* backward reader of the VLC segment (rev_read / rev_init, ojph_block_decoder32.cpp L296-395) */
   const uint8_t* d;
   const uint64_t* ap; /* aligned window holding the byte at `pos` */
-  uint64_t cur, nxt, tmp;
+  uint64_t cur, nxt, nx2, tmp; /* the window in use and the two below it, already in flight */
   int pos, lo, bits, unstuff;
 };
 __device__ __forceinline__ uint64_t vlcf_load(const VlcFast& v, const uint64_t* a)
@@ -192,9 +192,41 @@ __device__ __forceinline__ void vlcf_init(VlcFast& v)
   v.ap = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)7);
   v.cur = vlcf_load(v, v.ap);
   v.nxt = vlcf_load(v, v.ap - 1);
+  v.nx2 = vlcf_load(v, v.ap - 2);
 }
+__device__ __forceinline__ void vlcf_rotate(VlcFast& v)
+{
+  --v.ap;
+  v.cur = v.nxt;
+  v.nxt = v.nx2;
+  v.nx2 = vlcf_load(v, v.ap - 2); /* 16 bytes (six or seven quad pairs of parsing) ahead of its first use */
+}
+/* at least 32 un-stuffed bits buffered (a quad pair takes at most 31).  Four bytes per refill: only a byte whose low
+   seven bits are all ones can be a stuffed (7-bit) byte, so when none of the four is (97 % of the time) they go into
+   the bit buffer with one shift; otherwise, and at the segment's start, byte by byte as rev_read does */
 __device__ __forceinline__ void vlcf_fill32(VlcFast& v)
 {
+  if(v.bits >= 32)
+    return;
+  if(v.pos - 3 >= v.lo)
+  {
+    if(v.d + v.pos < reinterpret_cast<const uint8_t*>(v.ap))
+      vlcf_rotate(v); /* the byte-wise path below moves pos without moving the window */
+    const int o = (int)((v.d + v.pos) - reinterpret_cast<const uint8_t*>(v.ap)); /* byte `pos` inside cur: 0 .. 7 */
+    /* bytes pos-3 .. pos as a little-endian word, from cur (and the window below it when o < 3) */
+    const uint32_t le = o >= 3 ? (uint32_t)(v.cur >> (8 * (o - 3))) : (uint32_t)((v.nxt >> (8 * (o + 5))) | (v.cur << (8 * (3 - o))));
+    const uint32_t w = __byte_perm(le, 0, 0x0123); /* byte `pos` lowest: the order the stream is read in */
+    if((((w & 0x7F7F7F7Fu) + 0x01010101u) & 0x80808080u) == 0)
+    {
+      v.tmp |= (uint64_t)w << v.bits;
+      v.bits += 32;
+      v.unstuff = (w >> 24) > 0x8Fu;
+      v.pos -= 4;
+      if(v.d + v.pos < reinterpret_cast<const uint8_t*>(v.ap))
+        vlcf_rotate(v);
+      return;
+    }
+  }
   while(v.bits < 32)
   {
     uint32_t b = 0;
@@ -202,11 +234,7 @@ __device__ __forceinline__ void vlcf_fill32(VlcFast& v)
     {
       const uint8_t* a = v.d + v.pos;
       if(a < reinterpret_cast<const uint8_t*>(v.ap))
-      {
-        --v.ap;
-        v.cur = v.nxt;
-        v.nxt = vlcf_load(v, v.ap - 1);
-      }
+        vlcf_rotate(v);
       b = (uint32_t)(v.cur >> (8 * (int)(a - reinterpret_cast<const uint8_t*>(v.ap)))) & 0xFFu;
     }
     v.pos--;
@@ -730,6 +758,17 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
   uint32_t ms_head = 0, ms_tail = 0;
   bool ms_prevff = false;
   const uint32_t* rec = recs + B.rec_off;
+  uint32_t r_next = lane < nq ? __ldg(rec + (size_t)lane * 32) : 0u;
+  uint32_t pw0 = 0, pw1 = 0; /* this lane's two aligned words of the next 128-byte refill */
+  auto load_chunk = [&](int pos) {
+    if(pos + 4 * lane < ms_size)
+    {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(data + pos + 4 * lane) & ~(uintptr_t)3;
+      pw0 = __ldg(reinterpret_cast<const uint32_t*>(a));
+      pw1 = __ldg(reinterpret_cast<const uint32_t*>(a) + 1);
+    }
+  };
+  load_chunk(0);
 
   for(int y = 0; y < h && !bad; y += 2)
   {
@@ -747,13 +786,12 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
         uint32_t val = 0xFFFFFFFFu;
         if(ms_pos + 4 * lane < ms_size)
         {
-          const uintptr_t a = reinterpret_cast<uintptr_t>(pb) & ~(uintptr_t)3;
-          const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(a)), w1 = __ldg(reinterpret_cast<const uint32_t*>(a) + 1);
-          val = __funnelshift_r(w0, w1, 8 * (int)(reinterpret_cast<uintptr_t>(pb) & 3));
+          val = __funnelshift_r(pw0, pw1, 8 * (int)(reinterpret_cast<uintptr_t>(pb) & 3)); /* loaded one refill ago */
           const int left = ms_size - (ms_pos + 4 * lane);
           if(left < 4)
             val |= 0xFFFFFFFFu << (8 * left);
         }
+        load_chunk(ms_pos + 128); /* the next 128 bytes are in flight while these are parsed */
         const unsigned lastff = __ballot_sync(0xffffffffu, (val >> 24) == 0xFFu);
         bool f = lane == 0 ? ms_prevff : (((lastff >> (lane - 1)) & 1u) != 0);
         uint64_t acc = 0;
@@ -787,7 +825,18 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
 
       const int q = qb + lane, x = 2 * q;
       const bool qv = q < nq;
-      const uint32_t r = qv ? __ldg(rec + (size_t)q * 32) : 0u;
+      const uint32_t r = r_next; /* loaded one step ago (the interleaved records are a 32-sector gather: latency, not bandwidth) */
+      {
+        int qn = qb + 32 + lane, yn = y;
+        const uint32_t* recn = rec;
+        if(qb + 32 >= nq)
+        {
+          qn = lane;
+          yn = y + 2;
+          recn = rec + (size_t)nq * 32;
+        }
+        r_next = (yn < h && qn < nq) ? __ldg(recn + (size_t)qn * 32) : 0u;
+      }
       const int rho = r & 0xF, ekq = (r >> 4) & 0xF, e1q = (r >> 8) & 0xF, uq = (int)(r >> 12);
       int kappa = 1;
       if(y > 0 && qv)
