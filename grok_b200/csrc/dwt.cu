@@ -1391,6 +1391,30 @@ struct BandStage
       }
     }
   }
+  /* bulk path: every lane of the warp is `fast` on all four sources, so each band row of the pair is 512 contiguous,
+     16-byte aligned bytes starting at lane 0's column: lane 0 asks the copy engine (TMA, UBLKCP) for the 4 x NC rows,
+     which land in the same linear layout the per-lane cp.async path writes and complete on `bar` */
+  static __device__ __forceinline__ void fill_bulk(uint8_t* stage, const DwtLevelDesc& D, const Job& J, const BandGeom& g,
+                                                   const Lane& L, int t, uint64_t* bar)
+  {
+    const int jl = ((D.v0 + mirror_rel(2 * t - D.v0, J.hn)) >> 1), jh = ((D.v0 + mirror_rel(2 * t + 1 - D.v0, J.hn)) >> 1);
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+      const int32_t* src[4];
+      src[0] = reinterpret_cast<const int32_t*>(D.out_ll[c]) + (jl - g.y0l) * (int)D.ll_pitch;
+      src[1] = reinterpret_cast<const int32_t*>(D.out_c[c]) + (jl - g.y0l) * (int)D.c_pitch;
+      src[2] = reinterpret_cast<const int32_t*>(D.out_c[c]) + (g.sny + jh - g.y0h) * (int)D.c_pitch;
+      src[3] = src[2];
+#pragma unroll
+      for(int b = 0; b < 4; ++b)
+        bulk_g2s(stage + (b * NC + c) * ROWB, src[b] + L.col[b], ROWB, bar);
+    }
+  }
+  static __device__ __forceinline__ bool all_fast(const Lane& L)
+  {
+    return __all_sync(0xffffffffu, L.fast[0] && L.fast[1] && L.fast[2] && L.fast[3]);
+  }
   static __device__ __forceinline__ void read(const uint8_t* stage, const Job& J, int b, int c, int (&v)[4])
   {
     const int4 a = *reinterpret_cast<const int4*>(stage + (b * NC + c) * ROWB + J.lane * 16);
@@ -1518,14 +1542,41 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtL
   BS::setup(D, J, g, L);
   const OutCtx OC = out_ctx<OUT16>(D, J);
   uint8_t* wsm = smem_dwt + (size_t)(threadIdx.x >> 5) * STAGES * BS::PAIRB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dwt + (size_t)B2K_WARPS_PER_CTA * STAGES * BS::PAIRB) + (threadIdx.x >> 5) * STAGES;
+  const bool bulk = BS::all_fast(L); /* interior strip: band rows by bulk copy (TMA engine) on per-slot mbarriers */
+  if(bulk)
+  {
+    if(J.lane == 0)
+    {
+#pragma unroll
+      for(int s = 0; s < STAGES; ++s)
+        mbar_init(bars + s, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
 
   const int tfirst = J.jbeg - 1, tlast = J.jend;
+  auto fill_pair = [&](int tf) {
+    const int slot = (tf - tfirst) % STAGES;
+    uint8_t* st = wsm + (size_t)slot * BS::PAIRB;
+    if(bulk)
+    {
+      if(J.lane == 0)
+      {
+        mbar_expect_tx(bars + slot, BS::PAIRB);
+        BS::fill_bulk(st, D, J, g, L, tf, bars + slot);
+      }
+    }
+    else
+      BS::fill(st, D, J, g, L, tf);
+  };
   int tfill = tfirst;
 #pragma unroll
   for(int s = 0; s < STAGES - 1; ++s)
   {
     if(tfill <= tlast)
-      BS::fill(wsm + (size_t)((tfill - tfirst) % STAGES) * BS::PAIRB, D, J, g, L, tfill);
+      fill_pair(tfill);
     cp_async_commit();
     ++tfill;
   }
@@ -1538,11 +1589,16 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt53_inv(const DwtL
 
   for(int t = tfirst; t <= tlast; ++t)
   {
+    if(bulk)
+      __syncwarp(); /* every lane has read the slot that is refilled next */
     if(tfill <= tlast)
-      BS::fill(wsm + (size_t)((tfill - tfirst) % STAGES) * BS::PAIRB, D, J, g, L, tfill);
+      fill_pair(tfill);
     cp_async_commit();
     ++tfill;
-    cp_async_wait<STAGES - 1>();
+    if(bulk)
+      mbar_wait(bars + (t - tfirst) % STAGES, (unsigned)(((t - tfirst) / STAGES) & 1));
+    else
+      cp_async_wait<STAGES - 1>();
     const uint8_t* st = wsm + (size_t)((t - tfirst) % STAGES) * BS::PAIRB;
     int Er[NC][8], Or[NC][8];
 #pragma unroll
@@ -1708,15 +1764,42 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_inv(const DwtL
   BS::setup(D, J, g, L);
   const OutCtx OC = out_ctx<false>(D, J);
   uint8_t* wsm = smem_dwt + (size_t)(threadIdx.x >> 5) * STAGES * BS::PAIRB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dwt + (size_t)B2K_WARPS_PER_CTA * STAGES * BS::PAIRB) + (threadIdx.x >> 5) * STAGES;
+  const bool bulk = BS::all_fast(L); /* interior strip: band rows by bulk copy (TMA engine) on per-slot mbarriers */
+  if(bulk)
+  {
+    if(J.lane == 0)
+    {
+#pragma unroll
+      for(int s = 0; s < STAGES; ++s)
+        mbar_init(bars + s, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
   const float K = 1.230174105f, twice_invK = 1.625732422f;
 
   const int tfirst = J.jbeg - 2, tlast = J.jend + 1;
+  auto fill_pair = [&](int tf) {
+    const int slot = (tf - tfirst) % STAGES;
+    uint8_t* st = wsm + (size_t)slot * BS::PAIRB;
+    if(bulk)
+    {
+      if(J.lane == 0)
+      {
+        mbar_expect_tx(bars + slot, BS::PAIRB);
+        BS::fill_bulk(st, D, J, g, L, tf, bars + slot);
+      }
+    }
+    else
+      BS::fill(st, D, J, g, L, tf);
+  };
   int tfill = tfirst;
 #pragma unroll
   for(int s = 0; s < STAGES - 1; ++s)
   {
     if(tfill <= tlast)
-      BS::fill(wsm + (size_t)((tfill - tfirst) % STAGES) * BS::PAIRB, D, J, g, L, tfill);
+      fill_pair(tfill);
     cp_async_commit();
     ++tfill;
   }
@@ -1730,11 +1813,16 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32) k_dwt97_inv(const DwtL
 
   for(int t = tfirst; t <= tlast; ++t)
   {
+    if(bulk)
+      __syncwarp(); /* every lane has read the slot that is refilled next */
     if(tfill <= tlast)
-      BS::fill(wsm + (size_t)((tfill - tfirst) % STAGES) * BS::PAIRB, D, J, g, L, tfill);
+      fill_pair(tfill);
     cp_async_commit();
     ++tfill;
-    cp_async_wait<STAGES - 1>();
+    if(bulk)
+      mbar_wait(bars + (t - tfirst) % STAGES, (unsigned)(((t - tfirst) / STAGES) & 1));
+    else
+      cp_async_wait<STAGES - 1>();
     const uint8_t* st = wsm + (size_t)((t - tfirst) % STAGES) * BS::PAIRB;
     float Er[NC][8], Or[NC][8];
 #pragma unroll
@@ -1903,7 +1991,7 @@ void b2k_launch_dwt_fwd(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, 
 template <int NC, int STAGES, bool OUT16>
 static void launch_inv53(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
 {
-  const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * BandStage<NC>::PAIRB;
+  const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * BandStage<NC>::PAIRB + (size_t)B2K_WARPS_PER_CTA * STAGES * sizeof(uint64_t);
   static DeviceOnce once; /* function attributes are per device */
   once.run([&] {
     cudaFuncSetAttribute(k_dwt53_inv<NC, STAGES, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1914,7 +2002,7 @@ static void launch_inv53(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelD
 template <int NC, int STAGES>
 static void launch_inv97(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelDesc* d)
 {
-  const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * BandStage<NC>::PAIRB;
+  const size_t smem = (size_t)B2K_WARPS_PER_CTA * STAGES * BandStage<NC>::PAIRB + (size_t)B2K_WARPS_PER_CTA * STAGES * sizeof(uint64_t);
   static DeviceOnce once; /* function attributes are per device */
   once.run([&] {
     cudaFuncSetAttribute(k_dwt97_inv<NC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
