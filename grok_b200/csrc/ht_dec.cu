@@ -807,6 +807,14 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
         uint32_t tot;
         const uint32_t off = warp_excl_scan_d<uint32_t>((uint32_t)nb, lane, tot);
         const uint32_t pos = ms_tail + off;
+        { /* the words this refill lands in are cleared here (33 whole words after the one the tail sits in): the consumer
+             does not clean up behind itself any more */
+          const uint32_t wt = ms_tail >> 5;
+          ring[(wt + 1 + lane) & (MS_RING_WORDS - 1)] = 0;
+          if(lane == 0)
+            ring[(wt + 33) & (MS_RING_WORDS - 1)] = 0;
+          __syncwarp();
+        }
         {
           const int sh = pos & 31;
           const uint32_t wi = pos >> 5;
@@ -913,13 +921,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
       }
       if(qv)
         lcur[q + 1] = (uint16_t)(ebot[0] | (ebot[1] << 8));
-      {
-        const uint32_t nh = ms_head + total;
-        __syncwarp();
-        for(uint32_t wz = (ms_head >> 5) + lane; wz < (nh >> 5); wz += 32)
-          ring[wz & (MS_RING_WORDS - 1)] = 0;
-        ms_head = nh;
-      }
+      ms_head += total;
       bad = __any_sync(0xffffffffu, bad);
       __syncwarp();
     }

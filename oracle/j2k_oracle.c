@@ -334,21 +334,42 @@ DEFINE_DWT2D(dwt97, float, fwd97_line, inv97_line)
 /* Quantiser tables: t2/quantizer/part15/QuantizerOJPH.cpp L150-259, pulled by                 */
 /* t2/quantizer/part1/Quantizer.cpp L47-64; band step / Kmax: TileProcessor.cpp L398-419.      */
 /* ------------------------------------------------------------------------------------------ */
-static const float bibo_5x3_l[8] = {1.0000e+00f, 1.5000e+00f, 1.6250e+00f, 1.6875e+00f,
-                                    1.6963e+00f, 1.7067e+00f, 1.7116e+00f, 1.7129e+00f};
-static const float bibo_5x3_h[8] = {2.0000e+00f, 2.5000e+00f, 2.7500e+00f, 2.8047e+00f,
-                                    2.8198e+00f, 2.8410e+00f, 2.8558e+00f, 2.8601e+00f};
-static const float sqe_9x7_l[8] = {1.0000e+00f, 1.4021e+00f, 2.0304e+00f, 2.9012e+00f,
-                                   4.1153e+00f, 5.8245e+00f, 8.2388e+00f, 1.1652e+01f};
-static const float sqe_9x7_h[8] = {1.4425e+00f, 1.9669e+00f, 2.8839e+00f, 4.1475e+00f,
-                                   5.8946e+00f, 8.3472e+00f, 1.1809e+01f, 1.6701e+01f};
+/* the reference's tables in full (34 entries; emitted by tools/gen_gain_tables.py from QuantizerOJPH.cpp L103-185) */
+static const float bibo_5x3_l[34] = {
+    1.0000e+00f, 1.5000e+00f, 1.6250e+00f, 1.6875e+00f, 1.6963e+00f, 1.7067e+00f, 1.7116e+00f,
+    1.7129e+00f, 1.7141e+00f, 1.7145e+00f, 1.7151e+00f, 1.7152e+00f, 1.7155e+00f, 1.7155e+00f,
+    1.7156e+00f, 1.7156e+00f, 1.7156e+00f, 1.7156e+00f, 1.7156e+00f, 1.7156e+00f, 1.7156e+00f,
+    1.7156e+00f, 1.7156e+00f, 1.7156e+00f, 1.7156e+00f, 1.7156e+00f, 1.7156e+00f, 1.7156e+00f,
+    1.7156e+00f, 1.7156e+00f, 1.7156e+00f, 1.7156e+00f, 1.7156e+00f, 1.7156e+00f
+};
+static const float bibo_5x3_h[34] = {
+    2.0000e+00f, 2.5000e+00f, 2.7500e+00f, 2.8047e+00f, 2.8198e+00f, 2.8410e+00f, 2.8558e+00f,
+    2.8601e+00f, 2.8628e+00f, 2.8656e+00f, 2.8662e+00f, 2.8667e+00f, 2.8669e+00f, 2.8670e+00f,
+    2.8671e+00f, 2.8671e+00f, 2.8671e+00f, 2.8671e+00f, 2.8671e+00f, 2.8671e+00f, 2.8671e+00f,
+    2.8671e+00f, 2.8671e+00f, 2.8671e+00f, 2.8671e+00f, 2.8671e+00f, 2.8671e+00f, 2.8671e+00f,
+    2.8671e+00f, 2.8671e+00f, 2.8671e+00f, 2.8671e+00f, 2.8671e+00f, 2.8671e+00f
+};
+static const float sqe_9x7_l[34] = {
+    1.0000e+00f, 1.4021e+00f, 2.0304e+00f, 2.9012e+00f, 4.1153e+00f, 5.8245e+00f, 8.2388e+00f,
+    1.1652e+01f, 1.6479e+01f, 2.3304e+01f, 3.2957e+01f, 4.6609e+01f, 6.5915e+01f, 9.3217e+01f,
+    1.3183e+02f, 1.8643e+02f, 2.6366e+02f, 3.7287e+02f, 5.2732e+02f, 7.4574e+02f, 1.0546e+03f,
+    1.4915e+03f, 2.1093e+03f, 2.9830e+03f, 4.2185e+03f, 5.9659e+03f, 8.4371e+03f, 1.1932e+04f,
+    1.6874e+04f, 2.3864e+04f, 3.3748e+04f, 4.7727e+04f, 6.7496e+04f, 9.5454e+04f
+};
+static const float sqe_9x7_h[34] = {
+    1.4425e+00f, 1.9669e+00f, 2.8839e+00f, 4.1475e+00f, 5.8946e+00f, 8.3472e+00f, 1.1809e+01f,
+    1.6701e+01f, 2.3620e+01f, 3.3403e+01f, 4.7240e+01f, 6.6807e+01f, 9.4479e+01f, 1.3361e+02f,
+    1.8896e+02f, 2.6723e+02f, 3.7792e+02f, 5.3446e+02f, 7.5583e+02f, 1.0689e+03f, 1.5117e+03f,
+    2.1378e+03f, 3.0233e+03f, 4.2756e+03f, 6.0467e+03f, 8.5513e+03f, 1.2093e+04f, 1.7103e+04f,
+    2.4187e+04f, 3.4205e+04f, 4.8373e+04f, 6.8410e+04f, 9.6747e+04f, 1.3682e+05f
+};
 
 /* expn[3*decomps+1], mant[...]; band order LL, then per level coarsest->finest HL,LH,HH.
- * Supports decomps <= 7 (tables above truncated; the reference's go to 33). */
+ * decomps <= 32 (the tables' extent). */
 ORC_API int orc_ht_stepsizes(int decomps, int prec, int mct, int sgnd, int reversible,
                              uint8_t* expn, uint16_t* mant)
 {
-  if(decomps > 7)
+  if(decomps > 32)
     return -1;
   int s = 0;
   if(reversible)

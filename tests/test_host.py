@@ -299,7 +299,7 @@ def test_ht_bit_plane_limits_are_declined_with_a_reason():
         deep.qcd_expn[i] = 31
     assert lib.b2k_enumerate(C.byref(deep), 1, 0, None, 0) < 0
     assert b"bit planes" in lib.b2k_last_error()
-    for bad in (dict(prec=17), dict(numcomps=5), dict(cblk=(1024, 8)), dict(numres=9)):
+    for bad in (dict(prec=17), dict(numcomps=5), dict(cblk=(1024, 8)), dict(numres=17), dict(numres=1)):
         args = dict(width=64, height=64, numcomps=1, prec=8, numres=3)
         args.update(bad)
         assert lib.b2k_enumerate(C.byref(G.make_coding(**args)), 1, 0, None, 0) < 0, bad

@@ -65,12 +65,15 @@ REVERSIBLE = [
     dict(width=333, height=217, numcomps=3, prec=12),                                 # odd size, one tile
     dict(width=200, height=150, numcomps=4, prec=16, tile=(128, 64), numres=4),       # config 4 in small
     dict(width=300, height=260, numcomps=3, prec=8, numres=3, cblk=(32, 32)),
+    dict(width=1100, height=700, numcomps=3, prec=10, numres=10),                      # 9 decomposition levels (> 8 resolutions)
+    dict(width=900, height=600, numcomps=1, prec=12, numres=10, tile=(512, 512)),      # as many levels as a 512 tile takes (the host clamps more)
 ]
 IRREVERSIBLE = [
     dict(width=640, height=384, numcomps=3, prec=12, irreversible=True),              # config 3 in small
     dict(width=333, height=217, numcomps=3, prec=12, irreversible=True, tile=(128, 128), numres=4),
     dict(width=300, height=200, numcomps=1, prec=12, irreversible=True),
     dict(width=320, height=192, numcomps=3, prec=16, irreversible=True, numres=5),
+    dict(width=1100, height=700, numcomps=3, prec=10, irreversible=True, numres=10),
 ]
 
 
