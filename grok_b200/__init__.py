@@ -64,7 +64,8 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_roundtrip_n", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
            "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last",
-           "b2k_codestream_write", "b2k_codestream_parse", "b2k_codestream_parse_window", "b2k_jph_wrap", "b2k_jph_codestream", "b2k_result_merge",
+           "b2k_codestream_write", "b2k_codestream_parse", "b2k_codestream_parse_window",
+           "b2k_codestream_write_tiles", "b2k_codestream_write_header", "b2k_jph_wrap", "b2k_jph_codestream", "b2k_result_merge",
            "gpup_encode_mem_tiles", "gpup_tiles_free", "plugin_decompress_codestream", "b2k_coding_from_gpup",
            "b2k_stream_encode_begin", "b2k_stream_encode_submit", "b2k_stream_decode_begin", "b2k_stream_decode_submit",
            "b2k_stream_decode_submit_codestream", "b2k_stream_end",
@@ -241,6 +242,45 @@ def result_from_tables(blocks, data, num_tiles):
     r.num_bytes = len(data)
     r.num_tiles = num_tiles
     return r
+
+
+def codestream_write_tiles(cp, blocks, data, flags=CS_TLM | CS_PLT, tile_mod=1, tile_rem=0, out=None):
+    """A shard's tiles as finished tile parts (b2k_codestream_write_tiles) -> (bytes, per-tile lengths of the shard's tiles)."""
+    blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    r = Result()
+    r.num_blocks = len(blocks)
+    r.blocks = C.cast(blocks.ctypes.data, C.POINTER(Block))
+    r.bytes = C.cast(data.ctypes.data, C.POINTER(C.c_uint8))
+    r.num_bytes = len(data)
+    L = lib()
+    L.b2k_codestream_write_tiles.restype = C.c_int64
+    L.b2k_codestream_write_tiles.argtypes = [C.POINTER(Coding), C.POINTER(Result), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+    g_nx = -(-(cp.x1 - cp.tx0) // cp.tw) if cp.tw else 1
+    g_ny = -(-(cp.y1 - cp.ty0) // cp.th) if cp.th else 1
+    nmine = len(range(tile_rem, g_nx * g_ny, tile_mod))
+    lens = np.zeros(nmine, np.uint64)
+    n = L.b2k_codestream_write_tiles(C.byref(cp), C.byref(r), flags, tile_mod, tile_rem, None, 0, lens.ctypes.data)
+    if n < 0:
+        raise EngineError("b2k_codestream_write_tiles: " + (L.b2k_last_error() or b"").decode())
+    if out is None or out.size < n:
+        out = np.zeros(max(n, 1), np.uint8)
+    assert L.b2k_codestream_write_tiles(C.byref(cp), C.byref(r), flags, tile_mod, tile_rem, out.ctypes.data, out.size, lens.ctypes.data) == n
+    return out[:n], lens
+
+
+def codestream_write_header(cp, flags, tile_bytes_all):
+    """Main header (+ TLM) from the tile-part length of every tile (b2k_codestream_write_header)."""
+    tb = np.ascontiguousarray(tile_bytes_all, dtype=np.uint64)
+    L = lib()
+    L.b2k_codestream_write_header.restype = C.c_int64
+    L.b2k_codestream_write_header.argtypes = [C.POINTER(Coding), C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
+    n = L.b2k_codestream_write_header(C.byref(cp), flags, tb.ctypes.data, len(tb), None, 0)
+    if n < 0:
+        raise EngineError("b2k_codestream_write_header: " + (L.b2k_last_error() or b"").decode())
+    out = np.zeros(n, np.uint8)
+    assert L.b2k_codestream_write_header(C.byref(cp), flags, tb.ctypes.data, len(tb), out.ctypes.data, n) == n
+    return out
 
 
 def merge_shards(cp, shards):

@@ -654,6 +654,63 @@ void plan_tile_parts(TilePlan& P, bool split_res, bool want_plt)
 
 } // namespace
 
+
+namespace
+{
+/* SOT, [PLT], SOD and the packets of every tile part of one planned tile, written at w (plan.size() bytes) */
+void emit_tile_parts(const TilePlan& P, uint32_t t, const uint8_t* arena, uint8_t* w)
+{
+  for(size_t pi = 0; pi < P.parts.size(); ++pi)
+  {
+    const TilePlan::Part& pt = P.parts[pi];
+    const uint32_t psot = (uint32_t)pt.bytes;
+    const uint8_t sot[12] = {0xFF, 0x90, 0, 10, (uint8_t)(t >> 8), (uint8_t)t, (uint8_t)(psot >> 24), (uint8_t)(psot >> 16),
+                             (uint8_t)(psot >> 8), (uint8_t)psot, (uint8_t)pi, (uint8_t)P.parts.size()}; /* SOT (A.4.2) */
+    memcpy(w, sot, 12);
+    w += 12;
+    if(!pt.plt.empty())
+    {
+      memcpy(w, pt.plt.data(), pt.plt.size());
+      w += pt.plt.size();
+    }
+    *w++ = 0xFF; /* SOD */
+    *w++ = 0x93;
+    const uint8_t* h = P.hdrs.data() + pt.h0;
+    size_t sg = pt.s0;
+    for(size_t k = pt.p0; k < pt.p1; ++k)
+    {
+      memcpy(w, h, P.hdr_len[k]);
+      w += P.hdr_len[k];
+      h += P.hdr_len[k];
+      for(uint32_t i = 0; i < P.nseg[k]; ++i, ++sg)
+      {
+        memcpy(w, arena + P.seg_off[sg], P.seg_len[sg]);
+        w += P.seg_len[sg];
+      }
+    }
+  }
+}
+
+/* TLM (A.7.1): 16-bit tile index + 32-bit length per tile part, in codestream order; 10921 entries fit a segment */
+void append_tlm(std::vector<uint8_t>& head, const std::vector<std::pair<uint32_t, uint32_t>>& ent)
+{
+  uint8_t z = 0;
+  for(size_t e0 = 0; e0 < ent.size(); e0 += 10000)
+  {
+    const size_t n = std::min<size_t>(10000, ent.size() - e0);
+    put16(head, 0xFF55);
+    put16(head, (uint32_t)(4 + 6 * n));
+    head.push_back(z++);
+    head.push_back(0x60); /* ST = 2 (16-bit Ttlm), SP = 1 (32-bit Ptlm) */
+    for(size_t e = e0; e < e0 + n; ++e)
+    {
+      put16(head, ent[e].first);
+      put32(head, ent[e].second);
+    }
+  }
+}
+} // namespace
+
 /* ============================================================================================================ */
 extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(const b2k_coding* cp, const b2k_result* r,
                                                                                 uint32_t flags, uint8_t* out, uint64_t cap)
@@ -738,25 +795,12 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(c
     total += plans[t].size();
   }
   if(flags & B2K_CS_TLM)
-  { /* TLM (A.7.1): 16-bit tile index + 32-bit length per tile part, in codestream order; 10921 entries fit a segment */
+  {
     std::vector<std::pair<uint32_t, uint32_t>> ent;
     for(uint32_t t = 0; t < ntiles; ++t)
       for(const TilePlan::Part& pt : plans[t].parts)
         ent.push_back({t, (uint32_t)pt.bytes});
-    uint8_t z = 0;
-    for(size_t e0 = 0; e0 < ent.size(); e0 += 10000)
-    {
-      const size_t n = std::min<size_t>(10000, ent.size() - e0);
-      put16(head, 0xFF55);
-      put16(head, (uint32_t)(4 + 6 * n));
-      head.push_back(z++);
-      head.push_back(0x60); /* ST = 2 (16-bit Ttlm), SP = 1 (32-bit Ptlm) */
-      for(size_t e = e0; e < e0 + n; ++e)
-      {
-        put16(head, ent[e].first);
-        put32(head, ent[e].second);
-      }
-    }
+    append_tlm(head, ent);
   }
   total += head.size() + 2; /* + EOC */
   if(!out || cap < total)
@@ -767,43 +811,133 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(c
   for(uint32_t t = 0; t < ntiles; ++t)
     tile_at[t + 1] = tile_at[t] + plans[t].size();
   /* tile parts are independent byte ranges: copy them on the host pool */
-  b2k_host_parallel(ntiles, [&](size_t t) {
-    const TilePlan& P = plans[t];
-    uint8_t* w = out + tile_at[t];
-    for(size_t pi = 0; pi < P.parts.size(); ++pi)
-    {
-      const TilePlan::Part& pt = P.parts[pi];
-      const uint32_t psot = (uint32_t)pt.bytes;
-      const uint8_t sot[12] = {0xFF, 0x90, 0, 10, (uint8_t)(t >> 8), (uint8_t)t, (uint8_t)(psot >> 24), (uint8_t)(psot >> 16),
-                               (uint8_t)(psot >> 8), (uint8_t)psot, (uint8_t)pi, (uint8_t)P.parts.size()}; /* SOT (A.4.2) */
-      memcpy(w, sot, 12);
-      w += 12;
-      if(!pt.plt.empty())
-      {
-        memcpy(w, pt.plt.data(), pt.plt.size());
-        w += pt.plt.size();
-      }
-      *w++ = 0xFF; /* SOD */
-      *w++ = 0x93;
-      const uint8_t* h = P.hdrs.data() + pt.h0;
-      size_t sg = pt.s0;
-      for(size_t k = pt.p0; k < pt.p1; ++k)
-      {
-        memcpy(w, h, P.hdr_len[k]);
-        w += P.hdr_len[k];
-        h += P.hdr_len[k];
-        for(uint32_t i = 0; i < P.nseg[k]; ++i, ++sg)
-        {
-          memcpy(w, r->bytes + P.seg_off[sg], P.seg_len[sg]);
-          w += P.seg_len[sg];
-        }
-      }
-    }
-  });
+  b2k_host_parallel(ntiles, [&](size_t t) { emit_tile_parts(plans[t], (uint32_t)t, r->bytes, out + tile_at[t]); });
   uint8_t* w = out + tile_at[ntiles];
   *w++ = 0xFF; /* EOC */
   *w++ = 0xD9;
   return (int64_t)(w - out);
+}
+
+/* ---- per-rank writers ("T2 can itself be sharded per tile; the writer concatenates in index order") ------
+ * b2k_codestream_write_tiles: the finished tile parts (SOT [PLT] SOD packets, one tile part per tile) of the tiles a shard
+ * holds (tile t with t % tile_mod == tile_rem, as b2k_encode returned them), consecutively in tile order; tile_bytes[k] =
+ * length of the k-th of them.  b2k_codestream_write_header: SOC .. QCD [TLM] for the whole image from every tile's length.
+ * A code stream = header + the tile parts in tile-index order + EOC (0xFFD9): byte-identical to b2k_codestream_write's. */
+extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write_tiles(const b2k_coding* cp, const b2k_result* r, uint32_t flags,
+                                                                                      uint32_t tile_mod, uint32_t tile_rem, uint8_t* out,
+                                                                                      uint64_t cap, uint64_t* tile_bytes)
+{
+  if(!cp || !r || !tile_mod || tile_rem >= tile_mod)
+    return -1;
+  if(const char* why = unsupported_reason(*cp))
+  {
+    b2k_set_error(why);
+    return -1;
+  }
+  if(flags & B2K_CS_TPARTS_R)
+  {
+    b2k_set_error("per-rank writers emit one tile part per tile");
+    return -1;
+  }
+  const TileGrid g = tile_grid(*cp);
+  const uint32_t ntiles = g.nx * g.ny;
+  const int prog = (int)((flags >> 8) & 7);
+  if(prog > 4 || ntiles > 65535)
+  {
+    b2k_set_error("unknown progression order / too many tiles");
+    return -1;
+  }
+  const bool sop = (flags & B2K_CS_SOP) != 0, eph = (flags & B2K_CS_EPH) != 0;
+  std::vector<uint32_t> mine;
+  for(uint32_t t = tile_rem; t < ntiles; t += tile_mod)
+    mine.push_back(t);
+  std::vector<uint64_t> first(mine.size() + 1, 0);
+  {
+    uint64_t i = 0;
+    for(size_t k = 0; k < mine.size(); ++k)
+    {
+      first[k] = i;
+      while(i < r->num_blocks && r->blocks[i].tile == mine[k])
+        ++i;
+    }
+    first[mine.size()] = i;
+    if(i != r->num_blocks)
+    {
+      b2k_set_error("the block table is not the shard's tiles in tile order");
+      return -1;
+    }
+  }
+  std::vector<TilePlan> plans(mine.size());
+  std::vector<std::string> errs(mine.size());
+  b2k_host_parallel(mine.size(), [&](size_t k) {
+    TilePlan& P = plans[k];
+    if(plan_tile_packets(*cp, tile_rect(*cp, g, mine[k]), r->blocks + first[k], (uint32_t)(first[k + 1] - first[k]), r->num_bytes, P,
+                         errs[k], prog, sop, eph))
+    {
+      if(errs[k].empty())
+        errs[k] = "tile planning failed";
+      return;
+    }
+    plan_tile_parts(P, false, (flags & B2K_CS_PLT) != 0);
+  });
+  uint64_t total = 0;
+  std::vector<uint64_t> at(mine.size() + 1, 0);
+  for(size_t k = 0; k < mine.size(); ++k)
+  {
+    if(!errs[k].empty())
+    {
+      b2k_set_error(errs[k].c_str());
+      return -1;
+    }
+    if(plans[k].size() > 0xFFFFFFFFull)
+    {
+      b2k_set_error("tile part longer than 4 GiB");
+      return -1;
+    }
+    at[k] = total;
+    total += plans[k].size();
+    if(tile_bytes)
+      tile_bytes[k] = plans[k].size();
+  }
+  at[mine.size()] = total;
+  if(!out || cap < total)
+    return (int64_t)total;
+  b2k_host_parallel(mine.size(), [&](size_t k) { emit_tile_parts(plans[k], mine[k], r->bytes, out + at[k]); });
+  return (int64_t)total;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write_header(const b2k_coding* cp, uint32_t flags,
+                                                                                       const uint64_t* tile_bytes, uint32_t ntiles_in,
+                                                                                       uint8_t* out, uint64_t cap)
+{
+  if(!cp)
+    return -1;
+  if(const char* why = unsupported_reason(*cp))
+  {
+    b2k_set_error(why);
+    return -1;
+  }
+  const TileGrid g = tile_grid(*cp);
+  const uint32_t ntiles = g.nx * g.ny;
+  const int prog = (int)((flags >> 8) & 7);
+  if(prog > 4 || ((flags & B2K_CS_TLM) && (!tile_bytes || ntiles_in != ntiles)))
+  {
+    b2k_set_error("TLM needs the length of every tile's tile part");
+    return -1;
+  }
+  const std::vector<BandQuant> q = band_quant(*cp);
+  std::vector<uint8_t> head;
+  write_main_header(*cp, g, q, head, prog, (flags & B2K_CS_SOP) != 0, (flags & B2K_CS_EPH) != 0);
+  if(flags & B2K_CS_TLM)
+  {
+    std::vector<std::pair<uint32_t, uint32_t>> ent;
+    for(uint32_t t = 0; t < ntiles; ++t)
+      ent.push_back({t, (uint32_t)tile_bytes[t]});
+    append_tlm(head, ent);
+  }
+  if(out && cap >= head.size())
+    memcpy(out, head.data(), head.size());
+  return (int64_t)head.size();
 }
 
 namespace

@@ -497,6 +497,14 @@ B2K_API int32_t b2k_result_merge(const b2k_coding* cp, const b2k_result* const* 
 #define B2K_CS_PROG(n) (((n) & 7u) << 8)   /* progression order: 0 LRCP (default), 1 RLCP, 2 RPCL, 3 PCRL, 4 CPRL */
 B2K_API int64_t b2k_codestream_write(const b2k_coding* cp, const b2k_result* r, uint32_t flags, uint8_t* out, uint64_t cap);
 B2K_API int64_t b2k_codestream_parse(const uint8_t* cs, uint64_t len, b2k_coding* cp, b2k_block* blocks, uint64_t cap_blocks);
+/* Per-rank writers (tiles sharded over ranks): every rank turns ITS tiles (t % tile_mod == tile_rem, the result
+ * b2k_encode gave it) into finished tile parts -- consecutive in tile order in `out`, tile_bytes[k] = length of the k-th of its
+ * tiles -- and the writer rank only needs the lengths of all tiles for the header (+ TLM): code stream = header + tile parts in
+ * tile-index order + 0xFFD9, byte-identical to b2k_codestream_write over the merged result.  One tile part per tile. */
+B2K_API int64_t b2k_codestream_write_tiles(const b2k_coding* cp, const b2k_result* shard, uint32_t flags, uint32_t tile_mod,
+                                           uint32_t tile_rem, uint8_t* out, uint64_t cap, uint64_t* tile_bytes);
+B2K_API int64_t b2k_codestream_write_header(const b2k_coding* cp, uint32_t flags, const uint64_t* tile_bytes, uint32_t ntiles,
+                                            uint8_t* out, uint64_t cap);
 /* Windowed / reduced-resolution decode, tile-granular: `window` = x0,y0,x1,y1 on the full-resolution
  * canvas (NULL: whole image), `reduce` = highest resolutions to drop.  *cp becomes a VIRTUAL coding: the image made of the
  * tiles the window touches, at 1 / 2^reduce of the resolution -- decode it with b2k_decode(cp, blocks, ..., cs, ...) into

@@ -265,6 +265,36 @@ else:
     dist.gather(seg, None, dst=0)
     dist.gather(tab, None, dst=0)
 dist.barrier()
+# ---- per-rank writers: every rank packetises ITS tiles, the writer rank gets finished tile parts + their lengths ----
+parts, lens = G.codestream_write_tiles(cp, table, arena, G.CS_TLM | G.CS_PLT, world, rank)
+assert len(lens) == len(my_tiles) and int(lens.sum()) == len(parts)
+ntiles = len(rects)
+all_lens = [torch.zeros(ntiles, dtype=torch.int64) for _ in range(world)]
+mine = torch.zeros(ntiles, dtype=torch.int64)
+mine[torch.tensor(my_tiles)] = torch.from_numpy(lens.astype(np.int64))
+dist.all_gather(all_lens, mine)
+tile_len = sum(all_lens).numpy().astype(np.uint64)          # every tile's tile-part length, on every rank
+if rank == 0:
+    head = G.codestream_write_header(cp, G.CS_TLM | G.CS_PLT, tile_len)
+    out = np.zeros(len(head) + int(tile_len.sum()) + 2, np.uint8)
+    out[:len(head)] = head
+    at = len(head) + np.concatenate([[0], np.cumsum(tile_len)]).astype(np.int64)
+    pos = 0
+    for t, n in zip(my_tiles, lens):                         # own tile parts: straight into place
+        out[at[t]:at[t] + int(n)] = parts[pos:pos + int(n)]
+        pos += int(n)
+    buf = torch.zeros(int(sum(int(tile_len[t]) for t in range(ntiles) if t %% world == 1)), dtype=torch.uint8)
+    dist.recv(buf, src=1)                                    # the other rank's tile parts, in its tile order
+    pos = 0
+    for t in range(1, ntiles, world):
+        n = int(tile_len[t])
+        out[at[t]:at[t] + n] = buf[pos:pos + n].numpy()
+        pos += n
+    out[-2:] = [0xFF, 0xD9]
+    assert np.array_equal(out, cs), "header + per-rank tile parts differ from the merged writer's code stream"
+else:
+    dist.send(torch.from_numpy(parts.copy()), dst=0)
+dist.barrier()
 print("rank", rank, "ok")
 '''
 
