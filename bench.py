@@ -398,12 +398,15 @@ def run_config4(args, rank, world, local):
         tp = [time.perf_counter()]
         res = eng.encode(cp, planes, tile_mod=world, tile_rem=rank)
         tp.append(time.perf_counter())
-        if parts_buf[0] is None or parts_buf[0].size < res.num_bytes + (1 << 22):
-            parts_buf[0] = G.pinned_empty((int(res.num_bytes * 1.1) + (1 << 22),), np.uint8)
-        parts, lens = G.codestream_write_tiles(cp, res.blocks, res.bytes, FL, world, rank, out=parts_buf[0])
+        if rank == 0:       # the writer needs every tile's length before it can place its own: lengths now, bytes below
+            parts, lens = G.codestream_write_tiles(cp, res.blocks, res.bytes, FL, world, rank, sizes_only=True)
+        else:
+            if parts_buf[0] is None or parts_buf[0].size < res.num_bytes + (1 << 22):
+                parts_buf[0] = G.pinned_empty((int(res.num_bytes * 1.1) + (1 << 22),), np.uint8)
+            parts, lens = G.codestream_write_tiles(cp, res.blocks, res.bytes, FL, world, rank, out=parts_buf[0])
+            res.free()
         tp.append(time.perf_counter())
-        info["coded_bytes_rank0"] = int(res.num_bytes)
-        res.free()
+        info["coded_bytes_rank0"] = int(res.num_bytes) if rank == 0 else 0
         mine = torch.zeros(ntiles, dtype=torch.int64, device="cuda")
         mine[torch.tensor(my_tiles, device="cuda")] = torch.from_numpy(lens.astype(np.int64)).cuda()
         if world > 1:
@@ -423,10 +426,9 @@ def run_config4(args, rank, world, local):
                 for w_ in dist.batch_isend_irecv([dist.P2POp(dist.irecv, bufs[r], r) for r in range(1, world)]):
                     w_.wait()
             tp.append(time.perf_counter())
-            pos = 0
-            for t, n in zip(my_tiles, lens):            # own tile parts: host -> host
-                out[at[t]:at[t] + int(n)] = parts[pos:pos + int(n)]
-                pos += int(n)
+            # own tiles: packetised straight into their places (host pool)
+            G.codestream_write_tiles(cp, res.blocks, res.bytes, FL, world, rank, out=out, tile_at=at[my_tiles].astype(np.uint64))
+            res.free()
             for r in range(1, world):                   # the others': device -> their place in the pinned code stream
                 pos = 0
                 for t in range(r, ntiles, world):
@@ -438,7 +440,7 @@ def run_config4(args, rank, world, local):
             tp.append(time.perf_counter())
             cs_len = total
             info["codestream"] = out[:total]
-            info["phase_ms_rank0"] = dict(zip(["encode_own_tiles", "packetise_own_tiles", "nccl_lengths_and_recv", "place_tile_parts"],
+            info["phase_ms_rank0"] = dict(zip(["encode_own_tiles", "plan_own_tiles", "nccl_lengths_and_recv", "write_own_and_place_others"],
                                               [round((b_ - a_) * 1e3, 2) for a_, b_ in zip(tp, tp[1:])]))
         else:
             seg = torch.from_numpy(parts).cuda(non_blocking=True)

@@ -65,7 +65,7 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
            "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last",
            "b2k_codestream_write", "b2k_codestream_parse", "b2k_codestream_parse_window",
-           "b2k_codestream_write_tiles", "b2k_codestream_write_header", "b2k_jph_wrap", "b2k_jph_codestream", "b2k_result_merge",
+           "b2k_codestream_write_tiles", "b2k_codestream_write_tiles_at", "b2k_codestream_write_header", "b2k_jph_wrap", "b2k_jph_codestream", "b2k_result_merge",
            "gpup_encode_mem_tiles", "gpup_tiles_free", "plugin_decompress_codestream", "b2k_coding_from_gpup",
            "b2k_stream_encode_begin", "b2k_stream_encode_submit", "b2k_stream_decode_begin", "b2k_stream_decode_submit",
            "b2k_stream_decode_submit_codestream", "b2k_stream_end",
@@ -244,8 +244,10 @@ def result_from_tables(blocks, data, num_tiles):
     return r
 
 
-def codestream_write_tiles(cp, blocks, data, flags=CS_TLM | CS_PLT, tile_mod=1, tile_rem=0, out=None):
-    """A shard's tiles as finished tile parts (b2k_codestream_write_tiles) -> (bytes, per-tile lengths of the shard's tiles)."""
+def codestream_write_tiles(cp, blocks, data, flags=CS_TLM | CS_PLT, tile_mod=1, tile_rem=0, out=None, tile_at=None, sizes_only=False):
+    """A shard's tiles as finished tile parts (b2k_codestream_write_tiles) -> (bytes, per-tile lengths of the shard's tiles).
+    sizes_only: just the lengths.  tile_at (uint64 offsets, one per tile of the shard): write each tile part at out[tile_at[k]:]
+    (b2k_codestream_write_tiles_at) and return (out, None)."""
     blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
     data = np.ascontiguousarray(data, dtype=np.uint8)
     r = Result()
@@ -260,9 +262,19 @@ def codestream_write_tiles(cp, blocks, data, flags=CS_TLM | CS_PLT, tile_mod=1, 
     g_ny = -(-(cp.y1 - cp.ty0) // cp.th) if cp.th else 1
     nmine = len(range(tile_rem, g_nx * g_ny, tile_mod))
     lens = np.zeros(nmine, np.uint64)
+    if tile_at is not None:
+        L.b2k_codestream_write_tiles_at.restype = C.c_int64
+        L.b2k_codestream_write_tiles_at.argtypes = [C.POINTER(Coding), C.POINTER(Result), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+        ta = np.ascontiguousarray(tile_at, dtype=np.uint64)
+        n = L.b2k_codestream_write_tiles_at(C.byref(cp), C.byref(r), flags, tile_mod, tile_rem, out.ctypes.data, out.size, ta.ctypes.data)
+        if n < 0:
+            raise EngineError("b2k_codestream_write_tiles_at: " + (L.b2k_last_error() or b"").decode())
+        return out, None
     n = L.b2k_codestream_write_tiles(C.byref(cp), C.byref(r), flags, tile_mod, tile_rem, None, 0, lens.ctypes.data)
     if n < 0:
         raise EngineError("b2k_codestream_write_tiles: " + (L.b2k_last_error() or b"").decode())
+    if sizes_only:
+        return None, lens
     if out is None or out.size < n:
         out = np.zeros(max(n, 1), np.uint8)
     assert L.b2k_codestream_write_tiles(C.byref(cp), C.byref(r), flags, tile_mod, tile_rem, out.ctypes.data, out.size, lens.ctypes.data) == n

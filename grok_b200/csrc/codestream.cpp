@@ -823,9 +823,8 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write(c
  * holds (tile t with t % tile_mod == tile_rem, as b2k_encode returned them), consecutively in tile order; tile_bytes[k] =
  * length of the k-th of them.  b2k_codestream_write_header: SOC .. QCD [TLM] for the whole image from every tile's length.
  * A code stream = header + the tile parts in tile-index order + EOC (0xFFD9): byte-identical to b2k_codestream_write's. */
-extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write_tiles(const b2k_coding* cp, const b2k_result* r, uint32_t flags,
-                                                                                      uint32_t tile_mod, uint32_t tile_rem, uint8_t* out,
-                                                                                      uint64_t cap, uint64_t* tile_bytes)
+static int64_t write_tiles_impl(const b2k_coding* cp, const b2k_result* r, uint32_t flags, uint32_t tile_mod, uint32_t tile_rem, uint8_t* out,
+                                uint64_t cap, uint64_t* tile_bytes, const uint64_t* tile_at)
 {
   if(!cp || !r || !tile_mod || tile_rem >= tile_mod)
     return -1;
@@ -900,10 +899,35 @@ extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write_t
       tile_bytes[k] = plans[k].size();
   }
   at[mine.size()] = total;
-  if(!out || cap < total)
+  if(!out || (!tile_at && cap < total))
     return (int64_t)total;
-  b2k_host_parallel(mine.size(), [&](size_t k) { emit_tile_parts(plans[k], mine[k], r->bytes, out + at[k]); });
+  if(tile_at)
+    for(size_t k = 0; k < mine.size(); ++k)
+      if(tile_at[k] + plans[k].size() > cap)
+      {
+        b2k_set_error("a tile part would land outside the buffer");
+        return -1;
+      }
+  b2k_host_parallel(mine.size(), [&](size_t k) { emit_tile_parts(plans[k], mine[k], r->bytes, out + (tile_at ? tile_at[k] : at[k])); });
   return (int64_t)total;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write_tiles(const b2k_coding* cp, const b2k_result* r, uint32_t flags,
+                                                                                      uint32_t tile_mod, uint32_t tile_rem, uint8_t* out,
+                                                                                      uint64_t cap, uint64_t* tile_bytes)
+{
+  return write_tiles_impl(cp, r, flags, tile_mod, tile_rem, out, cap, tile_bytes, nullptr);
+}
+
+/* the same, each of the shard's tiles written at out + tile_at[k] (the writer rank puts its own tiles straight into their
+   places in the code stream once every tile's length is known) */
+extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write_tiles_at(const b2k_coding* cp, const b2k_result* r, uint32_t flags,
+                                                                                         uint32_t tile_mod, uint32_t tile_rem, uint8_t* out,
+                                                                                         uint64_t cap, const uint64_t* tile_at)
+{
+  if(!tile_at)
+    return -1;
+  return write_tiles_impl(cp, r, flags, tile_mod, tile_rem, out, cap, nullptr, tile_at);
 }
 
 extern "C" __attribute__((visibility("default"))) int64_t b2k_codestream_write_header(const b2k_coding* cp, uint32_t flags,

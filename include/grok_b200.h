@@ -505,6 +505,9 @@ B2K_API int64_t b2k_codestream_write_tiles(const b2k_coding* cp, const b2k_resul
                                            uint32_t tile_rem, uint8_t* out, uint64_t cap, uint64_t* tile_bytes);
 B2K_API int64_t b2k_codestream_write_header(const b2k_coding* cp, uint32_t flags, const uint64_t* tile_bytes, uint32_t ntiles,
                                             uint8_t* out, uint64_t cap);
+/* as b2k_codestream_write_tiles, the k-th of the shard's tiles written at out + tile_at[k] */
+B2K_API int64_t b2k_codestream_write_tiles_at(const b2k_coding* cp, const b2k_result* shard, uint32_t flags, uint32_t tile_mod,
+                                              uint32_t tile_rem, uint8_t* out, uint64_t cap, const uint64_t* tile_at);
 /* Windowed / reduced-resolution decode, tile-granular: `window` = x0,y0,x1,y1 on the full-resolution
  * canvas (NULL: whole image), `reduce` = highest resolutions to drop.  *cp becomes a VIRTUAL coding: the image made of the
  * tiles the window touches, at 1 / 2^reduce of the resolution -- decode it with b2k_decode(cp, blocks, ..., cs, ...) into
