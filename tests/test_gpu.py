@@ -871,3 +871,35 @@ int main(void){ O(numlayers) O(csty) O(numgbits) O(numresolution) O(cblockw_init
     assert sorted(got) == [i + 1 for i in range(len(frames))]
     for i in range(len(frames)):
         assert got[i + 1] == [bytes(b) for b in want[i]]
+
+
+def test_hybrid_packed_and_direct_chunks_with_pinned_planes(engine):
+    """With pinned caller planes and host packing on, every fourth pipeline chunk crosses PCIe as plain int32 DMA while the
+    host threads pack the others (engine.cu "Hybrid PCIe legs").  Same coded bytes as the all-direct call, lossless decode --
+    on an image with enough tiles for several chunks, odd tile sizes included."""
+    w, h = 2500, 1900
+    cp = G.make_coding(w, h, 3, 12, numres=5, tile=(300, 200))          # 9 x 10 tiles
+    src = P.synthetic_image(w, h, 3, 12, seed=41)
+    planes = [G.pinned_empty((h, w), np.int32) for _ in range(3)]
+    out = [G.pinned_empty((h, w), np.int32) for _ in range(3)]
+    for a, b in zip(planes, src):
+        a[:] = b
+    try:
+        G.set_host_threads(0)
+        r = engine.encode(cp, planes)
+        want_blocks, want = r.blocks.copy(), r.bytes.copy()
+        r.free()
+        G.set_host_threads(4)
+        for _ in range(2):
+            r = engine.encode(cp, planes)
+            assert G.host_pack_last()[0] == 1
+            assert np.array_equal(r.bytes, want) and np.array_equal(r.blocks["length"], want_blocks["length"])
+            for o in out:
+                o[:] = -1
+            engine.decode(cp, r.blocks, r.bytes, out)
+            assert G.host_pack_last()[1] == 1
+            r.free()
+            for a, b in zip(out, src):
+                assert np.array_equal(a, b)
+    finally:
+        G.set_host_threads(-1)
