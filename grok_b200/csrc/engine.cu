@@ -1132,42 +1132,14 @@ static int ring_upload_chunk(b2k_device_job* J, void* const* user, const uint32_
   }
   return 0;
 }
-/* Hybrid PCIe legs.  Narrowing int32 planes to 16-bit containers halves the bytes on the bus but costs host memory
-   bandwidth: with the host threads a 16-CPU quota allows, packing (not PCIe) bounds a packed call (encode of config 2:
-   14 ms against 9 ms for caller-owned 16-bit planes).  So every `every`-th pipeline chunk crosses as the caller's int32
-   samples by plain DMA -- no host work at all -- while the host threads are busy packing its neighbours: with one chunk
-   in four direct, host time (6 of 8 chunks x 1.5 ms) and bus time (6 x 0.9 + 2 x 1.8 ms) balance.  Needs pinned caller
-   planes (a pageable source makes the copy synchronous).  B2K_HYBRID_EVERY: 0 off, n >= 2 every n-th chunk (default 4). */
-static int hybrid_every()
-{
-  static const int v = [] {
-    const char* e = getenv("B2K_HYBRID_EVERY");
-    const int n = e ? atoi(e) : 4;
-    return n >= 2 ? n : 0;
-  }();
-  return v;
-}
-static bool host_pinned(const void* p)
-{
-  cudaPointerAttributes a;
-  if(cudaPointerGetAttributes(&a, p) != cudaSuccess)
-  {
-    (void)cudaGetLastError();
-    return false;
-  }
-  return a.type == cudaMemoryTypeHost;
-}
-static inline bool chunk_direct(bool hybrid, size_t k) { return hybrid && (int)(k % (size_t)hybrid_every()) == hybrid_every() - 1; }
-
-/* bring the packed chunks' pixels down through the ring and widen them into the caller's planes; chunk k's pixels are
+/* bring every chunk's pixels down through the ring and widen them into the caller's planes; chunk k's pixels are
    ready on the device when chunk_ev[CEV(0, k)] fires */
-static int ring_download_all(b2k_device_job* J, void* const* user, const uint32_t* strides, cudaStream_t cs, bool hybrid)
+static int ring_download_all(b2k_device_job* J, void* const* user, const uint32_t* strides, cudaStream_t cs)
 {
   const b2k_coding& cp = J->cp;
   std::vector<StagePiece> pcs;
   for(uint32_t k = 0; k + 1 < J->chunk_tile.size(); ++k)
-    if(!chunk_direct(hybrid, k))
-      chunk_pieces(J, k, pcs);
+    chunk_pieces(J, k, pcs);
   const size_t N = pcs.size(), S = J->ring_slots;
   auto issue = [&](size_t p) -> int {
     const StagePiece& pc = pcs[p];
@@ -1889,7 +1861,6 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
   if(!u16)
     g_last_pack[0].store(pack ? 1 : 0);
   const bool ring = pack && ring_geom(false).slot_mb > 0;
-  const bool hybrid = ring && hybrid_every() && J->chunk_tile.size() - 1 >= (size_t)hybrid_every() && host_pinned(planes[0]);
   uint64_t ring_counter = 0;
   if(pack)
   {
@@ -1974,12 +1945,7 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
   for(size_t k = 0; k < nchunks; ++k)
   {
     const size_t t0 = J->chunk_tile[k], t1 = J->chunk_tile[k + 1];
-    const bool direct = chunk_direct(hybrid, k);
-    if(direct)
-    { /* the caller's int32 samples as they are: DMA only, the host threads stay on the packed chunks */
-      if(copy_planes(J, J->img, user_planes, user_strides, true, cs, t0, t1)) return -1;
-    }
-    else if(ring)
+    if(ring)
     {
       if(ring_upload_chunk(J, user_planes, user_strides, (uint32_t)k, cs, ring_counter, [&] { return return_chunks(false); })) return -1;
     }
@@ -1994,7 +1960,7 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
     CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[CEV(0, k)], 0));
     if(k == nchunks - 1)
       CUDA_TRY(cudaEventRecord(J->ev[1], st)); /* all planes on the device */
-    if(u16 && !direct && convert_planes16(J, true, st, t0, t1)) return -1;
+    if(u16 && convert_planes16(J, true, st, t0, t1)) return -1;
     if(enqueue_forward(J, st, k == 0, t0, t1)) return -1;
     if(enqueue_t1_blocks(J, st, t0, t1)) return -1;
     if(streamed)
@@ -2123,7 +2089,6 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
   if(!u16)
     g_last_pack[1].store(pack ? 1 : 0);
   const bool ring = pack && ring_geom(true).slot_mb > 0;
-  const bool hybrid = ring && hybrid_every() && J->chunk_tile.size() - 1 >= (size_t)hybrid_every() && host_pinned(planes[0]);
   if(pack)
   {
     if(ring ? ensure_ring(J, true) : ensure_stage16(J)) return -1;
@@ -2218,15 +2183,8 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
                                     (J->cp.cblk_sty & 0x08) != 0, st);
     }
     if(enqueue_inverse(J, st, t0, t1)) return -1;
-    const bool direct = chunk_direct(hybrid, k);
-    if(u16 && !direct && convert_planes16(J, false, st, t0, t1)) return -1;
+    if(u16 && convert_planes16(J, false, st, t0, t1)) return -1;
     CUDA_TRY(cudaEventRecord(J->chunk_ev[CEV(0, k)], st));
-    if(direct)
-    { /* hybrid: this chunk goes home as int32 by plain DMA on the (by now idle) upload stream, beside the ring's pieces */
-      CUDA_TRY(cudaStreamWaitEvent(e->h2d_stream, J->chunk_ev[CEV(0, k)], 0));
-      if(copy_planes(J, J->img, user_planes, user_strides, false, e->h2d_stream, t0, t1)) return -1;
-      continue;
-    }
     if(ring)
       continue; /* pixels come down piece by piece below */
     CUDA_TRY(cudaStreamWaitEvent(cs, J->chunk_ev[CEV(0, k)], 0));
@@ -2238,9 +2196,7 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
   DBG_T("decode: chunks enqueued");
   if(ring)
   {
-    if(ring_download_all(J, user_planes, user_strides, cs, hybrid)) return -1;
-    if(hybrid)
-      CUDA_TRY(cudaStreamSynchronize(e->h2d_stream)); /* the direct chunks have landed too */
+    if(ring_download_all(J, user_planes, user_strides, cs)) return -1;
   }
   else if(pack) /* widen chunk k into the caller's planes while chunk k+1 is still coming down */
     for(size_t k = 0; k < nchunks; ++k)

@@ -873,10 +873,11 @@ int main(void){ O(numlayers) O(csty) O(numgbits) O(numresolution) O(cblockw_init
         assert got[i + 1] == [bytes(b) for b in want[i]]
 
 
-def test_hybrid_packed_and_direct_chunks_with_pinned_planes(engine):
-    """With pinned caller planes and host packing on, every fourth pipeline chunk crosses PCIe as plain int32 DMA while the
-    host threads pack the others (engine.cu "Hybrid PCIe legs").  Same coded bytes as the all-direct call, lossless decode --
-    on an image with enough tiles for several chunks, odd tile sizes included."""
+def test_host_packing_with_pinned_caller_planes(engine):
+    """Pinned caller planes + host packing (the bench's e2e configuration): same coded bytes as the all-direct call, lossless
+    decode -- on an image with enough tiles for several pipeline chunks, odd tile sizes included.
+    (Round 2 tried sending every n-th chunk as plain int32 DMA beside the packed ones: 21.1 -> 25.8 / 28.2 ms on config 2,
+    dropped)"""
     w, h = 2500, 1900
     cp = G.make_coding(w, h, 3, 12, numres=5, tile=(300, 200))          # 9 x 10 tiles
     src = P.synthetic_image(w, h, 3, 12, seed=41)
