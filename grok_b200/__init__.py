@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgrokj2k_plugin.so")
+LIB_PATH = os.environ.get("B2K_LIB") or os.path.join(_HERE, "libgrokj2k_plugin.so")   # B2K_LIB: an experimental build (tools/build_variant.py)
 
 GPUP_MAX_PASSES = 3 * (16 + 7) - 2
 

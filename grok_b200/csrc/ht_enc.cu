@@ -37,7 +37,13 @@
 
 namespace {
 
-constexpr int ENC_WARPS = 5;        /* warps (= code blocks in flight) per CTA: 5 x 9.6 KB + 8.3 KB of tables -> 4 CTAs, 20 warps per SM */
+#ifndef ENC_WARPS_N
+#define ENC_WARPS_N 5
+#endif
+#ifndef ENC_MIN_CTAS
+#define ENC_MIN_CTAS 4
+#endif
+constexpr int ENC_WARPS = ENC_WARPS_N; /* warps (= code blocks in flight) per CTA: 5 x 9.3 KB + 8.3 KB of tables -> 4 CTAs, 20 warps per SM */
 constexpr int UNIT_QUADS = 8;       /* quads per unit (even: the VLC stream codes quads in pairs) */
 constexpr int MS_RING_WORDS = 128;  /* 4096 bits: < 1024 left by the last drain + one 2048-bit gather batch */
 constexpr int VLC_RING_WORDS = 64;  /* 2048 bits: < 256 left over + one 1024-bit gather batch */
@@ -395,7 +401,7 @@ __host__ __device__ inline uint32_t enc_rows_per_round(uint32_t w)
 /* PACK: Kmax <= 24 in the whole launch, so a staged word has room for the sample's exponent in its top 6 bits
    (computed once, at staging, instead of by every lane that looks at the sample) */
 template <bool IRREV, bool PACK>
-__global__ void __launch_bounds__(ENC_WARPS * 32, 4)
+__global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS)
     k_ht_encode(const HtBlockDesc* __restrict__ blocks, HtBlockOut* __restrict__ outs, uint8_t* __restrict__ scratch,
                 uint32_t nblocks, EncLayout lay)
 {
@@ -469,6 +475,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4)
     {
       const uint32_t* cbase = reinterpret_cast<const uint32_t*>(B.coef);
       auto convert = [&](uint32_t raw) -> uint32_t {
+
         uint32_t mu, sgn;
         if(!IRREV)
         {
@@ -591,15 +598,15 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4)
           sx[k] = c + (c >> 5);
         }
         uint32_t sa[4], sb[4]; /* quad A: (x,y) (x,y+1) (x+1,y) (x+1,y+1); quad B two columns on */
-        sa[0] = r0[sx[0]]; sa[1] = r0[sx[0] + P]; sa[2] = r0[sx[1]]; sa[3] = r0[sx[1] + P];
-        sb[0] = r0[sx[2]]; sb[1] = r0[sx[2] + P]; sb[2] = r0[sx[3]]; sb[3] = r0[sx[3] + P];
+        sa[0] = CV(r0[sx[0]]); sa[1] = CV(r0[sx[0] + P]); sa[2] = CV(r0[sx[1]]); sa[3] = CV(r0[sx[1] + P]);
+        sb[0] = CV(r0[sx[2]]); sb[1] = CV(r0[sx[2] + P]); sb[2] = CV(r0[sx[3]]); sb[3] = CV(r0[sx[3] + P]);
         int ea1 = 0, ea2 = 0, ea3 = 0, ea4 = 0;
         if(!first_row)
         {
-          ea1 = SM_E(r0[sx[1] - P]);
-          ea2 = SM_E(r0[sx[2] - P]);
-          ea3 = SM_E(r0[sx[3] - P]);
-          ea4 = SM_E(r0[sx[4] - P]);
+          ea1 = SM_E(CV(r0[sx[1] - P]));
+          ea2 = SM_E(CV(r0[sx[2] - P]));
+          ea3 = SM_E(CV(r0[sx[3] - P]));
+          ea4 = SM_E(CV(r0[sx[4] - P]));
         }
         int uq2[2];
         uint32_t cw[2];
