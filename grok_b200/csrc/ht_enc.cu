@@ -598,15 +598,15 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS)
           sx[k] = c + (c >> 5);
         }
         uint32_t sa[4], sb[4]; /* quad A: (x,y) (x,y+1) (x+1,y) (x+1,y+1); quad B two columns on */
-        sa[0] = CV(r0[sx[0]]); sa[1] = CV(r0[sx[0] + P]); sa[2] = CV(r0[sx[1]]); sa[3] = CV(r0[sx[1] + P]);
-        sb[0] = CV(r0[sx[2]]); sb[1] = CV(r0[sx[2] + P]); sb[2] = CV(r0[sx[3]]); sb[3] = CV(r0[sx[3] + P]);
+        sa[0] = r0[sx[0]]; sa[1] = r0[sx[0] + P]; sa[2] = r0[sx[1]]; sa[3] = r0[sx[1] + P];
+        sb[0] = r0[sx[2]]; sb[1] = r0[sx[2] + P]; sb[2] = r0[sx[3]]; sb[3] = r0[sx[3] + P];
         int ea1 = 0, ea2 = 0, ea3 = 0, ea4 = 0;
         if(!first_row)
         {
-          ea1 = SM_E(CV(r0[sx[1] - P]));
-          ea2 = SM_E(CV(r0[sx[2] - P]));
-          ea3 = SM_E(CV(r0[sx[3] - P]));
-          ea4 = SM_E(CV(r0[sx[4] - P]));
+          ea1 = SM_E(r0[sx[1] - P]);
+          ea2 = SM_E(r0[sx[2] - P]);
+          ea3 = SM_E(r0[sx[3] - P]);
+          ea4 = SM_E(r0[sx[4] - P]);
         }
         int uq2[2];
         uint32_t cw[2];
