@@ -9,6 +9,10 @@
 #include <cstring>
 #include <memory>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "grok.h"
 
@@ -65,36 +69,12 @@ void grb_deinit() {
 
 // Compress planes[c] (int32, row stride `stride` elements) into out[0..cap); *out_len = codestream bytes.
 // Returns seconds spent inside grk_compress() alone (negative on failure).  codestream is raw J2K (.j2k/.jhc).
+static void grb_fill_cparameters(const grb_params* p, grk_cparameters& cp);
+
 double grb_compress(const grb_params* p, const int32_t* const* planes, uint32_t stride, uint8_t* out, uint64_t cap,
                     uint64_t* out_len) {
   grk_cparameters cp;
-  grk_compress_set_default_params(&cp);
-  cp.cod_format = GRK_FMT_J2K;
-  cp.numresolution = (uint8_t)p->numres;
-  cp.irreversible = p->irreversible != 0;
-  cp.mct = (uint8_t)p->mct;
-  if (p->tile_w && p->tile_h) {
-    cp.tile_size_on = true;
-    cp.t_width = p->tile_w;
-    cp.t_height = p->tile_h;
-  }
-  if (p->cblk_w) cp.cblockw_init = p->cblk_w;
-  if (p->cblk_h) cp.cblockh_init = p->cblk_h;
-  if (p->ht) {
-    cp.cblk_sty = GRK_CBLKSTY_HT_ONLY;
-    cp.numgbits = 1;
-  }
-  if (p->numgbits) cp.numgbits = (uint8_t)p->numgbits;
-  cp.write_tlm = p->tlm != 0;
-  cp.write_plt = p->plt != 0;
-  if (p->prc_w && p->prc_h) {
-    cp.csty |= 0x01;
-    cp.res_spec = 1;
-    cp.prcw_init[0] = p->prc_w;
-    cp.prch_init[0] = p->prc_h;
-  }
-  cp.device_id = p->device_id;
-  cp.num_threads = g_threads;
+  grb_fill_cparameters(p, cp);
 
   auto comps = std::make_unique<grk_image_comp[]>(p->ncomp);
   memset(comps.get(), 0, sizeof(grk_image_comp) * p->ncomp);
@@ -180,6 +160,175 @@ double grb_decompress(const uint8_t* cs, uint64_t len, int32_t* const* planes, u
   }
   grk_object_unref(codec);
   return dt;
+}
+
+static void grb_fill_cparameters(const grb_params* p, grk_cparameters& cp) {
+  grk_compress_set_default_params(&cp);
+  cp.cod_format = GRK_FMT_J2K;
+  cp.numresolution = (uint8_t)p->numres;
+  cp.irreversible = p->irreversible != 0;
+  cp.mct = (uint8_t)p->mct;
+  if (p->tile_w && p->tile_h) {
+    cp.tile_size_on = true;
+    cp.t_width = p->tile_w;
+    cp.t_height = p->tile_h;
+  }
+  if (p->cblk_w) cp.cblockw_init = p->cblk_w;
+  if (p->cblk_h) cp.cblockh_init = p->cblk_h;
+  if (p->ht) {
+    cp.cblk_sty = GRK_CBLKSTY_HT_ONLY;
+    cp.numgbits = 1;
+  }
+  if (p->numgbits) cp.numgbits = (uint8_t)p->numgbits;
+  cp.write_tlm = p->tlm != 0;
+  cp.write_plt = p->plt != 0;
+  if (p->prc_w && p->prc_h) {
+    cp.csty |= 0x01;
+    cp.res_spec = 1;
+    cp.prcw_init[0] = p->prc_w;
+    cp.prch_init[0] = p->prc_h;
+  }
+  cp.device_id = p->device_id;
+  cp.num_threads = g_threads;
+
+}
+
+// ---- the host's in-memory batch interfaces (grok.h grk_plugin_batch_memory_*, grk_plugin_batch_decompress_memory_*) ----
+namespace {
+struct BatchOut {
+  uint8_t* out;
+  uint64_t cap_per_frame;
+  uint64_t* lens;
+  std::mutex mu;
+};
+void batch_frame_done(void* user, void* frame, const uint8_t* codestream, size_t length) {
+  auto B = static_cast<BatchOut*>(user);
+  size_t i = (size_t)(uintptr_t)frame - 1;
+  if (length && length <= B->cap_per_frame) memcpy(B->out + i * B->cap_per_frame, codestream, length);
+  B->lens[i] = length <= B->cap_per_frame ? length : 0;
+}
+}  // namespace
+
+// nframes frames, frame f's component c at planes[f * ncomp + c] (int32 planar).  rgb48 != 0: the frames are handed over as
+// GRK_SOURCE_RGB48LE (one interleaved 16-bit buffer each, packed here).  Code streams land at out + f * cap_per_frame.
+// Returns the begin() code when it is not 0 (1 = the plugin declined), -2 on a submit failure, else 0; *seconds = submit..end.
+int grb_batch_compress(const grb_params* p, const int32_t* const* planes, uint32_t stride, uint32_t nframes, int rgb48,
+                       uint8_t* out, uint64_t cap_per_frame, uint64_t* out_lens, double* seconds) {
+  grk_cparameters cp;
+  grb_fill_cparameters(p, cp);
+  BatchOut B{out, cap_per_frame, out_lens, {}};
+  for (uint32_t f = 0; f < nframes; ++f) out_lens[f] = 0;
+  grk_plugin_batch_memory_info info = {};
+  info.compress_parameters = &cp;
+  info.width = p->w;
+  info.height = p->h;
+  info.numcomps = (uint16_t)p->ncomp;
+  info.prec = (uint8_t)p->prec;
+  info.source_prec = (uint8_t)p->prec;
+  info.callback = batch_frame_done;
+  info.user = &B;
+  info.source_format = rgb48 ? GRK_SOURCE_RGB48LE : GRK_SOURCE_PLANAR_RGB;
+  int32_t rc = grk_plugin_batch_memory_begin(info);
+  if (rc != 0) return rc;
+  std::vector<grk_image_comp> comps(p->ncomp);
+  std::vector<uint16_t> packed;
+  double t0 = now();
+  bool ok = true;
+  for (uint32_t f = 0; f < nframes && ok; ++f) {
+    memset(comps.data(), 0, sizeof(grk_image_comp) * p->ncomp);
+    grk_image img = {};
+    img.x1 = p->w;
+    img.y1 = p->h;
+    img.numcomps = (uint16_t)p->ncomp;
+    img.comps = comps.data();
+    for (uint32_t c = 0; c < p->ncomp; ++c) {
+      comps[c].w = p->w;
+      comps[c].h = p->h;
+      comps[c].dx = comps[c].dy = 1;
+      comps[c].prec = (uint8_t)p->prec;
+      comps[c].stride = stride;
+      comps[c].data = const_cast<int32_t*>(planes[(size_t)f * p->ncomp + c]);
+      comps[c].data_type = GRK_INT_32;
+    }
+    if (rgb48) {
+      packed.resize((size_t)p->w * p->h * p->ncomp);
+      for (uint32_t c = 0; c < p->ncomp; ++c)
+        for (uint32_t y = 0; y < p->h; ++y)
+          for (uint32_t x = 0; x < p->w; ++x)
+            packed[((size_t)y * p->w + x) * p->ncomp + c] = (uint16_t)planes[(size_t)f * p->ncomp + c][(size_t)y * stride + x];
+      for (uint32_t c = 0; c < p->ncomp; ++c) {
+        comps[c].data_type = GRK_INT_16;
+        comps[c].data = c == 0 ? packed.data() : nullptr;
+        comps[c].stride = c == 0 ? p->w * p->ncomp : 0;
+      }
+    }
+    ok = grk_plugin_batch_memory_submit(&img, (void*)(uintptr_t)(f + 1));
+  }
+  bool drained = grk_plugin_batch_memory_end();
+  if (seconds) *seconds = now() - t0;
+  return ok && drained ? 0 : -2;
+}
+
+namespace {
+struct BatchIn {
+  const uint8_t* cs;
+  const uint64_t* offs;  // nframes + 1
+  uint32_t nframes, ncomp, w, h, stride;
+  int32_t* const* planes;  // [nframes * ncomp]
+  std::atomic<uint32_t> next{0};
+  std::atomic<uint32_t> good{0};
+  std::atomic<bool> ended{false};
+};
+bool batch_pull(void* user, const uint8_t** codestream, size_t* length, void** frame_user) {
+  auto B = static_cast<BatchIn*>(user);
+  if (B->ended) return false;
+  uint32_t i = B->next.fetch_add(1);
+  if (i >= B->nframes) {
+    // nothing more: block the way a caller with an empty queue would, until end() flips the flag
+    while (!B->ended) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    return false;
+  }
+  *codestream = B->cs + B->offs[i];
+  *length = (size_t)(B->offs[i + 1] - B->offs[i]);
+  *frame_user = (void*)(uintptr_t)(i + 1);
+  return true;
+}
+void batch_decoded(void* user, void* frame, const grk_image* image) {
+  auto B = static_cast<BatchIn*>(user);
+  size_t i = (size_t)(uintptr_t)frame - 1;
+  if (!image || image->numcomps < B->ncomp) return;
+  for (uint32_t c = 0; c < B->ncomp; ++c) {
+    auto comp = image->comps + c;
+    if (!comp->data || comp->w != B->w || comp->h != B->h) return;
+    for (uint32_t y = 0; y < B->h; ++y)
+      memcpy(B->planes[i * B->ncomp + c] + (size_t)y * B->stride, (const int32_t*)comp->data + (size_t)y * comp->stride,
+             (size_t)B->w * 4);
+  }
+  B->good++;
+}
+}  // namespace
+
+// nframes code streams (frame f = cs[offs[f] .. offs[f+1])) through grk_plugin_batch_decompress_memory_begin/_end; decoded
+// int32 planes land in planes[f * ncomp + c].  Returns begin()'s code when not 0, else the number of frames that came back good.
+int grb_batch_decompress(const uint8_t* cs, const uint64_t* offs, uint32_t nframes, int32_t* const* planes, uint32_t stride,
+                         uint32_t ncomp, uint32_t w, uint32_t h, double* seconds) {
+  BatchIn B;
+  B.cs = cs; B.offs = offs; B.nframes = nframes; B.ncomp = ncomp; B.w = w; B.h = h; B.stride = stride; B.planes = planes;
+  grk_plugin_batch_decompress_memory_info info = {};
+  info.codestream = cs + offs[0];
+  info.codestream_length = (size_t)(offs[1] - offs[0]);
+  info.pull = batch_pull;
+  info.callback = batch_decoded;
+  info.user = &B;
+  double t0 = now();
+  int32_t rc = grk_plugin_batch_decompress_memory_begin(info);
+  if (rc != 0) return rc > 0 ? -100 - rc : rc;
+  // every frame handed out and reported back (good or not) -> the caller ends the batch
+  while (B.next.load() < nframes) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  B.ended = true;
+  bool drained = grk_plugin_batch_decompress_memory_end();
+  if (seconds) *seconds = now() - t0;
+  return drained ? (int)B.good.load() : -3;
 }
 
 }  // extern "C"

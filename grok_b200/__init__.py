@@ -59,7 +59,7 @@ assert BLOCK_DTYPE.itemsize == C.sizeof(Block), (BLOCK_DTYPE.itemsize, C.sizeof(
 # plugin_decompress (C++-ABI callback struct) is declared in csrc/plugin_decode_abi.h, not in the C header
 EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "gpup_encode_mem", "gpup_tile_free",
            "b2k_engine_create", "b2k_engine_destroy", "b2k_last_error", "b2k_host_alloc", "b2k_host_free",
-           "b2k_encode", "b2k_encode16", "b2k_result_free", "b2k_decode", "b2k_decode16", "b2k_enumerate",
+           "b2k_encode", "b2k_encode16", "b2k_encode16_interleaved", "b2k_result_free", "b2k_decode", "b2k_decode16", "b2k_enumerate",
            "b2k_result_to_gpup_tile", "b2k_job_create", "b2k_job_destroy", "b2k_job_upload", "b2k_job_forward",
            "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_roundtrip_n", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
@@ -69,7 +69,8 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "gpup_encode_mem_tiles", "gpup_tiles_free", "plugin_decompress_codestream", "b2k_coding_from_gpup",
            "b2k_stream_encode_begin", "b2k_stream_encode_submit", "b2k_stream_decode_begin", "b2k_stream_decode_submit",
            "b2k_stream_decode_submit_codestream", "b2k_stream_end",
-           "gpup_batch_memory_begin", "gpup_batch_memory_submit", "gpup_batch_memory_submit_planes", "gpup_batch_memory_end"]
+           "gpup_batch_memory_begin", "gpup_batch_memory_submit", "gpup_batch_memory_submit_planes", "gpup_batch_memory_end",
+           "plugin_decompress", "plugin_batch_decompress_memory_begin", "plugin_batch_decompress_memory_end"]
 
 _lib = None
 
@@ -93,6 +94,7 @@ def lib():
     L.b2k_host_free.argtypes = [vp]
     L.b2k_encode.argtypes = [vp, C.POINTER(Coding), pp, C.POINTER(u32), u32, u32, C.POINTER(C.POINTER(Result))]
     L.b2k_encode16.argtypes = L.b2k_encode.argtypes
+    L.b2k_encode16_interleaved.argtypes = [vp, C.POINTER(Coding), vp, u32, u32, u32, C.POINTER(C.POINTER(Result))]
     L.b2k_result_free.argtypes = [C.POINTER(Result)]
     L.b2k_decode.argtypes = [vp, C.POINTER(Coding), vp, u64, vp, u64, pp, C.POINTER(u32), u32, u32,
                              C.POINTER(C.c_double)]
@@ -390,6 +392,15 @@ class Engine:
         out = C.POINTER(Result)()
         fn = "b2k_encode16" if planes[0].itemsize == 2 else "b2k_encode"
         _check(getattr(lib(), fn)(self._h, C.byref(cp), ptrs, strides, tile_mod, tile_rem, C.byref(out)), fn)
+        return EncodeResult(out)
+
+    def encode_interleaved(self, cp, pixels, tile_mod=1, tile_rem=0):
+        """pixels: one (H, W, numcomps) uint16 / int16 array (RGB48LE rows; the row stride may exceed W * numcomps
+        samples): b2k_encode16_interleaved -- the rows cross PCIe as they are, planes are made on the device."""
+        assert pixels.ndim == 3 and pixels.itemsize == 2 and pixels.strides[2] == 2 and pixels.strides[1] == 2 * pixels.shape[2]
+        out = C.POINTER(Result)()
+        _check(lib().b2k_encode16_interleaved(self._h, C.byref(cp), pixels.ctypes.data, pixels.strides[0] // 2, tile_mod, tile_rem,
+                                              C.byref(out)), "b2k_encode16_interleaved")
         return EncodeResult(out)
 
     def encode_codestream(self, cp, planes, flags=CS_TLM | CS_PLT, out=None):

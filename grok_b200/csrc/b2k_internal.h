@@ -104,6 +104,8 @@ void b2k_launch_ht_decode_magsgn(const HtBlockDesc* d_blocks, const uint8_t* d_b
                                  const HtBlockOut* d_status, uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st);
 void b2k_launch_build_dec_desc(const HtBlockDesc* d_enc, const HtBlockOut* d_out, const uint64_t* d_offsets,
                                const float* d_dec_quant, HtBlockDesc* d_dec, uint32_t n, cudaStream_t st);
+void b2k_launch_widen16_interleaved(const uint16_t* src, uint32_t spitch, int32_t* const* dst, int nc, uint32_t dpitch, uint32_t w,
+                                    uint32_t h, int sgnd, cudaStream_t st);
 void b2k_launch_widen16(const uint16_t* src, uint32_t spitch, int32_t* dst, uint32_t dpitch, uint32_t w, uint32_t h, int sgnd,
                         cudaStream_t st);
 void b2k_launch_narrow16(const int32_t* src, uint32_t spitch, uint16_t* dst, uint32_t dpitch, uint32_t w, uint32_t h,

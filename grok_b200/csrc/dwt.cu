@@ -1890,6 +1890,55 @@ __global__ void k_widen16(const uint16_t* __restrict__ src, uint32_t spitch, int
     for(uint32_t i = 0; i < 8 && x8 + i < w; ++i)
       d[i] = sgnd ? (int)(int16_t)s[i] : (int)s[i];
 }
+struct Ptr4
+{
+  int32_t* p[4];
+};
+/* pixel-interleaved 16-bit samples (RGB48LE rows, the packed frames of gpup_batch_memory_submit: grok.cpp L1806-1836)
+   -> NC int32 planes.  A thread takes 8 pixels: NC 128-bit loads, 2*NC 128-bit stores. */
+template <int NC>
+__global__ void k_widen16_interleaved(const uint16_t* __restrict__ src, uint32_t spitch, Ptr4 dst, uint32_t dpitch, uint32_t w,
+                                      uint32_t h, int sgnd)
+{
+  const uint32_t x8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8, y = blockIdx.y;
+  if(x8 >= w || y >= h)
+    return;
+  const uint16_t* s = src + (size_t)y * spitch + (size_t)x8 * NC;
+  const size_t doff = (size_t)y * dpitch + x8;
+  if(x8 + 8 <= w && ((reinterpret_cast<uintptr_t>(s) & 15) == 0) && ((doff & 3) == 0))
+  {
+    uint32_t wd[4 * NC];
+#pragma unroll
+    for(int i = 0; i < NC; ++i)
+    {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(s) + i);
+      wd[4 * i] = a.x; wd[4 * i + 1] = a.y; wd[4 * i + 2] = a.z; wd[4 * i + 3] = a.w;
+    }
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+      int v[8];
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+      {
+        const int e = i * NC + c; /* 16-bit element index within the 8-pixel group */
+        const uint32_t u = (wd[e >> 1] >> ((e & 1) * 16)) & 0xFFFF;
+        v[i] = sgnd ? (int)(int16_t)u : (int)u;
+      }
+      int4* d = reinterpret_cast<int4*>(dst.p[c] + doff);
+      d[0] = make_int4(v[0], v[1], v[2], v[3]);
+      d[1] = make_int4(v[4], v[5], v[6], v[7]);
+    }
+  }
+  else
+    for(uint32_t i = 0; i < 8 && x8 + i < w; ++i)
+#pragma unroll
+      for(int c = 0; c < NC; ++c)
+      {
+        const uint16_t u = s[i * NC + c];
+        dst.p[c][doff + i] = sgnd ? (int)(int16_t)u : (int)u;
+      }
+}
 __global__ void k_narrow16(const int32_t* __restrict__ src, uint32_t spitch, uint16_t* __restrict__ dst, uint32_t dpitch,
                            uint32_t w, uint32_t h)
 {
@@ -1918,6 +1967,24 @@ void b2k_launch_widen16(const uint16_t* src, uint32_t spitch, int32_t* dst, uint
     return;
   dim3 grid((w + 8 * 128 - 1) / (8 * 128), h), block(128);
   k_widen16<<<grid, block, 0, st>>>(src, spitch, dst, dpitch, w, h, sgnd);
+  b2k_count_launch();
+}
+void b2k_launch_widen16_interleaved(const uint16_t* src, uint32_t spitch, int32_t* const* dst, int nc, uint32_t dpitch, uint32_t w,
+                                    uint32_t h, int sgnd, cudaStream_t st)
+{
+  if(!w || !h)
+    return;
+  Ptr4 P{};
+  for(int c = 0; c < nc && c < 4; ++c)
+    P.p[c] = dst[c];
+  dim3 grid((w + 8 * 128 - 1) / (8 * 128), h), block(128);
+  switch(nc)
+  {
+    case 1: k_widen16_interleaved<1><<<grid, block, 0, st>>>(src, spitch, P, dpitch, w, h, sgnd); break;
+    case 2: k_widen16_interleaved<2><<<grid, block, 0, st>>>(src, spitch, P, dpitch, w, h, sgnd); break;
+    case 3: k_widen16_interleaved<3><<<grid, block, 0, st>>>(src, spitch, P, dpitch, w, h, sgnd); break;
+    default: k_widen16_interleaved<4><<<grid, block, 0, st>>>(src, spitch, P, dpitch, w, h, sgnd); break;
+  }
   b2k_count_launch();
 }
 void b2k_launch_narrow16(const int32_t* src, uint32_t spitch, uint16_t* dst, uint32_t dpitch, uint32_t w, uint32_t h,

@@ -345,6 +345,8 @@ struct b2k_device_job
 
   Planes img, coef, ll[2];
   Planes16 img16;                      /* 16-bit sample containers (b2k_encode16 / b2k_decode16), lazily */
+  uint16_t* d_ileave = nullptr;        /* pixel-interleaved 16-bit frame (b2k_encode16_interleaved), lazily */
+  uint32_t ileave_pitch = 0;           /* in samples: numcomps * width, rounded up to 8 */
   std::vector<LevelLaunch> fwd, inv;   /* launch order */
   std::vector<LevelLaunch> fwd16, inv16; /* finest-level launches re-pointed at img16 (parallel to fwd / inv) */
   HtBlockDesc* d_enc_desc = nullptr;
@@ -778,6 +780,7 @@ extern "C" void b2k_job_destroy(b2k_device_job* J)
   cudaStreamSynchronize(J->eng->stream);
   cudaFree(J->img.base);
   cudaFree(J->img16.base);
+  cudaFree(J->d_ileave);
   for(LevelLaunch& L : J->fwd16) cudaFree(L.d_descs);
   for(LevelLaunch& L : J->inv16) cudaFree(L.d_descs);
   cudaFree(J->coef.base);
@@ -963,6 +966,69 @@ static int copy_planes16(b2k_device_job* J, void* const* host, const uint32_t* s
     }
     ti = tj;
   }
+  return 0;
+}
+
+/* ---- pixel-interleaved 16-bit frames: the rows cross PCIe as they are, the planes are made on the device ---- */
+static int ensure_ileave(b2k_device_job* J)
+{
+  if(J->d_ileave)
+    return 0;
+  const b2k_coding& cp = J->cp;
+  J->ileave_pitch = ((cp.x1 - cp.x0) * cp.numcomps + 7u) & ~7u;
+  CUDA_TRY(cudaMalloc(&J->d_ileave, (size_t)J->ileave_pitch * (cp.y1 - cp.y0) * sizeof(uint16_t)));
+  return 0;
+}
+
+template <typename F>
+static void for_tile_row_runs(const b2k_device_job* J, size_t t0, size_t t1, F&& fn)
+{
+  t1 = std::min(t1, J->tiles.size());
+  for(size_t ti = t0; ti < t1;)
+  {
+    Rect r = J->tile_rects[ti];
+    size_t tj = ti + 1;
+    while(tj < t1 && J->tile_rects[tj].y0 == r.y0 && J->tile_rects[tj].y1 == r.y1 && J->tile_rects[tj].x0 == r.x1)
+    {
+      r.x1 = J->tile_rects[tj].x1;
+      ++tj;
+    }
+    fn(r);
+    ti = tj;
+  }
+}
+
+static int upload_interleaved(b2k_device_job* J, const uint16_t* host, uint32_t stride, cudaStream_t st, size_t t0, size_t t1)
+{
+  const b2k_coding& cp = J->cp;
+  const uint32_t nc = cp.numcomps;
+  cudaError_t err = cudaSuccess;
+  for_tile_row_runs(J, t0, t1, [&](const Rect& r) {
+    uint16_t* dev = J->d_ileave + (size_t)(r.y0 - cp.y0) * J->ileave_pitch + (size_t)(r.x0 - cp.x0) * nc;
+    const uint16_t* hst = host + (size_t)(r.y0 - cp.y0) * stride + (size_t)(r.x0 - cp.x0) * nc;
+    const size_t row_bytes = (size_t)r.w() * nc * 2;
+    cudaError_t e = (stride == J->ileave_pitch && r.w() == cp.x1 - cp.x0)
+                        ? cudaMemcpyAsync(dev, hst, (size_t)stride * 2 * (r.h() - 1) + row_bytes, cudaMemcpyHostToDevice, st)
+                        : cudaMemcpy2DAsync(dev, (size_t)J->ileave_pitch * 2, hst, (size_t)stride * 2, row_bytes, r.h(),
+                                            cudaMemcpyHostToDevice, st);
+    if(e != cudaSuccess)
+      err = e;
+  });
+  CUDA_TRY(err);
+  return 0;
+}
+
+static int split_interleaved(b2k_device_job* J, cudaStream_t st, size_t t0, size_t t1)
+{
+  const b2k_coding& cp = J->cp;
+  for_tile_row_runs(J, t0, t1, [&](const Rect& r) {
+    int32_t* dst[4] = {nullptr, nullptr, nullptr, nullptr};
+    for(int c = 0; c < cp.numcomps; ++c)
+      dst[c] = J->img.at(c, r.x0, r.y0);
+    b2k_launch_widen16_interleaved(J->d_ileave + (size_t)(r.y0 - cp.y0) * J->ileave_pitch + (size_t)(r.x0 - cp.x0) * cp.numcomps,
+                                   J->ileave_pitch, dst, cp.numcomps, J->img.pitch, r.w(), r.h(), cp.sgnd, st);
+  });
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
@@ -1839,7 +1905,7 @@ static b2k_device_job* cached_job(b2k_engine* e, const b2k_coding* cp, uint32_t 
 }
 
 static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* planes, const uint32_t* strides,
-                             uint32_t mod, uint32_t rem, b2k_result** out, bool u16)
+                             uint32_t mod, uint32_t rem, b2k_result** out, bool u16, bool interleaved = false)
 {
   if(!e || !cp || !planes || !strides || !out)
     return -1;
@@ -1880,7 +1946,7 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
     ~SessionEnd() { if(on) b2k_host_session(false); }
   } session_end{pack};
   if(u16)
-    if(int urc = ensure_u16(J))
+    if(int urc = interleaved ? ensure_ileave(J) : ensure_u16(J))
       return urc;
   cudaStream_t st = e->stream;
   /* software pipeline over tile chunks: chunk k+1 crosses PCIe on the copy stream while chunk k
@@ -1953,14 +2019,16 @@ static int32_t encode_common(b2k_engine* e, const b2k_coding* cp, void* const* p
     {
       if(pack)
         host_convert_chunk(J, user_planes, user_strides, false, t0, t1); /* overlaps chunk k-1's H2D */
-      if(u16 ? copy_planes16(J, planes, strides, true, cs, t0, t1) : copy_planes(J, J->img, planes, strides, true, cs, t0, t1))
+      if(interleaved ? upload_interleaved(J, static_cast<const uint16_t*>(planes[0]), strides[0], cs, t0, t1)
+         : u16       ? copy_planes16(J, planes, strides, true, cs, t0, t1)
+                     : copy_planes(J, J->img, planes, strides, true, cs, t0, t1))
         return -1;
     }
     CUDA_TRY(cudaEventRecord(J->chunk_ev[CEV(0, k)], cs));
     CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[CEV(0, k)], 0));
     if(k == nchunks - 1)
       CUDA_TRY(cudaEventRecord(J->ev[1], st)); /* all planes on the device */
-    if(u16 && convert_planes16(J, true, st, t0, t1)) return -1;
+    if(u16 && (interleaved ? split_interleaved(J, st, t0, t1) : convert_planes16(J, true, st, t0, t1))) return -1;
     if(enqueue_forward(J, st, k == 0, t0, t1)) return -1;
     if(enqueue_t1_blocks(J, st, t0, t1)) return -1;
     if(streamed)
@@ -2044,6 +2112,16 @@ extern "C" int32_t b2k_encode16(b2k_engine* e, const b2k_coding* cp, const uint1
                                 uint32_t tile_mod, uint32_t tile_rem, b2k_result** out)
 {
   return encode_common(e, cp, (void* const*)planes, strides, tile_mod, tile_rem, out, true);
+}
+
+extern "C" int32_t b2k_encode16_interleaved(b2k_engine* e, const b2k_coding* cp, const uint16_t* pixels, uint32_t stride,
+                                            uint32_t tile_mod, uint32_t tile_rem, b2k_result** out)
+{
+  if(!cp || !pixels || stride < (uint32_t)(cp->x1 - cp->x0) * cp->numcomps)
+    return -1;
+  void* planes[4] = {const_cast<uint16_t*>(pixels), nullptr, nullptr, nullptr};
+  const uint32_t strides[4] = {stride, 0, 0, 0};
+  return encode_common(e, cp, planes, strides, tile_mod, tile_rem, out, true, true);
 }
 
 static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks, uint64_t num_blocks,

@@ -8,6 +8,8 @@
  *   gpup_batch_memory_end            L1842-1853: drains the batch
  * Every finished frame comes back through the host's GPUP_COMPRESS_USER_CALLBACK (gpu_plugin_shared.h L428-442) with the
  * stock gpup_tile tree, on a plugin thread; the host runs T2 inside it (batchMemoryEncodeCallback, grok.cpp L1620-1653).
+ * Frames stay pixel-interleaved across PCIe and are unpacked into planes by a device kernel ("on-device input
+ * unpack"); the host only does the copy the contract requires.
  * The stock contract is whole image = one tile; YUV sources (on-device chroma upsampling + matrix) and the on-device
  * X'Y'Z' transform are declined (begin returns 1: the host keeps that batch on the CPU).
  */
@@ -28,7 +30,7 @@ namespace {
 
 struct Slot
 {
-  uint16_t* planes[4] = {nullptr, nullptr, nullptr, nullptr}; /* pinned, planar */
+  uint16_t* pixels = nullptr; /* pinned, pixel-interleaved as submitted (rows packed: stride = numcomps * width) */
   void* host_data = nullptr;
   bool busy = false;
 };
@@ -147,24 +149,22 @@ extern "C" int32_t gpup_batch_memory_begin(gpup_batch_memory_info* info)
   B.nc = info->numcomps;
   B.prec = info->prec;
   const uint32_t depth = 3;
-  if(b2k_stream_encode_begin(b2k_plugin_device(), &B.cp, depth, 2, on_encoded, &B, &B.stream) != 0)
+  if(b2k_stream_encode_begin(b2k_plugin_device(), &B.cp, depth, B2K_SAMPLES_U16_INTERLEAVED, on_encoded, &B, &B.stream) != 0)
   {
     b2k_plugin_log(2, "batch: no engine: %s", b2k_last_error());
     return -1;
   }
   B.slots.assign(depth + 1, Slot());
-  const size_t plane_bytes = (size_t)B.w * B.h * sizeof(uint16_t);
   for(Slot& s : B.slots)
-    for(uint32_t c = 0; c < B.nc; ++c)
+  {
+    s.pixels = static_cast<uint16_t*>(b2k_host_alloc((size_t)B.w * B.h * B.nc * sizeof(uint16_t)));
+    if(!s.pixels)
     {
-      s.planes[c] = static_cast<uint16_t*>(b2k_host_alloc(plane_bytes));
-      if(!s.planes[c])
-      {
-        b2k_plugin_log(2, "batch: pinned staging allocation failed");
-        gpup_batch_memory_end();
-        return -1;
-      }
+      b2k_plugin_log(2, "batch: pinned staging allocation failed");
+      gpup_batch_memory_end();
+      return -1;
     }
+  }
   info->xyz_on_device = false;
   B.running = true;
   return 0;
@@ -181,23 +181,21 @@ extern "C" bool gpup_batch_memory_submit_planes(const uint8_t* const planes[3], 
   const uint32_t w = B.w, h = B.h, nc = B.nc;
   const uint8_t* base = planes[0];
   const size_t stride = stride_bytes[0];
-  /* the copy the contract asks for, done as the de-interleave into pinned planar planes: rows in parallel */
-  const size_t rows_per_task = 16;
+  /* the copy the contract asks for ("the frame is copied before this returns") is a plain copy into pinned memory,
+     rows in parallel; the samples are split into planes on the device (b2k_encode16_interleaved) */
+  const size_t row_bytes = (size_t)w * nc * sizeof(uint16_t);
+  const size_t rows_per_task = 64;
   b2k_host_parallel((h + rows_per_task - 1) / rows_per_task, [&](size_t t) {
     const uint32_t y0 = (uint32_t)(t * rows_per_task), y1 = y0 + rows_per_task < h ? (uint32_t)(y0 + rows_per_task) : h;
-    for(uint32_t y = y0; y < y1; ++y)
-    {
-      const uint16_t* src = reinterpret_cast<const uint16_t*>(base + (size_t)y * stride);
-      for(uint32_t c = 0; c < nc; ++c)
-      {
-        uint16_t* dst = slot->planes[c] + (size_t)y * w;
-        for(uint32_t x = 0; x < w; ++x)
-          dst[x] = src[(size_t)x * nc + c];
-      }
-    }
+    uint8_t* dst = reinterpret_cast<uint8_t*>(slot->pixels) + (size_t)y0 * row_bytes;
+    if(stride == row_bytes)
+      memcpy(dst, base + (size_t)y0 * stride, (size_t)(y1 - y0) * row_bytes);
+    else
+      for(uint32_t y = y0; y < y1; ++y)
+        memcpy(dst + (size_t)(y - y0) * row_bytes, base + (size_t)y * stride, row_bytes);
   });
-  const void* p[4] = {slot->planes[0], slot->planes[1], slot->planes[2], slot->planes[3]};
-  const uint32_t strides[4] = {w, w, w, w};
+  const void* p[4] = {slot->pixels, nullptr, nullptr, nullptr};
+  const uint32_t strides[4] = {w * nc, 0, 0, 0};
   if(b2k_stream_encode_submit(B.stream, p, strides, slot) != 0)
   {
     std::lock_guard<std::mutex> lk(B.mu);
@@ -225,12 +223,11 @@ extern "C" bool gpup_batch_memory_end(void)
     rc = b2k_stream_end(B.stream); /* drains: every callback has returned */
   B.stream = nullptr;
   for(Slot& s : B.slots)
-    for(uint16_t*& p : s.planes)
-      if(p)
-      {
-        b2k_host_free(p);
-        p = nullptr;
-      }
+    if(s.pixels)
+    {
+      b2k_host_free(s.pixels);
+      s.pixels = nullptr;
+    }
   B.slots.clear();
   const bool was = B.running;
   B.running = false;

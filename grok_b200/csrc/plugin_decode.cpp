@@ -17,6 +17,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "plugin_decode_abi.h"
@@ -154,22 +156,26 @@ int init_decompressors(gpup_header_info* h, gpup_image* image)
 
 } // namespace
 
-extern "C" int32_t plugin_decompress(gpup_decompress_params* params, PLUGIN_DECODE_USER_CALLBACK cb)
+namespace {
+
+/* One frame through the HEADER -> T2 -> POST_T1 -> CLEAN protocol.  `codestream` != NULL: a frame of an in-memory batch
+   (the host reads it instead of a file: PluginDecodeCallbackInfo::codestream, plugin_interface.h L111-114); a failed
+   batch frame still reaches the host's frame callback, with a NULL image (grok.h "NULL when this frame failed"). */
+int32_t decode_frame(b2k_engine* eng, gpup_decompress_params* params, PLUGIN_DECODE_USER_CALLBACK cb, const uint8_t* codestream,
+                     size_t codestream_length, void* frame_user)
 {
-  if(!cb)
-    return -1;
-  b2k_engine* eng = b2k_plugin_engine();
-  if(!eng)
-    return -1;
+  const bool batch = codestream != nullptr;
   DecodeCtx ctx;
   g_ctx = &ctx;
   PluginDecodeCallbackInfo info("", "", params, 1 /* J2K */, GPUP_DECODE_HEADER);
   info.init_decompressors_func = init_decompressors;
   info.deviceId = 0;
+  info.codestream = codestream;
+  info.codestreamLength = codestream_length;
+  info.frameUser = frame_user;
   int32_t rc = -1;
-  int32_t** planes = nullptr;
-  gpup_image out_img{};
-  std::vector<gpup_image_comp> comps;
+  gpup_image* host_img = nullptr;
+  bool delivered = false;
   std::vector<int32_t*> plane_ptrs;
   std::vector<uint32_t> strides;
   do
@@ -240,7 +246,6 @@ extern "C" int32_t plugin_decompress(gpup_decompress_params* params, PLUGIN_DECO
     /* ---- decode into pinned planes ---- */
     const uint32_t w = cp.x1 - cp.x0, hgt = cp.y1 - cp.y0;
     const uint32_t stride = (w + 15u) & ~15u; /* 64-byte aligned rows (gpu_plugin_shared.h L540-544) */
-    comps.resize(cp.numcomps);
     plane_ptrs.resize(cp.numcomps);
     strides.assign(cp.numcomps, stride);
     bool alloc_ok = true;
@@ -262,11 +267,15 @@ extern "C" int32_t plugin_decompress(gpup_decompress_params* params, PLUGIN_DECO
       plane_ptrs.clear();
       break;
     }
-    /* ---- POST_T1: hand the planes over ---- */
+    /* ---- POST_T1: hand the planes over.  The image shell is made the way the host makes its own (grk_to_gpup_image,
+       plugin_gpup_bridge.h L160-189: new + new[]): a batch host drops it with gpup_image_free_shell after its frame callback
+       (grok.cpp L1992-1996), the per-call host leaves it to us. ---- */
+    gpup_image* out_img = new gpup_image();
+    memset(out_img, 0, sizeof(*out_img));
+    out_img->comps = new gpup_image_comp[cp.numcomps]();
     for(int c = 0; c < cp.numcomps; ++c)
     {
-      gpup_image_comp& k = comps[c];
-      memset(&k, 0, sizeof(k));
+      gpup_image_comp& k = out_img->comps[c];
       k.x0 = cp.x0; k.y0 = cp.y0; k.w = w; k.h = hgt; k.stride = stride;
       k.dx = k.dy = 1;
       k.prec = cp.prec;
@@ -274,22 +283,35 @@ extern "C" int32_t plugin_decompress(gpup_decompress_params* params, PLUGIN_DECO
       k.data = plane_ptrs[c];
       k.owns_data = false;
     }
-    out_img.x0 = cp.x0; out_img.y0 = cp.y0; out_img.x1 = cp.x1; out_img.y1 = cp.y1;
-    out_img.numcomps = cp.numcomps;
-    out_img.color_space = info.image ? info.image->color_space : 0;
-    out_img.comps = comps.data();
-    gpup_image* host_img = info.image;
-    info.image = &out_img;
+    out_img->x0 = cp.x0; out_img->y0 = cp.y0; out_img->x1 = cp.x1; out_img->y1 = cp.y1;
+    out_img->numcomps = cp.numcomps;
+    out_img->color_space = info.image ? info.image->color_space : 0;
+    host_img = info.image;
+    info.image = out_img;
     info.plugin_owns_image = true;
     info.decompress_flags = GPUP_DECODE_POST_T1;
     const int32_t prc = cb(&info);
+    delivered = true;
+    if(info.image == out_img)
+    {
+      delete[] out_img->comps;
+      delete out_img;
+    }
     info.image = host_img;
+    host_img = nullptr;
     for(int32_t* p : plane_ptrs)
       b2k_host_free(p);
     plane_ptrs.clear();
     rc = prc == 0 ? 0 : -1;
   } while(false);
-  (void)planes;
+  if(batch && !delivered)
+  { /* the frame's owner hears about it: NULL image */
+    host_img = info.image;
+    info.image = nullptr;
+    info.decompress_flags = GPUP_DECODE_POST_T1;
+    cb(&info);
+    info.image = host_img;
+  }
   /* ---- CLEAN ---- */
   info.decompress_flags = GPUP_DECODE_CLEAN;
   cb(&info);
@@ -298,4 +320,110 @@ extern "C" int32_t plugin_decompress(gpup_decompress_params* params, PLUGIN_DECO
   free(ctx.slab);
   g_ctx = nullptr;
   return rc;
+}
+
+} // namespace
+
+extern "C" int32_t plugin_decompress(gpup_decompress_params* params, PLUGIN_DECODE_USER_CALLBACK cb)
+{
+  if(!cb)
+    return -1;
+  b2k_engine* eng = b2k_plugin_engine();
+  if(!eng)
+    return -1;
+  return decode_frame(eng, params, cb, nullptr, 0, nullptr);
+}
+
+/* ---- in-memory batch decompress (host side grok.cpp L2023-2188) -------------------------------------------
+ *   plugin_batch_decompress_memory_begin(gpup_batch_decompress_memory_info*, PLUGIN_DECODE_USER_CALLBACK)
+ *       typedef plugin_interface.h L130-131; info gpu_plugin_shared.h L492-506
+ *   plugin_batch_decompress_memory_end()          L133
+ * The plugin's workers PULL code streams from the host (info->pull; false ends a worker), run each through the same
+ * four-step protocol as plugin_decompress with the frame's bytes in PluginDecodeCallbackInfo::codestream, and the host's
+ * frame callback runs inside POST_T1 on the worker's thread (batchDecompressMemoryCallback, grok.cpp L2052-2092).
+ * Design: `depth` workers, each a host thread with its OWN engine (own streams, own cached job), so one frame's
+ * host T2 parse and copies overlap its neighbours' kernels.  8-bit RGB output packing (srgb8_output / display_transform) is
+ * not taken: rgb8_on_device stays false and the frames come back as planes, which the contract allows. */
+namespace {
+struct DecodeBatch
+{
+  bool running = false;
+  gpup_decompress_params params{};
+  PLUGIN_DECODE_USER_CALLBACK cb = nullptr;
+  GPUP_BATCH_DECOMPRESS_PULL pull = nullptr;
+  void* pull_user = nullptr;
+  std::vector<b2k_engine*> engines;
+  std::vector<std::thread> workers;
+  std::atomic<int32_t> failures{0};
+};
+DecodeBatch g_dbatch;
+} // namespace
+
+extern int32_t b2k_plugin_device(void);
+
+extern "C" int32_t plugin_batch_decompress_memory_begin(gpup_batch_decompress_memory_info* info, PLUGIN_DECODE_USER_CALLBACK cb)
+{
+  DecodeBatch& B = g_dbatch;
+  if(!info || !cb || !info->pull || B.running)
+    return -1;
+  const gpup_header_info& h = info->header_info;
+  /* the shape check plugin_decompress does per frame, up front: anything else stays on the host (return 1) */
+  if(!(h.cblk_sty & GPUP_CBLKSTY_HT) || h.t_grid_width != 1 || h.t_grid_height != 1 || h.mct > 1 || !info->image ||
+     info->image->numcomps < 1 || info->image->numcomps > 4)
+    return 1;
+  for(uint16_t c = 0; c < info->image->numcomps; ++c)
+    if(info->image->comps[c].dx != 1 || info->image->comps[c].dy != 1 || info->image->comps[c].prec != info->image->comps[0].prec)
+      return 1;
+  if(info->decompress_parameters)
+    B.params = *info->decompress_parameters;
+  B.cb = cb;
+  B.pull = info->pull;
+  B.pull_user = info->pull_user;
+  B.failures = 0;
+  const uint32_t depth = 3;
+  for(uint32_t i = 0; i < depth; ++i)
+  {
+    b2k_engine* e = nullptr;
+    if(b2k_engine_create(b2k_plugin_device(), &e) != 0)
+    {
+      for(b2k_engine* x : B.engines)
+        b2k_engine_destroy(x);
+      B.engines.clear();
+      return -1;
+    }
+    B.engines.push_back(e);
+  }
+  info->rgb8_on_device = false;
+  B.running = true;
+  for(uint32_t i = 0; i < depth; ++i)
+    B.workers.emplace_back([&B, i] {
+      for(;;)
+      {
+        const uint8_t* cs = nullptr;
+        size_t len = 0;
+        void* frame_user = nullptr;
+        if(!B.pull(B.pull_user, &cs, &len, &frame_user))
+          return;
+        if(!cs || !len)
+          continue;
+        if(decode_frame(B.engines[i], &B.params, B.cb, cs, len, frame_user) != 0)
+          B.failures++;
+      }
+    });
+  return 0;
+}
+
+extern "C" bool plugin_batch_decompress_memory_end(void)
+{
+  DecodeBatch& B = g_dbatch;
+  if(!B.running)
+    return false;
+  for(std::thread& t : B.workers)
+    t.join(); /* the host's pull answers false from here on (grok.cpp L2173-2181) */
+  B.workers.clear();
+  for(b2k_engine* e : B.engines)
+    b2k_engine_destroy(e);
+  B.engines.clear();
+  B.running = false;
+  return true;
 }

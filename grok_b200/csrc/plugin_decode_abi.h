@@ -48,3 +48,6 @@ typedef int32_t (*PLUGIN_DECODE_USER_CALLBACK)(PluginDecodeCallbackInfo* info);
 
 /* plugin_interface.h L117-120 */
 extern "C" B2K_API int32_t plugin_decompress(gpup_decompress_params* decoding_parameters, PLUGIN_DECODE_USER_CALLBACK userCallback);
+/* plugin_interface.h L130-131 */
+extern "C" B2K_API int32_t plugin_batch_decompress_memory_begin(gpup_batch_decompress_memory_info* info,
+                                                                PLUGIN_DECODE_USER_CALLBACK userCallback);

@@ -83,7 +83,9 @@ void worker_loop(b2k_stream* S, b2k_engine* eng)
     if(!S->decode)
     {
       b2k_result* R = nullptr;
-      if(S->sample_bytes == 2)
+      if(S->sample_bytes == B2K_SAMPLES_U16_INTERLEAVED)
+        rc = b2k_encode16_interleaved(eng, &S->cp, static_cast<const uint16_t*>(f.planes[0]), f.strides[0], 1, 0, &R);
+      else if(S->sample_bytes == 2)
         rc = b2k_encode16(eng, &S->cp, reinterpret_cast<const uint16_t* const*>(f.planes), f.strides, 1, 0, &R);
       else
         rc = b2k_encode(eng, &S->cp, reinterpret_cast<const int32_t* const*>(f.planes), f.strides, 1, 0, &R);
@@ -179,7 +181,7 @@ int32_t stream_submit(b2k_stream* S, const Frame& f)
 extern "C" int32_t b2k_stream_encode_begin(int32_t device, const b2k_coding* cp, uint32_t depth, uint32_t sample_bytes,
                                            b2k_encoded_fn on_encoded, void* user, b2k_stream** out)
 {
-  if(!cp || !out || (sample_bytes != 2 && sample_bytes != 4))
+  if(!cp || !out || (sample_bytes != 2 && sample_bytes != 4 && sample_bytes != B2K_SAMPLES_U16_INTERLEAVED))
     return -1;
   *out = nullptr;
   b2k_stream* S = new b2k_stream();
@@ -196,7 +198,8 @@ extern "C" int32_t b2k_stream_encode_submit(b2k_stream* S, const void* const* pl
   if(!S || S->decode || !planes || !strides)
     return -1;
   Frame f;
-  for(uint16_t c = 0; c < S->cp.numcomps && c < 4; ++c)
+  const uint16_t nplanes = S->sample_bytes == B2K_SAMPLES_U16_INTERLEAVED ? 1 : S->cp.numcomps;
+  for(uint16_t c = 0; c < nplanes && c < 4; ++c)
   {
     f.planes[c] = planes[c];
     f.strides[c] = strides[c];

@@ -319,6 +319,27 @@ B2K_API int32_t gpup_batch_memory_begin(gpup_batch_memory_info* info);
 B2K_API bool gpup_batch_memory_submit(const uint8_t* packed, void* host_data);
 B2K_API bool gpup_batch_memory_submit_planes(const uint8_t* const planes[3], const size_t stride_bytes[3], void* host_data);
 B2K_API bool gpup_batch_memory_end(void);
+/* --- in-memory batch decompress (grok.cpp L2023-2188): the plugin's workers pull code streams of one shape --- */
+typedef bool (*GPUP_BATCH_DECOMPRESS_PULL)(void* user, const uint8_t** codestream, size_t* length, void** frame_user); /* L477-478 */
+typedef struct _gpup_display_transform /* L481-487 */
+{
+  const float* transfer;
+  const float* matrix;
+} gpup_display_transform;
+typedef struct _gpup_batch_decompress_memory_info /* L492-506 */
+{
+  gpup_decompress_params* decompress_parameters;
+  gpup_header_info header_info;
+  gpup_image* image;
+  GPUP_BATCH_DECOMPRESS_PULL pull;
+  void* pull_user;
+  bool srgb8_output;
+  const gpup_display_transform* display_transform;
+  bool rgb8_on_device; /* written by begin: stays false here (frames come back as int32 planes) */
+} gpup_batch_decompress_memory_info;
+/* plugin_batch_decompress_memory_begin(info, PLUGIN_DECODE_USER_CALLBACK) takes the same C++ callback type as
+ * plugin_decompress (below), so it is declared with it; its end has a plain C signature: */
+B2K_API bool plugin_batch_decompress_memory_end(void);            /* plugin_interface.h L133 */
 /* plugin_decompress (plugin_interface.h L117-120) takes a C++ struct with std::string members
  * (PluginDecodeCallbackInfo L78-115): it is declared in grok_b200/csrc/plugin_decode.cpp and
  * documented in INTEGRATION.md, not here, so that this header stays C. */
@@ -421,6 +442,12 @@ B2K_API int32_t b2k_encode(b2k_engine* e, const b2k_coding* cp, const int32_t* c
 B2K_API int32_t b2k_encode16(b2k_engine* e, const b2k_coding* cp, const uint16_t* const* planes,
                              const uint32_t* strides, uint32_t tile_mod, uint32_t tile_rem,
                              b2k_result** out);
+/* same, ONE pixel-interleaved buffer of 16-bit samples (component c of pixel x at pixels[y*stride + x*numcomps + c],
+ * stride in samples >= numcomps * width): the layout of gpup_batch_memory_submit's packed frames and of
+ * GPUP_SOURCE_RGB48LE (grok.cpp L1806-1836, grok.h "GRK_SOURCE_RGB48LE").  The rows cross PCIe as they are and are
+ * split into planes on the device -- no host pass over the samples. */
+B2K_API int32_t b2k_encode16_interleaved(b2k_engine* e, const b2k_coding* cp, const uint16_t* pixels, uint32_t stride,
+                                         uint32_t tile_mod, uint32_t tile_rem, b2k_result** out);
 B2K_API void b2k_result_free(b2k_result* r);
 
 /* Decode: blocks[] (same enumeration, with length/offset filled by the host's T2 parse) and the
@@ -532,7 +559,8 @@ B2K_API int32_t b2k_jph_codestream(const uint8_t* file, uint64_t len, uint64_t* 
 typedef struct b2k_stream b2k_stream;
 typedef int32_t (*b2k_encoded_fn)(void* user, void* frame_user, b2k_result* result, int32_t status);
 typedef void (*b2k_decoded_fn)(void* user, void* frame_user, int32_t status);
-B2K_API int32_t b2k_stream_encode_begin(int32_t device, const b2k_coding* cp, uint32_t depth, uint32_t sample_bytes /* 2 or 4 */,
+#define B2K_SAMPLES_U16_INTERLEAVED 0x102u /* sample_bytes of an encode stream fed b2k_encode16_interleaved frames: planes[0] = pixels */
+B2K_API int32_t b2k_stream_encode_begin(int32_t device, const b2k_coding* cp, uint32_t depth, uint32_t sample_bytes /* 2, 4 or B2K_SAMPLES_U16_INTERLEAVED */,
                                         b2k_encoded_fn on_encoded, void* user, b2k_stream** out);
 B2K_API int32_t b2k_stream_encode_submit(b2k_stream* s, const void* const* planes, const uint32_t* strides, void* frame_user);
 B2K_API int32_t b2k_stream_decode_begin(int32_t device, uint32_t depth, uint32_t sample_bytes /* 2 or 4 */, b2k_decoded_fn on_decoded,

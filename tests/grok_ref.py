@@ -44,6 +44,12 @@ def lib():
         L.grb_decompress.restype = C.c_double
         L.grb_decompress.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_int32, C.c_uint32, C.POINTER(C.c_double)]
+        L.grb_batch_compress.restype = C.c_int
+        L.grb_batch_compress.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_int, C.c_void_p,
+                                         C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+        L.grb_batch_decompress.restype = C.c_int
+        L.grb_batch_decompress.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32,
+                                           C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
         L.grb_accelerated_frames.restype = C.c_uint64
         L.grb_plugin_set_enabled.argtypes = [C.c_int]
         _lib = L
@@ -95,6 +101,37 @@ def decompress(cs, w, h, ncomp, device_id=-1, reduce=0, out=None):
     if sec < 0:
         raise RuntimeError("grk_decompress failed (%g)" % sec)
     return out, sec, hs.value
+
+
+def batch_compress(frames, prec, rgb48=False, numres=6, irreversible=False, mct=None, cblk=(64, 64)):
+    """grk_plugin_batch_memory_begin / _submit / _end (grok.h) over `frames` (each a list of int32 planes of one shape).
+    -> (return code: 0 ran, 1 the plugin declined, <0 failure; list of code streams; seconds)"""
+    frames = [[np.ascontiguousarray(p, dtype=np.int32) for p in f] for f in frames]
+    h, w = frames[0][0].shape
+    n = len(frames[0])
+    p = Params(w=w, h=h, ncomp=n, prec=prec, sgnd=0, tile_w=0, tile_h=0, numres=numres, cblk_w=cblk[0], cblk_h=cblk[1],
+               irreversible=int(irreversible), mct=int(n >= 3 if mct is None else mct), ht=1, tlm=0, plt=0, device_id=0,
+               numgbits=0, prc_w=0, prc_h=0)
+    cap = w * h * n * 4 + (1 << 20)
+    out = np.zeros((len(frames), cap), np.uint8)
+    lens = (C.c_uint64 * len(frames))()
+    ptrs = (C.c_void_p * (n * len(frames)))(*[q.ctypes.data for f in frames for q in f])
+    sec = C.c_double(0)
+    rc = lib().grb_batch_compress(C.byref(p), ptrs, w, len(frames), int(rgb48), out.ctypes.data, cap, lens, C.byref(sec))
+    return rc, [out[i, :lens[i]].copy() for i in range(len(frames))], sec.value
+
+
+def batch_decompress(streams, w, h, ncomp):
+    """grk_plugin_batch_decompress_memory_begin / _end over code streams of one shape.
+    -> (frames that came back good, or a negative code: -101 = the plugin declined; decoded frames; seconds)"""
+    streams = [np.ascontiguousarray(s, dtype=np.uint8) for s in streams]
+    blob = np.concatenate(streams)
+    offs = (C.c_uint64 * (len(streams) + 1))(*np.concatenate([[0], np.cumsum([s.size for s in streams])]).tolist())
+    out = [[np.zeros((h, w), np.int32) for _ in range(ncomp)] for _ in streams]
+    ptrs = (C.c_void_p * (ncomp * len(streams)))(*[q.ctypes.data for f in out for q in f])
+    sec = C.c_double(0)
+    rc = lib().grb_batch_decompress(blob.ctypes.data, offs, len(streams), ptrs, w, ncomp, w, h, C.byref(sec))
+    return rc, out, sec.value
 
 
 def cli_env(extra=None):

@@ -16,8 +16,38 @@ import grok_ref as R            # noqa: E402
 import oracle_pipeline as P     # noqa: E402
 
 
+def batch(case):
+    """the host's in-memory batch interfaces with the plugin loaded: grk_plugin_batch_memory_* (frames in, code streams out)
+    and grk_plugin_batch_decompress_memory_* (code streams in, frames out), against the host's own CPU results"""
+    w, h, n, prec, nframes = case["width"], case["height"], case["numcomps"], case["prec"], case["frames"]
+    frames = [P.synthetic_image(w, h, n, prec, seed=case.get("seed", 7) + f) for f in range(nframes)]
+    kw = dict(numres=case.get("numres", 6), irreversible=case.get("irreversible", False))
+    out = {"flavour": R.FLAVOUR}
+    R.init(case.get("threads", 4))
+    cpu = [R.compress(f, prec, **kw)[0].copy() for f in frames]
+    out["declined_without_plugin"] = R.batch_compress(frames, prec, **kw)[0]
+    out["plugin_loaded"] = bool(R.init(case.get("threads", 4), plugin_path=R.PLUGIN_DIR, device_id=0))
+    for name, rgb48 in (("planar", False), ("rgb48le", True)):
+        rc, streams, sec = R.batch_compress(frames, prec, rgb48=rgb48, **kw)
+        out["compress_" + name] = {"rc": rc, "seconds": sec, "identical": bool(
+            rc == 0 and all(a.size == b.size and np.array_equal(a, b) for a, b in zip(streams, cpu)))}
+    good, decoded, sec = R.batch_decompress(cpu, w, h, n)
+    ref = [R.decompress(c, w, h, n)[0] for c in cpu]     # batch over: this decompresses per call again
+    out["decompress"] = {"good": good, "seconds": sec, "maxdiff": int(max(
+        np.abs(a.astype(np.int64) - b).max() for fa, fb in zip(decoded, ref) for a, b in zip(fa, fb)))}
+    # a frame of another shape inside the batch fails alone (NULL image), the others still arrive
+    if case.get("odd_one"):
+        other = R.compress(P.synthetic_image(w // 2, h, n, prec, seed=3), prec, **kw)[0].copy()
+        good, decoded, _ = R.batch_decompress([cpu[0], other, cpu[-1]], w, h, n)
+        out["decompress_odd"] = {"good": good, "first_ok": bool(all(np.array_equal(a, b) for a, b in zip(decoded[0], ref[0]))),
+                                 "last_ok": bool(all(np.array_equal(a, b) for a, b in zip(decoded[2], ref[-1])))}
+    print("REALHOST " + json.dumps(out))
+
+
 def main():
     case = json.loads(sys.argv[1])
+    if case.get("batch"):
+        return batch(case)
     w, h, n, prec = case["width"], case["height"], case["numcomps"], case["prec"]
     kw = dict(tile=tuple(case["tile"]) if case.get("tile") else None, numres=case.get("numres", 6),
               irreversible=case.get("irreversible", False), tlm=True, plt=True,

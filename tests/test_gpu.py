@@ -300,6 +300,34 @@ def test_16bit_containers(engine, sgnd):
     b.free()
 
 
+@pytest.mark.parametrize("case", [
+    dict(w=600, h=300, n=3, tile=(256, 128), origin=(8, 0), sgnd=False, pad=0),    # tiled: partial-width runs, 2-D copies
+    dict(w=501, h=77, n=3, tile=None, origin=(0, 0), sgnd=False, pad=5),           # rows not 16-byte aligned, padded stride
+    dict(w=640, h=256, n=4, tile=None, origin=(0, 0), sgnd=True, pad=0),
+    dict(w=333, h=64, n=1, tile=None, origin=(0, 0), sgnd=False, pad=0),
+])
+def test_interleaved_16bit_frames(engine, case):
+    """b2k_encode16_interleaved (RGB48LE rows / gpup_batch_memory_submit's packed frames, grok.cpp L1806-1836): the frame
+    crosses PCIe pixel-interleaved and is split into planes on the device; code blocks equal the planar entry point's."""
+    w, h, n, prec = case["w"], case["h"], case["n"], 12
+    cp = G.make_coding(w, h, n, prec, sgnd=case["sgnd"], numres=5, tile=case["tile"], origin=case["origin"])
+    planes = P.synthetic_image(w, h, n, prec, seed=5)
+    if case["sgnd"]:
+        planes = [p - 2048 for p in planes]
+    dt = np.int16 if case["sgnd"] else np.uint16
+    buf = np.zeros((h, w * n + case["pad"]), dt)
+    pixels = buf[:, :w * n].reshape(h, w, n) if case["pad"] == 0 else np.lib.stride_tricks.as_strided(
+        buf, shape=(h, w, n), strides=(buf.strides[0], 2 * n, 2))
+    for c in range(n):
+        pixels[:, :, c] = planes[c].astype(dt)
+    a = engine.encode(cp, planes)
+    b = engine.encode_interleaved(cp, pixels)
+    assert a.num_blocks == b.num_blocks and np.array_equal(a.blocks["length"], b.blocks["length"])
+    assert np.array_equal(a.bytes, b.bytes)
+    a.free()
+    b.free()
+
+
 def _mock_host():
     import os
     import subprocess

@@ -18,6 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "grok_b200.h")).read()
+    # the two entry points that take Grok's C++ callback type live beside its restated layout
+    hdr += open(os.path.join(ROOT, "grok_b200", "csrc", "plugin_decode_abi.h")).read()
     hdr = hdr.replace("#define B2K_API __attribute__((visibility(\"default\")))", "")
     declared = set(re.findall(r"B2K_API[^;(]*?\b(\w+)\s*\(", hdr))
     assert declared, "no declarations parsed"
@@ -32,14 +34,16 @@ _ABI_PROBE = r'''
 #include <stddef.h>
 %s
 int main(void){
-  printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\n", sizeof(gpup_code_block), sizeof(gpup_compress_params),
+  printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\n", sizeof(gpup_code_block), sizeof(gpup_compress_params),
    offsetof(gpup_compress_params, cblk_sty), sizeof(gpup_image_comp), sizeof(gpup_image), sizeof(gpup_tile), sizeof(gpup_band),
    sizeof(gpup_header_info), sizeof(gpup_decompress_params), sizeof(gpup_decompress_callback_info),
    offsetof(gpup_compress_params, apply_xyz_transform), sizeof(gpup_batch_memory_info), offsetof(gpup_batch_memory_info, source_format),
-   sizeof(gpup_compress_callback_info), offsetof(gpup_compress_callback_info, host_data));
+   sizeof(gpup_compress_callback_info), offsetof(gpup_compress_callback_info, host_data),
+   sizeof(gpup_batch_decompress_memory_info), offsetof(gpup_batch_decompress_memory_info, pull),
+   offsetof(gpup_batch_decompress_memory_info, rgb8_on_device));
   return 0; }'''
 # measured from the reference's own gpu_plugin_shared.h (g++ 13, x86-64); re-checked live below when the tree is here
-_ABI_REFERENCE = [1672, 12696, 4152, 40, 32, 24, 32, 312, 8272, 424, 12694, 56, 44, 96, 88]
+_ABI_REFERENCE = [1672, 12696, 4152, 40, 32, 24, 32, 312, 8272, 424, 12694, 56, 44, 96, 88, 368, 328, 360]
 
 
 def _probe(include_line, flags, compiler):

@@ -108,3 +108,45 @@ def test_patched_host_still_serves_single_tile_through_the_stock_symbols():
     r = run(dict(width=512, height=512, numcomps=1, prec=8), "_ref_patched")
     assert r["plugin_loaded"] and r["plugin"]["enc_accelerated"] == 1 and r["plugin"]["codestream_identical"]
     assert r["plugin"]["dec_accelerated"] == 1 and r["plugin"]["decode_identical"]
+
+
+BATCH_CASES = [
+    dict(batch=True, width=640, height=384, numcomps=3, prec=12, frames=5, odd_one=True),
+    dict(batch=True, width=500, height=333, numcomps=3, prec=16, frames=4, numres=5),      # W * 3 * 2 bytes not 16-aligned
+    dict(batch=True, width=512, height=256, numcomps=3, prec=12, frames=4, irreversible=True),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", BATCH_CASES)
+def test_stock_host_batch_interfaces_through_the_plugin(case):
+    """grk_plugin_batch_memory_begin/_submit/_end and grk_plugin_batch_decompress_memory_begin/_end (grok.h; host side
+    grok.cpp L1655-1857, L2094-2188) with the plugin loaded by the unmodified host: planar int32 frames (the host packs
+    them pixel-interleaved, L1806-1836) and GRK_SOURCE_RGB48LE frames go in, the host runs T2 in the plugin's callback,
+    and every code stream equals the one grk_compress() writes on its own; code streams go in through the pull callback,
+    the frames that come back equal grk_decompress()'s."""
+    if not built("_ref"):
+        pytest.skip("baseline/_ref not built")
+    r = run(case, "_ref")
+    assert r["declined_without_plugin"] == 1
+    assert r["plugin_loaded"]
+    for name in ("compress_planar", "compress_rgb48le"):
+        assert r[name]["rc"] == 0, r
+        assert r[name]["identical"], "%s: a batch code stream differs from the host's own" % name
+    assert r["decompress"]["good"] == case["frames"], r
+    assert r["decompress"]["maxdiff"] <= (1 if case.get("irreversible") else 0), r
+    if case.get("odd_one"):
+        assert r["decompress_odd"] == {"good": 2, "first_ok": True, "last_ok": True}, r
+
+
+def test_batch_interfaces_decline_without_a_device():
+    """no GPU: plugin_init fails, so both batch begins answer 1 and the caller stays on the CPU (grok.h)"""
+    if not built("_ref"):
+        pytest.skip("baseline/_ref not built")
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    r = run(dict(batch=True, width=128, height=96, numcomps=3, prec=12, frames=2), "_ref")
+    assert r["declined_without_plugin"] == 1 and r["plugin_loaded"] is False
+    assert r["compress_planar"]["rc"] == 1 and r["compress_rgb48le"]["rc"] == 1
+    assert r["decompress"]["good"] == -101
