@@ -61,7 +61,7 @@ EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "g
            "b2k_engine_create", "b2k_engine_destroy", "b2k_last_error", "b2k_host_alloc", "b2k_host_free",
            "b2k_encode", "b2k_encode16", "b2k_encode16_interleaved", "b2k_result_free", "b2k_decode", "b2k_decode16", "b2k_enumerate",
            "b2k_result_to_gpup_tile", "b2k_job_create", "b2k_job_destroy", "b2k_job_upload", "b2k_job_forward",
-           "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_roundtrip_n", "b2k_job_download",
+           "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_roundtrip_n", "b2k_job_roundtrip_pipelined_n", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
            "b2k_launch_count", "b2k_job_last_kernel_stats", "b2k_set_host_threads", "b2k_host_pack_last",
            "b2k_codestream_write", "b2k_codestream_parse", "b2k_codestream_parse_window",
@@ -115,6 +115,8 @@ def lib():
     L.b2k_job_t1_decode_blocks.argtypes = [vp, vp, u64, vp, u64, C.POINTER(C.c_float)]
     L.b2k_job_roundtrip.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
     L.b2k_job_roundtrip_n.argtypes = [vp, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
+    L.b2k_job_roundtrip_pipelined_n.argtypes = [vp, u32, u32, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                                C.POINTER(u64)]
     L.b2k_job_fetch_result.argtypes = [vp, C.POINTER(C.POINTER(Result))]
     L.b2k_job_num_blocks.argtypes = [vp]
     L.b2k_job_num_blocks.restype = u64
@@ -534,6 +536,17 @@ class Job:
         if rc == 2:
             rc = lib().b2k_job_roundtrip_n(self._h, steps, C.byref(ms), st, C.byref(l1), C.byref(nb))
         _check(rc, "b2k_job_roundtrip_n")
+        return ms.value, [float(v) for v in st], l1.value, int(nb.value)
+
+    def roundtrip_pipelined_n(self, steps, chunks=0, streams=0):
+        """`steps` round trips with the block-coder stage pipelined over block ranges on side streams
+        (b2k_job_roundtrip_pipelined_n).  Returns (total ms, [fwd, block coder, inv] ms summed, level-1 kernel ms summed, bytes)."""
+        ms, st, l1, nb = C.c_float(), (C.c_float * 3)(), C.c_float(), C.c_uint64()
+        args = (self._h, steps, chunks, streams, C.byref(ms), st, C.byref(l1), C.byref(nb))
+        rc = lib().b2k_job_roundtrip_pipelined_n(*args)
+        if rc == 2:
+            rc = lib().b2k_job_roundtrip_pipelined_n(*args)
+        _check(rc, "b2k_job_roundtrip_pipelined_n")
         return ms.value, [float(v) for v in st], l1.value, int(nb.value)
 
     def roundtrip(self):

@@ -97,11 +97,12 @@ void b2k_launch_scan_lengths(const HtBlockOut* d_out, uint64_t* d_offsets, uint3
 void b2k_launch_ht_decode_refine(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, const HtBlockOut* d_status,
                                  uint32_t nblocks, int stripe_causal, cudaStream_t st);
 void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
-                          uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st);
+                          uint32_t nblocks, uint32_t max_w, int* d_err, int irreversible, int any_refinement, cudaStream_t st);
 void b2k_launch_ht_decode_vlc(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
                               uint32_t nblocks, uint32_t max_w, cudaStream_t st);
 void b2k_launch_ht_decode_magsgn(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, const uint32_t* d_recs,
-                                 const HtBlockOut* d_status, uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st);
+                                 const HtBlockOut* d_status, uint32_t nblocks, uint32_t max_w, int* d_err, int irreversible,
+                                 int any_refinement, cudaStream_t st);
 void b2k_launch_build_dec_desc(const HtBlockDesc* d_enc, const HtBlockOut* d_out, const uint64_t* d_offsets,
                                const float* d_dec_quant, HtBlockDesc* d_dec, uint32_t n, cudaStream_t st);
 void b2k_launch_widen16_interleaved(const uint16_t* src, uint32_t spitch, int32_t* const* dst, int nc, uint32_t dpitch, uint32_t w,

@@ -381,6 +381,8 @@ struct b2k_device_job
   cudaEvent_t ring_ev[16]{};
   PackTuner tune_enc, tune_dec;
   std::vector<cudaEvent_t> q_ev;   /* per-step events of b2k_job_roundtrip_n */
+  std::vector<cudaEvent_t> p_ev;   /* per-chunk events of b2k_job_roundtrip_pipelined_n (scan done, chunk done) */
+  std::vector<cudaStream_t> p_streams; /* its block-coder streams */
   bool dec_has_refinement = false; /* the block table of the current decode carries SigProp / MagRef passes */
 };
 
@@ -805,6 +807,10 @@ extern "C" void b2k_job_destroy(b2k_device_job* J)
   cudaFreeHost(J->h_ring);
   for(cudaEvent_t ev : J->q_ev)
     cudaEventDestroy(ev);
+  for(cudaEvent_t ev : J->p_ev)
+    cudaEventDestroy(ev);
+  for(cudaStream_t ps : J->p_streams)
+    cudaStreamDestroy(ps);
   for(cudaEvent_t& ev : J->ring_ev)
     if(ev)
       cudaEventDestroy(ev);
@@ -1414,7 +1420,7 @@ static int enqueue_t1_decode_own(b2k_device_job* J, cudaStream_t st)
 {
   const uint32_t n = (uint32_t)J->h_enc_desc.size();
   b2k_launch_build_dec_desc(J->d_enc_desc, J->d_out, J->d_offsets, J->d_dec_quant, J->d_dec_desc, n, st);
-  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, J->d_recs, J->d_dec_status, n, J->max_cblk_w, J->d_err, st);
+  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, J->d_recs, J->d_dec_status, n, J->max_cblk_w, J->d_err, J->cp.irreversible, 0, st);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -1470,7 +1476,8 @@ extern "C" int32_t b2k_job_t1_decode_blocks(b2k_device_job* J, const b2k_block* 
   if(num_bytes)
     CUDA_TRY(cudaMemcpyAsync(J->d_bytes, bytes, num_bytes, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaEventRecord(J->ev[0], st));
-  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, J->d_recs, J->d_dec_status, n, J->max_cblk_w, J->d_err, st);
+  b2k_launch_ht_decode(J->d_dec_desc, J->d_bytes, J->d_recs, J->d_dec_status, n, J->max_cblk_w, J->d_err, J->cp.irreversible,
+                       J->dec_has_refinement, st);
   if(J->dec_has_refinement)
     b2k_launch_ht_decode_refine(J->d_dec_desc, J->d_bytes, J->d_dec_status, n, (J->cp.cblk_sty & 0x08) != 0, st);
   CUDA_TRY(cudaEventRecord(J->ev[1], st));
@@ -1619,6 +1626,127 @@ extern "C" int32_t b2k_job_roundtrip_n(b2k_device_job* J, uint32_t steps, float*
   if(ms_total) *ms_total = tot;
   if(stage_ms)
     for(int i = 0; i < 4; ++i)
+      stage_ms[i] = sums[i];
+  if(level1_ms) *level1_ms = l1;
+  if(total_bytes) *total_bytes = J->bytes_used;
+  int herr = 0;
+  CUDA_TRY(cudaMemcpy(&herr, J->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if(herr)
+  {
+    g_err = "HT decoder rejected " + std::to_string(herr) + " block(s)";
+    return -2;
+  }
+  return 0;
+}
+
+/* The same n round trips with the BLOCK-CODER stage software-pipelined over tile-independent block ranges: the forward
+   transform of the whole image runs alone on the main stream (its kernels are HBM-bound and are timed as such), then the
+   coded blocks are cut into `chunks` ranges (0: 2) and each range goes encode -> scan -> compact -> parse (phase A) -> MagSgn
+   (phase B) on one of `streams` side streams, so that the latency-bound kernels of one range (phase A is a serial chain
+   per block, the scan a single CTA) run under the issue-bound kernels of its neighbours; the inverse transform again
+   runs alone after all ranges have joined.  Ranges are independent except for the byte offsets of the compacted arena,
+   which chain from one range's scan to the next (event per range).  stage_ms[3] = forward, block coder (encode + decode
+   together), inverse.  Same results as b2k_job_roundtrip_n, byte for byte. */
+extern "C" int32_t b2k_job_roundtrip_pipelined_n(b2k_device_job* J, uint32_t steps, uint32_t chunks, uint32_t streams, float* ms_total,
+                                                 float* stage_ms, float* level1_ms, uint64_t* total_bytes)
+{
+  if(!J || !steps) return -1;
+  CUDA_TRY(cudaSetDevice(J->eng->device));
+  cudaStream_t st = J->eng->stream;
+  const uint32_t n = (uint32_t)J->h_enc_desc.size();
+  if(J->bytes_cap == 0)
+  { /* first use: size the arena (one synchronising pass) */
+    float t;
+    uint64_t b;
+    if(int rc = b2k_job_forward(J, &t)) return rc;
+    if(int rc = b2k_job_t1_encode(J, &t, &b)) return rc;
+  }
+  /* measured on config 2 (tools/stage_times.py): 2 ranges on 2 streams 2.62 ms against 2.82 ms back to
+     back; more ranges per stream lose (phase A's serial chain is a ~0.35 ms floor per launch, the persistent encoder grid
+     fills every SM's shared memory), and so does a dedicated encoder stream with a capped grid */
+  chunks = std::max(1u, std::min(chunks ? chunks : 2u, 64u));
+  streams = std::max(1u, std::min(streams ? streams : 2u, 8u));
+  /* ranges start on multiples of 128 blocks: whole CTAs of both decode kernels, whole record-interleave groups */
+  const uint32_t per_chunk = std::max(128u, (((n + chunks - 1) / chunks) + 127u) & ~127u);
+  const uint32_t nch = n ? (n + per_chunk - 1) / per_chunk : 0;
+  while(J->p_streams.size() < streams)
+  {
+    cudaStream_t ps;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    J->p_streams.push_back(ps);
+  }
+  while(J->p_ev.size() < 2 * (size_t)nch)
+  {
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    J->p_ev.push_back(ev);
+  }
+  const size_t per = 5; /* start, l1 begin, l1 end, after forward, after the block coder; the next step's start ends the inverse */
+  while(J->q_ev.size() < per * steps + 1)
+  {
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreate(&ev));
+    J->q_ev.push_back(ev);
+  }
+  CUDA_TRY(cudaMemsetAsync(J->d_err, 0, sizeof(int), st));
+  for(uint32_t s = 0; s < steps; ++s)
+  {
+    cudaEvent_t* e = J->q_ev.data() + per * s;
+    CUDA_TRY(cudaEventRecord(e[0], st));
+    if(enqueue_forward(J, st, true, 0, (size_t)-1, false, e[1], e[2])) return -1;
+    CUDA_TRY(cudaEventRecord(e[3], st));
+    for(uint32_t k = 0; k < streams && k < nch; ++k)
+      CUDA_TRY(cudaStreamWaitEvent(J->p_streams[k], e[3], 0));
+    for(uint32_t c = 0; c < nch; ++c)
+    {
+      cudaStream_t ps = J->p_streams[c % streams];
+      const uint32_t b0 = c * per_chunk, b1 = std::min(n, b0 + per_chunk), nb = b1 - b0;
+      b2k_launch_ht_encode(J->d_enc_desc + b0, J->d_out + b0, J->d_scratch, nb, J->enc_limits, J->cp.irreversible, ps);
+      if(c > 0)
+        CUDA_TRY(cudaStreamWaitEvent(ps, J->p_ev[2 * (c - 1)], 0)); /* the previous range's end offset */
+      b2k_launch_scan_lengths(J->d_out + b0, J->d_offsets + b0, nb, ps);
+      CUDA_TRY(cudaEventRecord(J->p_ev[2 * c], ps));
+      b2k_launch_ht_gather(J->d_enc_desc + b0, J->d_out + b0, J->d_offsets + b0, J->d_scratch, J->d_bytes, nb, J->bytes_cap, ps);
+      b2k_launch_build_dec_desc(J->d_enc_desc + b0, J->d_out + b0, J->d_offsets + b0, J->d_dec_quant + b0, J->d_dec_desc + b0, nb, ps);
+      b2k_launch_ht_decode(J->d_dec_desc + b0, J->d_bytes, J->d_recs, J->d_dec_status + b0, nb, J->max_cblk_w, J->d_err,
+                           J->cp.irreversible, 0, ps);
+      CUDA_TRY(cudaEventRecord(J->p_ev[2 * c + 1], ps));
+    }
+    for(uint32_t c = 0; c < nch; ++c)
+      CUDA_TRY(cudaStreamWaitEvent(st, J->p_ev[2 * c + 1], 0));
+    if(s + 1 == steps)
+      CUDA_TRY(cudaMemcpyAsync(&J->h_offsets[n], J->d_offsets + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(e[4], st));
+    if(enqueue_inverse(J, st)) return -1;
+  }
+  cudaEvent_t last = J->q_ev[per * steps];
+  CUDA_TRY(cudaEventRecord(last, st));
+  CUDA_TRY(cudaEventSynchronize(last));
+  CUDA_TRY(cudaGetLastError());
+  if(J->h_offsets[n] > J->bytes_cap)
+  {
+    cudaFree(J->d_bytes);
+    J->bytes_cap = J->h_offsets[n] + J->h_offsets[n] / 8 + 4096;
+    CUDA_TRY(cudaMalloc(&J->d_bytes, J->bytes_cap));
+    g_err = "coded size grew past the arena: arena resized, call again";
+    return 2;
+  }
+  J->bytes_used = J->h_offsets[n];
+  float sums[3] = {0, 0, 0}, l1 = 0, tot = 0;
+  for(uint32_t s = 0; s < steps; ++s)
+  {
+    cudaEvent_t* e = J->q_ev.data() + per * s;
+    float t = 0;
+    cudaEventElapsedTime(&t, e[0], e[3]); sums[0] += t;
+    cudaEventElapsedTime(&t, e[3], e[4]); sums[1] += t;
+    cudaEventElapsedTime(&t, e[4], e[per]); sums[2] += t; /* e[per] = the next step's start, or `last` */
+    cudaEventElapsedTime(&t, e[1], e[2]); l1 += t;
+  }
+  cudaEventElapsedTime(&tot, J->q_ev[0], last);
+  J->last_level1_ms = l1 / steps;
+  if(ms_total) *ms_total = tot;
+  if(stage_ms)
+    for(int i = 0; i < 3; ++i)
       stage_ms[i] = sums[i];
   if(level1_ms) *level1_ms = l1;
   if(total_bytes) *total_bytes = J->bytes_used;
@@ -2255,7 +2383,7 @@ static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_bloc
       CUDA_TRY(cudaEventRecord(J->chunk_ev[CEV(2, k)], ax));
       CUDA_TRY(cudaStreamWaitEvent(st, J->chunk_ev[CEV(2, k)], 0));
       b2k_launch_ht_decode_magsgn(J->d_dec_desc + b0, J->d_bytes, J->d_recs, J->d_dec_status + b0, b1 - b0, J->max_cblk_w,
-                                  J->d_err, st);
+                                  J->d_err, J->cp.irreversible, J->dec_has_refinement, st);
       if(J->dec_has_refinement)
         b2k_launch_ht_decode_refine(J->d_dec_desc + b0, J->d_bytes, J->d_dec_status + b0, b1 - b0,
                                     (J->cp.cblk_sty & 0x08) != 0, st);

@@ -710,6 +710,9 @@ __global__ void __launch_bounds__(32)
 }
 
 /* record per quad: rho[3:0] | e_k[7:4] | e_1[11:8] | u[17:12] */
+/* IRREV: the launch's blocks are dequantised to float (one coding per launch); REFINE: some block of the launch carries
+   SigProp / MagRef passes (foreign streams), so B.passes is looked at -- the common launch has neither branch compiled in */
+template <bool IRREV, bool REFINE>
 __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
     k_ht_decode_magsgn(const HtBlockDesc* __restrict__ blocks, const uint8_t* __restrict__ bytes,
                        const uint32_t* __restrict__ recs, const HtBlockOut* __restrict__ status, uint32_t nblocks,
@@ -759,75 +762,94 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
   bool ms_prevff = false;
   const uint32_t* rec = recs + B.rec_off;
   uint32_t r_next = lane < nq ? __ldg(rec + (size_t)lane * 32) : 0u;
-  uint32_t pw0 = 0, pw1 = 0; /* this lane's two aligned words of the next 128-byte refill */
+  uint32_t pw0 = 0, pw1 = 0, pw2 = 0; /* this lane's three aligned words of the next 256-byte refill */
   auto load_chunk = [&](int pos) {
-    if(pos + 4 * lane < ms_size)
+    if(pos + 8 * lane < ms_size)
     {
-      const uintptr_t a = reinterpret_cast<uintptr_t>(data + pos + 4 * lane) & ~(uintptr_t)3;
-      pw0 = __ldg(reinterpret_cast<const uint32_t*>(a));
-      pw1 = __ldg(reinterpret_cast<const uint32_t*>(a) + 1);
+      const uint32_t* a = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(data + pos + 8 * lane) & ~(uintptr_t)3);
+      pw0 = __ldg(a);
+      pw1 = __ldg(a + 1);
+      pw2 = __ldg(a + 2); /* at most 11 bytes past the lane's first: inside the arena's slack */
     }
   };
   load_chunk(0);
 
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(coef) | ((uintptr_t)B.pitch << 2)) & 7u) == 0;
   for(int y = 0; y < h && !bad; y += 2)
   {
     const int cur = (y >> 1) & 1;
     const uint16_t* labove = line[cur ^ 1];
     uint16_t* lcur = line[cur];
+    int32_t* const crow = coef + (size_t)y * B.pitch;
     for(int qb = 0; qb < nq; qb += 32)
     {
-      /* keep at least 4096 un-stuffed bits (or the rest of the segment + 1-fill) in the ring:
-         128 segment bytes per round, 4 per lane, read as two aligned words (frwd_read L628-669:
-         a byte after 0xFF carries 7 bits, 0xFF is fed once the segment is exhausted) */
+      /* keep at least 4096 un-stuffed bits (or the rest of the segment + 1-fill) in the ring: 256 segment bytes per
+         round, 8 per lane, read as three aligned words (frwd_read L628-669: a byte after 0xFF carries 7 bits, 0xFF is fed
+         once the segment is exhausted).  The un-stuffing is done on whole words: ff = the bytes equal to 0xFF (bit 7 of
+         each), d = the bytes that follow one (their top bit is dropped), then two 16-bit halves are closed up. */
       while(ms_tail - ms_head < 4096u)
       {
-        const uint8_t* pb = data + ms_pos + 4 * lane;
-        uint32_t val = 0xFFFFFFFFu;
-        if(ms_pos + 4 * lane < ms_size)
+        const int at = ms_pos + 8 * lane;
+        uint32_t v0 = 0xFFFFFFFFu, v1 = 0xFFFFFFFFu;
+        if(at < ms_size)
         {
-          val = __funnelshift_r(pw0, pw1, 8 * (int)(reinterpret_cast<uintptr_t>(pb) & 3)); /* loaded one refill ago */
-          const int left = ms_size - (ms_pos + 4 * lane);
-          if(left < 4)
-            val |= 0xFFFFFFFFu << (8 * left);
+          const int bsh = 8 * (int)(reinterpret_cast<uintptr_t>(data + at) & 3); /* loaded one refill ago */
+          v0 = __funnelshift_r(pw0, pw1, bsh);
+          v1 = __funnelshift_r(pw1, pw2, bsh);
+          const int left = ms_size - at;
+          if(left < 8)
+          {
+            if(left < 4)
+              v0 |= 0xFFFFFFFFu << (8 * left);
+            v1 = left > 4 ? (v1 | (0xFFFFFFFFu << (8 * (left - 4)))) : 0xFFFFFFFFu;
+          }
         }
-        load_chunk(ms_pos + 128); /* the next 128 bytes are in flight while these are parsed */
-        const unsigned lastff = __ballot_sync(0xffffffffu, (val >> 24) == 0xFFu);
-        bool f = lane == 0 ? ms_prevff : (((lastff >> (lane - 1)) & 1u) != 0);
-        uint64_t acc = 0;
-        int nb = 0;
-#pragma unroll
-        for(int j = 0; j < 4; ++j)
-        {
-          const uint32_t b = (val >> (8 * j)) & 0xFFu;
-          acc |= (uint64_t)(b & (f ? 0x7Fu : 0xFFu)) << nb;
-          nb += f ? 7 : 8;
-          f = (b == 0xFFu);
-        }
+        load_chunk(ms_pos + 256); /* the next 256 bytes are in flight while these are parsed */
+        const uint32_t ff0 = ((v0 & 0x7F7F7F7Fu) + 0x01010101u) & v0 & 0x80808080u;
+        const uint32_t ff1 = ((v1 & 0x7F7F7F7Fu) + 0x01010101u) & v1 & 0x80808080u;
+        const unsigned lastff = __ballot_sync(0xffffffffu, (ff1 >> 31) != 0);
+        const uint32_t fin = lane == 0 ? (ms_prevff ? 1u : 0u) : ((lastff >> (lane - 1)) & 1u);
+        const uint32_t d0 = (ff0 << 8) | (fin << 7), d1 = (ff1 << 8) | (ff0 >> 24);
+        auto squeeze = [](uint32_t v, uint32_t d, int& nb) -> uint32_t {
+          v &= ~d;
+          uint32_t h0 = v & 0xFFFFu, h1 = v >> 16;
+          if(d & 0x80u)
+            h0 = (h0 & 0xFFu) | ((h0 & 0xFF00u) >> 1);
+          if(d & 0x800000u)
+            h1 = (h1 & 0xFFu) | ((h1 & 0xFF00u) >> 1);
+          nb = 32 - __popc(d);
+          return h0 | (h1 << (16 - __popc(d & 0x8080u))); /* a dropped top bit was masked to 0: the next piece lands on it */
+        };
+        int nb0, nb1;
+        const uint32_t a0 = squeeze(v0, d0, nb0), a1 = squeeze(v1, d1, nb1);
+        const uint64_t acc = (uint64_t)a0 | ((uint64_t)a1 << nb0);
         uint32_t tot;
-        const uint32_t off = warp_excl_scan_d<uint32_t>((uint32_t)nb, lane, tot);
+        const uint32_t off = warp_excl_scan_d<uint32_t>((uint32_t)(nb0 + nb1), lane, tot);
         const uint32_t pos = ms_tail + off;
-        { /* the words this refill lands in are cleared here (33 whole words after the one the tail sits in): the consumer
-             does not clean up behind itself any more */
+        { /* the words this refill lands in are cleared here (65 whole words after the one the tail sits in; the unread
+             bits span fewer than 128 of the ring's 256 words): the consumer does not clean up behind itself */
           const uint32_t wt = ms_tail >> 5;
           ring[(wt + 1 + lane) & (MS_RING_WORDS - 1)] = 0;
+          ring[(wt + 33 + lane) & (MS_RING_WORDS - 1)] = 0;
           if(lane == 0)
-            ring[(wt + 33) & (MS_RING_WORDS - 1)] = 0;
+            ring[(wt + 65) & (MS_RING_WORDS - 1)] = 0;
           __syncwarp();
         }
         {
           const int sh = pos & 31;
           const uint32_t wi = pos >> 5;
           const uint64_t sft = acc << sh;
-          const uint32_t lo = (uint32_t)sft, hi = (uint32_t)(sft >> 32);
+          const uint32_t lo = (uint32_t)sft, mid = (uint32_t)(sft >> 32), hi = sh ? (uint32_t)(acc >> (64 - sh)) : 0u;
           if(lo)
             atomicOr(&ring[wi & (MS_RING_WORDS - 1)], lo);
+          if(mid)
+            atomicOr(&ring[(wi + 1) & (MS_RING_WORDS - 1)], mid);
           if(hi)
-            atomicOr(&ring[(wi + 1) & (MS_RING_WORDS - 1)], hi);
+            atomicOr(&ring[(wi + 2) & (MS_RING_WORDS - 1)], hi);
         }
         ms_tail += tot;
         ms_prevff = (lastff >> 31) & 1u;
-        ms_pos += 128;
+        ms_pos += 256;
         __syncwarp();
       }
 
@@ -856,13 +878,14 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
       const uint32_t U = (uint32_t)(uq + kappa);
       if(qv && U > mmsbp2)
         bad = true;
+      /* the samples this lane reads MagSgn bits for: none past the block's right edge (the reference never reads bits for
+         the missing right column, L1138-1139), none once the block is known to be damaged */
+      const int rho_eff = (qv && !bad) ? ((x + 1 < w) ? rho : (rho & 3)) : 0;
       int m[4], mlen = 0;
 #pragma unroll
       for(int i = 0; i < 4; ++i)
       {
-        /* the reference never reads MagSgn bits for the missing right column (L1138-1139) */
-        const bool col_ok = (x + (i >> 1)) < w;
-        m[i] = ((rho >> i) & 1) && col_ok && !bad ? (int)U - ((ekq >> i) & 1) : 0;
+        m[i] = ((rho_eff >> i) & 1) ? (int)U - ((ekq >> i) & 1) : 0;
         mlen += m[i];
       }
       uint32_t total;
@@ -880,12 +903,13 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
         bits[i] = __funnelshift_r(wv[i], wv[i + 1], sh);
       uint64_t blo = ((uint64_t)bits[1] << 32) | bits[0], bhi = ((uint64_t)bits[3] << 32) | bits[2];
       int ebot[2] = {0, 0};
+      uint32_t outv[4];
+      const bool refine = REFINE && B.passes > 1;
 #pragma unroll
       for(int i = 0; i < 4; ++i)
       {
-        const int xx = x + (i >> 1), yy = y + (i & 1);
-        uint32_t outv = 0;
-        if(m[i] > 0 || (((rho >> i) & 1) && (x + (i >> 1)) < w && !bad))
+        outv[i] = 0;
+        if((rho_eff >> i) & 1)
         {
           const int mi = m[i];
           const uint32_t msv = (uint32_t)blo;
@@ -897,27 +921,42 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
           uint32_t v_n = msv & (mi >= 32 ? 0xFFFFFFFFu : ((1u << mi) - 1u));
           v_n |= (uint32_t)((e1q >> i) & 1) << mi;
           v_n |= 1u;
-          const uint32_t mag = (v_n + 2u) << (p - 1);
+          const uint32_t mag = ((v_n + 2u) << (p - 1)) & 0x7FFFFFFFu;
           const uint32_t sgn = msv & 1u;
           if(i & 1)
             ebot[i >> 1] = 31 - __clz(v_n | 2u);
-          if(B.passes > 1)
-            outv = (sgn << 31) | (mag & 0x7FFFFFFFu); /* k_ht_decode_refine finishes and dequantises the block */
-          else if(!B.irreversible)
+          if(refine)
+            outv[i] = (sgn << 31) | mag; /* k_ht_decode_refine finishes and dequantises the block */
+          else if(!IRREV)
           {
-            const int32_t mv = (int32_t)((mag & 0x7FFFFFFFu) >> post_shift);
-            outv = (uint32_t)(sgn ? -mv : mv);
+            const int32_t mv = (int32_t)(mag >> post_shift);
+            outv[i] = (uint32_t)(sgn ? -mv : mv);
           }
           else
+            outv[i] = __float_as_uint(__fmul_rn((float)(int32_t)mag, B.quant)) | (sgn << 31); /* quant > 0: the sign bit is free */
+        }
+      }
+      if(qv)
+      {
+        int32_t* c0 = crow + x; /* (x, y); the row below at + pitch */
+        if(vec_ok && x + 1 < w)
+        { /* the lane's two columns of a row are one aligned 8-byte store: a row of the warp is 256 contiguous bytes */
+          *reinterpret_cast<uint2*>(c0) = make_uint2(outv[0], outv[2]);
+          if(y + 1 < h)
+            *reinterpret_cast<uint2*>(c0 + B.pitch) = make_uint2(outv[1], outv[3]);
+        }
+        else
+        {
+          c0[0] = (int32_t)outv[0];
+          if(x + 1 < w)
+            c0[1] = (int32_t)outv[2];
+          if(y + 1 < h)
           {
-            float outf = __fmul_rn((float)(int32_t)(mag & 0x7FFFFFFFu), B.quant);
-            if(sgn)
-              outf = -outf;
-            outv = __float_as_uint(outf);
+            c0[B.pitch] = (int32_t)outv[1];
+            if(x + 1 < w)
+              c0[B.pitch + 1] = (int32_t)outv[3];
           }
         }
-        if(qv && xx < w && yy < h)
-          coef[(size_t)yy * B.pitch + xx] = (int32_t)outv;
       }
       if(qv)
         lcur[q + 1] = (uint16_t)(ebot[0] | (ebot[1] << 8));
@@ -1218,7 +1257,8 @@ void b2k_launch_ht_decode_vlc(const HtBlockDesc* d_blocks, const uint8_t* d_byte
 }
 
 void b2k_launch_ht_decode_magsgn(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, const uint32_t* d_recs,
-                                 const HtBlockOut* d_status, uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st)
+                                 const HtBlockOut* d_status, uint32_t nblocks, uint32_t max_w, int* d_err, int irreversible,
+                                 int any_refinement, cudaStream_t st)
 {
   if(!nblocks)
     return;
@@ -1226,8 +1266,11 @@ void b2k_launch_ht_decode_magsgn(const HtBlockDesc* d_blocks, const uint8_t* d_b
   const size_t smem = (size_t)B2K_WARPS_PER_CTA * MS_RING_WORDS * sizeof(uint32_t) +
                       (size_t)B2K_WARPS_PER_CTA * 2 * line_entries * sizeof(uint16_t);
   const uint32_t grid = (nblocks + B2K_WARPS_PER_CTA - 1) / B2K_WARPS_PER_CTA;
-  k_ht_decode_magsgn<<<grid, B2K_WARPS_PER_CTA * 32, smem, st>>>(d_blocks, d_bytes, d_recs, d_status, nblocks, line_entries,
-                                                                d_err);
+  using Kernel = void (*)(const HtBlockDesc*, const uint8_t*, const uint32_t*, const HtBlockOut*, uint32_t, uint32_t, int*);
+  static const Kernel variants[4] = {k_ht_decode_magsgn<false, false>, k_ht_decode_magsgn<false, true>,
+                                     k_ht_decode_magsgn<true, false>, k_ht_decode_magsgn<true, true>};
+  variants[(irreversible ? 2 : 0) + (any_refinement ? 1 : 0)]<<<grid, B2K_WARPS_PER_CTA * 32, smem, st>>>(
+      d_blocks, d_bytes, d_recs, d_status, nblocks, line_entries, d_err);
   b2k_count_launch();
 }
 
@@ -1242,8 +1285,8 @@ void b2k_launch_ht_decode_refine(const HtBlockDesc* d_blocks, const uint8_t* d_b
 }
 
 void b2k_launch_ht_decode(const HtBlockDesc* d_blocks, const uint8_t* d_bytes, uint32_t* d_recs, HtBlockOut* d_status,
-                          uint32_t nblocks, uint32_t max_w, int* d_err, cudaStream_t st)
+                          uint32_t nblocks, uint32_t max_w, int* d_err, int irreversible, int any_refinement, cudaStream_t st)
 {
   b2k_launch_ht_decode_vlc(d_blocks, d_bytes, d_recs, d_status, nblocks, max_w, st);
-  b2k_launch_ht_decode_magsgn(d_blocks, d_bytes, d_recs, d_status, nblocks, max_w, d_err, st);
+  b2k_launch_ht_decode_magsgn(d_blocks, d_bytes, d_recs, d_status, nblocks, max_w, d_err, irreversible, any_refinement, st);
 }

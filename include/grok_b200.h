@@ -490,6 +490,12 @@ B2K_API int32_t b2k_job_roundtrip(b2k_device_job* j, float* ms_total, float* sta
  * host in it); stage_ms[4] and level1_ms are sums over the steps, ms_total spans first start to last end. */
 B2K_API int32_t b2k_job_roundtrip_n(b2k_device_job* j, uint32_t steps, float* ms_total, float* stage_ms, float* level1_ms,
                                     uint64_t* total_bytes);
+/* the same round trips with the block-coder stage pipelined over `chunks` block ranges on `streams` side streams (0: the
+ * defaults, 2 and 2): the transforms run alone, between them every range goes encode -> compact -> decode on its stream, so
+ * the latency-bound kernels of one range run under the issue-bound kernels of its neighbours.  stage_ms[3] = forward, block
+ * coder (encode + decode), inverse.  Results are those of b2k_job_roundtrip_n, byte for byte. */
+B2K_API int32_t b2k_job_roundtrip_pipelined_n(b2k_device_job* j, uint32_t steps, uint32_t chunks, uint32_t streams, float* ms_total,
+                                              float* stage_ms, float* level1_ms, uint64_t* total_bytes);
 B2K_API int32_t b2k_job_download(b2k_device_job* j, int32_t* const* planes, const uint32_t* strides);
 /* copy the coefficient planes (Mallat layout per tile, image-shaped, int32 or float bits) */
 B2K_API int32_t b2k_job_download_coeffs(b2k_device_job* j, int32_t* const* planes, const uint32_t* strides);
