@@ -38,12 +38,17 @@
 namespace {
 
 #ifndef ENC_WARPS_N
-#define ENC_WARPS_N 5
+#define ENC_WARPS_N 20
 #endif
 #ifndef ENC_MIN_CTAS
-#define ENC_MIN_CTAS 4
+#define ENC_MIN_CTAS 1
 #endif
-constexpr int ENC_WARPS = ENC_WARPS_N; /* warps (= code blocks in flight) per CTA: 5 x 9.3 KB + 8.3 KB of tables -> 4 CTAs, 20 warps per SM */
+/* warps (= code blocks in flight) per CTA, at most: ONE persistent CTA per SM.  For 64-wide blocks a warp needs 9.3 KB of
+   shared memory and the CTA 8.3 KB of tables: 20 warps = 194 KB.  Measured on config 2 (tools/build_variant.py):
+   20 x 1 CTA 1.53 ms, 5 x 4 CTAs 1.66 ms (same warps per SM, but four table copies and 228 KB of shared memory leave the
+   L1 its minimum), 16 x 1 1.68, 23 x 1 1.53, 10 x 2 1.63.  Launches with wider blocks (more shared memory per warp) run
+   with fewer warps per CTA: the kernel takes its warp count from blockDim. */
+constexpr int ENC_WARPS = ENC_WARPS_N;
 constexpr int UNIT_QUADS = 8;       /* quads per unit (even: the VLC stream codes quads in pairs) */
 constexpr int MS_RING_WORDS = 128;  /* 4096 bits: < 1024 left by the last drain + one 2048-bit gather batch */
 constexpr int VLC_RING_WORDS = 64;  /* 2048 bits: < 256 left over + one 1024-bit gather batch */
@@ -431,8 +436,10 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS)
   uint32_t* offs_m = vlc_ring + VLC_RING_WORDS + MEL_CAP / 4; /* [0..32]: where unit u's MagSgn string starts in the round */
   uint32_t* offs_v = offs_m + OFFS_WORDS;
 
-  /* persistent CTAs: the tables above are loaded once per CTA, each warp then walks the block list */
-  for(uint32_t bidx = blockIdx.x * ENC_WARPS + warp; bidx < nblocks; bidx += gridDim.x * ENC_WARPS)
+  /* persistent CTAs: the tables above are loaded once per CTA, each warp then walks the block list with a fixed stride
+     (a work counter instead was measured and changes nothing: 1.524 against 1.529 ms on config 2) */
+  const uint32_t cta_warps = blockDim.x >> 5;
+  for(uint32_t bidx = blockIdx.x * cta_warps + warp; bidx < nblocks; bidx += gridDim.x * cta_warps)
   {
   const HtBlockDesc B = blocks[bidx];
   __syncwarp();
@@ -870,41 +877,74 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS)
   } /* block loop */
 }
 
-/* lengths -> exclusive byte offsets (single CTA scan; nblocks is ~5e4) */
-__global__ void k_scan_lengths(const HtBlockOut* __restrict__ outs, uint64_t* __restrict__ offsets, uint32_t n)
+/* lengths -> exclusive byte offsets.  One CTA of 1024 threads, SCAN_ITEMS consecutive blocks per thread and round:
+   thread-local sums, a shuffle scan inside each warp, one more over the 32 warp totals; ~5e4 blocks take 7 rounds.
+   offsets[0] is the running base: 0 for the first range, the previous range's end otherwise. */
+constexpr int SCAN_ITEMS = 8;
+__global__ void __launch_bounds__(1024) k_scan_lengths(const HtBlockOut* __restrict__ outs, uint64_t* __restrict__ offsets, uint32_t n)
 {
-  __shared__ uint64_t partial[1024];
-  __shared__ uint64_t carry;
+  __shared__ uint64_t warp_sum[32];
+  __shared__ uint64_t carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if(threadIdx.x == 0)
-    carry = offsets[0]; /* running base: 0 for the first range, the previous range's end otherwise */
+    carry_s = offsets[0];
   __syncthreads();
-  for(uint32_t base = 0; base < n; base += 1024)
+  for(uint32_t base = 0; base < n; base += 1024 * SCAN_ITEMS)
   {
-    const uint32_t i = base + threadIdx.x;
-    uint64_t v = 0;
-    if(i < n)
+    const uint32_t i0 = base + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint64_t local = 0;
+#pragma unroll
+    for(int k = 0; k < SCAN_ITEMS; ++k)
     {
-      const uint32_t t = outs[i].total;
-      v = (t == 0xFFFFFFFFu) ? 0 : t;
+      uint32_t t = 0;
+      if(i0 + k < n)
+      {
+        t = outs[i0 + k].total;
+        t = (t == 0xFFFFFFFFu) ? 0u : t;
+      }
+      v[k] = t;
+      local += t;
     }
-    partial[threadIdx.x] = v;
-    __syncthreads();
-    for(int o = 1; o < 1024; o <<= 1)
+    uint64_t incl = local;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1)
     {
-      uint64_t t = threadIdx.x >= o ? partial[threadIdx.x - o] : 0;
-      __syncthreads();
-      partial[threadIdx.x] += t;
-      __syncthreads();
+      const uint64_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if(lane >= o)
+        incl += y;
     }
-    if(i < n)
-      offsets[i] = carry + partial[threadIdx.x] - v;
+    if(lane == 31)
+      warp_sum[warp] = incl;
+    const uint64_t carry = carry_s;
     __syncthreads();
-    if(threadIdx.x == 1023)
-      carry += partial[1023];
+    if(warp == 0)
+    {
+      uint64_t w = warp_sum[lane], wi = w;
+#pragma unroll
+      for(int o = 1; o < 32; o <<= 1)
+      {
+        const uint64_t y = __shfl_up_sync(0xffffffffu, wi, o);
+        if(lane >= o)
+          wi += y;
+      }
+      warp_sum[lane] = wi - w; /* exclusive */
+      if(lane == 31)
+        carry_s = carry + wi;
+    }
     __syncthreads();
+    uint64_t at = carry + warp_sum[warp] + (incl - local);
+#pragma unroll
+    for(int k = 0; k < SCAN_ITEMS; ++k)
+      if(i0 + k < n)
+      {
+        offsets[i0 + k] = at;
+        at += v[k];
+      }
+    __syncthreads(); /* warp_sum and carry_s are rewritten by the next round */
   }
   if(threadIdx.x == 0)
-    offsets[n] = carry;
+    offsets[n] = carry_s;
 }
 
 /* compaction: MagSgn|MEL from the slot head, VLC from the slot tail (warp per block) */
@@ -942,14 +982,22 @@ void b2k_launch_ht_encode(const HtBlockDesc* d_blocks, HtBlockOut* d_out, uint8_
   const uint32_t bits = 4u * UNIT_QUADS * std::min<uint32_t>(32u, lim.max_kmax + 2u);
   lay.ms_w = ((bits + 31u) / 32u) | 1u; /* odd pitch: lanes storing word k of their strings hit 32 different banks */
   const uint32_t warp_words = lay.stage_words + 32u * lay.ms_w + 32u * VLC_UNIT_WORDS + MS_RING_WORDS + VLC_RING_WORDS + MEL_CAP / 4 + 2 * OFFS_WORDS;
-  const size_t smem = 2 * 2048 * sizeof(uint16_t) + 64 * sizeof(uint16_t) + (size_t)ENC_WARPS * warp_words * sizeof(uint32_t);
+  const size_t table_bytes = 2 * 2048 * sizeof(uint16_t) + 64 * sizeof(uint16_t), smem_max = 227 * 1024;
+  /* as many warps per CTA as the opt-in maximum of shared memory holds */
+  uint32_t cta_warps = (uint32_t)std::max<size_t>(1, std::min<size_t>(ENC_WARPS, (smem_max - table_bytes) / (warp_words * sizeof(uint32_t))));
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if(nblocks < (uint32_t)sms * cta_warps) /* a small launch: fewer warps per CTA, every SM still gets one */
+    cta_warps = std::max(1u, (nblocks + (uint32_t)sms - 1u) / (uint32_t)sms);
+  const size_t smem = table_bytes + (size_t)cta_warps * warp_words * sizeof(uint32_t);
   typedef void (*Kernel)(const HtBlockDesc*, HtBlockOut*, uint8_t*, uint32_t, EncLayout);
   const Kernel variants[4] = {k_ht_encode<false, false>, k_ht_encode<false, true>, k_ht_encode<true, false>, k_ht_encode<true, true>};
   static DeviceOnce once; /* function attributes are per device */
   once.run([&] {
     for(Kernel k : variants)
     {
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); /* the opt-in maximum of sm_100 */
       /* the kernel lives on shared memory (staged samples, per-lane bit strings): without this hint the driver may
          size the carve-out for fewer CTAs per SM than fit */
       cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -957,13 +1005,10 @@ void b2k_launch_ht_encode(const HtBlockDesc* d_blocks, HtBlockOut* d_out, uint8_
   });
   const Kernel kern = variants[(irreversible ? 2 : 0) + (lim.max_kmax <= 24 ? 1 : 0)];
   /* persistent grid: as many CTAs as fit on the device at once (the tables are loaded once per CTA) */
-  int dev = 0, sms = 148, per_sm = 1;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ENC_WARPS * 32, smem);
-  const uint32_t want = (nblocks + ENC_WARPS - 1) / ENC_WARPS;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)cta_warps * 32, smem);
+  const uint32_t want = (nblocks + cta_warps - 1) / cta_warps;
   const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(sms * std::max(per_sm, 1)));
-  kern<<<grid, ENC_WARPS * 32, smem, st>>>(d_blocks, d_out, d_scratch, nblocks, lay);
+  kern<<<grid, cta_warps * 32, smem, st>>>(d_blocks, d_out, d_scratch, nblocks, lay);
   b2k_count_launch();
 }
 
