@@ -572,6 +572,18 @@ def main():
     launches = lib.b2k_launch_count() - l0
     job.download(out)
     assert all(np.array_equal(a, b) for a, b in zip(out, planes)), "device-resident round trip is not lossless"
+    pipe = None
+    if world == 1 or bool(os.environ.get("B2K_BENCH_ALL_LEGS")):
+        # extra: the same K round trips with the block-coder stage pipelined over 2 block ranges on 2 streams
+        # (b2k_job_roundtrip_pipelined_n); `value` stays the back-to-back schedule, whose stage times add up
+        job.roundtrip_pipelined_n(2, 2, 2)
+        ms_p, st_p, _, nb_p = job.roundtrip_pipelined_n(args.steps, 2, 2)
+        job.download(out)
+        assert nb_p == nbytes and all(np.array_equal(a, b) for a, b in zip(out, planes)), "pipelined round trip differs"
+        pipe = {"ms_per_step": ms_p / args.steps, "value": W * H / (ms_p / args.steps * 1e-3) / 1e6, "unit": "Mpixels/s",
+                "stage_ms": {"fwd_mct_dwt": st_p[0] / args.steps, "ht_encode_and_decode": st_p[1] / args.steps,
+                             "inv_dwt_mct": st_p[2] / args.steps},
+                "api": "b2k_job_roundtrip_pipelined_n: block-coder stage cut into 2 block ranges on 2 streams, transforms alone"}
     job.close()
 
     # ---------------- end to end through the C ABI with host buffers: `e2e` ----------------
@@ -765,6 +777,8 @@ def main():
                          "algorithmic_bytes_per_launch": int(l1_bytes),
                          "ms_per_launch": l1_ms, "traffic": TRAFFIC_NCU},
         }
+        if pipe is not None:
+            line["device_pipelined"] = pipe
         if extras:
             line.update({
                 "e2e_i32_direct": {"value": pix / dt_e2e32 / 1e6, "unit": "Mpixels/s", "ms_per_step": dt_e2e32 * 1e3,
