@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
   const HtBlockDesc B = blocks[bidx];
   const HtBlockOut st = status[bidx];
   uint32_t* ring = rings + warp * MS_RING_WORDS;
-  uint16_t* line[2] = {lines_all + (size_t)warp * 2 * line_entries, lines_all + (size_t)warp * 2 * line_entries + line_entries};
+  uint16_t* const lines = lines_all + (size_t)warp * 2 * line_entries; /* two rows of bottom-sample exponents, used alternately */
 
   const int w = B.w, h = B.h, nq = (w + 1) >> 1;
   const int kmax = B.kmax;
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
   for(int i = lane; i < MS_RING_WORDS; i += 32)
     ring[i] = 0;
   for(uint32_t i = lane; i < 2 * line_entries; i += 32)
-    line[0][i] = 0;
+    lines[i] = 0;
   __syncwarp();
 
   const int ms_size = (int)st.ms_len;
@@ -778,8 +778,8 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
   for(int y = 0; y < h && !bad; y += 2)
   {
     const int cur = (y >> 1) & 1;
-    const uint16_t* labove = line[cur ^ 1];
-    uint16_t* lcur = line[cur];
+    const uint16_t* labove = lines + (cur ^ 1) * line_entries;
+    uint16_t* lcur = lines + cur * line_entries;
     int32_t* const crow = coef + (size_t)y * B.pitch;
     for(int qb = 0; qb < nq; qb += 32)
     {
@@ -901,40 +901,51 @@ __global__ void __launch_bounds__(B2K_WARPS_PER_CTA * 32)
 #pragma unroll
       for(int i = 0; i < 4; ++i)
         bits[i] = __funnelshift_r(wv[i], wv[i + 1], sh);
-      uint64_t blo = ((uint64_t)bits[1] << 32) | bits[0], bhi = ((uint64_t)bits[3] << 32) | bits[2];
+      /* branch-free over the quad's four samples (an insignificant one has m = 0 and its value is dropped at the end):
+         the window moves on by m bits after each sample; a later sample can only need what is left of 93, 62 and 31 bits,
+         so the shifts shrink from three words to one */
+      uint32_t w0 = bits[0], w1 = bits[1], w2 = bits[2];
+      const uint32_t w3 = bits[3];
       int ebot[2] = {0, 0};
       uint32_t outv[4];
       const bool refine = REFINE && B.passes > 1;
 #pragma unroll
       for(int i = 0; i < 4; ++i)
       {
-        outv[i] = 0;
-        if((rho_eff >> i) & 1)
+        const bool on = ((rho_eff >> i) & 1) != 0;
+        const int mi = m[i]; /* <= 31 (U <= mmsbs + 2 <= 31) */
+        const uint32_t msv = w0;
+        if(i == 0)
         {
-          const int mi = m[i];
-          const uint32_t msv = (uint32_t)blo;
-          if(mi)
-          {
-            blo = (blo >> mi) | (bhi << (64 - mi));
-            bhi >>= mi;
-          }
-          uint32_t v_n = msv & (mi >= 32 ? 0xFFFFFFFFu : ((1u << mi) - 1u));
-          v_n |= (uint32_t)((e1q >> i) & 1) << mi;
-          v_n |= 1u;
-          const uint32_t mag = ((v_n + 2u) << (p - 1)) & 0x7FFFFFFFu;
-          const uint32_t sgn = msv & 1u;
-          if(i & 1)
-            ebot[i >> 1] = 31 - __clz(v_n | 2u);
-          if(refine)
-            outv[i] = (sgn << 31) | mag; /* k_ht_decode_refine finishes and dequantises the block */
-          else if(!IRREV)
-          {
-            const int32_t mv = (int32_t)(mag >> post_shift);
-            outv[i] = (uint32_t)(sgn ? -mv : mv);
-          }
-          else
-            outv[i] = __float_as_uint(__fmul_rn((float)(int32_t)mag, B.quant)) | (sgn << 31); /* quant > 0: the sign bit is free */
+          w0 = __funnelshift_r(w0, w1, mi);
+          w1 = __funnelshift_r(w1, w2, mi);
+          w2 = __funnelshift_r(w2, w3, mi);
         }
+        else if(i == 1)
+        {
+          w0 = __funnelshift_r(w0, w1, mi);
+          w1 = __funnelshift_r(w1, w2, mi);
+        }
+        else if(i == 2)
+          w0 = __funnelshift_r(w0, w1, mi);
+        uint32_t v_n = msv & ((1u << mi) - 1u);
+        v_n |= (uint32_t)((e1q >> i) & 1) << mi;
+        v_n |= 1u;
+        const uint32_t mag = ((v_n + 2u) << (p - 1)) & 0x7FFFFFFFu;
+        const uint32_t sgn = msv & 1u;
+        if(i & 1)
+          ebot[i >> 1] = on ? 31 - __clz(v_n | 2u) : 0;
+        uint32_t val;
+        if(refine)
+          val = (sgn << 31) | mag; /* k_ht_decode_refine finishes and dequantises the block */
+        else if(!IRREV)
+        {
+          const int32_t mv = (int32_t)(mag >> post_shift);
+          val = (uint32_t)(sgn ? -mv : mv);
+        }
+        else
+          val = __float_as_uint(__fmul_rn((float)(int32_t)mag, B.quant)) | (sgn << 31); /* quant > 0: the sign bit is free */
+        outv[i] = on ? val : 0u;
       }
       if(qv)
       {
