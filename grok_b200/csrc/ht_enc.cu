@@ -498,10 +498,10 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS)
           const uint32_t m = (uint32_t)(t < 0 ? -t : t);
           mu = ((m + m) >> shift) >> 1;
         }
-        if(!mu)
-          return 0u;
+        /* branch-free: a zero sample stages as 0 (selected, not branched around) */
         const uint32_t sm = (mu << 1) | sgn;
-        return PACK ? (((uint32_t)(32 - __clz((int)(2u * mu - 1u))) << 26) | sm) : sm;
+        const uint32_t wd = PACK ? (((uint32_t)(32 - __clz((int)(2u * mu - 1u))) << 26) | sm) : sm;
+        return mu ? wd : 0u;
       };
       const bool vec = (((reinterpret_cast<uintptr_t>(cbase) | ((uintptr_t)B.pitch << 2)) & 7u) == 0) && !(w & 1);
       if(vec)
@@ -523,11 +523,10 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS)
             uint32_t* d1 = stage + rr0 * P + c1 + (c1 >> 5);
 #pragma unroll
             for(int k = 0; k < 6; ++k)
-              if(rr0 + k <= 2 * R)
-              {
-                d0[k * P] = convert(raw[k].x);
-                d1[k * P] = convert(raw[k].y);
-              }
+            { /* rows past 2R land in the buffer's spare rows (b2k_ht_encode_stage_words) */
+              d0[k * P] = convert(raw[k].x);
+              d1[k * P] = convert(raw[k].y);
+            }
           }
       }
       else
@@ -642,12 +641,10 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS)
           const int Uq = max(emax, kappa);
           const int uq = Uq - kappa;
           int eps = 0;
-          if(uq > 0)
-          {
 #pragma unroll
-            for(int i = 0; i < 4; ++i)
-              eps |= (e[i] == emax) << i;
-          }
+          for(int i = 0; i < 4; ++i)
+            eps |= (e[i] == emax) << i;
+          eps = uq > 0 ? eps : 0;
           const uint32_t tuple = qv ? (uint32_t)tbl[(cq << 8) + (rho << 4) + eps] : 0u;
           cw[j] = tuple >> 8;
           cwl[j] = (tuple >> 4) & 7;
@@ -656,9 +653,10 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, ENC_MIN_CTAS)
 #pragma unroll
           for(int i = 0; i < 4; ++i)
           {
-            const int m = Uq - (int)((tuple >> i) & 1u);
-            if(qv && sq[i])
-              bits_put(macc, mcnt, mwp, (SM_V(sq[i]) - 2u) & (m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u)), m);
+            /* unconditional append: an insignificant (or absent) sample adds zero bits */
+            const bool on = qv && sq[i] != 0;
+            const int m = on ? Uq - (int)((tuple >> i) & 1u) : 0;
+            bits_put(macc, mcnt, mwp, (SM_V(sq[i]) - 2u) & (m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u)), m);
           }
           /* ---- MEL event of the quad (L664-665, L883-884) ---- */
           if(qv && cq == 0)
@@ -1015,7 +1013,8 @@ void b2k_launch_ht_encode(const HtBlockDesc* d_blocks, HtBlockOut* d_out, uint8_
 /* words of shared memory one warp needs to stage the sample rows of one round of a w-wide block */
 uint32_t b2k_ht_encode_stage_words(uint32_t w)
 {
-  return (2u * enc_rows_per_round(w) + 1u) * enc_stage_pitch(w);
+  /* rows rounded up to the six of a staging trip: the trip's stores need no row test (the spare rows are never read) */
+  return ((2u * enc_rows_per_round(w) + 1u + 5u) / 6u) * 6u * enc_stage_pitch(w);
 }
 
 void b2k_launch_scan_lengths(const HtBlockOut* d_out, uint64_t* d_offsets, uint32_t nblocks, cudaStream_t st)
