@@ -82,6 +82,9 @@ void b2k_launch_dwt_fwd(const DwtLevelDesc* d_descs, int ndesc, int max_jobs, in
                         bool in_u16, cudaStream_t st);
 void b2k_launch_dwt_inv(const DwtLevelDesc* d_descs, int ndesc, int max_jobs, int nc, bool irreversible, bool out_u16,
                         cudaStream_t st);
+/* numres = 1: DC shift + colour transform only (forward: image -> coefficient planes; else back, rounded and clamped) */
+void b2k_launch_point_transform(const DwtLevelDesc* d_descs, int ndesc, uint32_t max_w, uint32_t max_h, int nc, bool irreversible,
+                                bool forward, cudaStream_t st);
 /* per-launch limits the encoder sizes its shared memory from (host: build_block_plan) */
 struct HtEncodeLimits
 {

@@ -2077,6 +2077,130 @@ static void launch_inv97(dim3 grid, dim3 block, cudaStream_t st, const DwtLevelD
   k_dwt97_inv<NC, STAGES><<<grid, block, smem, st>>>(d);
 }
 
+/* ---- tiles with NO wavelet level (numres = 1): what is left of the stage is the point transform -- DC shift + RCT / ICT
+ * forwards, its inverse + rounding + clamp backwards (mct.cpp L497-636 / L201-391; with one resolution the tile itself is the
+ * LL band, TileProcessor.cpp L366-425).  The arithmetic is the level-1 kernels' own (rct_fwd_inplace / ict_fwd_convert,
+ * store_rows53 / store_rows97), one sample per thread; the descriptors reuse DwtLevelDesc: in = image samples of the tile
+ * component(s), out_c = the tile's place in the coefficient planes. */
+template <int NC, bool IRREV, bool FWD>
+__global__ void k_point_transform(const DwtLevelDesc* __restrict__ descs, int ndesc)
+{
+  for(int di = blockIdx.z; di < ndesc; di += gridDim.z)
+  {
+  const DwtLevelDesc& D = descs[di];
+  const int w = D.u1 - D.u0, h = D.v1 - D.v0;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if(x >= w)
+    continue;
+  for(int y = blockIdx.y; y < h; y += gridDim.y)
+  {
+  const size_t ii = (size_t)y * D.in_pitch + x, oi = (size_t)y * D.c_pitch + x;
+  if(FWD)
+  {
+    int v[3];
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+      v[c] = static_cast<const int32_t*>(D.in[c])[ii] + D.shift[c];
+    if(!IRREV)
+    {
+      if(NC == 3)
+      {
+        const int r = v[0], g = v[NC > 1 ? 1 : 0], b = v[NC > 2 ? 2 : 0];
+        v[0] = ((g + g) + b + r) >> 2;
+        v[NC > 1 ? 1 : 0] = b - g;
+        v[NC > 2 ? 2 : 0] = r - g;
+      }
+#pragma unroll
+      for(int c = 0; c < NC; ++c)
+        static_cast<int32_t*>(D.out_c[c])[oi] = v[c];
+    }
+    else
+    {
+      float f[3];
+      if(NC == 3)
+      {
+        const float a_r = 0.299f, a_g = 0.587f, a_b = 0.114f;
+        const float cb = __fdiv_rn(0.5f, __fsub_rn(1.0f, a_b)), cr = __fdiv_rn(0.5f, __fsub_rn(1.0f, a_r));
+        const float r = (float)v[0], g = (float)v[NC > 1 ? 1 : 0], b = (float)v[NC > 2 ? 2 : 0];
+        const float yy = __fmaf_rn(a_b, b, __fmaf_rn(a_g, g, __fmul_rn(a_r, r)));
+        f[0] = yy;
+        f[NC > 1 ? 1 : 0] = __fmul_rn(cb, __fsub_rn(b, yy));
+        f[NC > 2 ? 2 : 0] = __fmul_rn(cr, __fsub_rn(r, yy));
+      }
+      else
+        f[0] = (float)v[0];
+#pragma unroll
+      for(int c = 0; c < NC; ++c)
+        static_cast<float*>(D.out_c[c])[oi] = f[c];
+    }
+  }
+  else
+  {
+    int o[3];
+    if(!IRREV)
+    {
+      int v[3];
+#pragma unroll
+      for(int c = 0; c < NC; ++c)
+        v[c] = static_cast<const int32_t*>(D.out_c[c])[oi];
+      if(NC == 3)
+      {
+        const int yy = v[0], u = v[NC > 1 ? 1 : 0], ww = v[NC > 2 ? 2 : 0];
+        const int gg = yy - ((u + ww) >> 2);
+        v[0] = ww + gg;
+        v[NC > 1 ? 1 : 0] = gg;
+        v[NC > 2 ? 2 : 0] = u + gg;
+      }
+#pragma unroll
+      for(int c = 0; c < NC; ++c)
+        o[c] = v[c];
+    }
+    else
+    {
+      float f[3];
+#pragma unroll
+      for(int c = 0; c < NC; ++c)
+        f[c] = static_cast<const float*>(D.out_c[c])[oi];
+      if(NC == 3)
+      {
+        const float yy = f[0], u = f[NC > 1 ? 1 : 0], ww = f[NC > 2 ? 2 : 0];
+        f[0] = __fmaf_rn(ww, 1.402f, yy);
+        f[NC > 1 ? 1 : 0] = __fmaf_rn(-ww, 0.71414f, __fmaf_rn(-u, 0.34413f, yy));
+        f[NC > 2 ? 2 : 0] = __fmaf_rn(u, 1.772f, yy);
+      }
+#pragma unroll
+      for(int c = 0; c < NC; ++c)
+        o[c] = __float2int_rn(f[c]);
+    }
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+      static_cast<int32_t*>(const_cast<void*>(D.in[c]))[ii] = min(max(o[c] - D.shift[c], D.lo[c]), D.hi[c]);
+  }
+  } /* rows */
+  } /* descriptors */
+}
+
+void b2k_launch_point_transform(const DwtLevelDesc* d, int ndesc, uint32_t max_w, uint32_t max_h, int nc, bool irreversible,
+                                bool forward, cudaStream_t st)
+{
+  if(ndesc <= 0 || !max_w || !max_h)
+    return;
+  dim3 grid((max_w + 127) / 128, std::min<uint32_t>(max_h, 65535u), (unsigned)std::min(ndesc, 65535)), block(128);
+#define B2K_PT(NC_, IR_, FW_) k_point_transform<NC_, IR_, FW_><<<grid, block, 0, st>>>(d, ndesc)
+  if(nc == 3)
+  {
+    if(irreversible) { if(forward) B2K_PT(3, true, true); else B2K_PT(3, true, false); }
+    else { if(forward) B2K_PT(3, false, true); else B2K_PT(3, false, false); }
+  }
+  else
+  {
+    if(irreversible) { if(forward) B2K_PT(1, true, true); else B2K_PT(1, true, false); }
+    else { if(forward) B2K_PT(1, false, true); else B2K_PT(1, false, false); }
+  }
+#undef B2K_PT
+  b2k_count_launch();
+}
+
 void b2k_launch_dwt_inv(const DwtLevelDesc* d, int ndesc, int max_jobs, int nc, bool irreversible, bool out_u16,
                         cudaStream_t st)
 {

@@ -269,6 +269,8 @@ struct LevelLaunch
   std::vector<DwtLevelDesc> descs;
   DwtLevelDesc* d_descs = nullptr;
   int nc = 1, max_jobs = 0;
+  bool point = false;              /* numres = 1: no wavelet level, the launch is the point transform alone */
+  uint32_t max_w = 0, max_h = 0;   /* point launches: largest tile component */
   uint64_t alg_bytes = 0; /* one read + one write of every sample of the level */
   std::vector<uint32_t> tile_first; /* descs of selected tile ti are [tile_first[ti], tile_first[ti+1]) */
 };
@@ -522,6 +524,62 @@ static int build_dwt_plan(b2k_device_job* J)
   const int32_t dc = cp.sgnd ? 0 : -(1 << (cp.prec - 1));
   const int32_t lo = cp.sgnd ? -(1 << (cp.prec - 1)) : 0, hi = cp.sgnd ? (1 << (cp.prec - 1)) - 1 : (1 << cp.prec) - 1;
 
+  if(L == 0)
+  { /* one resolution: the tile is its own LL band; what is left is DC shift + colour transform (dwt.cu k_point_transform) */
+    for(int dir = 0; dir < 2; ++dir)
+    {
+      std::vector<LevelLaunch>& out = dir == 0 ? J->fwd : J->inv;
+      LevelLaunch mctL, sglL;
+      mctL.nc = 3;
+      sglL.nc = 1;
+      mctL.point = sglL.point = true;
+      for(size_t ti = 0; ti < J->tiles.size(); ++ti)
+      {
+        mctL.tile_first.push_back((uint32_t)mctL.descs.size());
+        sglL.tile_first.push_back((uint32_t)sglL.descs.size());
+        const Rect tc = J->tile_rects[ti];
+        if(tc.empty())
+          continue;
+        for(int c = 0; c < ncomp;)
+        {
+          const bool group = cp.mct && c == 0;
+          const int nc = group ? 3 : 1;
+          LevelLaunch& LL = group ? mctL : sglL;
+          DwtLevelDesc d{};
+          d.u0 = (int32_t)tc.x0; d.v0 = (int32_t)tc.y0; d.u1 = (int32_t)tc.x1; d.v1 = (int32_t)tc.y1;
+          d.first_level = 1;
+          d.comp0 = (uint8_t)c;
+          for(int k = 0; k < nc; ++k)
+          {
+            d.in[k] = J->img.at(c + k, tc.x0, tc.y0);
+            d.in_pitch = J->img.pitch;
+            d.out_c[k] = J->coef.at(c + k, tc.x0, tc.y0);
+            d.out_ll[k] = d.out_c[k];
+            d.c_pitch = d.ll_pitch = J->coef.pitch;
+            d.shift[k] = dc;
+            d.lo[k] = lo;
+            d.hi[k] = hi;
+          }
+          LL.descs.push_back(d);
+          LL.max_w = std::max(LL.max_w, tc.w());
+          LL.max_h = std::max(LL.max_h, tc.h());
+          LL.alg_bytes += (uint64_t)tc.w() * tc.h() * nc * 8;
+          c += nc;
+        }
+      }
+      mctL.tile_first.push_back((uint32_t)mctL.descs.size());
+      sglL.tile_first.push_back((uint32_t)sglL.descs.size());
+      if(!mctL.descs.empty()) out.push_back(std::move(mctL));
+      if(!sglL.descs.empty()) out.push_back(std::move(sglL));
+      for(LevelLaunch& Lh : out)
+      {
+        Lh.max_jobs = 1;
+        if(upload_descs(Lh))
+          return -1;
+      }
+    }
+    return 0;
+  }
   /* forward: level 1 (MCT group, then the rest), then levels 2..L component-wise */
   for(int dir = 0; dir < 2; ++dir)
   {
@@ -1261,7 +1319,9 @@ static int enqueue_forward(b2k_device_job* J, cudaStream_t st, bool time_level1,
     const uint32_t d0 = L.tile_first[t0], d1 = L.tile_first[t1];
     if(first && time_level1)
       CUDA_TRY(cudaEventRecord(l1_begin, st));
-    if(d1 > d0)
+    if(d1 > d0 && L.point)
+      b2k_launch_point_transform(L.d_descs + d0, (int)(d1 - d0), L.max_w, L.max_h, L.nc, J->cp.irreversible, true, st);
+    else if(d1 > d0)
       b2k_launch_dwt_fwd(L.d_descs + d0, (int)(d1 - d0), L.max_jobs, L.nc, J->cp.irreversible, l16, st);
     if(first && time_level1)
     {
@@ -1283,7 +1343,9 @@ static int enqueue_inverse(b2k_device_job* J, cudaStream_t st, size_t t0 = 0, si
     (void)use16;
     LevelLaunch& L = J->inv[li];
     const uint32_t d0 = L.tile_first[t0], d1 = L.tile_first[t1];
-    if(d1 > d0)
+    if(d1 > d0 && L.point)
+      b2k_launch_point_transform(L.d_descs + d0, (int)(d1 - d0), L.max_w, L.max_h, L.nc, J->cp.irreversible, false, st);
+    else if(d1 > d0)
       b2k_launch_dwt_inv(L.d_descs + d0, (int)(d1 - d0), L.max_jobs, L.nc, J->cp.irreversible, l16, st);
   }
   CUDA_TRY(cudaGetLastError());

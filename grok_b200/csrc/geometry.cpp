@@ -167,8 +167,8 @@ const char* unsupported_reason(const b2k_coding& cp)
 {
   if(cp.numcomps < 1 || cp.numcomps > 4)
     return "1..4 components supported";
-  if(cp.numres < 2 || cp.numres > 16)
-    return "2..16 resolutions supported (a tile with no wavelet level is left to the host)";
+  if(cp.numres < 1 || cp.numres > 16)
+    return "1..16 resolutions supported";
   if(cp.prec < 1 || cp.prec > 16)
     return "precision 1..16 supported";
   if(cp.cblkw_exp < 2 || cp.cblkh_exp < 2 || cp.cblkw_exp > 10 || cp.cblkh_exp > 10 || cp.cblkw_exp + cp.cblkh_exp > 12)

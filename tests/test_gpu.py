@@ -30,6 +30,8 @@ GEOMS = [
     dict(width=500, height=300, numcomps=3, prec=12, numres=3, cblk=(128, 32)),
     dict(width=300, height=500, numcomps=1, prec=9, numres=3, cblk=(32, 128), tile=(150, 250)),
     dict(width=700, height=90, numcomps=1, prec=8, numres=3, cblk=(256, 16)),
+    dict(width=333, height=217, numcomps=3, prec=12, numres=1, origin=(3, 5), tile=(100, 90)),     # no wavelet level, ragged tiles
+    dict(width=200, height=120, numcomps=4, prec=16, numres=1),
 ]
 
 
@@ -654,6 +656,7 @@ def test_explicit_qcd_on_the_device(engine):
     dict(width=64, height=64, numcomps=3, prec=10, numres=3, tile=(1, 64)),                          # 1-pixel-wide tiles
     dict(width=40, height=33, numcomps=1, prec=12, numres=2, tile=(7, 1), cblk=(4, 4)),              # 1-pixel-high tiles
     dict(width=333, height=217, numcomps=3, prec=12, numres=4, origin=(3, 5), tile=(100, 90)),       # odd origin, ragged tiles
+    dict(width=333, height=217, numcomps=3, prec=12, numres=1, origin=(3, 5), tile=(100, 90)),       # no wavelet level
 ])
 def test_irreversible_degenerate_geometry(engine, args):
     """GrkDegenerate97Test / GrkShortTileRoundTripTest shapes on the 9/7 + ICT path: width / height 1 special cases

@@ -126,8 +126,10 @@ def test_engine_fails_loudly_without_gpu():
 
 
 def test_unsupported_coding_is_not_handled_not_an_error():
-    cp = G.make_coding(64, 64, 1, 8, numres=1)  # no wavelet level: left to the host
+    cp = G.make_coding(64, 64, 1, 8, numres=17)  # more resolutions than the engine plans for: left to the host
     assert G.lib().b2k_enumerate(C.byref(cp), 1, 0, None, 0) < 0
+    cp = G.make_coding(64, 64, 1, 8, numres=1)   # no wavelet level is fine (DC shift + colour transform only)
+    assert G.lib().b2k_enumerate(C.byref(cp), 1, 0, None, 0) == 1
 
 
 _WORKER = r'''
@@ -333,7 +335,7 @@ def test_ht_bit_plane_limits_are_declined_with_a_reason():
         deep.qcd_expn[i] = 31
     assert lib.b2k_enumerate(C.byref(deep), 1, 0, None, 0) < 0
     assert b"bit planes" in lib.b2k_last_error()
-    for bad in (dict(prec=17), dict(numcomps=5), dict(cblk=(1024, 8)), dict(numres=17), dict(numres=1)):
+    for bad in (dict(prec=17), dict(numcomps=5), dict(cblk=(1024, 8)), dict(numres=17), dict(numres=0)):
         args = dict(width=64, height=64, numcomps=1, prec=8, numres=3)
         args.update(bad)
         assert lib.b2k_enumerate(C.byref(G.make_coding(**args)), 1, 0, None, 0) < 0, bad

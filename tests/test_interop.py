@@ -67,6 +67,8 @@ REVERSIBLE = [
     dict(width=300, height=260, numcomps=3, prec=8, numres=3, cblk=(32, 32)),
     dict(width=1100, height=700, numcomps=3, prec=10, numres=10),                      # 9 decomposition levels (> 8 resolutions)
     dict(width=900, height=600, numcomps=1, prec=12, numres=10, tile=(512, 512)),      # as many levels as a 512 tile takes (the host clamps more)
+    dict(width=333, height=217, numcomps=3, prec=12, numres=1, tile=(128, 128)),       # no wavelet level: DC shift + RCT only
+    dict(width=130, height=90, numcomps=4, prec=16, numres=1),                         # ... with an untransformed 4th component
 ]
 IRREVERSIBLE = [
     dict(width=640, height=384, numcomps=3, prec=12, irreversible=True),              # config 3 in small
@@ -74,6 +76,8 @@ IRREVERSIBLE = [
     dict(width=300, height=200, numcomps=1, prec=12, irreversible=True),
     dict(width=320, height=192, numcomps=3, prec=16, irreversible=True, numres=5),
     dict(width=1100, height=700, numcomps=3, prec=10, irreversible=True, numres=10),
+    dict(width=200, height=150, numcomps=3, prec=12, irreversible=True, numres=1),     # no wavelet level: ICT + quantiser only
+    dict(width=130, height=90, numcomps=1, prec=10, irreversible=True, numres=1, tile=(64, 64)),
 ]
 
 

@@ -58,6 +58,7 @@ STOCK_CASES = [
     dict(width=600, height=500, numcomps=3, prec=12, numres=5, precinct=[128, 128]),    # res_spec < numresolution
     dict(width=640, height=384, numcomps=3, prec=12, irreversible=True),
     dict(width=333, height=217, numcomps=4, prec=16, numres=4),
+    dict(width=300, height=200, numcomps=3, prec=12, numres=1),                          # no wavelet level
 ]
 
 
