@@ -59,7 +59,7 @@ assert BLOCK_DTYPE.itemsize == C.sizeof(Block), (BLOCK_DTYPE.itemsize, C.sizeof(
 # plugin_decompress (C++-ABI callback struct) is declared in csrc/plugin_decode_abi.h, not in the C header
 EXPORTS = ["minpf_post_load_plugin", "plugin_init", "plugin_get_debug_state", "gpup_encode_mem", "gpup_tile_free",
            "b2k_engine_create", "b2k_engine_destroy", "b2k_last_error", "b2k_host_alloc", "b2k_host_free",
-           "b2k_encode", "b2k_encode16", "b2k_encode16_interleaved", "b2k_result_free", "b2k_decode", "b2k_decode16", "b2k_enumerate",
+           "b2k_encode", "b2k_encode16", "b2k_encode16_interleaved", "b2k_result_free", "b2k_decode", "b2k_decode16", "b2k_decode_window", "b2k_enumerate",
            "b2k_result_to_gpup_tile", "b2k_job_create", "b2k_job_destroy", "b2k_job_upload", "b2k_job_forward",
            "b2k_job_t1_encode", "b2k_job_t1_decode", "b2k_job_t1_decode_blocks", "b2k_job_inverse", "b2k_job_roundtrip", "b2k_job_roundtrip_n", "b2k_job_roundtrip_pipelined_n", "b2k_job_download",
            "b2k_job_download_coeffs", "b2k_job_upload_coeffs", "b2k_job_fetch_result", "b2k_job_num_blocks",
@@ -424,7 +424,7 @@ class Engine:
 
     def decode_window(self, cs, window=None, reduce=0, dtype=np.int32):
         """Tile-granular windowed / reduced-resolution decode of an HTJ2K codestream (b2k_codestream_parse_window +
-        b2k_decode + crop).  window = (x0, y0, x1, y1) on the full-resolution canvas or None; returns (virtual Coding,
+        b2k_decode_window: the touched tiles are decoded, the window's pixels alone are copied back).  window = (x0, y0, x1, y1) on the full-resolution canvas or None; returns (virtual Coding,
         planes of the window at 1 / 2**reduce resolution).  The planes are views of pinned buffers the engine keeps and
         reuses for later windows of the same tile-box shape: copy them to keep them."""
         cs = np.ascontiguousarray(cs, dtype=np.uint8)
@@ -440,21 +440,28 @@ class Engine:
         m = L.b2k_codestream_parse_window(cs.ctypes.data, len(cs), win, reduce, C.byref(cp), blocks.ctypes.data, n)
         if m != n:
             raise EngineError("b2k_codestream_parse_window: %d %s" % (m, (L.b2k_last_error() or b"").decode()))
-        # pinned landing planes, kept per shape (windows of one size keep hitting the same few tile-box shapes)
+        if window is None:
+            rect = (cp.x0, cp.y0, cp.x1, cp.y1)
+        else:
+            sh = (1 << reduce) - 1
+            x0, y0, x1, y1 = [(v + sh) >> reduce for v in window]
+            rect = (max(x0, cp.x0), max(y0, cp.y0), min(x1, cp.x1), min(y1, cp.y1))
+        # pinned landing planes of the WINDOW's size, kept per shape: only the window's pixels come back over PCIe
         cache = self.__dict__.setdefault("_win_planes", {})
-        key = (cp.y1 - cp.y0, cp.x1 - cp.x0, cp.numcomps, np.dtype(dtype).str)
-        full = cache.get(key)
-        if full is None:
+        key = (rect[3] - rect[1], rect[2] - rect[0], cp.numcomps, np.dtype(dtype).str)
+        out = cache.get(key)
+        if out is None:
             if len(cache) >= 8:
                 cache.pop(next(iter(cache)))
-            full = cache[key] = [pinned_empty((cp.y1 - cp.y0, cp.x1 - cp.x0), dtype) for _ in range(cp.numcomps)]
-        self.decode(cp, blocks, cs, full)
-        if window is None:
-            return cp, full
-        sh = (1 << reduce) - 1
-        x0, y0, x1, y1 = [(v + sh) >> reduce for v in window]
-        x0, y0, x1, y1 = max(x0, cp.x0), max(y0, cp.y0), min(x1, cp.x1), min(y1, cp.y1)
-        return cp, [p[y0 - cp.y0:y1 - cp.y0, x0 - cp.x0:x1 - cp.x0] for p in full]
+            out = cache[key] = [pinned_empty((key[0], key[1]), dtype) for _ in range(cp.numcomps)]
+        ptrs, strides = _plane_ptrs(out)
+        ms = C.c_double()
+        L.b2k_decode_window.argtypes = [C.c_void_p, C.POINTER(Coding), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32,
+                                        C.POINTER(C.c_double)]
+        _check(L.b2k_decode_window(self._h, C.byref(cp), blocks.ctypes.data, n, cs.ctypes.data, len(cs), ptrs, strides,
+                                   (C.c_uint32 * 4)(*rect), np.dtype(dtype).itemsize, C.byref(ms)), "b2k_decode_window")
+        return cp, out
 
     def decode(self, cp, blocks, data, out_planes, tile_mod=1, tile_rem=0):
         ptrs, strides = _plane_ptrs(out_planes)

@@ -357,6 +357,8 @@ struct b2k_device_job
   HtBlockDesc* h_dec_desc = nullptr;   /* pinned staging */
   HtBlockOut* d_out = nullptr;
   uint64_t* d_offsets = nullptr;
+  bool has_crop = false;           /* b2k_decode_window: only this rectangle of the pixels goes back to the host, */
+  Rect crop{};                     /* and the host planes are the rectangle's (row 0 / column 0 = crop.y0 / crop.x0) */
   uint32_t* d_recs = nullptr;     /* decode: per-quad records between the two decode phases */
   float* d_dec_quant = nullptr;
   HtBlockOut* d_dec_status = nullptr;
@@ -899,10 +901,22 @@ static int copy_planes(b2k_device_job* J, const Planes& P, void* const* host, co
       r.x1 = J->tile_rects[tj].x1;
       ++tj;
     }
+    uint32_t ox = cp.x0, oy = cp.y0; /* canvas position of the host planes' first sample */
+    if(!to_device && J->has_crop)
+    {
+      r.x0 = std::max(r.x0, J->crop.x0); r.y0 = std::max(r.y0, J->crop.y0);
+      r.x1 = std::min(r.x1, J->crop.x1); r.y1 = std::min(r.y1, J->crop.y1);
+      ox = J->crop.x0; oy = J->crop.y0;
+      if(r.x1 <= r.x0 || r.y1 <= r.y0)
+      {
+        ti = tj;
+        continue;
+      }
+    }
     for(int c = 0; c < cp.numcomps; ++c)
     {
       int32_t* dev = P.at(c, r.x0, r.y0);
-      int32_t* hst = reinterpret_cast<int32_t*>(host[c]) + (size_t)(r.y0 - cp.y0) * strides[c] + (r.x0 - cp.x0);
+      int32_t* hst = reinterpret_cast<int32_t*>(host[c]) + (size_t)(r.y0 - oy) * strides[c] + (r.x0 - ox);
       if(to_device)
         CUDA_TRY(cudaMemcpy2DAsync(dev, (size_t)P.pitch * 4, hst, (size_t)strides[c] * 4, (size_t)r.w() * 4, r.h(),
                                    cudaMemcpyHostToDevice, st));
@@ -1009,10 +1023,22 @@ static int copy_planes16(b2k_device_job* J, void* const* host, const uint32_t* s
       r.x1 = J->tile_rects[tj].x1;
       ++tj;
     }
+    uint32_t ox = cp.x0, oy = cp.y0;
+    if(!to_device && J->has_crop)
+    {
+      r.x0 = std::max(r.x0, J->crop.x0); r.y0 = std::max(r.y0, J->crop.y0);
+      r.x1 = std::min(r.x1, J->crop.x1); r.y1 = std::min(r.y1, J->crop.y1);
+      ox = J->crop.x0; oy = J->crop.y0;
+      if(r.x1 <= r.x0 || r.y1 <= r.y0)
+      {
+        ti = tj;
+        continue;
+      }
+    }
     for(int c = 0; c < cp.numcomps; ++c)
     {
       uint16_t* dev = P.at(c, r.x0, r.y0);
-      uint16_t* hst = reinterpret_cast<uint16_t*>(host[c]) + (size_t)(r.y0 - cp.y0) * strides[c] + (r.x0 - cp.x0);
+      uint16_t* hst = reinterpret_cast<uint16_t*>(host[c]) + (size_t)(r.y0 - oy) * strides[c] + (r.x0 - ox);
       if(strides[c] == P.pitch && r.w() == P.pitch)
       { /* contiguous on both sides: one linear copy */
         if(to_device)
@@ -2316,7 +2342,7 @@ extern "C" int32_t b2k_encode16_interleaved(b2k_engine* e, const b2k_coding* cp,
 
 static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks, uint64_t num_blocks,
                              const uint8_t* bytes, uint64_t num_bytes, void* const* planes, const uint32_t* strides,
-                             uint32_t tile_mod, uint32_t tile_rem, double* ms_total, bool u16);
+                             uint32_t tile_mod, uint32_t tile_rem, double* ms_total, bool u16, const uint32_t* crop = nullptr);
 
 extern "C" int32_t b2k_decode(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks, uint64_t num_blocks,
                               const uint8_t* bytes, uint64_t num_bytes, int32_t* const* planes, const uint32_t* strides,
@@ -2333,26 +2359,52 @@ extern "C" int32_t b2k_decode16(b2k_engine* e, const b2k_coding* cp, const b2k_b
                        ms_total, true);
 }
 
+/* b2k_decode / b2k_decode16 with only `window` (x0, y0, x1, y1 in cp's canvas coordinates) of the pixels returned: planes[c]
+   holds window rows of strides[c] samples.  With b2k_codestream_parse_window this is the windowed decode of SURVEY 8f N3: the
+   tiles the window touches are decoded, the window's pixels alone cross PCIe. */
+extern "C" int32_t b2k_decode_window(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks, uint64_t num_blocks,
+                                     const uint8_t* bytes, uint64_t num_bytes, void* const* planes, const uint32_t* strides,
+                                     const uint32_t* window, uint32_t sample_bytes, double* ms_total)
+{
+  if(!window || (sample_bytes != 2 && sample_bytes != 4))
+    return -1;
+  return decode_common(e, cp, blocks, num_blocks, bytes, num_bytes, planes, strides, 1, 0, ms_total, sample_bytes == 2, window);
+}
+
 static int32_t decode_common(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks, uint64_t num_blocks,
                              const uint8_t* bytes, uint64_t num_bytes, void* const* planes, const uint32_t* strides,
-                             uint32_t tile_mod, uint32_t tile_rem, double* ms_total, bool u16)
+                             uint32_t tile_mod, uint32_t tile_rem, double* ms_total, bool u16, const uint32_t* crop)
 {
   if(!e || !cp || !blocks || !planes || !strides)
     return -1;
+  if(crop && (crop[0] >= crop[2] || crop[1] >= crop[3] || crop[0] < cp->x0 || crop[1] < cp->y0 || crop[2] > cp->x1 || crop[3] > cp->y1))
+  {
+    g_err = "window outside the image";
+    return -1;
+  }
   std::lock_guard<std::mutex> lock(e->mu);
   int rc = 0;
   b2k_device_job* J = cached_job(e, cp, tile_mod, tile_rem, &rc);
   if(rc)
     return rc;
   CUDA_TRY(cudaSetDevice(e->device));
+  /* a window: only its pixels cross PCIe on the way back, into planes of the window's size (copy_planes / copy_planes16) */
+  J->has_crop = crop != nullptr;
+  if(crop)
+    J->crop = Rect{crop[0], crop[1], crop[2], crop[3]};
+  struct CropEnd
+  {
+    b2k_device_job* j;
+    ~CropEnd() { j->has_crop = false; }
+  } crop_end{J};
   void* const* user_planes = planes;
   const uint32_t* user_strides = strides;
   void* stage_planes[4];
   uint32_t stage_strides[4];
   /* several ranks on one host share its DRAM and CPU quota: measured packing loses there,
      so the automatic policy only considers it for a process that has the host to itself */
-  const bool tuned = !u16 && host_pack_eligible(J) && g_pack_policy.load() < 0 && b2k_host_local_peers() == 1;
-  const bool pack = !u16 && host_pack_eligible(J) && (tuned ? J->tune_dec.next_mode() : g_pack_policy.load() > 0);
+  const bool tuned = !crop && !u16 && host_pack_eligible(J) && g_pack_policy.load() < 0 && b2k_host_local_peers() == 1;
+  const bool pack = !crop && !u16 && host_pack_eligible(J) && (tuned ? J->tune_dec.next_mode() : g_pack_policy.load() > 0);
   const auto wall0 = std::chrono::steady_clock::now();
   if(!u16)
     g_last_pack[1].store(pack ? 1 : 0);

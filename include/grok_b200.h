@@ -456,6 +456,13 @@ B2K_API int32_t b2k_decode(b2k_engine* e, const b2k_coding* cp, const b2k_block*
                            uint64_t num_blocks, const uint8_t* bytes, uint64_t num_bytes,
                            int32_t* const* planes, const uint32_t* strides, uint32_t tile_mod,
                            uint32_t tile_rem, double* ms_total);
+/* b2k_decode / b2k_decode16 returning only `window` = (x0, y0, x1, y1), in cp's canvas coordinates, of the pixels:
+ * planes[c] holds the window's rows (strides[c] samples apart), sample_bytes = 4 (int32) or 2 (16-bit containers).  The tiles
+ * of cp are decoded as usual; only the window's pixels cross PCIe.  Made for the virtual coding of
+ * b2k_codestream_parse_window (windowed / reduced decode). */
+B2K_API int32_t b2k_decode_window(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks, uint64_t num_blocks,
+                                  const uint8_t* bytes, uint64_t num_bytes, void* const* planes, const uint32_t* strides,
+                                  const uint32_t* window, uint32_t sample_bytes, double* ms_total);
 /* same, pixels returned in 16-bit containers (reversible path) */
 B2K_API int32_t b2k_decode16(b2k_engine* e, const b2k_coding* cp, const b2k_block* blocks,
                              uint64_t num_blocks, const uint8_t* bytes, uint64_t num_bytes,
