@@ -1396,6 +1396,33 @@ static int64_t parse_impl(const uint8_t* cs, uint64_t len, const uint32_t* windo
     if(const char* why = unsupported_reason(vcp))
       return fail(why, 1);
   }
+  /* ---- which code blocks a window needs ("only the code blocks ... an ROI needs") ----
+   * need[r] = the samples of resolution r (canvas coordinates of the virtual coding) that the window's pixels depend on.
+   * The top resolution needs the window itself; one synthesis step down, a sample at x depends on the low / high band
+   * samples around x / 2: within 1 for the 5/3 filter pair (x[2n+1] uses L[n], L[n+1], H[n-1..n+1]), within 3 for the
+   * four lifting steps of 9/7 -- taken as 2 and 5.  A block of resolution r >= 1 lives in band coordinates, i.e. those
+   * of resolution r - 1.  Blocks outside are handed back with length 0 ("not in any packet": decoded as zeros): their
+   * coefficients cannot reach the window. */
+  std::vector<Rect> need;
+  if(window && !whole)
+  {
+    const uint32_t m = (1u << reduce) - 1u;
+    Rect w{(std::max(window[0], cp.x0) + m) >> reduce, (std::max(window[1], cp.y0) + m) >> reduce,
+           (std::min(window[2], cp.x1) + m) >> reduce, (std::min(window[3], cp.y1) + m) >> reduce};
+    w.x0 = std::max(w.x0, vcp.x0); w.y0 = std::max(w.y0, vcp.y0);
+    w.x1 = std::min(w.x1, vcp.x1); w.y1 = std::min(w.y1, vcp.y1);
+    if(w.x1 > w.x0 && w.y1 > w.y0)
+    {
+      const uint32_t M = vcp.irreversible ? 5u : 2u;
+      need.assign(vcp.numres, w);
+      for(int r = (int)vcp.numres - 2; r >= 0; --r)
+      {
+        const Rect& f = need[r + 1];
+        need[r] = Rect{(f.x0 >> 1) > M ? (f.x0 >> 1) - M : 0u, (f.y0 >> 1) > M ? (f.y0 >> 1) - M : 0u, ((f.x1 + 1) >> 1) + M,
+                       ((f.y1 + 1) >> 1) + M};
+      }
+    }
+  }
   const TileGrid vg = tile_grid(vcp);
   const uint32_t vnt = vg.nx * vg.ny;
   if(!whole && (vg.nx != tb_x - ta_x || vg.ny != tb_y - ta_y))
@@ -1500,11 +1527,20 @@ static int64_t parse_impl(const uint8_t* cs, uint64_t len, const uint32_t* windo
         errs[vt] = "internal: virtual and original block enumerations disagree";
         return;
       }
-      vb[k].length = b.length;
-      vb[k].length2 = b.length2;
-      vb[k].offset = b.offset;
-      vb[k].numbps = b.numbps;
-      vb[k].numpasses = b.numpasses;
+      bool wanted = true;
+      if(!need.empty())
+      { /* the block's rectangle is in band coordinates = those of resolution max(resno - 1, 0) */
+        const Rect& n = need[vb[k].resno ? vb[k].resno - 1 : 0];
+        wanted = vb[k].x0 < n.x1 && vb[k].x1 > n.x0 && vb[k].y0 < n.y1 && vb[k].y1 > n.y0;
+      }
+      if(wanted)
+      {
+        vb[k].length = b.length;
+        vb[k].length2 = b.length2;
+        vb[k].offset = b.offset;
+        vb[k].numbps = b.numbps;
+        vb[k].numpasses = b.numpasses;
+      }
       ++k;
     }
     if(k != vb.size() || vb.size() != tile_first[vt + 1] - tile_first[vt])

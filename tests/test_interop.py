@@ -277,6 +277,9 @@ WINDOW_CASES = [
     (dict(width=700, height=500, numcomps=3, prec=12, tile=(256, 128), numres=5), (10, 300, 400, 500), 2),
     (dict(width=640, height=384, numcomps=1, prec=8, tile=(128, 128), numres=4), (129, 1, 255, 127), 1),
     (dict(width=333, height=217, numcomps=3, prec=12, numres=5), None, 2),                      # single tile, reduce only
+    (dict(width=900, height=700, numcomps=1, prec=12, numres=6), (411, 303, 475, 351), 0),      # a window far smaller than its tile
+    (dict(width=900, height=700, numcomps=3, prec=12, numres=6, irreversible=True), (411, 303, 475, 351), 0),   # ... with the 9/7 support
+    (dict(width=1000, height=600, numcomps=3, prec=12, tile=(512, 512), numres=5, irreversible=True), (500, 100, 530, 140), 1),
 ]
 
 
@@ -290,7 +293,7 @@ def test_window_and_reduce_parse_matches_grok(args, window, reduce):
     w, h, n = args["width"], args["height"], args["numcomps"]
     rw, rh = -(-w >> reduce), -(-h >> reduce)
     ref, _, _ = R.decompress(theirs, rw, rh, n, reduce=reduce)                # Grok's own reduced decode of the whole image
-    if reduce == 0:
+    if reduce == 0 and not args.get("irreversible"):
         for a, b in zip(ref, planes):
             assert np.array_equal(a, b)
     vcp, blocks = _parse_window(theirs, window, reduce)
@@ -300,10 +303,35 @@ def test_window_and_reduce_parse_matches_grok(args, window, reduce):
     x0, y0, x1, y1 = [(v + sh) >> reduce for v in full_win]
     assert vcp.x0 <= x0 and vcp.y0 <= y0 and vcp.x1 >= x1 and vcp.y1 >= y1
     if window is not None:       # tile-granular: at most the touched tiles are decoded
-        tw, th = args["tile"]
+        tw, th = args.get("tile", (w, h))
         assert (vcp.x1 - vcp.x0) <= ((-(-window[2] // tw) - window[0] // tw) * tw + sh) >> reduce
     for a, b in zip(rec, ref):
         assert np.array_equal(a[y0 - vcp.y0:y1 - vcp.y0, x0 - vcp.x0:x1 - vcp.x0], b[y0:y1, x0:x1])
+
+
+@pytest.mark.parametrize("irreversible", [False, True])
+def test_window_parse_keeps_exactly_the_blocks_a_window_can_depend_on(irreversible):
+    """Block-granular selection inside the touched tiles: code blocks whose coefficients cannot reach the
+    window come back with length 0.  Random small windows of one image: every window's pixels equal the crop of the full
+    decode, and most of the touched tiles' coded bytes are not needed."""
+    args = dict(width=768, height=640, numcomps=1, prec=12, tile=(512, 512), numres=6, irreversible=irreversible)
+    planes = synth(args, seed=21)
+    theirs = grok_compress(args, planes)
+    fcp, fblocks = G.codestream_parse(theirs)
+    full = oracle_decode(fcp, fblocks, theirs)
+    rng = np.random.default_rng(7)
+    saved = []
+    for _ in range(8):
+        x0, y0 = int(rng.integers(0, 700)), int(rng.integers(0, 580))
+        win = (x0, y0, min(768, x0 + int(rng.integers(1, 90))), min(640, y0 + int(rng.integers(1, 70))))
+        vcp, blocks = _parse_window(theirs, win, 0)
+        rec = oracle_decode(vcp, blocks, theirs)
+        a = rec[0][win[1] - vcp.y0:win[3] - vcp.y0, win[0] - vcp.x0:win[2] - vcp.x0]
+        assert np.array_equal(a, full[0][win[1]:win[3], win[0]:win[2]]), win
+        # against the same tiles parsed whole
+        tiles_cp, tiles_blocks = _parse_window(theirs, (vcp.x0, vcp.y0, vcp.x1, vcp.y1), 0)
+        saved.append(1.0 - blocks["length"].sum() / max(1, tiles_blocks["length"].sum()))
+    assert min(saved) > 0.3 and np.mean(saved) > 0.6, saved
 
 
 @pytest.mark.gpu
