@@ -68,6 +68,7 @@ CASES = [
     dict(width=200, height=120, numcomps=1, prec=16, numres=3, cblk=(32, 32)),                    # 16-bit grey
     dict(width=61, height=9, numcomps=1, prec=8, numres=6),                                       # levels run out of samples
     dict(width=130, height=70, numcomps=3, prec=8, numres=3, tile=(64, 64), origin=(64, 33), tile_origin=(1, 1), cblk=(16, 64)),   # tile grid anchored before the image
+    dict(width=150, height=110, numcomps=3, prec=8, numres=1, tile=(64, 64)),                     # no wavelet level at all
 ]
 
 
