@@ -1244,7 +1244,7 @@ static int64_t parse_impl(const uint8_t* cs, uint64_t len, const uint32_t* windo
         const uint32_t style = sqcd & 0x1F;
         if(style > 2)
           return fail("unknown quantisation style", -1);
-        while(s.p < s.end)
+        while(s.ok && s.p < s.end) /* an odd byte left over in a 16-bit QCD ends the loop through s.ok */
           qcd_vals.push_back(style == 0 ? s.u8() : s.u16());
         have_qcd = s.ok;
         break;

@@ -5,6 +5,7 @@ with this repo or with the reference, and must give back the source image exactl
 the reference's lossy tolerances (irreversible path).  That pins, end to end: marker segments, packet headers
 (tag trees, Lblock, HT segment lengths), TLM/PLT, and with them the oracle's DWT / RCT / quantiser / HT coder."""
 import io
+import os
 
 import numpy as np
 import pytest
@@ -358,3 +359,32 @@ def test_writer_matches_the_python_t2_oracle_byte_for_byte(args):
         dec = openjpeg_pillow(want)
         src = planes[0] if len(planes) == 1 else np.stack(planes, axis=-1)
         assert np.array_equal(dec.astype(np.int64), src)
+
+
+def test_parser_survives_mutated_streams():
+    """Untrusted input: mutated / truncated code streams and JPH files (tests/fuzz_parser_driver.py, in a subprocess) always
+    come back as an error, "not handled" or a block table inside the buffer.  (The same driver runs against an
+    AddressSanitizer + UBSan build of codestream.cpp / geometry.cpp when one is passed to it; that is how the endless QCD loop
+    pinned below was found.)"""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    p = subprocess.run([sys.executable, os.path.join(here, "fuzz_parser_driver.py"), "11", "300"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=600)
+    assert p.returncode == 0 and "FUZZ ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_qcd_with_a_dangling_byte_is_an_error_not_a_loop():
+    """A 16-bit-per-band QCD (style 1 / 2) whose payload has an odd byte left over used to spin forever, allocating."""
+    args = dict(width=64, height=48, numcomps=1, prec=8, numres=3, irreversible=True)
+    cp = G.make_coding(**args)
+    planes = P.synthetic_image(64, 48, 1, 8, seed=3)
+    table, data, _ = oracle_encode(cp, planes)
+    cs = bytearray(G.codestream_write(cp, table, data, 0).tobytes())
+    i = cs.index(b"\xff\x5c")                       # QCD
+    lqcd = (cs[i + 2] << 8) | cs[i + 3]
+    assert (cs[i + 4] & 0x1F) == 2                    # expounded: 16-bit entries
+    cs[i + 2:i + 4] = bytes([(lqcd + 1) >> 8, (lqcd + 1) & 0xFF])
+    cs.insert(i + 2 + lqcd, 0)                        # one dangling byte inside the segment
+    with pytest.raises((G.EngineError, G.NotHandled)):
+        G.codestream_parse(np.frombuffer(bytes(cs), np.uint8))
